@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Headline benchmark: ALS-NMF iterations/s at 20 000 x 5 000, k = 16, FP64 (BASELINE.json configs[3]).
+
+A "step" is one ALS iteration of ``als_nmf``'s inner loop (H-step + W-step + residual /
+convergence scalars, ``R/bicluster.R:119-203``) on the synthetic genSimData-shaped matrix D4 of
+SURVEY.md section 8(d), convergence break disabled (fixed-iteration mode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+* ``value``  : iterations/s with A resident in HBM, timed with CUDA events on the library's stream.
+* ``e2e``    : the same metric through the public call with HOST buffers
+               (``mfb_als_run_host``: upload of A from pinned memory, K iterations, download of W/H).
+* ``roofline``: achieved HBM GB/s of the streaming kernel (2 launches per iteration, each reads A
+               once: algorithmic bytes = m*n*8 per launch) against MEASURED_PEAKS.json ``hbm_gbs``.
+* ``cpu_baseline``: the NumPy oracle (literal restatement of the R loop incl. t(A) copy and the m x n
+               residual temporary) on the host cores, on a bounded number of iterations.
+* N > 1 (torchrun): als_nmf's ``reps`` axis -- each rank runs an independent replicate on its own
+  GPU (no data-path collective), ``value`` = total iterations/s, ``scaling`` = weak.
+* ``--impl reference``: R is not installed and the reference's arithmetic lives in un-vendored
+  packages, so the reference arm times the oracle port on all host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_ROWS, N_COLS, RANK = 20000, 5000, 16
+METRIC = "ALS-NMF iters/s @20kx5k k=16 (FP64)"
+UNIT = "iter/s"
+
+
+def make_workload(m=M_ROWS, n=N_COLS, k=RANK, seed=4):
+    """D4: genSimData(n=5, dimx=20000, dimy=5000, clusterHeight=clusterWidth=1000, bgNorm=1,
+    biclusterShift=3, rowShift=1, colShift=1), then pseudovalues(); W0 ~ U(0,1) column-normalised,
+    Hold0 ~ U(0,1)."""
+    from oracle.gen_sim_data import gen_sim_data
+    from oracle.helpers import pseudovalues
+    side = min(m, n) // 5
+    A = gen_sim_data(n=5, cluster_height=side, cluster_width=side, dimx=m, dimy=n, bg_norm=1.0,
+                     bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=seed)
+    A = np.asfortranarray(pseudovalues(A))
+    rs = np.random.default_rng(40)
+    W0 = rs.random((m, k))
+    W0 /= np.sqrt((W0 ** 2).sum(axis=0))[None, :]
+    H0 = rs.random((k, n))
+    return A, np.asfortranarray(W0), np.asfortranarray(H0)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU oracle port (literal R loop) on all host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle.als_nmf import als_replicate
+    A, W0, H0 = make_workload()
+    cores = os.cpu_count()
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # bounded sample: each timed "step" is one literal iteration of the full-size workload
+    steps = min(steps, 4)
+    warm = min(warm, 1)
+    t_w = time.perf_counter()
+    als_replicate(A, W0, H0, max_iter=max(1, warm), fixed_iters=True, literal=True)
+    t0 = time.perf_counter()
+    als_replicate(A, W0, H0, max_iter=steps, fixed_iters=True, literal=True)
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "ALS-NMF 20000x5000 k=16 FP64, genSimData-shaped (D4), fixed iterations",
+                      "note": "R absent and NMF::.fcnnls un-vendored: oracle port (NumPy/OpenBLAS, literal R loop)"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{steps} literal ALS iterations of the full 20000x5000 k=16 workload "
+                                      f"(after {warm} warm-up); steps capped at 4 to bound the run"},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (mfbiclust_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import mfbiclust_b200 as mfb
+    ctx = mfb.Context(local_rank)
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    A, W0, H0 = make_workload()
+    m, n = A.shape
+    # ---- resident-input timing -------------------------------------------------------------
+    Ad = mfb.Matrix(ctx, host=A)
+    stats = Ad.stats()
+    sess = mfb.AlsSession(Ad, RANK, W0, H0, stats["max"])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    st, _, _ = sess.iterate(W, fixed_iters=True)          # warm-up iterations (untimed)
+    assert st == 0, f"warm-up failed with status {st}"
+    ctx.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    st, total, _ = sess.iterate(K, fixed_iters=True)      # EXACTLY K timed iterations, 2K kernel launches
+    e1.record(stream)
+    e1.synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert st == 0 and total == W + K, (st, total)
+    clocks = sampler.stop() if rank == 0 else None
+    Wg, Hg, resid, trace = sess.result()
+    sess.close()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end through the host-buffer API ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = torch.empty((n, m), dtype=torch.float64, pin_memory=True)   # column-major m x n == row-major n x m
+        pin.numpy()[...] = A.T
+        Ah = pin.numpy().T                                              # F-contiguous view on pinned memory
+        assert Ah.flags["F_CONTIGUOUS"]
+        import ctypes as C
+        from mfbiclust_b200._cabi import dptr, lib, check
+        Wout = np.zeros((m, RANK), order="F")
+        Hout = np.zeros((RANK, n), order="F")
+        residc, itc, convc = C.c_double(0), C.c_int(0), C.c_int(0)
+        tr = np.zeros((K, 3))
+
+        def one_call():
+            check(lib().mfb_als_run_host(ctx.handle, dptr(Ah), m, n, RANK, dptr(W0), dptr(H0), K, 1e-4, 1,
+                                         dptr(Wout), dptr(Hout), C.byref(residc), C.byref(itc), C.byref(convc),
+                                         dptr(tr)))
+        one_call()                                  # warm-up call
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        reps = 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one_call()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        # per step (= per iteration) byte counts, from the buffers actually copied by the call
+        h2d = (A.nbytes + W0.nbytes + H0.nbytes) / K
+        d2h = (Wout.nbytes + Hout.nbytes + tr.nbytes) / K
+        e2e = {"value": world * K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": f"mfb_als_run_host: upload A from pinned host memory + {K} iterations + download W,H; "
+                       f"one call = {K} steps"}
+        assert np.allclose(Wout, Wout) and itc.value == K
+    Ad.free()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    bytes_per_launch = float(m) * n * 8
+    launches = 2 * K
+    achieved = bytes_per_launch * launches / (ms_max * 1e-3) / 1e9
+    value = world * K / (ms_max * 1e-3)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.als_nmf import als_replicate
+        cores = os.cpu_count()
+        nit = 3
+        t0 = time.perf_counter()
+        ref = als_replicate(A, W0, H0, max_iter=nit, fixed_iters=True, literal=True)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nit / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{nit} literal ALS iterations (oracle/als_nmf.py, NumPy/OpenBLAS) of the same "
+                         f"20000x5000 k=16 workload"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "ALS-NMF 20000x5000 k=16 FP64, genSimData-shaped (D4, BASELINE configs[3]), "
+                                  "fixed iterations, given W0/Hold0",
+                      "l2": "input (800 MB) larger than L2 (126 MB); no flush needed",
+                      "parallelism": "1 GPU" if world == 1 else f"{world} independent replicates (als_nmf reps axis)"},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                        "kernel": "als_half_kernel<2,*> (2 launches per iteration, m*n*8 algorithmic bytes each)"},
+           "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+           "final_resid": resid}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

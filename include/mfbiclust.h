@@ -1,0 +1,152 @@
+/*
+ * mfbiclust.h -- C ABI of libmfbiclust_cuda.so (B200 / sm_100a).
+ *
+ * The reference (jonalim/mfBiclust) is pure R with no native boundary: its
+ * back-ends are reached by *function name* through
+ *   do.call(get(method), c(list(A = obj, k = k), list(...)))   R/BiclusterStrategy.R:82-87
+ * and its arithmetic lives in NMF::.fcnnls, nipals::nipals, stats::prcomp,
+ * MASS::ginv, EBImage::otsu.  This header declares the entry points an R
+ * `.Call` shim binds so that als_nmf / svd_pca /
+ * nipals_pca / bcv / auto_bcv / otsuHelper / threshold keep their R
+ * signatures while the arithmetic runs on the GPU.  Each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes; all matrices COLUMN-MAJOR (R layout), FP64;
+ *   - caller-owned HOST buffers unless the name says `_dev`; inputs are never
+ *     written;
+ *   - return value: 0 = MFB_OK; > 0 = algorithmic condition the R wrapper
+ *     reacts to (restart, fallback); < 0 = bad argument / CUDA error, with a
+ *     message available from mfb_last_error();
+ *   - no global mutable state besides the explicit mfb_context; one host
+ *     thread per context;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     MFB_ERR_CUDA.
+ */
+#ifndef MFBICLUST_H
+#define MFBICLUST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+#define MFB_OK               0
+#define MFB_SINGULAR         1  /* Gram matrix not invertible: R's solve() error inside .fcnnls (caught by try(), R/bicluster.R:123,150) */
+#define MFB_ZERO_ROW         2  /* any(rowSums(H) == 0), R/bicluster.R:137 */
+#define MFB_NOT_CONVERGED    3  /* informational (nipals maxiter, auto_bcv maxIter) */
+#define MFB_ERR_ARG         -1
+#define MFB_ERR_CUDA        -2
+#define MFB_ERR_ALLOC       -3
+#define MFB_ERR_NEGATIVE    -4  /* "Negative values are not allowed", R/bicluster.R:76 */
+#define MFB_ERR_UNSUPPORTED -5
+
+typedef struct mfb_context mfb_context;
+typedef struct mfb_matrix mfb_matrix;   /* an m x n FP64 matrix resident in HBM */
+typedef struct mfb_als mfb_als;         /* one als_nmf replicate in flight */
+
+/* ---- context ----------------------------------------------------------- */
+int         mfb_version(void);
+const char *mfb_last_error(void);
+int  mfb_device_count(void);
+int  mfb_context_create(int device, mfb_context **out);
+void mfb_context_destroy(mfb_context *ctx);
+int  mfb_context_sync(mfb_context *ctx);
+/* CUDA stream (cudaStream_t) every kernel of this context is launched on; for callers that time with CUDA events. */
+void *mfb_context_stream(mfb_context *ctx);
+
+/* ---- resident matrix ---------------------------------------------------- */
+/* Upload a column-major host matrix (the `A` / `Y` argument of every back-end). */
+int  mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t n, mfb_matrix **out);
+/* Wrap an existing device buffer (column-major, ld = m); not owned. */
+int  mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb_matrix **out);
+void mfb_matrix_free(mfb_matrix *A);
+/* stats[0..4] = min, max, sum of squares, #NaN/NA, sum  (max(A): R/bicluster.R:81; any(A<0): :76; pseudovalues: R/helperFunctions.R:270-278) */
+int  mfb_matrix_stats(mfb_matrix *A, double stats[5]);
+/* A <- A + shift  (pseudovalues(), R/helperFunctions.R:275) */
+int  mfb_matrix_shift(mfb_matrix *A, double shift);
+void *mfb_matrix_dev_ptr(mfb_matrix *A);
+
+/* ---- als_nmf (R/bicluster.R:70-216; NMF::.fcnnls call sites :123, :150) --- */
+/*
+ * One replicate of the `while (i < maxIter)` loop from a GIVEN start:
+ *   W0     m x k, column-normalised   (R/bicluster.R:95-101)
+ *   Hold0  k x n                      (R/bicluster.R:104)
+ *   resid_old0 = max(A)               (R/bicluster.R:105)
+ * The session keeps W, Wold, H, Hold, residNormOld on the device.
+ */
+int  mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k,
+                   const double *W0, const double *Hold0, double resid_old0,
+                   mfb_als **out);
+/*
+ * Run up to `max_new_iters` further iterations (R/bicluster.R:119-203).
+ * fixed_iters != 0 disables the convergence break (:179).
+ * Returns MFB_OK (converged flag in *converged, or iteration budget used),
+ * MFB_SINGULAR / MFB_ZERO_ROW when the iteration that was running failed the
+ * way .fcnnls / the zero-row test fail in R: the iteration counter has been
+ * advanced (R's `i <- i + 1` precedes the failure), W/Wold/Hold/residNormOld
+ * are those of the last completed iteration, and the caller is expected to
+ * call mfb_als_restart() with a fresh W (R's restart(), :107-116) and iterate
+ * again.
+ *   *iters_total  iterations counted so far (R's `i`)
+ *   *converged    1 if the break at :179 fired
+ */
+int  mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters,
+                     int *iters_total, int *converged);
+int  mfb_als_restart(mfb_als *s, const double *Wnew);
+/* trace: iters_total x 3 row-major (residNorm, rms dW, rms dH) per completed iteration (NaN rows for failed ones). */
+int  mfb_als_result(mfb_als *s, double *W, double *H, double *resid, double *trace);
+void mfb_als_end(mfb_als *s);
+
+/* Convenience: begin + iterate + result + end on a resident matrix. */
+int  mfb_als_run(mfb_context *ctx, mfb_matrix *A, int k,
+                 const double *W0, const double *Hold0, double resid_old0,
+                 int max_iter, double eps_conv, int fixed_iters,
+                 double *W, double *H, double *resid, int *iters_done, int *converged,
+                 double *trace);
+/* Same from a HOST matrix (upload inside): the end-to-end call bench.py times. */
+int  mfb_als_run_host(mfb_context *ctx, const double *A_host, int64_t m, int64_t n, int k,
+                      const double *W0, const double *Hold0,
+                      int max_iter, double eps_conv, int fixed_iters,
+                      double *W, double *H, double *resid, int *iters_done, int *converged,
+                      double *trace);
+
+/* Exact NNLS  min ||C K - B||_F, K >= 0  for every column of B: the unit-testable
+ * equivalent of NMF::.fcnnls(x = C, y = B)[[1]].  C is r x k, B is r x p, K is k x p. */
+int  mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t p, double *K);
+
+/* ---- otsuHelper / threshold (R/BiclusterStrategy.R:442-456, 508-528; EBImage::otsu call site :448) */
+/* One Otsu threshold per COLUMN of the rows x cols matrix M. */
+int  mfb_otsu(mfb_context *ctx, const double *M, int64_t rows, int64_t cols, double *th);
+/* margin = 2: th per column; margin = 1: th per row.  out: rows x cols int32 (R logical), column-major. */
+int  mfb_threshold(mfb_context *ctx, const double *M, int64_t rows, int64_t cols,
+                   const double *th, int margin, int32_t *out);
+
+/* ---- svd_pca (R/bicluster.R:528-539 -> stats::prcomp(t(A), rank. = k, center = FALSE)) */
+/* W: m x k (left singular vectors of A), H: k x n (= t(W) %*% A), sdev-free.  kout = min(k, m, n). */
+int  mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, int *kout);
+
+/* ---- nipals_pca (R/bicluster.R:218-242 -> nipals::nipals, call site :226) -- */
+/* scores: m x ncomp (unit-norm columns), loadings: n x ncomp, eig: ncomp, iters: ncomp.
+ * Complete data only (NA support is SURVEY.md 8f "next").  x is not modified. */
+int  mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale,
+                int maxiter, double tol, int gramschmidt,
+                double *scores, double *loadings, double *eig, int *iters);
+
+/* ---- bcv (R/bcv.R:164-239 bcvGivenKs; prcomp call site :184, MASS::ginv :222) */
+/*
+ * Errors of the cells [cell_begin, cell_end) of the h x h grid (cell = (x-1)*h + (y-1),
+ * x = row fold, y = column fold, both 1-based as drawn by sample() at :170-174) for
+ * every k in ks[0..nks).  err: (cell_end - cell_begin) x nks, row-major.  The caller
+ * (R wrapper / other ranks) sums over cells (:231-233).
+ */
+int  mfb_bcv_cells(mfb_context *ctx, mfb_matrix *Y,
+                   const int32_t *row_fold, const int32_t *col_fold, int holdouts,
+                   const int32_t *ks, int nks, int cell_begin, int cell_end, double *err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFBICLUST_H */

@@ -1,0 +1,11 @@
+"""mfbiclust_b200 -- B200-native (sm_100a) factorization hot path of mfBiclust.
+
+Host-side mirror of the reference's R API for the path (``als_nmf``, ``svd_pca``,
+``nipals_pca``, ``bcv``/``auto_bcv``, ``otsuHelper``/``threshold``, ``addStrat``) on top of the
+C ABI in ``include/mfbiclust.h`` (``libmfbiclust_cuda.so``, hand-written CUDA).  There is no
+CPU fallback: importing works anywhere the shared library is built, calling needs a B200.
+"""
+from . import _cabi  # noqa: F401
+from ._cabi import Context, Matrix, MfbError, default_context  # noqa: F401
+from .backends import (AlsSession, HostRng, als_nmf, als_replicate, genericFactorization,  # noqa: F401
+                       genericFit, nnls, otsuHelper, threshold)

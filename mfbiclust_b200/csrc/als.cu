@@ -1,0 +1,967 @@
+// ALS-NMF hot loop on B200 (sm_100a): replaces als_nmf's `while (i < maxIter)` body
+// (R/bicluster.R:119-203) and the two NMF::.fcnnls calls inside it (:123, :150).
+//
+// One ALS iteration = two launches of one templated kernel:
+//   H-step  (WSTEP = false): R = W'A  (k x n), then exact NNLS per column of A   -> H
+//   W-step  (WSTEP = true):  R = A H' (m x k), then exact NNLS per row of A      -> W,
+//                            plus residNorm / rms(dW) / rms(dH) and the convergence test.
+// A (m x n, column-major, FP64) is streamed from HBM exactly once per half-step:
+//   * a producer warp moves 16-row x 128-col (H-step) or 128-row x 32-col (W-step) boxes of A
+//     into a shared-memory ring with TMA (cp.async.bulk.tensor, SWIZZLE_128B) signalled on
+//     mbarriers;
+//   * eight consumer warps read the m8n8k4 FP64 tensor-core fragments straight out of the
+//     swizzled ring (conflict-free by construction, see frag_* below) and accumulate with
+//     DMMA.8x8x4; the k-row fragments of the fixed factor come through L1 from global memory;
+//   * work is cut stream-K style: the (tile, reduction-stage) space is split into 148 equal
+//     contiguous ranges, one persistent CTA per SM; a CTA writes one k x 128 partial per tile it
+//     touches and the LAST CTA to arrive at a tile (atomic counter) sums the partials in slot
+//     order (deterministic) and runs the NNLS epilogue for the tile's 128 columns / rows, one
+//     thread per problem (nnls.cuh);
+//   * the last tile epilogue of the launch reduces the per-tile Gram partials of the factor just
+//     produced, inverts the k x k Gram for the next half-step, and folds the iteration scalars.
+// Nothing but A's two passes touches HBM in bulk: factors, partials and Grams stay in L2.
+#include "common.cuh"
+#include "nnls.cuh"
+
+#define ALS_THREADS 288           // 8 consumer warps + 1 producer warp
+#define ALS_CONSUMERS 256
+#define TILE_UNITS 128            // columns (H-step) or rows (W-step) per tile
+#define XS_LD 129
+
+// ---------------------------------------------------------------------------
+// device control block (lives in global memory, mirrored to the host after a batch)
+// ---------------------------------------------------------------------------
+struct AlsCtrl {
+    int stop;                  // != 0: every later launch exits immediately
+    int reason;                // 0 none, 1 converged, 2 zero row in H, 3 singular W'W, 4 singular HH'
+    int iters_done;            // completed (successful) iterations in this batch epoch
+    int fixed;                 // 1: no convergence break
+    int tiles_done[2];         // per half-step tile completion counters
+    int max_trace;
+    int pad0;
+    unsigned long long nzmask; // bit c set when row c of H has a non-zero entry
+    double eps;
+    double resid_old;
+    double normA2;
+    double mn, mk, kn;         // element counts for the RMS values
+    double dH2;
+    double resid, dW, dH;
+};
+
+struct HalfParams {
+    const double *Fin;  int64_t ldin;     // fixed factor, [KP][ldin]
+    double *Fout; const double *Fold; int64_t ldout;   // factor being solved / its previous value
+    const double *G; const double *Minv;  // Gram of Fin and its inverse, KP x KP
+    double *Gout; double *Minvout;        // Gram of Fout (+ inverse), written by the last epilogue
+    double *P; int maxslots;              // partials [tile][slot][KP][128]
+    int *tile_counter;                    // [T]
+    double *gpart;                        // [T][KP*KP]
+    double *spart;                        // [T][4]
+    AlsCtrl *ctrl; double *trace;
+    int k, T, SPT;
+    long long U;                          // T * SPT
+    long long nvalid;                     // number of real units (n for H-step, m for W-step)
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000ll) {
+            printf("mfbiclust: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
+
+// cta index that owns unit u under the balanced partition u0(c) = floor(c * U / G)
+__device__ __forceinline__ int cta_of_unit(long long u, long long U, int G) {
+    return (int)(((u + 1) * (long long)G + U - 1) / U) - 1;
+}
+
+// ---------------------------------------------------------------------------
+// the half-step kernel
+// ---------------------------------------------------------------------------
+template <int KB, bool WSTEP>
+__global__ void __launch_bounds__(ALS_THREADS, 1)
+als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, const int nstage) {
+    constexpr int KP = KB * 8;
+    constexpr int STAGE_BYTES = WSTEP ? 32768 : 16384;
+    if (*(volatile int *)&p.ctrl->stop) return;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: ring | barriers | G | Minv | xs | misc
+    unsigned char *ring = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = (uint64_t *)(ring + (size_t)nstage * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + nstage;
+    double *sG = (double *)(empty_bar + nstage);
+    double *sM = sG + KP * KP;
+    double *xs = sM + KP * KP;
+    double *sred = xs + KP * XS_LD;          // 32 doubles of reduction scratch
+    int *sflag = (int *)(sred + 32);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const long long u0 = (long long)blockIdx.x * p.U / G;
+    const long long u1 = (long long)(blockIdx.x + 1) * p.U / G;
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // Gram of the fixed factor and its inverse (for the epilogues of this CTA)
+    for (int e = tid; e < KP * KP; e += ALS_THREADS) {
+        sG[e] = p.G[e];
+        sM[e] = p.Minv[e];
+    }
+    __syncthreads();
+    if (u0 >= u1) return;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = u0; u < u1; ++u) {
+                const int tile = (int)(u / p.SPT), st = (int)(u % p.SPT);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
+                if (!WSTEP) {
+                    tma_load_2d(dst, &tmA, st * 16, tile * TILE_UNITS, &full_bar[stage]);
+                } else {
+#pragma unroll
+                    for (int rg = 0; rg < 8; ++rg)
+                        tma_load_2d(dst + rg * 4096, &tmA, tile * TILE_UNITS + rg * 16, st * 32, &full_bar[stage]);
+                }
+                if (++stage == nstage) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers (warps 0..7) =====================
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NACC = WSTEP ? 2 : 2;          // W-step: s in {0,1}; H-step: v in {0,1}
+    double acc[KB][NACC][2];
+#pragma unroll
+    for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_tile = (int)(u0 / p.SPT);
+
+    auto flush = [&](int tile) {
+        const long long tb = (long long)tile * p.SPT;
+        int expected, slot;
+        if (p.U >= G) {          // every CTA owns >= 1 unit: contributors to a tile are contiguous CTAs
+            const int first = cta_of_unit(tb, p.U, G);
+            const int last = cta_of_unit(tb + p.SPT - 1, p.U, G);
+            expected = last - first + 1;
+            slot = (int)blockIdx.x - first;
+        } else {                 // fewer units than CTAs: each non-empty CTA owns exactly one unit
+            expected = p.SPT;
+            slot = (int)(u0 - tb);
+        }
+        double *Pb = p.P + ((size_t)tile * p.maxslots + slot) * (size_t)(KP * TILE_UNITS);
+#pragma unroll
+        for (int cb = 0; cb < KB; ++cb) {
+            if (!WSTEP) {
+                // acc[cb][v] = R[8cb+g][16w + 8v + 2t + {0,1}]
+#pragma unroll
+                for (int v = 0; v < 2; ++v)
+                    *(double2 *)&Pb[(size_t)(8 * cb + g) * TILE_UNITS + 16 * warp + 8 * v + 2 * t] =
+                        make_double2(acc[cb][v][0], acc[cb][v][1]);
+            } else {
+                // acc[cb][s][e] = R[row 16w + 2g + s][c = 8cb + 2t + e]
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    *(double2 *)&Pb[(size_t)(8 * cb + 2 * t + e) * TILE_UNITS + 16 * warp + 2 * g] =
+                        make_double2(acc[cb][0][e], acc[cb][1][e]);
+            }
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
+        }
+        __threadfence();
+        consumer_bar();
+        if (tid == 0) {
+            int prev = atomicAdd(&p.tile_counter[tile], 1);
+            int lastone = (prev == expected - 1);
+            if (lastone) p.tile_counter[tile] = 0;
+            sflag[0] = lastone;
+        }
+        consumer_bar();
+        if (!sflag[0]) return;
+        __threadfence();
+
+        // ---------------- tile epilogue: NNLS for 128 units ----------------
+        const long long unit = (long long)tile * TILE_UNITS + tid;
+        double d2 = 0.0, t1 = 0.0, t2 = 0.0;
+        unsigned long long nz = 0ull;
+        if (tid < TILE_UNITS) {
+            double r[KP], x[KP];
+#pragma unroll
+            for (int c = 0; c < KP; ++c) r[c] = 0.0;
+            for (int s = 0; s < expected; ++s) {
+                const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + tid;
+#pragma unroll
+                for (int c = 0; c < KP; ++c)
+                    if (c < p.k) r[c] += ldcg(Ps + (size_t)c * TILE_UNITS);
+            }
+#pragma unroll
+            for (int c = 0; c < KP; ++c) x[c] = 0.0;
+            const bool valid = unit < p.nvalid;
+            if (valid) nnls_thread<KP>(sG, sM, p.k, r, x);
+#pragma unroll
+            for (int c = 0; c < KP; ++c) {
+                if (c < p.k) {
+                    const size_t off = (size_t)c * p.ldout + unit;
+                    if (valid) {
+                        const double o = p.Fold[off];
+                        d2 += (x[c] - o) * (x[c] - o);
+                        if (x[c] != 0.0) nz |= (1ull << c);
+                    }
+                    p.Fout[off] = x[c];
+                    xs[c * XS_LD + tid] = x[c];
+                }
+            }
+            if (WSTEP && valid) {
+                for (int c = 0; c < p.k; ++c) {
+                    t1 += x[c] * r[c];
+                    double gx = 0.0;
+                    for (int j = 0; j < p.k; ++j) gx += sG[c * KP + j] * x[j];
+                    t2 += x[c] * gx;
+                }
+            }
+        }
+        // block reduction of the scalars (threads >= 128 contribute zeros)
+        d2 = warp_sum(d2);
+        t1 = warp_sum(t1);
+        t2 = warp_sum(t2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz |= __shfl_xor_sync(0xffffffffu, nz, o);
+        if (lane == 0) {
+            sred[warp * 3 + 0] = d2;
+            sred[warp * 3 + 1] = t1;
+            sred[warp * 3 + 2] = t2;
+            ((unsigned long long *)(sred + 24))[warp] = nz;
+        }
+        consumer_bar();
+        // Gram partial of the produced factor over this tile's units
+        for (int e = tid; e < p.k * p.k; e += ALS_CONSUMERS) {
+            const int c1 = e / p.k, c2 = e - c1 * p.k;
+            double s = 0.0;
+            for (int uu = 0; uu < TILE_UNITS; ++uu) s += xs[c1 * XS_LD + uu] * xs[c2 * XS_LD + uu];
+            p.gpart[(size_t)tile * (KP * KP) + c1 * KP + c2] = s;
+        }
+        if (tid == 0) {
+            double a = 0, b = 0, c = 0;
+            unsigned long long m = 0;
+            for (int w = 0; w < 8; ++w) {
+                a += sred[w * 3 + 0];
+                b += sred[w * 3 + 1];
+                c += sred[w * 3 + 2];
+                m |= ((unsigned long long *)(sred + 24))[w];
+            }
+            p.spart[tile * 4 + 0] = a;
+            p.spart[tile * 4 + 1] = b;
+            p.spart[tile * 4 + 2] = c;
+            if (!WSTEP) atomicOr(&p.ctrl->nzmask, m);
+        }
+        __threadfence();
+        consumer_bar();
+        if (tid == 0) {
+            int prev = atomicAdd(&p.ctrl->tiles_done[WSTEP ? 1 : 0], 1);
+            sflag[1] = (prev == p.T - 1);
+        }
+        consumer_bar();
+        if (!sflag[1]) return;
+        __threadfence();
+
+        // ---------------- launch finalisation (one CTA, once per half-step) ----------------
+        for (int e = tid; e < KP * KP; e += ALS_CONSUMERS) {
+            const int c1 = e / KP, c2 = e - c1 * KP;
+            double s = 0.0;
+            if (c1 < p.k && c2 < p.k)
+                for (int tt = 0; tt < p.T; ++tt) s += ldcg(&p.gpart[(size_t)tt * (KP * KP) + e]);
+            sG[e] = s;
+            p.Gout[e] = s;
+        }
+        consumer_bar();
+        const int sing = gauss_jordan_inverse(sG, p.k, KP, tid, ALS_CONSUMERS, sred, [] { consumer_bar(); });
+        for (int e = tid; e < KP * KP; e += ALS_CONSUMERS) {
+            const int c1 = e / KP, c2 = e - c1 * KP;
+            p.Minvout[e] = (c1 < p.k && c2 < p.k) ? sG[e] : 0.0;
+        }
+        if (tid == 0) {
+            AlsCtrl *c = p.ctrl;
+            double sd2 = 0, st1 = 0, st2 = 0;
+            for (int tt = 0; tt < p.T; ++tt) {
+                sd2 += ldcg(&p.spart[tt * 4 + 0]);
+                st1 += ldcg(&p.spart[tt * 4 + 1]);
+                st2 += ldcg(&p.spart[tt * 4 + 2]);
+            }
+            c->tiles_done[WSTEP ? 1 : 0] = 0;
+            if (!WSTEP) {
+                c->dH2 = sd2;
+                const unsigned long long fullm = (p.k >= 64) ? ~0ull : ((1ull << p.k) - 1ull);
+                const unsigned long long m = c->nzmask;
+                c->nzmask = 0ull;
+                if ((m & fullm) != fullm) { c->stop = 1; c->reason = 2; }
+                else if (sing) { c->stop = 1; c->reason = 4; }
+            } else {
+                double r2 = (c->normA2 - 2.0 * st1 + st2) / c->mn;
+                const double resid = sqrt(r2 > 0.0 ? r2 : 0.0);
+                const double dW = sqrt(sd2 / c->mk);
+                const double dH = sqrt(c->dH2 / c->kn);
+                const int it = c->iters_done;
+                if (it < c->max_trace) {
+                    p.trace[it * 3 + 0] = resid;
+                    p.trace[it * 3 + 1] = dW;
+                    p.trace[it * 3 + 2] = dH;
+                }
+                c->resid = resid;
+                c->dW = dW;
+                c->dH = dH;
+                c->iters_done = it + 1;
+                if (!c->fixed && (fabs(c->resid_old - resid) <= c->eps || (dW <= c->eps && dH <= c->eps))) {
+                    c->stop = 1;
+                    c->reason = 1;
+                } else {
+                    c->resid_old = resid;
+                    if (sing) { c->stop = 1; c->reason = 3; }
+                }
+            }
+            __threadfence();
+        }
+    };
+
+    for (long long u = u0; u < u1; ++u) {
+        const int tile = (int)(u / p.SPT), st = (int)(u % p.SPT);
+        if (tile != cur_tile) {
+            flush(cur_tile);
+            cur_tile = tile;
+        }
+        const unsigned char *sA = ring + (size_t)stage * STAGE_BYTES;
+        if (!WSTEP) {
+            // fixed-factor fragments: W[8cb+g][16 st + 4t + s], s = 0..3  (32 contiguous bytes)
+            double wf[KB][4];
+#pragma unroll
+            for (int cb = 0; cb < KB; ++cb) {
+                const double2 *src = (const double2 *)(p.Fin + (size_t)(8 * cb + g) * p.ldin + (size_t)st * 16 + 4 * t);
+                const double2 lo = __ldg(src), hi = __ldg(src + 1);
+                wf[cb][0] = lo.x; wf[cb][1] = lo.y; wf[cb][2] = hi.x; wf[cb][3] = hi.y;
+            }
+            mbar_wait(&full_bar[stage], phase);
+            // A fragments: column 16w + 8v + g of the box, rows 4t..4t+3 (chunks 2t, 2t+1 ^ g)
+            double b[2][4];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const unsigned char *rowp = sA + (16 * warp + 8 * v + g) * 128;
+                const double2 lo = *(const double2 *)(rowp + (((2 * t) ^ g) << 4));
+                const double2 hi = *(const double2 *)(rowp + (((2 * t + 1) ^ g) << 4));
+                b[v][0] = lo.x; b[v][1] = lo.y; b[v][2] = hi.x; b[v][3] = hi.y;
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], wf[cb][s], b[v][s]);
+        } else {
+            // fixed-factor fragments: H[8cb+g][32 st + 2t + 8q + {0,1}], q = 0..3
+            const double *hbase = p.Fin + (size_t)g * p.ldin + (size_t)st * 32 + 2 * t;
+            double2 hv[KB <= 2 ? KB : 1][4];
+            if constexpr (KB <= 2) {
+#pragma unroll
+                for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) hv[cb][q] = __ldg((const double2 *)(hbase + (size_t)(8 * cb) * p.ldin + 8 * q));
+            }
+            mbar_wait(&full_bar[stage], phase);
+            const unsigned char *blk = sA + warp * 4096;   // row group `warp` of the tile: [col 32][16 rows]
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double2 a[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    a[e] = *(const double2 *)(blk + (2 * t + e + 8 * q) * 128 + ((g ^ ((2 * t + e) & 7)) << 4));
+#pragma unroll
+                for (int cb = 0; cb < KB; ++cb) {
+                    double2 h;
+                    if constexpr (KB <= 2) h = hv[cb][q];
+                    else h = __ldg((const double2 *)(hbase + (size_t)(8 * cb) * p.ldin + 8 * q));
+                    dmma884(acc[cb][0][0], acc[cb][0][1], a[0].x, h.x);
+                    dmma884(acc[cb][1][0], acc[cb][1][1], a[0].y, h.x);
+                    dmma884(acc[cb][0][0], acc[cb][0][1], a[1].x, h.y);
+                    dmma884(acc[cb][1][0], acc[cb][1][1], a[1].y, h.y);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == nstage) { stage = 0; phase ^= 1; }
+    }
+    flush(cur_tile);
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone Gram + inverse of a factor [KP][ld] over `len` entries (start / restart only)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_partial_kernel(const double *__restrict__ F, int64_t ld, int64_t len,
+                                                           int k, int KP, double *__restrict__ part) {
+    extern __shared__ double sh[];   // [k][65]
+    const int nb = gridDim.x;
+    const int64_t per = (len + nb - 1) / nb;
+    const int64_t lo = blockIdx.x * per, hi = (lo + per < len) ? lo + per : len;
+    const int npairs = k * k;
+    double accp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) accp[i] = 0.0;
+    for (int64_t base = lo; base < hi; base += 64) {
+        const int cnt = (int)((hi - base < 64) ? hi - base : 64);
+        for (int idx = threadIdx.x; idx < k * 64; idx += 256) {
+            const int c = idx >> 6, u = idx & 63;
+            sh[c * 65 + u] = (u < cnt) ? F[c * ld + base + u] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = threadIdx.x + q * 256;
+            if (e < npairs) {
+                const int c1 = e / k, c2 = e - c1 * k;
+                double s = 0.0;
+                for (int u = 0; u < 64; ++u) s += sh[c1 * 65 + u] * sh[c2 * 65 + u];
+                accp[q] += s;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int e = threadIdx.x + q * 256;
+        if (e < npairs) {
+            const int c1 = e / k, c2 = e - c1 * k;
+            part[(size_t)blockIdx.x * KP * KP + c1 * KP + c2] = accp[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gram_finalize_kernel(const double *__restrict__ part, int nb, int k, int KP,
+                                                            double *__restrict__ Gout, double *__restrict__ Minvout,
+                                                            int *__restrict__ singular) {
+    extern __shared__ double sh[];   // KP*KP + 2
+    double *sG = sh, *scr = sh + KP * KP;
+    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        double s = 0.0;
+        if (c1 < k && c2 < k)
+            for (int b = 0; b < nb; ++b) s += part[(size_t)b * KP * KP + e];
+        sG[e] = s;
+        Gout[e] = s;
+    }
+    __syncthreads();
+    const int sing = gauss_jordan_inverse(sG, k, KP, threadIdx.x, 256, scr, [] { __syncthreads(); });
+    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        Minvout[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
+    }
+    if (threadIdx.x == 0) *singular = sing;
+}
+
+// r = F a  style helper for mfb_nnls: R[c][j] = sum_i C[i][c] B[i][j]  (small, test entry point)
+__global__ void __launch_bounds__(256) small_crossprod_kernel(const double *__restrict__ C, const double *__restrict__ B,
+                                                              int64_t r, int k, int64_t pcols, double *__restrict__ R) {
+    // one block per column j of B; thread c2 < k ... generic slow path, test-only sizes
+    const int64_t j = blockIdx.x;
+    __shared__ double red[256];
+    for (int c = 0; c < k; ++c) {
+        double s = 0.0;
+        for (int64_t i = threadIdx.x; i < r; i += 256) s += C[c * r + i] * B[j * r + i];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) R[j * k + c] = red[0];
+        __syncthreads();
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restrict__ G, const double *__restrict__ Minv,
+                                                           const double *__restrict__ R, int k, int64_t pcols,
+                                                           double *__restrict__ K) {
+    extern __shared__ double nn_sh[];
+    double *sG = nn_sh, *sM = nn_sh + KP * KP;
+    for (int e = threadIdx.x; e < KP * KP; e += 128) {
+        sG[e] = G[e];
+        sM[e] = Minv[e];
+    }
+    __syncthreads();
+    const int64_t j = blockIdx.x * 128ll + threadIdx.x;
+    if (j >= pcols) return;
+    double r[KP], x[KP];
+    for (int c = 0; c < KP; ++c) {
+        r[c] = (c < k) ? R[j * k + c] : 0.0;
+        x[c] = 0.0;
+    }
+    nnls_thread<KP>(sG, sM, k, r, x);
+    for (int c = 0; c < k; ++c) K[j * k + c] = x[c];
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct mfb_als {
+    mfb_context *ctx;
+    mfb_matrix *A;
+    int k, KB, KP;
+    int64_t m, n, ldw, ldh;
+    double *Wb[2], *Wr, *Hb[2];          // factor buffers [KP][ld]
+    double *G_W, *Minv_W, *G_H, *Minv_H; // Grams (+ inverses)
+    double *P_h, *P_w, *gpart, *spart;
+    int *counters;
+    AlsCtrl *ctrl;
+    double *trace_dev;
+    int maxslots_h, maxslots_w, T_h, T_w, SPT_h, SPT_w;
+    int nstage_h, nstage_w;
+    size_t smem_h, smem_w;
+    CUtensorMap tm_h, tm_w;
+    int cur;              // index of the buffer holding the last accepted W / H
+    bool restart_pending; // next H-step reads Wr instead of Wb[cur]
+    int iters_total;      // R's `i`
+    int max_trace;
+    std::vector<double> trace;   // host copy: iters_total x 3
+    double resid;
+    int *sing_dev;
+    double *gram_scratch;
+    std::vector<void *> allocs;
+};
+
+static int max_slots(long long T, long long SPT, int G) {
+    const long long U = T * SPT;
+    if (U < G) return (int)SPT;
+    int mx = 1;
+    for (long long t = 0; t < T; ++t) {
+        long long a = ((t * SPT + 1) * G + U - 1) / U - 1;
+        long long b = (((t + 1) * SPT) * G + U - 1) / U - 1;
+        if ((int)(b - a + 1) > mx) mx = (int)(b - a + 1);
+    }
+    return mx;
+}
+
+static int encode_map(CUtensorMap *tm, double *base, int64_t rows, int64_t cols, int64_t lda, int box_rows, int box_cols) {
+    mfb_encode_tiled_fn enc = mfb_get_encode_tiled();
+    if (!enc) {
+        mfb_set_error("cuTensorMapEncodeTiled unavailable");
+        return MFB_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        mfb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return MFB_ERR_CUDA;
+    }
+    return MFB_OK;
+}
+
+template <int KB>
+static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp) {
+    cudaStream_t st = s->ctx->stream;
+    const int G = s->ctx->sm_count;
+    if (wstep) {
+        MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
+        als_half_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>(s->tm_w, hp, s->nstage_w);
+    } else {
+        MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
+        als_half_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, hp, s->nstage_h);
+    }
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
+static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp) {
+    switch (s->KB) {
+        case 1: return launch_half<1>(s, wstep, hp);
+        case 2: return launch_half<2>(s, wstep, hp);
+        case 3: return launch_half<3>(s, wstep, hp);
+        case 4: return launch_half<4>(s, wstep, hp);
+        case 6: return launch_half<6>(s, wstep, hp);
+        case 8: return launch_half<8>(s, wstep, hp);
+    }
+    mfb_set_error("unsupported rank block %d", s->KB);
+    return MFB_ERR_UNSUPPORTED;
+}
+
+static int gram_of_factor(mfb_als *s, const double *F, int64_t ld, int64_t len, double *Gout, double *Minvout) {
+    cudaStream_t st = s->ctx->stream;
+    int nb = (int)((len + 2047) / 2048);
+    if (nb > 64) nb = 64;
+    if (nb < 1) nb = 1;
+    gram_partial_kernel<<<nb, 256, (size_t)s->k * 65 * sizeof(double), st>>>(F, ld, len, s->k, s->KP, s->gram_scratch);
+    gram_finalize_kernel<<<1, 256, (size_t)(s->KP * s->KP + 2) * sizeof(double), st>>>(s->gram_scratch, nb, s->k, s->KP,
+                                                                                     Gout, Minvout, s->sing_dev);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
+template <typename T>
+static int dev_alloc(mfb_als *s, T **p, size_t count, bool zero = true) {
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        mfb_set_error("cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return MFB_ERR_ALLOC;
+    }
+    s->allocs.push_back((void *)*p);
+    if (zero) MFB_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), s->ctx->stream));
+    return MFB_OK;
+}
+
+#define MFB_TRY(expr) do { int _r = (expr); if (_r != MFB_OK) return _r; } while (0)
+
+extern "C" {
+
+void mfb_als_end(mfb_als *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    delete s;
+}
+
+static int als_upload_H(mfb_als *s, const double *H_host, double *dst) {
+    // host H is k x n column-major; device layout is [c][j] (j contiguous, ld = ldh)
+    std::vector<double> tmp((size_t)s->k * s->n);
+    for (int64_t j = 0; j < s->n; ++j)
+        for (int c = 0; c < s->k; ++c) tmp[(size_t)c * s->n + j] = H_host[(size_t)j * s->k + c];
+    MFB_CUDA(cudaMemcpy2DAsync(dst, s->ldh * sizeof(double), tmp.data(), s->n * sizeof(double), s->n * sizeof(double),
+                               s->k, cudaMemcpyHostToDevice, s->ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return MFB_OK;
+}
+
+int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, const double *Hold0, double resid_old0,
+                  mfb_als **out) {
+    MFB_ARG(ctx && A && W0 && Hold0 && out, "NULL argument");
+    MFB_ARG(k >= 1 && k <= 64, "k must be in 1..64");
+    MFB_ARG(k <= A->m && k <= A->n, "k exceeds a matrix dimension");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    double stats[5];
+    MFB_TRY(mfb_matrix_stats(A, stats));
+    if (stats[3] > 0) {
+        mfb_set_error("als_nmf: matrix has NA/NaN entries");
+        return MFB_ERR_ARG;
+    }
+    if (stats[0] < 0) {
+        mfb_set_error("Negative values are not allowed");
+        return MFB_ERR_NEGATIVE;
+    }
+    mfb_als *s = new mfb_als();
+    s->ctx = ctx;
+    s->A = A;
+    s->k = k;
+    int KB = (k + 7) / 8;
+    if (KB == 5) KB = 6;
+    if (KB == 7) KB = 8;
+    s->KB = KB;
+    s->KP = KB * 8;
+    s->m = A->m;
+    s->n = A->n;
+    s->ldw = round_up(A->m, 128);
+    s->ldh = round_up(A->n, 128);
+    s->cur = 0;
+    s->restart_pending = false;
+    s->iters_total = 0;
+    s->resid = resid_old0;
+    const int G = ctx->sm_count;
+    s->T_h = (int)((s->n + 127) / 128);
+    s->SPT_h = (int)((s->m + 15) / 16);
+    s->T_w = (int)((s->m + 127) / 128);
+    s->SPT_w = (int)((s->n + 31) / 32);
+    s->maxslots_h = max_slots(s->T_h, s->SPT_h, G);
+    s->maxslots_w = max_slots(s->T_w, s->SPT_w, G);
+    const size_t KP = s->KP;
+    const size_t epi = (2 * KP * KP + KP * XS_LD + 32 + 8) * sizeof(double);
+    const size_t budget = 227 * 1024 - 1024 /*align*/ - epi - 2 * 16 * sizeof(uint64_t);
+    s->nstage_h = (int)(budget / 16384); if (s->nstage_h > 12) s->nstage_h = 12;
+    s->nstage_w = (int)(budget / 32768); if (s->nstage_w > 6) s->nstage_w = 6;
+    if (s->nstage_h < 2 || s->nstage_w < 2) {
+        mfb_als_end(s);
+        mfb_set_error("rank %d leaves no shared memory for the streaming ring", k);
+        return MFB_ERR_UNSUPPORTED;
+    }
+    s->smem_h = 1024 + (size_t)s->nstage_h * 16384 + 2 * s->nstage_h * sizeof(uint64_t) + epi;
+    s->smem_w = 1024 + (size_t)s->nstage_w * 32768 + 2 * s->nstage_w * sizeof(uint64_t) + epi;
+
+    int rc;
+#define ALLOC(ptr, cnt) if ((rc = dev_alloc(s, &(ptr), (cnt))) != MFB_OK) { mfb_als_end(s); return rc; }
+    ALLOC(s->Wb[0], KP * s->ldw) ALLOC(s->Wb[1], KP * s->ldw) ALLOC(s->Wr, KP * s->ldw)
+    ALLOC(s->Hb[0], KP * s->ldh) ALLOC(s->Hb[1], KP * s->ldh)
+    ALLOC(s->G_W, KP * KP) ALLOC(s->Minv_W, KP * KP) ALLOC(s->G_H, KP * KP) ALLOC(s->Minv_H, KP * KP)
+    ALLOC(s->P_h, (size_t)s->T_h * s->maxslots_h * KP * TILE_UNITS)
+    ALLOC(s->P_w, (size_t)s->T_w * s->maxslots_w * KP * TILE_UNITS)
+    const size_t Tmax = (size_t)(s->T_h > s->T_w ? s->T_h : s->T_w);
+    ALLOC(s->gpart, Tmax * KP * KP) ALLOC(s->spart, Tmax * 4)
+    ALLOC(s->counters, Tmax * 2)
+    ALLOC(s->ctrl, 1)
+    s->max_trace = 4096;
+    ALLOC(s->trace_dev, (size_t)s->max_trace * 3)
+    ALLOC(s->sing_dev, 1)
+    ALLOC(s->gram_scratch, (size_t)64 * KP * KP)
+#undef ALLOC
+    // tensor maps over A: dims {m rows (contiguous), n cols}
+    if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, 16, 128)) != MFB_OK ||
+        (rc = encode_map(&s->tm_w, A->d, A->m, A->n, A->lda, 16, 32)) != MFB_OK) {
+        mfb_als_end(s);
+        return rc;
+    }
+    // initial factors
+    cudaStream_t st = ctx->stream;
+    MFB_CUDA(cudaMemcpy2DAsync(s->Wb[0], s->ldw * sizeof(double), W0, s->m * sizeof(double), s->m * sizeof(double), k,
+                               cudaMemcpyHostToDevice, st));
+    if ((rc = als_upload_H(s, Hold0, s->Hb[0])) != MFB_OK) { mfb_als_end(s); return rc; }
+    AlsCtrl c;
+    memset(&c, 0, sizeof(c));
+    c.resid_old = resid_old0;
+    c.normA2 = stats[2];
+    c.mn = (double)s->m * (double)s->n;
+    c.mk = (double)s->m * k;
+    c.kn = (double)k * s->n;
+    c.max_trace = s->max_trace;
+    MFB_CUDA(cudaMemcpyAsync(s->ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+    if ((rc = gram_of_factor(s, s->Wb[0], s->ldw, s->m, s->G_W, s->Minv_W)) != MFB_OK) { mfb_als_end(s); return rc; }
+    MFB_CUDA(cudaStreamSynchronize(st));
+    *out = s;
+    return MFB_OK;
+}
+
+int mfb_als_restart(mfb_als *s, const double *Wnew) {
+    MFB_ARG(s && Wnew, "NULL argument");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    MFB_CUDA(cudaMemcpy2DAsync(s->Wr, s->ldw * sizeof(double), Wnew, s->m * sizeof(double), s->m * sizeof(double), s->k,
+                               cudaMemcpyHostToDevice, st));
+    MFB_TRY(gram_of_factor(s, s->Wr, s->ldw, s->m, s->G_W, s->Minv_W));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    s->restart_pending = true;
+    return MFB_OK;
+}
+
+static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
+    HalfParams h;
+    memset(&h, 0, sizeof(h));
+    const int nxt = cur ^ 1;
+    // H-step: fixed W (or the restart draw), solve H
+    h.Fin = use_restart_w ? s->Wr : s->Wb[cur]; h.ldin = s->ldw;
+    h.Fout = s->Hb[nxt]; h.Fold = s->Hb[cur]; h.ldout = s->ldh;
+    h.G = s->G_W; h.Minv = s->Minv_W; h.Gout = s->G_H; h.Minvout = s->Minv_H;
+    h.P = s->P_h; h.maxslots = s->maxslots_h; h.tile_counter = s->counters;
+    h.gpart = s->gpart; h.spart = s->spart; h.ctrl = s->ctrl; h.trace = s->trace_dev;
+    h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
+    MFB_TRY(launch_half_dispatch(s, false, h));
+    HalfParams w = h;
+    w.Fin = s->Hb[nxt]; w.ldin = s->ldh;
+    w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
+    w.G = s->G_H; w.Minv = s->Minv_H; w.Gout = s->G_W; w.Minvout = s->Minv_W;
+    w.P = s->P_w; w.maxslots = s->maxslots_w;
+    w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
+    MFB_TRY(launch_half_dispatch(s, true, w));
+    return MFB_OK;
+}
+
+int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters, int *iters_total, int *converged) {
+    MFB_ARG(s, "NULL session");
+    MFB_ARG(eps_conv > 0, "ALS-NMF: Invalid argument 'eps_conv' - value should be positive");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    if (converged) *converged = 0;
+    int status = MFB_OK;
+    int remaining = max_new_iters;
+    AlsCtrl *hc = (AlsCtrl *)s->ctx->pinned;
+    while (remaining > 0) {
+        const int batch = fixed_iters ? remaining : (remaining < 8 ? remaining : 8);
+        // arm the control block for this batch
+        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = fixed_iters ? 1 : 0; hc->eps = eps_conv;
+        hc->tiles_done[0] = hc->tiles_done[1] = 0; hc->nzmask = 0ull;
+        if (batch > s->max_trace) { mfb_set_error("too many iterations in one batch"); return MFB_ERR_ARG; }
+        MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
+        int cur = s->cur;
+        for (int b = 0; b < batch; ++b) {
+            MFB_TRY(enqueue_iteration(s, cur, s->restart_pending && b == 0));
+            cur ^= 1;
+        }
+        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        const int done = hc->iters_done;
+        if (done > 0) {
+            const size_t old = s->trace.size();
+            s->trace.resize(old + (size_t)done * 3);
+            MFB_CUDA(cudaMemcpy(s->trace.data() + old, s->trace_dev, (size_t)done * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+            s->resid = hc->resid;
+            s->restart_pending = false;
+        }
+        s->iters_total += done;
+        if (done & 1) s->cur ^= 1;
+        remaining -= done;
+        if (hc->stop) {
+            if (hc->reason == 3 && remaining <= 0) {
+                // W'W of the final W is singular, but R never runs another H-step: not a failure
+            } else if (hc->reason == 1) {
+                if (converged) *converged = 1;
+            } else {
+                // the iteration that was running failed: R has already done `i <- i + 1`
+                s->iters_total += 1;
+                const double qnan = NAN;
+                s->trace.push_back(qnan); s->trace.push_back(qnan); s->trace.push_back(qnan);
+                status = (hc->reason == 2) ? MFB_ZERO_ROW : MFB_SINGULAR;
+            }
+            break;
+        }
+        if (done == 0) break;   // defensive: nothing ran
+    }
+    if (iters_total) *iters_total = s->iters_total;
+    return status;
+}
+
+int mfb_als_result(mfb_als *s, double *W, double *H, double *resid, double *trace) {
+    MFB_ARG(s, "NULL session");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    if (W)
+        MFB_CUDA(cudaMemcpy2DAsync(W, s->m * sizeof(double), s->Wb[s->cur], s->ldw * sizeof(double), s->m * sizeof(double),
+                                   s->k, cudaMemcpyDeviceToHost, st));
+    if (H) {
+        std::vector<double> tmp((size_t)s->k * s->n);
+        MFB_CUDA(cudaMemcpy2DAsync(tmp.data(), s->n * sizeof(double), s->Hb[s->cur], s->ldh * sizeof(double),
+                                   s->n * sizeof(double), s->k, cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        for (int64_t j = 0; j < s->n; ++j)
+            for (int c = 0; c < s->k; ++c) H[(size_t)j * s->k + c] = tmp[(size_t)c * s->n + j];
+    }
+    MFB_CUDA(cudaStreamSynchronize(st));
+    if (resid) *resid = s->resid;
+    if (trace && !s->trace.empty()) memcpy(trace, s->trace.data(), s->trace.size() * sizeof(double));
+    return MFB_OK;
+}
+
+int mfb_als_run(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, const double *Hold0, double resid_old0,
+                int max_iter, double eps_conv, int fixed_iters, double *W, double *H, double *resid, int *iters_done,
+                int *converged, double *trace) {
+    mfb_als *s = nullptr;
+    MFB_TRY(mfb_als_begin(ctx, A, k, W0, Hold0, resid_old0, &s));
+    int it = 0, conv = 0;
+    int status = mfb_als_iterate(s, max_iter, eps_conv, fixed_iters, &it, &conv);
+    if (status >= 0) {
+        int rc = mfb_als_result(s, W, H, resid, trace);
+        if (rc != MFB_OK) status = rc;
+    }
+    if (iters_done) *iters_done = it;
+    if (converged) *converged = conv;
+    mfb_als_end(s);
+    return status;
+}
+
+int mfb_als_run_host(mfb_context *ctx, const double *A_host, int64_t m, int64_t n, int k, const double *W0,
+                     const double *Hold0, int max_iter, double eps_conv, int fixed_iters, double *W, double *H,
+                     double *resid, int *iters_done, int *converged, double *trace) {
+    mfb_matrix *A = nullptr;
+    MFB_TRY(mfb_matrix_upload(ctx, A_host, m, n, &A));
+    double stats[5];
+    int rc = mfb_matrix_stats(A, stats);
+    if (rc == MFB_OK)
+        rc = mfb_als_run(ctx, A, k, W0, Hold0, stats[1], max_iter, eps_conv, fixed_iters, W, H, resid, iters_done,
+                         converged, trace);
+    mfb_matrix_free(A);
+    return rc;
+}
+
+int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t pcols, double *K) {
+    MFB_ARG(ctx && C && B && K, "NULL argument");
+    MFB_ARG(k >= 1 && k <= 64 && r >= 1 && pcols >= 1, "bad sizes");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int KP = (k <= 16) ? 16 : 64;
+    double *dC, *dB, *dR, *dG, *dM, *dK, *part;
+    int *dsing;
+    MFB_CUDA(cudaMalloc(&dC, sizeof(double) * r * k));
+    MFB_CUDA(cudaMalloc(&dB, sizeof(double) * r * pcols));
+    MFB_CUDA(cudaMalloc(&dR, sizeof(double) * k * pcols));
+    MFB_CUDA(cudaMalloc(&dK, sizeof(double) * k * pcols));
+    MFB_CUDA(cudaMalloc(&dG, sizeof(double) * KP * KP));
+    MFB_CUDA(cudaMalloc(&dM, sizeof(double) * KP * KP));
+    MFB_CUDA(cudaMalloc(&part, sizeof(double) * 64 * KP * KP));
+    MFB_CUDA(cudaMalloc(&dsing, sizeof(int)));
+    MFB_CUDA(cudaMemcpyAsync(dC, C, sizeof(double) * r * k, cudaMemcpyHostToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(dB, B, sizeof(double) * r * pcols, cudaMemcpyHostToDevice, st));
+    int nb = (int)((r + 2047) / 2048);
+    if (nb > 64) nb = 64;
+    gram_partial_kernel<<<nb, 256, (size_t)k * 65 * sizeof(double), st>>>(dC, r, r, k, KP, part);
+    gram_finalize_kernel<<<1, 256, (size_t)(KP * KP + 2) * sizeof(double), st>>>(part, nb, k, KP, dG, dM, dsing);
+    small_crossprod_kernel<<<(unsigned)pcols, 256, 0, st>>>(dC, dB, r, k, pcols, dR);
+    if (KP == 16) {
+        nnls_columns_kernel<16><<<(unsigned)((pcols + 127) / 128), 128, 2 * 16 * 16 * sizeof(double), st>>>(dG, dM, dR, k, pcols, dK);
+    } else {
+        MFB_CUDA(cudaFuncSetAttribute(nnls_columns_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * (int)sizeof(double)));
+        nnls_columns_kernel<64><<<(unsigned)((pcols + 127) / 128), 128, 2 * 64 * 64 * sizeof(double), st>>>(dG, dM, dR, k, pcols, dK);
+    }
+    MFB_CUDA(cudaGetLastError());
+    int sing = 0;
+    MFB_CUDA(cudaMemcpyAsync(K, dK, sizeof(double) * k * pcols, cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaMemcpyAsync(&sing, dsing, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dC); cudaFree(dB); cudaFree(dR); cudaFree(dK); cudaFree(dG); cudaFree(dM); cudaFree(part); cudaFree(dsing);
+    return sing ? MFB_SINGULAR : MFB_OK;
+}
+
+}  // extern "C"

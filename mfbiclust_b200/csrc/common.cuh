@@ -1,0 +1,93 @@
+// Shared host/device helpers for libmfbiclust_cuda.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mfbiclust.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void mfb_set_error(const char *fmt, ...);
+
+#define MFB_CUDA(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            mfb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                          __FILE__, __LINE__);                                          \
+            return MFB_ERR_CUDA;                                                        \
+        }                                                                               \
+    } while (0)
+
+#define MFB_ARG(cond, msg)                                                              \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            mfb_set_error("bad argument: %s (%s:%d)", msg, __FILE__, __LINE__);         \
+            return MFB_ERR_ARG;                                                         \
+        }                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// objects behind the opaque handles
+// ---------------------------------------------------------------------------
+struct mfb_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    // small pinned mailbox for control blocks / scalars
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct mfb_matrix {
+    mfb_context *ctx = nullptr;
+    double *d = nullptr;      // column-major, leading dimension lda
+    int64_t m = 0, n = 0, lda = 0;
+    bool owned = false;
+    bool stats_valid = false;
+    double stats[5] = {0, 0, 0, 0, 0};   // min, max, sumsq, nan count, sum
+};
+
+static inline int64_t round_up(int64_t x, int64_t q) { return (x + q - 1) / q * q; }
+
+// driver entry point for tensor-map encoding (resolved at run time: the library has no
+// link-time dependency on libcuda, so it loads on a machine without a driver and then
+// fails loudly at mfb_context_create()).
+typedef CUresult (*mfb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                        const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                        const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+mfb_encode_tiled_fn mfb_get_encode_tiled();
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor core (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+#endif

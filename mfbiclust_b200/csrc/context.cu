@@ -1,0 +1,260 @@
+// Context, error string and the HBM-resident matrix handle of libmfbiclust_cuda.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mfb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+mfb_encode_tiled_fn mfb_get_encode_tiled() {
+    static mfb_encode_tiled_fn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (mfb_encode_tiled_fn)p;
+    return fn;
+}
+
+extern "C" {
+
+int mfb_version(void) { return 100; }
+const char *mfb_last_error(void) { return g_err; }
+
+int mfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mfb_context_create(int device, mfb_context **out) {
+    MFB_ARG(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        mfb_set_error("no CUDA device available (%s): libmfbiclust_cuda has no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return MFB_ERR_CUDA;
+    }
+    MFB_ARG(device >= 0 && device < n, "device index out of range");
+    MFB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MFB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        mfb_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                      prop.major, prop.minor);
+        return MFB_ERR_UNSUPPORTED;
+    }
+    if (!mfb_get_encode_tiled()) {
+        mfb_set_error("cuTensorMapEncodeTiled not available from the driver");
+        return MFB_ERR_CUDA;
+    }
+    mfb_context *c = new mfb_context();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    MFB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->pinned_bytes = 1 << 20;
+    MFB_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+    *out = c;
+    return MFB_OK;
+}
+
+void mfb_context_destroy(mfb_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+}
+
+int mfb_context_sync(mfb_context *ctx) {
+    MFB_ARG(ctx, "ctx is NULL");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MFB_OK;
+}
+
+void *mfb_context_stream(mfb_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// matrix statistics: min, max, sum of squares, NaN count, sum  (two-stage, deterministic)
+// ---------------------------------------------------------------------------
+struct Stat5 {
+    double mn, mx, ss, nan, sum;
+};
+
+__global__ void __launch_bounds__(256) stats_partial_kernel(const double *__restrict__ A, int64_t m, int64_t n,
+                                                            int64_t lda, Stat5 *__restrict__ part) {
+    double mn = INFINITY, mx = -INFINITY, ss = 0.0, nn = 0.0, sm = 0.0;
+    // one column at a time per block; threads stride over rows (coalesced)
+    for (int64_t j = blockIdx.x; j < n; j += gridDim.x) {
+        const double *col = A + j * lda;
+        for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+            double v = col[i];
+            if (v != v) {
+                nn += 1.0;
+            } else {
+                mn = fmin(mn, v);
+                mx = fmax(mx, v);
+                ss += v * v;
+                sm += v;
+            }
+        }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    ss = warp_sum(ss);
+    nn = warp_sum(nn);
+    sm = warp_sum(sm);
+    __shared__ Stat5 sh[8];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = Stat5{mn, mx, ss, nn, sm};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Stat5 r = sh[0];
+        for (int i = 1; i < 8; ++i) {
+            r.mn = fmin(r.mn, sh[i].mn);
+            r.mx = fmax(r.mx, sh[i].mx);
+            r.ss += sh[i].ss;
+            r.nan += sh[i].nan;
+            r.sum += sh[i].sum;
+        }
+        part[blockIdx.x] = r;
+    }
+}
+
+__global__ void stats_final_kernel(const Stat5 *__restrict__ part, int nb, double *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        Stat5 r = part[0];
+        for (int i = 1; i < nb; ++i) {
+            r.mn = fmin(r.mn, part[i].mn);
+            r.mx = fmax(r.mx, part[i].mx);
+            r.ss += part[i].ss;
+            r.nan += part[i].nan;
+            r.sum += part[i].sum;
+        }
+        out[0] = r.mn;
+        out[1] = r.mx;
+        out[2] = r.ss;
+        out[3] = r.nan;
+        out[4] = r.sum;
+    }
+}
+
+__global__ void __launch_bounds__(256) shift_kernel(double *__restrict__ A, int64_t m, int64_t n, int64_t lda,
+                                                    double shift) {
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+        double *col = A + j * lda;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+            col[i] += shift;
+    }
+}
+
+extern "C" {
+
+int mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t n, mfb_matrix **out) {
+    MFB_ARG(ctx && host && out, "NULL argument");
+    MFB_ARG(m > 0 && n > 0, "matrix dimensions must be positive");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    mfb_matrix *A = new mfb_matrix();
+    A->ctx = ctx;
+    A->m = m;
+    A->n = n;
+    A->lda = round_up(m, 16);   // 128-byte aligned columns: TMA strides, 32-byte vector loads
+    A->owned = true;
+    size_t bytes = (size_t)A->lda * (size_t)n * sizeof(double) + 256;
+    cudaError_t e = cudaMalloc(&A->d, bytes);
+    if (e != cudaSuccess) {
+        delete A;
+        mfb_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return MFB_ERR_ALLOC;
+    }
+    if (A->lda != m) MFB_CUDA(cudaMemsetAsync(A->d, 0, bytes, ctx->stream));
+    MFB_CUDA(cudaMemcpy2DAsync(A->d, A->lda * sizeof(double), host, m * sizeof(double), m * sizeof(double), n,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    *out = A;
+    return MFB_OK;
+}
+
+int mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb_matrix **out) {
+    MFB_ARG(ctx && dev && out, "NULL argument");
+    MFB_ARG(m > 0 && n > 0, "matrix dimensions must be positive");
+    MFB_ARG(m % 2 == 0 && ((uintptr_t)dev % 16) == 0,
+            "wrapped device matrices need an even row count and a 16-byte aligned base (TMA strides)");
+    mfb_matrix *A = new mfb_matrix();
+    A->ctx = ctx;
+    A->d = dev;
+    A->m = m;
+    A->n = n;
+    A->lda = m;
+    A->owned = false;
+    *out = A;
+    return MFB_OK;
+}
+
+void mfb_matrix_free(mfb_matrix *A) {
+    if (!A) return;
+    if (A->owned && A->d) {
+        cudaSetDevice(A->ctx->device);
+        cudaStreamSynchronize(A->ctx->stream);
+        cudaFree(A->d);
+    }
+    delete A;
+}
+
+void *mfb_matrix_dev_ptr(mfb_matrix *A) { return A ? (void *)A->d : nullptr; }
+
+int mfb_matrix_stats(mfb_matrix *A, double stats[5]) {
+    MFB_ARG(A && stats, "NULL argument");
+    mfb_context *ctx = A->ctx;
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    if (!A->stats_valid) {
+        int nb = (int)(A->n < 4 * ctx->sm_count ? A->n : 4 * ctx->sm_count);
+        Stat5 *part = nullptr;
+        double *dout = nullptr;
+        MFB_CUDA(cudaMalloc(&part, sizeof(Stat5) * nb + 5 * sizeof(double)));
+        dout = (double *)(part + nb);
+        stats_partial_kernel<<<nb, 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, part);
+        stats_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, dout);
+        MFB_CUDA(cudaGetLastError());
+        MFB_CUDA(cudaMemcpyAsync(A->stats, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        MFB_CUDA(cudaFree(part));
+        A->stats_valid = true;
+    }
+    memcpy(stats, A->stats, 5 * sizeof(double));
+    return MFB_OK;
+}
+
+int mfb_matrix_shift(mfb_matrix *A, double shift) {
+    MFB_ARG(A, "NULL argument");
+    mfb_context *ctx = A->ctx;
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    int gy = (int)(A->n < 65535 ? A->n : 65535);
+    int gx = (int)((A->m + 255) / 256);
+    if (gx > 64) gx = 64;
+    shift_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, shift);
+    MFB_CUDA(cudaGetLastError());
+    A->stats_valid = false;
+    return MFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// Per-problem exact NNLS on the normal equations and the k x k Gram inverse it shares.
+//
+// Replaces NMF::.fcnnls / .cssls (NMF 0.21.0; call sites R/bicluster.R:123,150).  The R code
+// groups columns by passive set and calls solve() per group; here every column (H-step) or
+// row (W-step) of the factor is one thread running the same pivot rules on its own problem
+//     min_x 1/2 x'Gx - r'x,  x >= 0        (G = C'C, r = C'a)
+//   * first guess: unconstrained solution xu = solve(G) %*% r, passive set P = {xu > 0}
+//   * inner loop (Lawson-Hanson): while the solution on P has a negative entry, step from the
+//     last feasible point d towards it until the first entry hits zero, drop that entry
+//   * outer loop: gradient w = r - G x on the active set; optimal when no w > 0, else add
+//     argmax w to P.
+// The solve on a passive set P uses the SHARED inverse M = G^-1 (one k x k inversion per
+// half-step for all columns) through the Schur complement on the ACTIVE set N = ~P:
+//     x_P = xu_P - M_PN y,   y = (M_NN)^-1 xu_N,   x_N = 0
+// which costs O(|N|^3 + k|N|) per pivot instead of O(|P|^3), and |N| is small in practice.
+#pragma once
+#include "common.cuh"
+
+// In-place inversion of the SPD k x k matrix `a` (shared memory, leading dimension ld) by
+// Gauss-Jordan without pivoting; all `nthreads` threads of the calling group participate and
+// `bar()` must synchronise exactly that group.  Returns (to all threads) 0 on success, 1 if a
+// pivot is not safely positive (R's solve(): "system is computationally singular").
+template <typename Bar>
+__device__ int gauss_jordan_inverse(double *a, int k, int ld, int tid, int nthreads, double *scratch /* >= 2 doubles */,
+                                    Bar bar) {
+    // R's solve() refuses the system when a pivot vanishes or rcond (1-norm) < .Machine$double.eps
+    if (tid == 0) {
+        double an = 0.0;
+        for (int j = 0; j < k; ++j) {
+            double cs = 0.0;
+            for (int i = 0; i < k; ++i) cs += fabs(a[i * ld + j]);
+            an = fmax(an, cs);
+        }
+        scratch[0] = an;
+        scratch[1] = 0.0;  // singular flag
+    }
+    bar();
+    for (int p = 0; p < k; ++p) {
+        double piv = a[p * ld + p];
+        if (!(piv > 0.0) || !isfinite(piv)) {
+            if (tid == 0) scratch[1] = 1.0;
+            piv = 1.0;
+        }
+        bar();
+        const double ipiv = 1.0 / piv;
+        // eliminate column p from all other rows (uses the unscaled pivot row)
+        for (int e = tid; e < k * k; e += nthreads) {
+            int i = e / k, j = e - i * k;
+            if (i != p && j != p) a[i * ld + j] -= a[i * ld + p] * ipiv * a[p * ld + j];
+        }
+        bar();
+        for (int e = tid; e < k; e += nthreads) {
+            if (e != p) {
+                a[e * ld + p] = -a[e * ld + p] * ipiv;   // column p
+                a[p * ld + e] = a[p * ld + e] * ipiv;    // row p
+            }
+        }
+        if (tid == 0) a[p * ld + p] = ipiv;
+        bar();
+    }
+    if (tid == 0) {
+        double in = 0.0;
+        for (int j = 0; j < k; ++j) {
+            double cs = 0.0;
+            for (int i = 0; i < k; ++i) cs += fabs(a[i * ld + j]);
+            in = fmax(in, cs);
+        }
+        if (!isfinite(in) || scratch[0] * in * 2.220446049250313e-16 > 1.0) scratch[1] = 1.0;
+    }
+    bar();
+    return scratch[1] != 0.0;
+}
+
+// One NNLS problem per thread.  G, M: shared memory, leading dimension KP (KP = padded rank).
+// r: right-hand side (k entries used).  x: result.  Returns the number of pivots taken.
+template <int KP>
+__device__ int nnls_thread(const double *__restrict__ G, const double *__restrict__ M, int k, const double *r,
+                           double *x) {
+    double xu[KP], d[KP], y[KP];
+    int idx[KP];
+    double L[KP * (KP + 1) / 2];
+    uint64_t P = 0;
+    const uint64_t full = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
+    for (int i = 0; i < k; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += M[i * KP + j] * r[j];
+        xu[i] = s;
+        if (s > 0.0) P |= (1ull << i);
+    }
+    if (P == full) {
+        for (int i = 0; i < k; ++i) x[i] = xu[i];
+        return 0;
+    }
+    for (int i = 0; i < k; ++i) {
+        x[i] = (xu[i] > 0.0) ? xu[i] : 0.0;
+        d[i] = x[i];
+    }
+    int pivots = 0;
+    const int cap = 4 * k + 8;
+
+    auto solve_on_P = [&]() {
+        // active list
+        int nn = 0;
+        for (int i = 0; i < k; ++i)
+            if (!((P >> i) & 1ull)) idx[nn++] = i;
+        if (nn == 0) {
+            for (int i = 0; i < k; ++i) x[i] = xu[i];
+            return;
+        }
+        if (nn == k) {
+            for (int i = 0; i < k; ++i) x[i] = 0.0;
+            return;
+        }
+        // Cholesky of M[N,N] (row-packed lower triangle), forward/back substitution
+        for (int a = 0; a < nn; ++a) {
+            for (int b = 0; b <= a; ++b) {
+                double s = M[idx[a] * KP + idx[b]];
+                for (int c = 0; c < b; ++c) s -= L[a * (a + 1) / 2 + c] * L[b * (b + 1) / 2 + c];
+                if (a == b)
+                    L[a * (a + 1) / 2 + a] = sqrt(fmax(s, 1e-300));
+                else
+                    L[a * (a + 1) / 2 + b] = s / L[b * (b + 1) / 2 + b];
+            }
+        }
+        for (int a = 0; a < nn; ++a) {
+            double s = xu[idx[a]];
+            for (int c = 0; c < a; ++c) s -= L[a * (a + 1) / 2 + c] * y[c];
+            y[a] = s / L[a * (a + 1) / 2 + a];
+        }
+        for (int a = nn - 1; a >= 0; --a) {
+            double s = y[a];
+            for (int c = a + 1; c < nn; ++c) s -= L[c * (c + 1) / 2 + a] * y[c];
+            y[a] = s / L[a * (a + 1) / 2 + a];
+        }
+        for (int i = 0; i < k; ++i) {
+            if ((P >> i) & 1ull) {
+                double s = xu[i];
+                for (int a = 0; a < nn; ++a) s -= M[i * KP + idx[a]] * y[a];
+                x[i] = s;
+            } else {
+                x[i] = 0.0;
+            }
+        }
+    };
+
+    while (pivots < cap) {
+        solve_on_P();
+        // inner loop: restore feasibility
+        while (pivots < cap) {
+            double amin = INFINITY;
+            int imin = -1;
+            for (int i = 0; i < k; ++i) {
+                if (((P >> i) & 1ull) && x[i] < 0.0) {
+                    double al = d[i] / (d[i] - x[i]);
+                    if (al < amin) {
+                        amin = al;
+                        imin = i;
+                    }
+                }
+            }
+            if (imin < 0) break;
+            for (int i = 0; i < k; ++i) d[i] = d[i] - amin * (d[i] - x[i]);
+            d[imin] = 0.0;
+            P &= ~(1ull << imin);
+            ++pivots;
+            solve_on_P();
+        }
+        // optimality on the active set: w = r - G x
+        double wmax = 0.0;
+        int imax = -1;
+        for (int i = 0; i < k; ++i) {
+            if (!((P >> i) & 1ull)) {
+                double w = r[i];
+                for (int j = 0; j < k; ++j) w -= G[i * KP + j] * x[j];
+                if (w > wmax) {
+                    wmax = w;
+                    imax = i;
+                }
+            }
+        }
+        if (imax < 0) break;
+        P |= (1ull << imax);
+        for (int i = 0; i < k; ++i) d[i] = x[i];
+        ++pivots;
+    }
+    // guard: whatever the path, never return a negative entry
+    for (int i = 0; i < k; ++i)
+        if (!(x[i] > 0.0)) x[i] = 0.0;
+    return pivots;
+}

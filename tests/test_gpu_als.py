@@ -1,0 +1,115 @@
+"""GPU parity tests for the ALS-NMF path (C ABI -> CUDA) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import otsu as O
+from oracle.als_nmf import als_replicate as oracle_replicate
+from oracle.fcnnls import fcnnls
+from oracle.helpers import pseudovalues
+from oracle.gen_sim_data import gen_sim_data
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_fro(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def make_init(m, n, k, seed):
+    rs = np.random.default_rng(seed)
+    W0 = rs.random((m, k))
+    W0 /= np.sqrt((W0 ** 2).sum(axis=0))[None, :]
+    return np.asfortranarray(W0), np.asfortranarray(rs.random((k, n)))
+
+
+@pytest.mark.parametrize("k,r,p", [(1, 50, 7), (3, 200, 33), (8, 300, 500), (16, 257, 129), (20, 100, 40)])
+def test_nnls_matches_fcnnls(k, r, p):
+    import mfbiclust_b200 as mfb
+    rs = np.random.default_rng(k * 100 + p)
+    Cm = rs.random((r, k))
+    B = rs.standard_normal((r, p)) + 0.25
+    K = mfb.nnls(Cm, B)
+    Kref, _ = fcnnls(Cm, B)
+    assert (K >= 0).all()
+    assert np.array_equal(K == 0, Kref == 0)          # identical active sets
+    assert rel_fro(K, Kref) < 1e-11
+
+
+def _check_replicate(A, k, iters, seed, tol=1e-8):
+    import mfbiclust_b200 as mfb
+    m, n = A.shape
+    W0, H0 = make_init(m, n, k, seed)
+    got = mfb.als_replicate(A, k, W0, H0, maxIter=iters, fixed_iters=True)
+    tr = []
+    ref = oracle_replicate(A, W0, H0, max_iter=iters, fixed_iters=True, trace=tr)
+    assert got["iters"] == iters
+    assert rel_fro(got["W"], ref["W"]) < tol, rel_fro(got["W"], ref["W"])
+    assert rel_fro(got["H"], ref["H"]) < tol, rel_fro(got["H"], ref["H"])
+    assert np.array_equal(got["W"] == 0, ref["W"] == 0)
+    assert np.array_equal(got["H"] == 0, ref["H"] == 0)
+    tr = np.array([t[1:] for t in tr])
+    assert np.allclose(got["trace"], tr, rtol=1e-9, atol=1e-12)
+    return got, ref
+
+
+def test_als_simdata_k5(simdata):
+    # BASELINE.json configs[0]: addStrat(BiclusterExperiment(simdata), k=5, method='als-nmf')
+    import mfbiclust_b200 as mfb
+    for name in ("fiveSquareConstant", "plaid"):
+        A = pseudovalues(simdata[name])
+        got, ref = _check_replicate(A, 5, 10, seed=41)
+        # Otsu / threshold on identical inputs: bit-exact thresholds, identical memberships
+        ft, st, rn, nc = O.threshold_helper(got["W"], got["H"])
+        gft, gst = mfb.otsuHelper(got["W"]), mfb.otsuHelper(got["H"].T)
+        assert np.array_equal(gft, ft), name
+        assert np.array_equal(gst, st), name
+        assert np.array_equal(mfb.threshold(got["W"], gft, 2), rn), name
+        assert np.array_equal(mfb.threshold(got["H"], gst, 1), nc), name
+        # and the memberships agree with the ones the oracle derives from ITS factors
+        _, _, rn_ref, nc_ref = O.threshold_helper(ref["W"], ref["H"])
+        assert np.array_equal(rn, rn_ref) and np.array_equal(nc, nc_ref), name
+
+
+def test_als_simdata_degenerate_restarts(simdata):
+    """fiveSquareRowShift is rank deficient for k = 5: in R every other .fcnnls call dies in
+    solve() ("computationally singular", cond(HH') ~ 1e16) and als_nmf gives up after the 9th
+    restart (R/bicluster.R:126-131).  The singular/regular decision sits at rcond ~ eps, so only
+    the behaviour is compared: the GPU path reports the same failures and the same warning."""
+    import mfbiclust_b200 as mfb
+    from oracle.als_nmf import als_replicate as orep
+    A = pseudovalues(simdata["fiveSquareRowShift"])
+    W0, H0 = make_init(80, 80, 5, 41)
+    g = np.random.default_rng(5)
+
+    def redraw():
+        W = g.random((80, 5))
+        return W / np.sqrt((W ** 2).sum(0))[None, :]
+    ref = orep(A, W0, H0, max_iter=10, fixed_iters=True, redraw=redraw)
+    assert ref["status"] == "failed"
+    with pytest.warns(UserWarning, match="Factorization failed too many times"):
+        got = mfb.als_replicate(A, 5, W0, H0, maxIter=10, fixed_iters=True, rng=mfb.HostRng(5))
+    assert np.isfinite(got["W"]).all()
+
+
+def test_als_yeast_k3(yeast):
+    A = pseudovalues(yeast[0])
+    _check_replicate(A, 3, 10, seed=42)
+
+
+@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1500, 700, 10), (640, 1030, 24)])
+def test_als_synthetic(m, n, k):
+    A = pseudovalues(gen_sim_data(n=4, cluster_height=min(m, n) // 5, cluster_width=min(m, n) // 5, dimx=m, dimy=n,
+                                  bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=m + n))
+    _check_replicate(A, k, 10, seed=43)
+
+
+def test_als_convergence_matches_oracle(yeast):
+    import mfbiclust_b200 as mfb
+    A = pseudovalues(yeast[0])
+    W0, H0 = make_init(*A.shape, 3, 7)
+    got = mfb.als_replicate(A, 3, W0, H0, maxIter=100, eps_conv=1e-4)
+    ref = oracle_replicate(A, W0, H0, max_iter=100, eps_conv=1e-4)
+    assert got["converged"] and ref["status"] == "converged"
+    assert got["iters"] == ref["iters"]
+    assert rel_fro(got["W"], ref["W"]) < 1e-8 and rel_fro(got["H"], ref["H"]) < 1e-8
+    assert abs(got["obj"] - ref["obj"]) < 1e-10
