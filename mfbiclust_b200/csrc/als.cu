@@ -117,11 +117,19 @@ __device__ __forceinline__ int cta_of_unit(long long u, long long U, int G) {
 // ---------------------------------------------------------------------------
 // the half-step kernel
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(ALS_THREADS, 1)
 als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, const int nstage) {
     constexpr int KP = KB * 8;
     constexpr int STAGE_BYTES = WSTEP ? 32768 : 16384;
+    constexpr int NF = WSTEP ? 4 : 2;            // double2 fragments of the fixed factor per rank block and unit
+    constexpr bool PREFETCH = (KB <= 2);
     if (*(volatile int *)&p.ctrl->stop) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -132,8 +140,9 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
     double *sG = (double *)(empty_bar + nstage);
     double *sM = sG + KP * KP;
     double *xs = sM + KP * KP;
-    double *sred = xs + KP * XS_LD;          // 32 doubles of reduction scratch
-    int *sflag = (int *)(sred + 32);
+    double *sred = xs + KP * XS_LD;          // 40 doubles of reduction scratch
+    int *sflag = (int *)(sred + 40);
+    const uint32_t ring_s = smem_u32(ring);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -156,14 +165,15 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
     }
     __syncthreads();
     if (u0 >= u1) return;
+    const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
+    const int nunits = (int)(u1 - u0);
 
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int stage = 0;
+            int stage = 0, tile = tile0, st = st0;
             uint32_t phase = 0;
-            for (long long u = u0; u < u1; ++u) {
-                const int tile = (int)(u / p.SPT), st = (int)(u % p.SPT);
+            for (int it = 0; it < nunits; ++it) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                 unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
@@ -175,6 +185,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
                         tma_load_2d(dst + rg * 4096, &tmA, tile * TILE_UNITS + rg * 16, st * 32, &full_bar[stage]);
                 }
                 if (++stage == nstage) { stage = 0; phase ^= 1; }
+                if (++st == p.SPT) { st = 0; ++tile; }
             }
         }
         return;
@@ -182,16 +193,11 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
 
     // ===================== consumers (warps 0..7) =====================
     const int g = lane >> 2, t = lane & 3;
-    constexpr int NACC = WSTEP ? 2 : 2;          // W-step: s in {0,1}; H-step: v in {0,1}
-    double acc[KB][NACC][2];
+    double acc[KB][2][2];                        // [rank block][v (H-step) or s (W-step)][2]
 #pragma unroll
     for (int cb = 0; cb < KB; ++cb)
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
-
-    int stage = 0;
-    uint32_t phase = 0;
-    int cur_tile = (int)(u0 / p.SPT);
+        for (int a = 0; a < 2; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
 
     auto flush = [&](int tile) {
         const long long tb = (long long)tile * p.SPT;
@@ -222,7 +228,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
                         make_double2(acc[cb][0][e], acc[cb][1][e]);
             }
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
+            for (int a = 0; a < 2; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
         }
         __threadfence();
         consumer_bar();
@@ -238,45 +244,93 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
 
         // ---------------- tile epilogue: NNLS for 128 units ----------------
         const long long unit = (long long)tile * TILE_UNITS + tid;
+        const bool valid = (tid < TILE_UNITS) && (unit < p.nvalid);
         double d2 = 0.0, t1 = 0.0, t2 = 0.0;
         unsigned long long nz = 0ull;
-        if (tid < TILE_UNITS) {
-            double r[KP], x[KP];
+        if constexpr (KP <= 32) {
+            // (a) right-hand sides: sum the partials in slot order, one thread per unit
+            if (tid < TILE_UNITS) {
+                double r[KP];
 #pragma unroll
-            for (int c = 0; c < KP; ++c) r[c] = 0.0;
-            for (int s = 0; s < expected; ++s) {
-                const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + tid;
+                for (int c = 0; c < KP; ++c) r[c] = 0.0;
+                for (int s = 0; s < expected; ++s) {
+                    const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + tid;
 #pragma unroll
-                for (int c = 0; c < KP; ++c)
-                    if (c < p.k) r[c] += ldcg(Ps + (size_t)c * TILE_UNITS);
+                    for (int c = 0; c < KP; ++c)
+                        if (c < p.k) r[c] += ldcg(Ps + (size_t)c * TILE_UNITS);
+                }
+#pragma unroll
+                for (int c = 0; c < KP; ++c) xs[c * XS_LD + tid] = valid ? r[c] : 0.0;
             }
+            consumer_bar();
+            // (b) lane-distributed principal-pivoting NNLS, 16 units per warp
+            t1 = nnls_tile_lanes<KP, XS_LD>(sM, p.k, xs, warp, lane, 8);
+            consumer_bar();
+            // (c) write-back and statistics, one thread per unit
+            if (tid < TILE_UNITS) {
+                double x[KP];
 #pragma unroll
-            for (int c = 0; c < KP; ++c) x[c] = 0.0;
-            const bool valid = unit < p.nvalid;
-            if (valid) nnls_thread<KP>(sG, sM, p.k, r, x);
+                for (int c = 0; c < KP; ++c) x[c] = (c < p.k) ? xs[c * XS_LD + tid] : 0.0;
 #pragma unroll
-            for (int c = 0; c < KP; ++c) {
-                if (c < p.k) {
-                    const size_t off = (size_t)c * p.ldout + unit;
-                    if (valid) {
-                        const double o = p.Fold[off];
-                        d2 += (x[c] - o) * (x[c] - o);
-                        if (x[c] != 0.0) nz |= (1ull << c);
+                for (int c = 0; c < KP; ++c) {
+                    if (c < p.k) {
+                        const size_t off = (size_t)c * p.ldout + unit;
+                        if (valid) {
+                            const double o = p.Fold[off];
+                            d2 += (x[c] - o) * (x[c] - o);
+                            if (x[c] != 0.0) nz |= (1ull << c);
+                        }
+                        p.Fout[off] = x[c];
                     }
-                    p.Fout[off] = x[c];
-                    xs[c * XS_LD + tid] = x[c];
+                }
+                if (WSTEP && valid) {
+#pragma unroll
+                    for (int c = 0; c < KP; ++c) {
+                        double gx = 0.0;
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) gx += sG[c * KP + j] * x[j];
+                        t2 += x[c] * gx;
+                    }
                 }
             }
-            if (WSTEP && valid) {
-                for (int c = 0; c < p.k; ++c) {
-                    t1 += x[c] * r[c];
-                    double gx = 0.0;
-                    for (int j = 0; j < p.k; ++j) gx += sG[c * KP + j] * x[j];
-                    t2 += x[c] * gx;
+        } else {
+            if (tid < TILE_UNITS) {
+                double r[KP], x[KP];
+#pragma unroll
+                for (int c = 0; c < KP; ++c) r[c] = 0.0;
+                for (int s = 0; s < expected; ++s) {
+                    const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + tid;
+#pragma unroll
+                    for (int c = 0; c < KP; ++c)
+                        if (c < p.k) r[c] += ldcg(Ps + (size_t)c * TILE_UNITS);
+                }
+#pragma unroll
+                for (int c = 0; c < KP; ++c) x[c] = 0.0;
+                if (valid) nnls_thread<KP>(sG, sM, p.k, r, x);
+#pragma unroll
+                for (int c = 0; c < KP; ++c) {
+                    if (c < p.k) {
+                        const size_t off = (size_t)c * p.ldout + unit;
+                        if (valid) {
+                            const double o = p.Fold[off];
+                            d2 += (x[c] - o) * (x[c] - o);
+                            if (x[c] != 0.0) nz |= (1ull << c);
+                        }
+                        p.Fout[off] = x[c];
+                        xs[c * XS_LD + tid] = x[c];
+                    }
+                }
+                if (WSTEP && valid) {
+                    for (int c = 0; c < p.k; ++c) {
+                        t1 += x[c] * r[c];
+                        double gx = 0.0;
+                        for (int j = 0; j < p.k; ++j) gx += sG[c * KP + j] * x[j];
+                        t2 += x[c] * gx;
+                    }
                 }
             }
         }
-        // block reduction of the scalars (threads >= 128 contribute zeros)
+        // block reduction of the scalars
         d2 = warp_sum(d2);
         t1 = warp_sum(t1);
         t2 = warp_sum(t2);
@@ -378,73 +432,84 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
         }
     };
 
-    for (long long u = u0; u < u1; ++u) {
-        const int tile = (int)(u / p.SPT), st = (int)(u % p.SPT);
-        if (tile != cur_tile) {
-            flush(cur_tile);
-            cur_tile = tile;
-        }
-        const unsigned char *sA = ring + (size_t)stage * STAGE_BYTES;
-        if (!WSTEP) {
-            // fixed-factor fragments: W[8cb+g][16 st + 4t + s], s = 0..3  (32 contiguous bytes)
-            double wf[KB][4];
+    // fragments of the fixed factor for one unit (both kinds are `NF` 16-byte loads per rank block):
+    //   H-step: W[8cb+g][16 st + 4t + {0..3}]                  W-step: H[8cb+g][32 st + 2t + 8q + {0,1}], q = 0..3
+    auto load_frag = [&](double2 (&f)[KB][NF], int st) {
+        const double *base = p.Fin + (size_t)g * p.ldin + (WSTEP ? ((size_t)st * 32 + 2 * t) : ((size_t)st * 16 + 4 * t));
 #pragma unroll
-            for (int cb = 0; cb < KB; ++cb) {
-                const double2 *src = (const double2 *)(p.Fin + (size_t)(8 * cb + g) * p.ldin + (size_t)st * 16 + 4 * t);
-                const double2 lo = __ldg(src), hi = __ldg(src + 1);
-                wf[cb][0] = lo.x; wf[cb][1] = lo.y; wf[cb][2] = hi.x; wf[cb][3] = hi.y;
-            }
-            mbar_wait(&full_bar[stage], phase);
-            // A fragments: column 16w + 8v + g of the box, rows 4t..4t+3 (chunks 2t, 2t+1 ^ g)
-            double b[2][4];
+        for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+                f[cb][q] = __ldg((const double2 *)(base + (size_t)(8 * cb) * p.ldin + (WSTEP ? 8 * q : 2 * q)));
+    };
+
+    int stage = 0, tile = tile0, st = st0;
+    uint32_t phase = 0;
+    double2 fr[KB][NF];
+    if constexpr (PREFETCH) load_frag(fr, st);
+    for (int it = 0; it < nunits; ++it) {
+        int nst = st + 1, ntile = tile;
+        if (nst == p.SPT) { nst = 0; ntile = tile + 1; }
+        double2 fn[KB][NF];
+        if constexpr (PREFETCH) {
+            if (it + 1 < nunits) load_frag(fn, nst);
+        } else {
+            load_frag(fr, st);
+        }
+        const uint32_t sA = ring_s + (uint32_t)stage * STAGE_BYTES;
+        mbar_wait(&full_bar[stage], phase);
+        if (!WSTEP) {
+            // A fragments: column 16w + 8v + g of the box, rows 4t..4t+3 (16-byte chunks 2t, 2t+1, XOR-swizzled by g)
+            double2 b[2][2];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
-                const unsigned char *rowp = sA + (16 * warp + 8 * v + g) * 128;
-                const double2 lo = *(const double2 *)(rowp + (((2 * t) ^ g) << 4));
-                const double2 hi = *(const double2 *)(rowp + (((2 * t + 1) ^ g) << 4));
-                b[v][0] = lo.x; b[v][1] = lo.y; b[v][2] = hi.x; b[v][3] = hi.y;
+                const uint32_t rowp = sA + (16 * warp + 8 * v + g) * 128;
+                b[v][0] = lds128(rowp + (((2 * t) ^ g) << 4));
+                b[v][1] = lds128(rowp + (((2 * t + 1) ^ g) << 4));
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int cb = 0; cb < KB; ++cb)
 #pragma unroll
-                    for (int v = 0; v < 2; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], wf[cb][s], b[v][s]);
+                    for (int v = 0; v < 2; ++v) {
+                        dmma884(acc[cb][v][0], acc[cb][v][1], fr[cb][h].x, b[v][h].x);
+                        dmma884(acc[cb][v][0], acc[cb][v][1], fr[cb][h].y, b[v][h].y);
+                    }
         } else {
-            // fixed-factor fragments: H[8cb+g][32 st + 2t + 8q + {0,1}], q = 0..3
-            const double *hbase = p.Fin + (size_t)g * p.ldin + (size_t)st * 32 + 2 * t;
-            double2 hv[KB <= 2 ? KB : 1][4];
-            if constexpr (KB <= 2) {
+            // row group `warp` of the tile: [col 32][16 rows]; lane reads rows 2g,2g+1 of column 2t + e + 8q
+            const uint32_t blk = sA + warp * 4096;
+            double2 a[4][2];
 #pragma unroll
-                for (int cb = 0; cb < KB; ++cb)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) hv[cb][q] = __ldg((const double2 *)(hbase + (size_t)(8 * cb) * p.ldin + 8 * q));
-            }
-            mbar_wait(&full_bar[stage], phase);
-            const unsigned char *blk = sA + warp * 4096;   // row group `warp` of the tile: [col 32][16 rows]
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double2 a[2];
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    a[e] = *(const double2 *)(blk + (2 * t + e + 8 * q) * 128 + ((g ^ ((2 * t + e) & 7)) << 4));
+                    a[q][e] = lds128(blk + (2 * t + e + 8 * q) * 128 + ((g ^ ((2 * t + e) & 7)) << 4));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int cb = 0; cb < KB; ++cb) {
-                    double2 h;
-                    if constexpr (KB <= 2) h = hv[cb][q];
-                    else h = __ldg((const double2 *)(hbase + (size_t)(8 * cb) * p.ldin + 8 * q));
-                    dmma884(acc[cb][0][0], acc[cb][0][1], a[0].x, h.x);
-                    dmma884(acc[cb][1][0], acc[cb][1][1], a[0].y, h.x);
-                    dmma884(acc[cb][0][0], acc[cb][0][1], a[1].x, h.y);
-                    dmma884(acc[cb][1][0], acc[cb][1][1], a[1].y, h.y);
+                    dmma884(acc[cb][0][0], acc[cb][0][1], a[q][0].x, fr[cb][q].x);
+                    dmma884(acc[cb][1][0], acc[cb][1][1], a[q][0].y, fr[cb][q].x);
+                    dmma884(acc[cb][0][0], acc[cb][0][1], a[q][1].x, fr[cb][q].y);
+                    dmma884(acc[cb][1][0], acc[cb][1][1], a[q][1].y, fr[cb][q].y);
                 }
-            }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == nstage) { stage = 0; phase ^= 1; }
+        if (ntile != tile || it + 1 == nunits) flush(tile);
+        tile = ntile;
+        st = nst;
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                for (int q = 0; q < NF; ++q) fr[cb][q] = fn[cb][q];
+        }
     }
-    flush(cur_tile);
 }
 
 // ---------------------------------------------------------------------------
@@ -730,7 +795,7 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->maxslots_h = max_slots(s->T_h, s->SPT_h, G);
     s->maxslots_w = max_slots(s->T_w, s->SPT_w, G);
     const size_t KP = s->KP;
-    const size_t epi = (2 * KP * KP + KP * XS_LD + 32 + 8) * sizeof(double);
+    const size_t epi = (2 * KP * KP + KP * XS_LD + 40 + 8) * sizeof(double);
     const size_t budget = 227 * 1024 - 1024 /*align*/ - epi - 2 * 16 * sizeof(uint64_t);
     s->nstage_h = (int)(budget / 16384); if (s->nstage_h > 12) s->nstage_h = 12;
     s->nstage_w = (int)(budget / 32768); if (s->nstage_w > 6) s->nstage_w = 6;

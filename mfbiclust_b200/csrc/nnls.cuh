@@ -188,3 +188,121 @@ __device__ int nnls_thread(const double *__restrict__ G, const double *__restric
         if (!(x[i] > 0.0)) x[i] = 0.0;
     return pivots;
 }
+
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative NNLS for a tile of 128 problems (rank padded to KP <= 32).
+//
+// Same pivot rules as nnls_thread / one column of .fcnnls, but carried as a principal-pivoting
+// tableau  z_B = q + T z_NB  (basic variables: x_i on the passive set S, the gradient
+// w_i = (r - Gx)_i on the active set; start S = all, q = xu = G^-1 r, T = -G^-1), so that one
+// exchange x_i <-> w_i is a rank-1 update of a KP x KP matrix that lives in REGISTERS: lane i of
+// an LP-lane group owns row i.  Both the primal values (q on S) and the KKT gradient (q on ~S) come
+// for free after every pivot: no refactorisation, no local memory, no per-pivot division chain
+// beyond one reciprocal.  LP = 16 for KP <= 16 (two problems per warp), 32 otherwise.
+//
+// xs: shared [KP][XS] -- right-hand sides r on entry, solutions x on exit (column = problem).
+// sM: shared G^-1 (ld KP, symmetric).  Returns this lane's partial of sum_i x_i r_i.
+// ---------------------------------------------------------------------------
+template <int KP, int XS>
+__device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *xs, int warp, int lane, int nwarps) {
+    constexpr int LP = (KP <= 16) ? 16 : 32;
+    constexpr int PPW = 32 / LP;
+    const unsigned FULL = 0xffffffffu;
+    const int sub = lane / LP, i = lane % LP, base = sub * LP;
+    const bool rowvalid = i < k;
+    const int units_per_warp = 128 / nwarps;
+    const unsigned gmask = (LP == 32) ? 0xffffffffu : (0xffffu << base);
+    double t1 = 0.0;
+    for (int rd = 0; rd < units_per_warp / PPW; ++rd) {
+        const int unit = warp * units_per_warp + rd * PPW + sub;
+        const double ri = rowvalid ? xs[i * XS + unit] : 0.0;
+        double T[KP];
+        double qv = 0.0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const double rj = __shfl_sync(FULL, ri, base + (j % LP));
+            const double mij = (rowvalid && j < k) ? sM[j * KP + i] : 0.0;
+            T[j] = -mij;
+            qv += mij * rj;
+        }
+        bool inS = rowvalid;
+        double dv = qv > 0.0 ? qv : 0.0;
+        unsigned pend = (__ballot_sync(FULL, rowvalid && !(qv > 0.0)) & gmask) >> base;
+        bool done = false;
+        int iters = 0;
+        const int cap = 6 * k + 16;
+        while (true) {
+            int piv = -1;
+            if (!done) {
+                if (pend) {
+                    piv = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                } else {
+                    const double x = inS ? qv : 0.0;
+                    // Lawson-Hanson step length: min over passive entries that went negative
+                    double al = (inS && x < 0.0) ? dv / (dv - x) : INFINITY;
+                    int ai = i;
+#pragma unroll
+                    for (int o = LP / 2; o > 0; o >>= 1) {
+                        const double oa = __shfl_xor_sync(gmask, al, o);
+                        const int oi = __shfl_xor_sync(gmask, ai, o);
+                        if (oa < al || (oa == al && oi < ai)) { al = oa; ai = oi; }
+                    }
+                    if (al < INFINITY) {
+                        dv = dv - al * (dv - x);
+                        if (i == ai) dv = 0.0;
+                        piv = ai;
+                    } else {
+                        double w = (!inS && rowvalid) ? qv : -1.0;
+                        int wi = i;
+#pragma unroll
+                        for (int o = LP / 2; o > 0; o >>= 1) {
+                            const double ow = __shfl_xor_sync(gmask, w, o);
+                            const int oi = __shfl_xor_sync(gmask, wi, o);
+                            if (ow > w || (ow == w && oi < wi)) { w = ow; wi = oi; }
+                        }
+                        if (w > 0.0) {
+                            dv = x;
+                            piv = wi;
+                        } else {
+                            done = true;
+                        }
+                    }
+                }
+                if (++iters > cap) { done = true; piv = -1; }
+            }
+            if (!__any_sync(FULL, piv >= 0)) break;
+            // exchange x_piv <-> w_piv (predicated per problem)
+            const int pq = piv >= 0 ? piv : 0;
+            const int src = base + pq;
+            double rowq[KP];
+            double tiq = 0.0;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                rowq[j] = __shfl_sync(FULL, T[j], src);
+                tiq = (j == pq) ? T[j] : tiq;
+            }
+            const double qq = __shfl_sync(FULL, qv, src);
+            const double pp = __shfl_sync(FULL, tiq, src);
+            if (piv >= 0) {
+                const double ip = 1.0 / pp;
+                if (i != piv) {
+                    const double f = tiq * ip;
+                    qv -= f * qq;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) T[j] = (j == piv) ? f : (T[j] - f * rowq[j]);
+                } else {
+                    qv = -qq * ip;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) T[j] = (j == piv) ? ip : (-rowq[j] * ip);
+                    inS = !inS;
+                }
+            }
+        }
+        const double x = (inS && rowvalid && qv > 0.0) ? qv : 0.0;
+        t1 += x * ri;
+        if (rowvalid) xs[i * XS + unit] = x;
+    }
+    return t1;
+}
