@@ -125,11 +125,14 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(ALS_THREADS, 1)
-als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, const int nstage) {
+als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmF, const HalfParams p,
+                const int nstage) {
     constexpr int KP = KB * 8;
-    constexpr int STAGE_BYTES = WSTEP ? 32768 : 16384;
-    constexpr int NF = WSTEP ? 4 : 2;            // double2 fragments of the fixed factor per rank block and unit
-    constexpr bool PREFETCH = (KB <= 2);
+    constexpr int A_BYTES = WSTEP ? 32768 : 16384;       // A box(es) of one stage
+    constexpr int F_BOX = KP * 128;                      // one 16-unit box of the fixed factor: [KP][16] doubles
+    constexpr int NFB = WSTEP ? 2 : 1;                   // factor boxes per stage (32 columns / 16 rows of reduction)
+    constexpr int STAGE_BYTES = A_BYTES + NFB * F_BOX;
+    constexpr int NF = WSTEP ? 4 : 2;                    // double2 fragments of the fixed factor per rank block and unit
     if (*(volatile int *)&p.ctrl->stop) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -179,10 +182,13 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
                 unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
                 if (!WSTEP) {
                     tma_load_2d(dst, &tmA, st * 16, tile * TILE_UNITS, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES, &tmF, st * 16, 0, &full_bar[stage]);
                 } else {
 #pragma unroll
                     for (int rg = 0; rg < 8; ++rg)
                         tma_load_2d(dst + rg * 4096, &tmA, tile * TILE_UNITS + rg * 16, st * 32, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES, &tmF, st * 32, 0, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES + F_BOX, &tmF, st * 32 + 16, 0, &full_bar[stage]);
                 }
                 if (++stage == nstage) { stage = 0; phase ^= 1; }
                 if (++st == p.SPT) { st = 0; ++tile; }
@@ -221,10 +227,10 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
                     *(double2 *)&Pb[(size_t)(8 * cb + g) * TILE_UNITS + 16 * warp + 8 * v + 2 * t] =
                         make_double2(acc[cb][v][0], acc[cb][v][1]);
             } else {
-                // acc[cb][s][e] = R[row 16w + 2g + s][c = 8cb + 2t + e]
+                // acc[cb][s][e] = R[row 16w + 2g + s][c = 8cb + t + 4e]   (rank index permuted, see the W-step loop)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    *(double2 *)&Pb[(size_t)(8 * cb + 2 * t + e) * TILE_UNITS + 16 * warp + 2 * g] =
+                    *(double2 *)&Pb[(size_t)(8 * cb + t + 4 * e) * TILE_UNITS + 16 * warp + 2 * g] =
                         make_double2(acc[cb][0][e], acc[cb][1][e]);
             }
 #pragma unroll
@@ -432,40 +438,35 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
         }
     };
 
-    // fragments of the fixed factor for one unit (both kinds are `NF` 16-byte loads per rank block):
-    //   H-step: W[8cb+g][16 st + 4t + {0..3}]                  W-step: H[8cb+g][32 st + 2t + 8q + {0,1}], q = 0..3
-    auto load_frag = [&](double2 (&f)[KB][NF], int st) {
-        const double *base = p.Fin + (size_t)g * p.ldin + (WSTEP ? ((size_t)st * 32 + 2 * t) : ((size_t)st * 16 + 4 * t));
-#pragma unroll
-        for (int cb = 0; cb < KB; ++cb)
-#pragma unroll
-            for (int q = 0; q < NF; ++q)
-                f[cb][q] = __ldg((const double2 *)(base + (size_t)(8 * cb) * p.ldin + (WSTEP ? 8 * q : 2 * q)));
-    };
-
+    // Main loop.  One stage = one unit: an A box plus the matching 16- (H-step) or 32-wide (W-step) slab of
+    // the fixed factor, both landed by TMA with SWIZZLE_128B: a "row" of a box is 128 bytes (16 doubles along
+    // the contiguous direction) whose 16-byte chunk c sits at chunk c ^ (row & 7).  Every fragment read below
+    // is a 16-byte ld.shared whose quarter-warp (g in {2a, 2a+1}, t = 0..3) touches 8 distinct chunks.
     int stage = 0, tile = tile0, st = st0;
     uint32_t phase = 0;
-    double2 fr[KB][NF];
-    if constexpr (PREFETCH) load_frag(fr, st);
     for (int it = 0; it < nunits; ++it) {
         int nst = st + 1, ntile = tile;
         if (nst == p.SPT) { nst = 0; ntile = tile + 1; }
-        double2 fn[KB][NF];
-        if constexpr (PREFETCH) {
-            if (it + 1 < nunits) load_frag(fn, nst);
-        } else {
-            load_frag(fr, st);
-        }
         const uint32_t sA = ring_s + (uint32_t)stage * STAGE_BYTES;
+        const uint32_t sF = sA + A_BYTES;
         mbar_wait(&full_bar[stage], phase);
+        double2 fr[KB][NF];
         if (!WSTEP) {
-            // A fragments: column 16w + 8v + g of the box, rows 4t..4t+3 (16-byte chunks 2t, 2t+1, XOR-swizzled by g)
+            // m8n8k4: A-operand = W fragment [M = rank 8cb+g][K = row 4t+s], B-operand = A fragment [K = row 4t+s][N = column g]
+            // A box: [column 0..127][16 rows]; lane reads rows 4t..4t+3 (chunks 2t, 2t+1) of column 16w + 8v + g
             double2 b[2][2];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
                 const uint32_t rowp = sA + (16 * warp + 8 * v + g) * 128;
                 b[v][0] = lds128(rowp + (((2 * t) ^ g) << 4));
                 b[v][1] = lds128(rowp + (((2 * t + 1) ^ g) << 4));
+            }
+            // W box: [rank 0..KP-1][16 rows]; lane reads rows 4t..4t+3 of rank 8cb + g
+#pragma unroll
+            for (int cb = 0; cb < KB; ++cb) {
+                const uint32_t rowp = sF + (8 * cb + g) * 128;
+                fr[cb][0] = lds128(rowp + (((2 * t) ^ g) << 4));
+                fr[cb][1] = lds128(rowp + (((2 * t + 1) ^ g) << 4));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -479,7 +480,9 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
                         dmma884(acc[cb][v][0], acc[cb][v][1], fr[cb][h].y, b[v][h].y);
                     }
         } else {
-            // row group `warp` of the tile: [col 32][16 rows]; lane reads rows 2g,2g+1 of column 2t + e + 8q
+            // m8n8k4: A-operand = A fragment [M = row 2g+s][K = column j(t)], B-operand = H fragment [K = column j(t)][N = rank pi(g)]
+            // with j(t) = 8q + 2t + e and pi(g) = (g >> 1) | ((g & 1) << 2), so that D column 2t+e is rank t + 4e.
+            // A boxes: row group `warp`: [column 0..31][16 rows]; lane reads rows 2g, 2g+1 (chunk g) of column 8q + 2t + e
             const uint32_t blk = sA + warp * 4096;
             double2 a[4][2];
 #pragma unroll
@@ -487,6 +490,13 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     a[q][e] = lds128(blk + (2 * t + e + 8 * q) * 128 + ((g ^ ((2 * t + e) & 7)) << 4));
+            // H boxes: two of [rank 0..KP-1][16 columns]; lane reads columns 8q + 2t + {0,1} (box q >> 1, chunk 4(q&1) + t) of rank 8cb + pi(g)
+            const int pg = (g >> 1) | ((g & 1) << 2);
+#pragma unroll
+            for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    fr[cb][q] = lds128(sF + (q >> 1) * F_BOX + (8 * cb + pg) * 128 + (((4 * (q & 1) + t) ^ pg) << 4));
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
 #pragma unroll
@@ -503,12 +513,6 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const HalfParams p, con
         if (ntile != tile || it + 1 == nunits) flush(tile);
         tile = ntile;
         st = nst;
-        if constexpr (PREFETCH) {
-#pragma unroll
-            for (int cb = 0; cb < KB; ++cb)
-#pragma unroll
-                for (int q = 0; q < NF; ++q) fr[cb][q] = fn[cb][q];
-        }
     }
 }
 
@@ -636,6 +640,7 @@ struct mfb_als {
     int nstage_h, nstage_w;
     size_t smem_h, smem_w;
     CUtensorMap tm_h, tm_w;
+    CUtensorMap tm_W[3], tm_H[2];   // factor slabs: Wb[0], Wb[1], Wr / Hb[0], Hb[1]
     int cur;              // index of the buffer holding the last accepted W / H
     bool restart_pending; // next H-step reads Wr instead of Wb[cur]
     int iters_total;      // R's `i`
@@ -680,28 +685,28 @@ static int encode_map(CUtensorMap *tm, double *base, int64_t rows, int64_t cols,
 }
 
 template <int KB>
-static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp) {
+static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
     cudaStream_t st = s->ctx->stream;
     const int G = s->ctx->sm_count;
     if (wstep) {
         MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
-        als_half_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>(s->tm_w, hp, s->nstage_w);
+        als_half_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>(s->tm_w, tmF, hp, s->nstage_w);
     } else {
         MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
-        als_half_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, hp, s->nstage_h);
+        als_half_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, tmF, hp, s->nstage_h);
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
 
-static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp) {
+static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
     switch (s->KB) {
-        case 1: return launch_half<1>(s, wstep, hp);
-        case 2: return launch_half<2>(s, wstep, hp);
-        case 3: return launch_half<3>(s, wstep, hp);
-        case 4: return launch_half<4>(s, wstep, hp);
-        case 6: return launch_half<6>(s, wstep, hp);
-        case 8: return launch_half<8>(s, wstep, hp);
+        case 1: return launch_half<1>(s, wstep, hp, tmF);
+        case 2: return launch_half<2>(s, wstep, hp, tmF);
+        case 3: return launch_half<3>(s, wstep, hp, tmF);
+        case 4: return launch_half<4>(s, wstep, hp, tmF);
+        case 6: return launch_half<6>(s, wstep, hp, tmF);
+        case 8: return launch_half<8>(s, wstep, hp, tmF);
     }
     mfb_set_error("unsupported rank block %d", s->KB);
     return MFB_ERR_UNSUPPORTED;
@@ -797,15 +802,16 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     const size_t KP = s->KP;
     const size_t epi = (2 * KP * KP + KP * XS_LD + 40 + 8) * sizeof(double);
     const size_t budget = 227 * 1024 - 1024 /*align*/ - epi - 2 * 16 * sizeof(uint64_t);
-    s->nstage_h = (int)(budget / 16384); if (s->nstage_h > 12) s->nstage_h = 12;
-    s->nstage_w = (int)(budget / 32768); if (s->nstage_w > 6) s->nstage_w = 6;
+    const size_t stage_h = 16384 + KP * 128, stage_w = 32768 + 2 * KP * 128;
+    s->nstage_h = (int)(budget / stage_h); if (s->nstage_h > 12) s->nstage_h = 12;
+    s->nstage_w = (int)(budget / stage_w); if (s->nstage_w > 6) s->nstage_w = 6;
     if (s->nstage_h < 2 || s->nstage_w < 2) {
         mfb_als_end(s);
         mfb_set_error("rank %d leaves no shared memory for the streaming ring", k);
         return MFB_ERR_UNSUPPORTED;
     }
-    s->smem_h = 1024 + (size_t)s->nstage_h * 16384 + 2 * s->nstage_h * sizeof(uint64_t) + epi;
-    s->smem_w = 1024 + (size_t)s->nstage_w * 32768 + 2 * s->nstage_w * sizeof(uint64_t) + epi;
+    s->smem_h = 1024 + (size_t)s->nstage_h * stage_h + 2 * s->nstage_h * sizeof(uint64_t) + epi;
+    s->smem_w = 1024 + (size_t)s->nstage_w * stage_w + 2 * s->nstage_w * sizeof(uint64_t) + epi;
 
     int rc;
 #define ALLOC(ptr, cnt) if ((rc = dev_alloc(s, &(ptr), (cnt))) != MFB_OK) { mfb_als_end(s); return rc; }
@@ -828,6 +834,14 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
         (rc = encode_map(&s->tm_w, A->d, A->m, A->n, A->lda, 16, 32)) != MFB_OK) {
         mfb_als_end(s);
         return rc;
+    }
+    // tensor maps over the factor buffers [KP][ld]: dims {ld (contiguous), KP}, box {16, KP}
+    {
+        double *wb[3] = {s->Wb[0], s->Wb[1], s->Wr};
+        for (int i = 0; i < 3; ++i)
+            if ((rc = encode_map(&s->tm_W[i], wb[i], s->ldw, s->KP, s->ldw, 16, s->KP)) != MFB_OK) { mfb_als_end(s); return rc; }
+        for (int i = 0; i < 2; ++i)
+            if ((rc = encode_map(&s->tm_H[i], s->Hb[i], s->ldh, s->KP, s->ldh, 16, s->KP)) != MFB_OK) { mfb_als_end(s); return rc; }
     }
     // initial factors
     cudaStream_t st = ctx->stream;
@@ -872,14 +886,14 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.P = s->P_h; h.maxslots = s->maxslots_h; h.tile_counter = s->counters;
     h.gpart = s->gpart; h.spart = s->spart; h.ctrl = s->ctrl; h.trace = s->trace_dev;
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
-    MFB_TRY(launch_half_dispatch(s, false, h));
+    MFB_TRY(launch_half_dispatch(s, false, h, use_restart_w ? s->tm_W[2] : s->tm_W[cur]));
     HalfParams w = h;
     w.Fin = s->Hb[nxt]; w.ldin = s->ldh;
     w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
     w.G = s->G_H; w.Minv = s->Minv_H; w.Gout = s->G_W; w.Minvout = s->Minv_W;
     w.P = s->P_w; w.maxslots = s->maxslots_w;
     w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
-    MFB_TRY(launch_half_dispatch(s, true, w));
+    MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt]));
     return MFB_OK;
 }
 
