@@ -23,7 +23,7 @@
 #include "common.cuh"
 #include "nnls.cuh"
 
-#define ALS_THREADS 288           // 8 consumer warps + 1 producer warp
+#define ALS_THREADS 384           // 2 consumer warpgroups (8 warps) + 1 producer warpgroup (one elected lane)
 #define ALS_CONSUMERS 256
 #define TILE_UNITS 128            // columns (H-step) or rows (W-step) per tile
 #define XS_LD 129
@@ -61,6 +61,7 @@ struct HalfParams {
     int k, T, SPT;
     long long U;                          // T * SPT
     long long nvalid;                     // number of real units (n for H-step, m for W-step)
+    int debug;                            // development aid: bit 0 = skip tile epilogues
 };
 
 // ---------------------------------------------------------------------------
@@ -88,14 +89,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug must trap, never hang the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// bounded wait: a protocol bug must never hang the GPU.  On a time-out the first waiter records who / where
+// in a global debug record, raises a global abort flag (every later wait returns at once) and the launch
+// drains; the host reports MFB_ERR_CUDA with the record.
+__device__ int g_mbar_abort = 0;
+__device__ int g_mbar_record[8];
+__device__ __noinline__ void mbar_timeout(int code, int a, int b, int c) {
+    if (atomicCAS(&g_mbar_abort, 0, 1) == 0) {
+        g_mbar_record[0] = code; g_mbar_record[1] = (int)blockIdx.x; g_mbar_record[2] = (int)threadIdx.x;
+        g_mbar_record[3] = a; g_mbar_record[4] = b; g_mbar_record[5] = c;
+        __threadfence();
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int code = 0, int a = 0, int b = 0) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000ll) {
-            printf("mfbiclust: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
+        if (*(volatile int *)&g_mbar_abort) return;
+        if (clock64() - t0 > 400000000ll) {      // ~0.2 s
+            mbar_timeout(code, a, b, (int)parity);
+            return;
         }
     }
 }
@@ -104,6 +117,17 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int x, int y, int z, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+// keep a loop-invariant value in a register (stops the compiler from re-reading it from the constant bank every iteration)
+__device__ __forceinline__ int pin_reg(int v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -123,131 +147,15 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
     return v;
 }
 
+// Tile epilogue (cold path, kept out of line so that the streaming loop's registers stay clean):
+// sums the partials of a finished tile, solves its 128 NNLS problems, writes the factor, and -- for the last
+// tile of the launch -- folds the Gram / inverse / iteration scalars.
 template <int KB, bool WSTEP>
-__global__ void __launch_bounds__(ALS_THREADS, 1)
-als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmF, const HalfParams p,
-                const int nstage) {
+__device__ __noinline__ void tile_epilogue(const HalfParams &p, const int tile, const int expected, double *sG,
+                                           double *sM, double *xs, double *sred, int *sflag) {
     constexpr int KP = KB * 8;
-    constexpr int A_BYTES = WSTEP ? 32768 : 16384;       // A box(es) of one stage
-    constexpr int F_BOX = KP * 128;                      // one 16-unit box of the fixed factor: [KP][16] doubles
-    constexpr int NFB = WSTEP ? 2 : 1;                   // factor boxes per stage (32 columns / 16 rows of reduction)
-    constexpr int STAGE_BYTES = A_BYTES + NFB * F_BOX;
-    constexpr int NF = WSTEP ? 4 : 2;                    // double2 fragments of the fixed factor per rank block and unit
-    if (*(volatile int *)&p.ctrl->stop) return;
-
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: ring | barriers | G | Minv | xs | misc
-    unsigned char *ring = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = (uint64_t *)(ring + (size_t)nstage * STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + nstage;
-    double *sG = (double *)(empty_bar + nstage);
-    double *sM = sG + KP * KP;
-    double *xs = sM + KP * KP;
-    double *sred = xs + KP * XS_LD;          // 40 doubles of reduction scratch
-    int *sflag = (int *)(sred + 40);
-    const uint32_t ring_s = smem_u32(ring);
-
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int G = gridDim.x;
-    const long long u0 = (long long)blockIdx.x * p.U / G;
-    const long long u1 = (long long)(blockIdx.x + 1) * p.U / G;
-
-    if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 8);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    // Gram of the fixed factor and its inverse (for the epilogues of this CTA)
-    for (int e = tid; e < KP * KP; e += ALS_THREADS) {
-        sG[e] = p.G[e];
-        sM[e] = p.Minv[e];
-    }
-    __syncthreads();
-    if (u0 >= u1) return;
-    const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
-    const int nunits = (int)(u1 - u0);
-
-    if (warp == 8) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0, tile = tile0, st = st0;
-            uint32_t phase = 0;
-            for (int it = 0; it < nunits; ++it) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
-                if (!WSTEP) {
-                    tma_load_2d(dst, &tmA, st * 16, tile * TILE_UNITS, &full_bar[stage]);
-                    tma_load_2d(dst + A_BYTES, &tmF, st * 16, 0, &full_bar[stage]);
-                } else {
-#pragma unroll
-                    for (int rg = 0; rg < 8; ++rg)
-                        tma_load_2d(dst + rg * 4096, &tmA, tile * TILE_UNITS + rg * 16, st * 32, &full_bar[stage]);
-                    tma_load_2d(dst + A_BYTES, &tmF, st * 32, 0, &full_bar[stage]);
-                    tma_load_2d(dst + A_BYTES + F_BOX, &tmF, st * 32 + 16, 0, &full_bar[stage]);
-                }
-                if (++stage == nstage) { stage = 0; phase ^= 1; }
-                if (++st == p.SPT) { st = 0; ++tile; }
-            }
-        }
-        return;
-    }
-
-    // ===================== consumers (warps 0..7) =====================
-    const int g = lane >> 2, t = lane & 3;
-    double acc[KB][2][2];                        // [rank block][v (H-step) or s (W-step)][2]
-#pragma unroll
-    for (int cb = 0; cb < KB; ++cb)
-#pragma unroll
-        for (int a = 0; a < 2; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
-
-    auto flush = [&](int tile) {
-        const long long tb = (long long)tile * p.SPT;
-        int expected, slot;
-        if (p.U >= G) {          // every CTA owns >= 1 unit: contributors to a tile are contiguous CTAs
-            const int first = cta_of_unit(tb, p.U, G);
-            const int last = cta_of_unit(tb + p.SPT - 1, p.U, G);
-            expected = last - first + 1;
-            slot = (int)blockIdx.x - first;
-        } else {                 // fewer units than CTAs: each non-empty CTA owns exactly one unit
-            expected = p.SPT;
-            slot = (int)(u0 - tb);
-        }
-        double *Pb = p.P + ((size_t)tile * p.maxslots + slot) * (size_t)(KP * TILE_UNITS);
-#pragma unroll
-        for (int cb = 0; cb < KB; ++cb) {
-            if (!WSTEP) {
-                // acc[cb][v] = R[8cb+g][16w + 8v + 2t + {0,1}]
-#pragma unroll
-                for (int v = 0; v < 2; ++v)
-                    *(double2 *)&Pb[(size_t)(8 * cb + g) * TILE_UNITS + 16 * warp + 8 * v + 2 * t] =
-                        make_double2(acc[cb][v][0], acc[cb][v][1]);
-            } else {
-                // acc[cb][s][e] = R[row 16w + 2g + s][c = 8cb + t + 4e]   (rank index permuted, see the W-step loop)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    *(double2 *)&Pb[(size_t)(8 * cb + t + 4 * e) * TILE_UNITS + 16 * warp + 2 * g] =
-                        make_double2(acc[cb][0][e], acc[cb][1][e]);
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
-        }
-        __threadfence();
-        consumer_bar();
-        if (tid == 0) {
-            int prev = atomicAdd(&p.tile_counter[tile], 1);
-            int lastone = (prev == expected - 1);
-            if (lastone) p.tile_counter[tile] = 0;
-            sflag[0] = lastone;
-        }
-        consumer_bar();
-        if (!sflag[0]) return;
-        __threadfence();
-
         // ---------------- tile epilogue: NNLS for 128 units ----------------
         const long long unit = (long long)tile * TILE_UNITS + tid;
         const bool valid = (tid < TILE_UNITS) && (unit < p.nvalid);
@@ -436,83 +344,243 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             __threadfence();
         }
+}
+
+template <int KB, bool WSTEP>
+__global__ void __launch_bounds__(ALS_THREADS, 1)
+als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmF, const HalfParams p,
+                const int nstage) {
+    constexpr int KP = KB * 8;
+    constexpr int A_BYTES = WSTEP ? 32768 : 16384;       // A box(es) of one stage
+    constexpr int F_BOX = KP * 128;                      // one 16-unit box of the fixed factor: [KP][16] doubles
+    constexpr int NFB = WSTEP ? 2 : 1;                   // factor boxes per stage (32 columns / 16 rows of reduction)
+    constexpr int STAGE_BYTES = A_BYTES + NFB * F_BOX;
+    constexpr int NF = WSTEP ? 4 : 2;                    // double2 fragments of the fixed factor per rank block and unit
+    if (*(volatile int *)&p.ctrl->stop) return;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: ring | barriers | G | Minv | xs | misc
+    unsigned char *ring = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = (uint64_t *)(ring + (size_t)nstage * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + nstage;
+    double *sG = (double *)(empty_bar + nstage);
+    double *sM = sG + KP * KP;
+    double *xs = sM + KP * KP;
+    double *sred = xs + KP * XS_LD;          // 40 doubles of reduction scratch
+    int *sflag = (int *)(sred + 40);
+    const uint32_t ring_s = smem_u32(ring);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const long long u0 = (long long)blockIdx.x * p.U / G;
+    const long long u1 = (long long)(blockIdx.x + 1) * p.U / G;
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // Gram of the fixed factor and its inverse (for the epilogues of this CTA)
+    for (int e = tid; e < KP * KP; e += ALS_THREADS) {
+        sG[e] = p.G[e];
+        sM[e] = p.Minv[e];
+    }
+    __syncthreads();
+    if (u0 >= u1) return;
+    const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
+    const int nunits = (int)(u1 - u0);
+
+    if (warp >= 8) {
+        // ===================== TMA producer (warpgroup 2 hands its registers to the consumers) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8 && lane == 0) {
+            int stage = 0, tile = tile0, st = st0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nunits; ++it) {
+                mbar_wait(&empty_bar[stage], phase ^ 1, 1, it, stage);
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
+                if (!WSTEP) {
+                    tma_load_2d(dst, &tmA, st * 16, tile * TILE_UNITS, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES, &tmF, st * 16, 0, &full_bar[stage]);
+                } else {
+                    // one 3-D box {16 rows, 32 columns, 8 row groups}: lands as [row group][column][16 rows]
+                    if (p.debug & 2) {
+#pragma unroll
+                        for (int rg = 0; rg < 8; ++rg)
+                            tma_load_2d(dst + rg * 4096, &tmA, tile * TILE_UNITS + rg * 16, st * 32, &full_bar[stage]);
+                    } else {
+                        tma_load_3d(dst, &tmA, 0, st * 32, tile * 8, &full_bar[stage]);
+                    }
+                    tma_load_2d(dst + A_BYTES, &tmF, st * 32, 0, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES + F_BOX, &tmF, st * 32 + 16, 0, &full_bar[stage]);
+                }
+                if (++stage == nstage) { stage = 0; phase ^= 1; }
+                if (++st == p.SPT) { st = 0; ++tile; }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: NG groups of 4 warps (one warp per SM sub-partition) =====================
+    // Group `grp` owns the units it == grp (mod NG) of this CTA's range, so the two warps that share a
+    // sub-partition are one stage out of phase: one issues DMMAs while the other waits / loads fragments.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    constexpr int NG = 2;
+    const int grp = warp >> 2, wg = warp & 3;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[KB][4][2];                        // [rank block][v (H-step: column block) or 2*rg+s (W-step: row)][2]
+#pragma unroll
+    for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
+
+    auto flush = [&](int tile) {
+        const long long tb = (long long)tile * p.SPT;
+        int expected, slot;
+        if (p.U >= G) {          // every CTA owns >= 1 unit: contributors to a tile are contiguous CTAs
+            const int first = cta_of_unit(tb, p.U, G);
+            const int last = cta_of_unit(tb + p.SPT - 1, p.U, G);
+            expected = last - first + 1;                       // CTAs contributing to this tile
+            slot = NG * ((int)blockIdx.x - first) + grp;       // one partial per consumer group of each CTA
+        } else {                 // fewer units than CTAs: each non-empty CTA owns exactly one unit
+            expected = p.SPT;
+            slot = NG * (int)(u0 - tb) + grp;
+        }
+        double *Pb = p.P + ((size_t)tile * p.maxslots + slot) * (size_t)(KP * TILE_UNITS);
+#pragma unroll
+        for (int cb = 0; cb < KB; ++cb) {
+            if (!WSTEP) {
+                // acc[cb][v] = R[8cb+g][32wg + 8v + 2t + {0,1}]
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    *(double2 *)&Pb[(size_t)(8 * cb + g) * TILE_UNITS + 32 * wg + 8 * v + 2 * t] =
+                        make_double2(acc[cb][v][0], acc[cb][v][1]);
+            } else {
+                // acc[cb][2rg+s][e] = R[row 32wg + 16rg + 2g + s][c = 8cb + t + 4e]   (rank index permuted, see the W-step loop)
+#pragma unroll
+                for (int rg = 0; rg < 2; ++rg)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        *(double2 *)&Pb[(size_t)(8 * cb + t + 4 * e) * TILE_UNITS + 32 * wg + 16 * rg + 2 * g] =
+                            make_double2(acc[cb][2 * rg][e], acc[cb][2 * rg + 1][e]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
+        }
+        __threadfence();
+        consumer_bar();
+        if (tid == 0) {
+            int prev = atomicAdd(&p.tile_counter[tile], 1);
+            int lastone = (prev == expected - 1);
+            if (lastone) p.tile_counter[tile] = 0;
+            sflag[0] = lastone;
+        }
+        consumer_bar();
+        if (!sflag[0]) return;
+        __threadfence();
+        if (p.debug & 1) return;
+
+        tile_epilogue<KB, WSTEP>(p, tile, NG * expected, sG, sM, xs, sred, sflag);
     };
 
     // Main loop.  One stage = one unit: an A box plus the matching 16- (H-step) or 32-wide (W-step) slab of
     // the fixed factor, both landed by TMA with SWIZZLE_128B: a "row" of a box is 128 bytes (16 doubles along
     // the contiguous direction) whose 16-byte chunk c sits at chunk c ^ (row & 7).  Every fragment read below
     // is a 16-byte ld.shared whose quarter-warp (g in {2a, 2a+1}, t = 0..3) touches 8 distinct chunks.
-    int stage = 0, tile = tile0, st = st0;
+    const int nst_r = pin_reg(nstage), spt_r = pin_reg(p.SPT);
+    const int pg = (g >> 1) | ((g & 1) << 2);
+    // per-lane byte offsets inside a stage (everything else is an immediate)
+    uint32_t offA, offF;
+    if (!WSTEP) {
+        offA = (uint32_t)((32 * wg + g) * 128 + (((2 * t) ^ g) << 4));      // column 32wg + g (+8v), chunk 2t (^1 for rows 4t+2..)
+        offF = (uint32_t)(A_BYTES + g * 128 + (((2 * t) ^ g) << 4));        // rank g (+8cb)
+    } else {
+        offA = (uint32_t)(2 * wg * 4096 + (2 * t) * 128 + ((g ^ (2 * t)) << 4));   // row group 2wg (+rg), column 2t (+e +8q), chunk g
+        offF = (uint32_t)(A_BYTES + pg * 128 + ((t ^ pg) << 4));                   // rank pi(g) (+8cb), chunk t (+4(q&1)) ^ pi(g)
+    }
+    int tile = tile0, st = st0;
+    int stage = grp;                     // this group's first unit sits in stage `grp`
     uint32_t phase = 0;
     for (int it = 0; it < nunits; ++it) {
-        int nst = st + 1, ntile = tile;
-        if (nst == p.SPT) { nst = 0; ntile = tile + 1; }
-        const uint32_t sA = ring_s + (uint32_t)stage * STAGE_BYTES;
-        const uint32_t sF = sA + A_BYTES;
-        mbar_wait(&full_bar[stage], phase);
-        double2 fr[KB][NF];
-        if (!WSTEP) {
-            // m8n8k4: A-operand = W fragment [M = rank 8cb+g][K = row 4t+s], B-operand = A fragment [K = row 4t+s][N = column g]
-            // A box: [column 0..127][16 rows]; lane reads rows 4t..4t+3 (chunks 2t, 2t+1) of column 16w + 8v + g
-            double2 b[2][2];
+        if ((it % NG) == grp) {
+            const uint32_t sb = ring_s + (uint32_t)stage * STAGE_BYTES;
+            mbar_wait(&full_bar[stage], phase, 2, it, stage);
+            if (p.debug & 4) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            } else if (!WSTEP) {
+                // m8n8k4: A-operand = W fragment [M = rank 8cb+g][K = row 4t+s], B-operand = A fragment [K = row 4t+s][N = column g]
+                double2 b[4][2], f[KB][2];
 #pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const uint32_t rowp = sA + (16 * warp + 8 * v + g) * 128;
-                b[v][0] = lds128(rowp + (((2 * t) ^ g) << 4));
-                b[v][1] = lds128(rowp + (((2 * t + 1) ^ g) << 4));
-            }
-            // W box: [rank 0..KP-1][16 rows]; lane reads rows 4t..4t+3 of rank 8cb + g
+                for (int v = 0; v < 4; ++v) {
+                    b[v][0] = lds128(sb + offA + v * 1024);
+                    b[v][1] = lds128(sb + (offA ^ 16) + v * 1024);
+                }
 #pragma unroll
-            for (int cb = 0; cb < KB; ++cb) {
-                const uint32_t rowp = sF + (8 * cb + g) * 128;
-                fr[cb][0] = lds128(rowp + (((2 * t) ^ g) << 4));
-                fr[cb][1] = lds128(rowp + (((2 * t + 1) ^ g) << 4));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                for (int cb = 0; cb < KB; ++cb) {
+                    f[cb][0] = lds128(sb + offF + cb * 1024);
+                    f[cb][1] = lds128(sb + (offF ^ 16) + cb * 1024);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f[cb][h].x, b[v][h].x);
+#pragma unroll
+                    for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f[cb][h].y, b[v][h].y);
+                }
+            } else {
+                // m8n8k4: A-operand = A fragment [M = row 2g+s][K = column j(t)], B-operand = H fragment [K = column j(t)][N = rank pi(g)]
+                // with j(t) = 8q + 2t + e and pi(g) = (g >> 1) | ((g & 1) << 2), so that D column 2t+e is rank t + 4e.
+                double2 f[KB][4];
 #pragma unroll
                 for (int cb = 0; cb < KB; ++cb)
 #pragma unroll
-                    for (int v = 0; v < 2; ++v) {
-                        dmma884(acc[cb][v][0], acc[cb][v][1], fr[cb][h].x, b[v][h].x);
-                        dmma884(acc[cb][v][0], acc[cb][v][1], fr[cb][h].y, b[v][h].y);
+                    for (int q = 0; q < 4; ++q)
+                        f[cb][q] = lds128(sb + (q >> 1) * F_BOX + ((offF + cb * 1024) ^ ((q & 1) << 6)));
+#pragma unroll
+                for (int rg = 0; rg < 2; ++rg) {
+                    double2 a[4][2];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        a[q][0] = lds128(sb + offA + rg * 4096 + q * 1024);
+                        a[q][1] = lds128(sb + ((offA + 128) ^ 16) + rg * 4096 + q * 1024);
                     }
-        } else {
-            // m8n8k4: A-operand = A fragment [M = row 2g+s][K = column j(t)], B-operand = H fragment [K = column j(t)][N = rank pi(g)]
-            // with j(t) = 8q + 2t + e and pi(g) = (g >> 1) | ((g & 1) << 2), so that D column 2t+e is rank t + 4e.
-            // A boxes: row group `warp`: [column 0..31][16 rows]; lane reads rows 2g, 2g+1 (chunk g) of column 8q + 2t + e
-            const uint32_t blk = sA + warp * 4096;
-            double2 a[4][2];
+                    if (rg == 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    a[q][e] = lds128(blk + (2 * t + e + 8 * q) * 128 + ((g ^ ((2 * t + e) & 7)) << 4));
-            // H boxes: two of [rank 0..KP-1][16 columns]; lane reads columns 8q + 2t + {0,1} (box q >> 1, chunk 4(q&1) + t) of rank 8cb + pi(g)
-            const int pg = (g >> 1) | ((g & 1) << 2);
+                        for (int cb = 0; cb < KB; ++cb) {
+                            dmma884(acc[cb][2 * rg][0], acc[cb][2 * rg][1], a[q][0].x, f[cb][q].x);
+                            dmma884(acc[cb][2 * rg + 1][0], acc[cb][2 * rg + 1][1], a[q][0].y, f[cb][q].x);
+                        }
 #pragma unroll
-            for (int cb = 0; cb < KB; ++cb)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    fr[cb][q] = lds128(sF + (q >> 1) * F_BOX + (8 * cb + pg) * 128 + (((4 * (q & 1) + t) ^ pg) << 4));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int cb = 0; cb < KB; ++cb) {
-                    dmma884(acc[cb][0][0], acc[cb][0][1], a[q][0].x, fr[cb][q].x);
-                    dmma884(acc[cb][1][0], acc[cb][1][1], a[q][0].y, fr[cb][q].x);
-                    dmma884(acc[cb][0][0], acc[cb][0][1], a[q][1].x, fr[cb][q].y);
-                    dmma884(acc[cb][1][0], acc[cb][1][1], a[q][1].y, fr[cb][q].y);
+                        for (int cb = 0; cb < KB; ++cb) {
+                            dmma884(acc[cb][2 * rg][0], acc[cb][2 * rg][1], a[q][1].x, f[cb][q].y);
+                            dmma884(acc[cb][2 * rg + 1][0], acc[cb][2 * rg + 1][1], a[q][1].y, f[cb][q].y);
+                        }
+                    }
                 }
+            }
+            stage += NG;
+            if (stage >= nst_r) { stage -= nst_r; phase ^= 1; }
         }
-        if (++stage == nstage) { stage = 0; phase ^= 1; }
-        if (ntile != tile || it + 1 == nunits) flush(tile);
-        tile = ntile;
-        st = nst;
+        const bool last_of_tile = (st + 1 == spt_r) || (it + 1 == nunits);
+        if (last_of_tile && !(p.debug & 8)) flush(tile);
+        if (++st == spt_r) { st = 0; ++tile; }
     }
 }
 
@@ -639,7 +707,7 @@ struct mfb_als {
     int maxslots_h, maxslots_w, T_h, T_w, SPT_h, SPT_w;
     int nstage_h, nstage_w;
     size_t smem_h, smem_w;
-    CUtensorMap tm_h, tm_w;
+    CUtensorMap tm_h, tm_w, tm_w2d;
     CUtensorMap tm_W[3], tm_H[2];   // factor slabs: Wb[0], Wb[1], Wr / Hb[0], Hb[1]
     int cur;              // index of the buffer holding the last accepted W / H
     bool restart_pending; // next H-step reads Wr instead of Wb[cur]
@@ -684,19 +752,47 @@ static int encode_map(CUtensorMap *tm, double *base, int64_t rows, int64_t cols,
     return MFB_OK;
 }
 
+static int encode_map_rowgroups(CUtensorMap *tm, double *base, int64_t cols, int64_t lda) {
+    // 3-D view of the column-major matrix: {16 rows, cols, lda/16 row groups}, strides {lda*8, 128} bytes;
+    // box {16, 32, 8} = a 128-row x 32-column tile that lands as [row group][column][16 rows].
+    mfb_encode_tiled_fn enc = mfb_get_encode_tiled();
+    if (!enc) { mfb_set_error("cuTensorMapEncodeTiled unavailable"); return MFB_ERR_CUDA; }
+    cuuint64_t dims[3] = {16, (cuuint64_t)cols, (cuuint64_t)(lda / 16)};
+    cuuint64_t strides[2] = {(cuuint64_t)lda * sizeof(double), 128};
+    cuuint32_t box[3] = {16, 32, 8};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { mfb_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r); return MFB_ERR_CUDA; }
+    return MFB_OK;
+}
+
 template <int KB>
 static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
     cudaStream_t st = s->ctx->stream;
     const int G = s->ctx->sm_count;
     if (wstep) {
         MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
-        als_half_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>(s->tm_w, tmF, hp, s->nstage_w);
+        als_half_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>((hp.debug & 2) ? s->tm_w2d : s->tm_w, tmF, hp, s->nstage_w);
     } else {
         MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
         als_half_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, tmF, hp, s->nstage_h);
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
+}
+
+static int check_mbar_abort(const char *where) {
+    int flag = 0, rec[8];
+    if (cudaMemcpyFromSymbol(&flag, g_mbar_abort, sizeof(int)) != cudaSuccess) return MFB_OK;
+    if (!flag) return MFB_OK;
+    cudaMemcpyFromSymbol(rec, g_mbar_record, sizeof(rec));
+    int zero = 0;
+    cudaMemcpyToSymbol(g_mbar_abort, &zero, sizeof(int));
+    mfb_set_error("%s: mbarrier wait timed out (kind %d [1=producer/empty, 2=consumer/full], block %d, thread %d, unit %d, stage %d, parity %d)",
+                  where, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5]);
+    return MFB_ERR_CUDA;
 }
 
 static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
@@ -797,14 +893,19 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->SPT_h = (int)((s->m + 15) / 16);
     s->T_w = (int)((s->m + 127) / 128);
     s->SPT_w = (int)((s->n + 31) / 32);
-    s->maxslots_h = max_slots(s->T_h, s->SPT_h, G);
-    s->maxslots_w = max_slots(s->T_w, s->SPT_w, G);
+    s->maxslots_h = 2 * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
+    s->maxslots_w = 2 * max_slots(s->T_w, s->SPT_w, G);
     const size_t KP = s->KP;
     const size_t epi = (2 * KP * KP + KP * XS_LD + 40 + 8) * sizeof(double);
     const size_t budget = 227 * 1024 - 1024 /*align*/ - epi - 2 * 16 * sizeof(uint64_t);
     const size_t stage_h = 16384 + KP * 128, stage_w = 32768 + 2 * KP * 128;
     s->nstage_h = (int)(budget / stage_h); if (s->nstage_h > 12) s->nstage_h = 12;
     s->nstage_w = (int)(budget / stage_w); if (s->nstage_w > 6) s->nstage_w = 6;
+    // The ring depth must be a multiple of the number of consumer groups (2): a stage is then always drained by
+    // the same group, which therefore waits on EVERY phase of that stage's full-barrier.  With an odd depth a
+    // group skips every other phase and the parity wait aliases (returns on a phase two fills old).
+    s->nstage_h &= ~1;
+    s->nstage_w &= ~1;
     if (s->nstage_h < 2 || s->nstage_w < 2) {
         mfb_als_end(s);
         mfb_set_error("rank %d leaves no shared memory for the streaming ring", k);
@@ -831,7 +932,8 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
 #undef ALLOC
     // tensor maps over A: dims {m rows (contiguous), n cols}
     if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, 16, 128)) != MFB_OK ||
-        (rc = encode_map(&s->tm_w, A->d, A->m, A->n, A->lda, 16, 32)) != MFB_OK) {
+        (rc = encode_map_rowgroups(&s->tm_w, A->d, A->n, A->lda)) != MFB_OK ||
+        (rc = encode_map(&s->tm_w2d, A->d, A->m, A->n, A->lda, 16, 32)) != MFB_OK) {
         mfb_als_end(s);
         return rc;
     }
@@ -922,6 +1024,7 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
         }
         MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
         MFB_CUDA(cudaStreamSynchronize(st));
+        MFB_TRY(check_mbar_abort("mfb_als_iterate"));
         const int done = hc->iters_done;
         if (done > 0) {
             const size_t old = s->trace.size();
@@ -951,6 +1054,47 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
     }
     if (iters_total) *iters_total = s->iters_total;
     return status;
+}
+
+// development aid (not in the public header): relaunch one half-step `count` times on unchanged inputs
+int mfb_als_debug_repeat(mfb_als *s, int which, int count) {
+    const int dbg = which >> 4;
+    which &= 15;
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    AlsCtrl *hc = (AlsCtrl *)s->ctx->pinned;
+    for (int i = 0; i < count; ++i) {
+        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = 1; hc->eps = 1e-4;
+        hc->tiles_done[0] = hc->tiles_done[1] = 0; hc->nzmask = 0ull;
+        MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
+        HalfParams h;
+        memset(&h, 0, sizeof(h));
+        const int cur = s->cur, nxt = cur ^ 1;
+        h.Fin = s->Wb[cur]; h.ldin = s->ldw;
+        h.Fout = s->Hb[nxt]; h.Fold = s->Hb[cur]; h.ldout = s->ldh;
+        h.G = s->G_W; h.Minv = s->Minv_W; h.Gout = s->G_H; h.Minvout = s->Minv_H;
+        h.P = s->P_h; h.maxslots = s->maxslots_h; h.tile_counter = s->counters;
+        h.gpart = s->gpart; h.spart = s->spart; h.ctrl = s->ctrl; h.trace = s->trace_dev;
+        h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
+        h.debug = dbg;
+        if (which == 0) {
+            MFB_TRY(launch_half_dispatch(s, false, h, s->tm_W[cur]));
+        } else {
+            HalfParams w = h;
+            w.Fin = s->Hb[cur]; w.ldin = s->ldh;
+            w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
+            w.G = s->G_H; w.Minv = s->Minv_H; w.Gout = s->gram_scratch; w.Minvout = s->gram_scratch + 4096;
+            w.P = s->P_w; w.maxslots = s->maxslots_w;
+            w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
+            MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[cur]));
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { mfb_set_error("debug repeat %d of kind %d failed: %s", i, which, cudaGetErrorString(e)); return MFB_ERR_CUDA; }
+        MFB_TRY(check_mbar_abort("debug repeat"));
+    }
+    return MFB_OK;
 }
 
 int mfb_als_result(mfb_als *s, double *W, double *H, double *resid, double *trace) {

@@ -197,8 +197,8 @@ int mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t n
 int mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb_matrix **out) {
     MFB_ARG(ctx && dev && out, "NULL argument");
     MFB_ARG(m > 0 && n > 0, "matrix dimensions must be positive");
-    MFB_ARG(m % 2 == 0 && ((uintptr_t)dev % 16) == 0,
-            "wrapped device matrices need an even row count and a 16-byte aligned base (TMA strides)");
+    MFB_ARG(m % 16 == 0 && ((uintptr_t)dev % 128) == 0,
+            "wrapped device matrices need a row count that is a multiple of 16 and a 128-byte aligned base (TMA boxes)");
     mfb_matrix *A = new mfb_matrix();
     A->ctx = ctx;
     A->d = dev;
