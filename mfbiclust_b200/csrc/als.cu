@@ -92,6 +92,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // bounded wait: a protocol bug must never hang the GPU.  On a time-out the first waiter records who / where
 // in a global debug record, raises a global abort flag (every later wait returns at once) and the launch
 // drains; the host reports MFB_ERR_CUDA with the record.
+__device__ unsigned long long g_dbg_times[148 * 8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_dbg_marks[8];
 __device__ int g_mbar_abort = 0;
 __device__ int g_mbar_record[8];
 __device__ __noinline__ void mbar_timeout(int code, int a, int b, int c) {
@@ -157,29 +160,35 @@ __device__ __noinline__ void tile_epilogue(const HalfParams &p, const int tile, 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
         // ---------------- tile epilogue: NNLS for 128 units ----------------
+        if ((p.debug & 16) && tid == 0 && tile == 3) { g_mark_block = (int)blockIdx.x; g_dbg_marks[0] = gtimer(); }
         const long long unit = (long long)tile * TILE_UNITS + tid;
         const bool valid = (tid < TILE_UNITS) && (unit < p.nvalid);
         double d2 = 0.0, t1 = 0.0, t2 = 0.0;
         unsigned long long nz = 0ull;
         if constexpr (KP <= 32) {
-            // (a) right-hand sides: sum the partials in slot order, one thread per unit
-            if (tid < TILE_UNITS) {
-                double r[KP];
+            // (a) right-hand sides: sum the partials in slot order; thread = (unit, half of the ranks)
+            {
+                constexpr int HK = KP / 2;
+                const int u = tid & (TILE_UNITS - 1), c0 = (tid >> 7) * HK;
+                const bool uvalid = ((long long)tile * TILE_UNITS + u) < p.nvalid;
+                double r[HK];
 #pragma unroll
-                for (int c = 0; c < KP; ++c) r[c] = 0.0;
+                for (int c = 0; c < HK; ++c) r[c] = 0.0;
                 for (int s = 0; s < expected; ++s) {
-                    const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + tid;
+                    const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + u;
 #pragma unroll
-                    for (int c = 0; c < KP; ++c)
-                        if (c < p.k) r[c] += ldcg(Ps + (size_t)c * TILE_UNITS);
+                    for (int c = 0; c < HK; ++c)
+                        if (c0 + c < p.k) r[c] += ldcg(Ps + (size_t)(c0 + c) * TILE_UNITS);
                 }
 #pragma unroll
-                for (int c = 0; c < KP; ++c) xs[c * XS_LD + tid] = valid ? r[c] : 0.0;
+                for (int c = 0; c < HK; ++c) xs[(c0 + c) * XS_LD + u] = uvalid ? r[c] : 0.0;
             }
             consumer_bar();
+        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[1] = gtimer();
             // (b) lane-distributed principal-pivoting NNLS, 16 units per warp
             t1 = nnls_tile_lanes<KP, XS_LD>(sM, p.k, xs, warp, lane, 8);
             consumer_bar();
+        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[2] = gtimer();
             // (c) write-back and statistics, one thread per unit
             if (tid < TILE_UNITS) {
                 double x[KP];
@@ -257,6 +266,7 @@ __device__ __noinline__ void tile_epilogue(const HalfParams &p, const int tile, 
             ((unsigned long long *)(sred + 24))[warp] = nz;
         }
         consumer_bar();
+        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[3] = gtimer();
         // Gram partial of the produced factor over this tile's units
         for (int e = tid; e < p.k * p.k; e += ALS_CONSUMERS) {
             const int c1 = e / p.k, c2 = e - c1 * p.k;
@@ -280,37 +290,58 @@ __device__ __noinline__ void tile_epilogue(const HalfParams &p, const int tile, 
         }
         __threadfence();
         consumer_bar();
+        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[4] = gtimer();
         if (tid == 0) {
             int prev = atomicAdd(&p.ctrl->tiles_done[WSTEP ? 1 : 0], 1);
             sflag[1] = (prev == p.T - 1);
         }
         consumer_bar();
+        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[5] = gtimer();
         if (!sflag[1]) return;
         __threadfence();
 
         // ---------------- launch finalisation (one CTA, once per half-step) ----------------
+        if ((p.debug & 16) && tid == 0) g_nnls_marks[8] = gtimer();
+        // Gram of the new factor: sum the per-tile partials with eight independent chains per entry (fixed
+        // association, so the result does not depend on which CTA runs this)
         for (int e = tid; e < KP * KP; e += ALS_CONSUMERS) {
             const int c1 = e / KP, c2 = e - c1 * KP;
-            double s = 0.0;
-            if (c1 < p.k && c2 < p.k)
-                for (int tt = 0; tt < p.T; ++tt) s += ldcg(&p.gpart[(size_t)tt * (KP * KP) + e]);
+            double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (c1 < p.k && c2 < p.k) {
+                for (int t0 = 0; t0 < p.T; t0 += 8) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (t0 + j < p.T) a8[j] += ldcg(&p.gpart[(size_t)(t0 + j) * (KP * KP) + e]);
+                }
+            }
+            const double s = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
             sG[e] = s;
             p.Gout[e] = s;
         }
+        // iteration scalars: warp 0 sums the per-tile partials, lane = tile mod 32, then a fixed butterfly
+        if (warp == 0) {
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            for (int tt = lane; tt < p.T; tt += 32) {
+                v0 += ldcg(&p.spart[tt * 4 + 0]);
+                v1 += ldcg(&p.spart[tt * 4 + 1]);
+                v2 += ldcg(&p.spart[tt * 4 + 2]);
+            }
+            v0 = warp_sum(v0);
+            v1 = warp_sum(v1);
+            v2 = warp_sum(v2);
+            if (lane == 0) { sred[32] = v0; sred[33] = v1; sred[34] = v2; }
+        }
         consumer_bar();
+        if ((p.debug & 16) && tid == 0) g_nnls_marks[9] = gtimer();
         const int sing = gauss_jordan_inverse(sG, p.k, KP, tid, ALS_CONSUMERS, sred, [] { consumer_bar(); });
+        if ((p.debug & 16) && tid == 0) g_nnls_marks[10] = gtimer();
         for (int e = tid; e < KP * KP; e += ALS_CONSUMERS) {
             const int c1 = e / KP, c2 = e - c1 * KP;
             p.Minvout[e] = (c1 < p.k && c2 < p.k) ? sG[e] : 0.0;
         }
         if (tid == 0) {
             AlsCtrl *c = p.ctrl;
-            double sd2 = 0, st1 = 0, st2 = 0;
-            for (int tt = 0; tt < p.T; ++tt) {
-                sd2 += ldcg(&p.spart[tt * 4 + 0]);
-                st1 += ldcg(&p.spart[tt * 4 + 1]);
-                st2 += ldcg(&p.spart[tt * 4 + 2]);
-            }
+            const double sd2 = sred[32], st1 = sred[33], st2 = sred[34];
             c->tiles_done[WSTEP ? 1 : 0] = 0;
             if (!WSTEP) {
                 c->dH2 = sd2;
@@ -343,6 +374,7 @@ __device__ __noinline__ void tile_epilogue(const HalfParams &p, const int tile, 
                 }
             }
             __threadfence();
+            if (p.debug & 16) g_nnls_marks[11] = gtimer();
         }
 }
 
@@ -390,6 +422,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         sM[e] = p.Minv[e];
     }
     __syncthreads();
+    if ((p.debug & 16) && tid == 0) g_dbg_times[blockIdx.x * 8 + 0] = gtimer();
     if (u0 >= u1) return;
     const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
     const int nunits = (int)(u1 - u0);
@@ -579,7 +612,11 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (stage >= nst_r) { stage -= nst_r; phase ^= 1; }
         }
         const bool last_of_tile = (st + 1 == spt_r) || (it + 1 == nunits);
-        if (last_of_tile && !(p.debug & 8)) flush(tile);
+        if (last_of_tile && !(p.debug & 8)) {
+            if ((p.debug & 16) && tid == 0) { if (it + 1 == nunits) g_dbg_times[blockIdx.x * 8 + 2] = gtimer(); else g_dbg_times[blockIdx.x * 8 + 1] = gtimer(); }
+            flush(tile);
+            if ((p.debug & 16) && tid == 0) { if (it + 1 == nunits) g_dbg_times[blockIdx.x * 8 + 4] = gtimer(); else g_dbg_times[blockIdx.x * 8 + 3] = gtimer(); }
+        }
         if (++st == spt_r) { st = 0; ++tile; }
     }
 }
@@ -896,7 +933,7 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->maxslots_h = 2 * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
     s->maxslots_w = 2 * max_slots(s->T_w, s->SPT_w, G);
     const size_t KP = s->KP;
-    const size_t epi = (2 * KP * KP + KP * XS_LD + 40 + 8) * sizeof(double);
+    const size_t epi = (2 * KP * KP + KP * XS_LD + 40 + 8) * sizeof(double);   // sred has 40 doubles
     const size_t budget = 227 * 1024 - 1024 /*align*/ - epi - 2 * 16 * sizeof(uint64_t);
     const size_t stage_h = 16384 + KP * 128, stage_w = 32768 + 2 * KP * 128;
     s->nstage_h = (int)(budget / stage_h); if (s->nstage_h > 12) s->nstage_h = 12;
@@ -1094,6 +1131,13 @@ int mfb_als_debug_repeat(mfb_als *s, int which, int count) {
         if (e != cudaSuccess) { mfb_set_error("debug repeat %d of kind %d failed: %s", i, which, cudaGetErrorString(e)); return MFB_ERR_CUDA; }
         MFB_TRY(check_mbar_abort("debug repeat"));
     }
+    return MFB_OK;
+}
+
+int mfb_als_debug_times(unsigned long long *out) {
+    MFB_CUDA(cudaMemcpyFromSymbol(out, g_dbg_times, sizeof(unsigned long long) * 148 * 8));
+    MFB_CUDA(cudaMemcpyFromSymbol(out + 148 * 8, g_dbg_marks, sizeof(unsigned long long) * 8));
+    MFB_CUDA(cudaMemcpyFromSymbol(out + 148 * 8 + 8, g_nnls_marks, sizeof(unsigned long long) * 16));
     return MFB_OK;
 }
 

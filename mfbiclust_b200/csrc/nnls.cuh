@@ -204,6 +204,8 @@ __device__ int nnls_thread(const double *__restrict__ G, const double *__restric
 // xs: shared [KP][XS] -- right-hand sides r on entry, solutions x on exit (column = problem).
 // sM: shared G^-1 (ld KP, symmetric).  Returns this lane's partial of sum_i x_i r_i.
 // ---------------------------------------------------------------------------
+__device__ unsigned long long g_nnls_marks[16];
+__device__ int g_mark_block = -1;
 template <int KP, int XS>
 __device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *xs, int warp, int lane, int nwarps) {
     constexpr int LP = (KP <= 16) ? 16 : 32;
@@ -215,6 +217,7 @@ __device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *
     const unsigned gmask = (LP == 32) ? 0xffffffffu : (0xffffu << base);
     double t1 = 0.0;
     for (int rd = 0; rd < units_per_warp / PPW; ++rd) {
+        if (threadIdx.x == 0 && (int)blockIdx.x == g_mark_block) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); g_nnls_marks[rd] = tt; }
         const int unit = warp * units_per_warp + rd * PPW + sub;
         const double ri = rowvalid ? xs[i * XS + unit] : 0.0;
         double T[KP];
@@ -240,29 +243,31 @@ __device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *
                     pend &= pend - 1;
                 } else {
                     const double x = inS ? qv : 0.0;
-                    // Lawson-Hanson step length: min over passive entries that went negative
-                    double al = (inS && x < 0.0) ? dv / (dv - x) : INFINITY;
-                    int ai = i;
+                    const bool isneg = inS && x < 0.0;
+                    if (__ballot_sync(gmask, isneg) != 0u) {
+                        // Lawson-Hanson step length: min over passive entries that went negative
+                        double al = isneg ? dv / (dv - x) : INFINITY;
+                        int ai = i;
 #pragma unroll
-                    for (int o = LP / 2; o > 0; o >>= 1) {
-                        const double oa = __shfl_xor_sync(gmask, al, o);
-                        const int oi = __shfl_xor_sync(gmask, ai, o);
-                        if (oa < al || (oa == al && oi < ai)) { al = oa; ai = oi; }
-                    }
-                    if (al < INFINITY) {
+                        for (int o = LP / 2; o > 0; o >>= 1) {
+                            const double oa = __shfl_xor_sync(gmask, al, o);
+                            const int oi = __shfl_xor_sync(gmask, ai, o);
+                            if (oa < al || (oa == al && oi < ai)) { al = oa; ai = oi; }
+                        }
                         dv = dv - al * (dv - x);
                         if (i == ai) dv = 0.0;
                         piv = ai;
                     } else {
-                        double w = (!inS && rowvalid) ? qv : -1.0;
-                        int wi = i;
+                        const bool ispos = (!inS && rowvalid) && qv > 0.0;
+                        if (__ballot_sync(gmask, ispos) != 0u) {
+                            double w = ispos ? qv : -1.0;
+                            int wi = i;
 #pragma unroll
-                        for (int o = LP / 2; o > 0; o >>= 1) {
-                            const double ow = __shfl_xor_sync(gmask, w, o);
-                            const int oi = __shfl_xor_sync(gmask, wi, o);
-                            if (ow > w || (ow == w && oi < wi)) { w = ow; wi = oi; }
-                        }
-                        if (w > 0.0) {
+                            for (int o = LP / 2; o > 0; o >>= 1) {
+                                const double ow = __shfl_xor_sync(gmask, w, o);
+                                const int oi = __shfl_xor_sync(gmask, wi, o);
+                                if (ow > w || (ow == w && oi < wi)) { w = ow; wi = oi; }
+                            }
                             dv = x;
                             piv = wi;
                         } else {
