@@ -7,5 +7,7 @@ CPU fallback: importing works anywhere the shared library is built, calling need
 """
 from . import _cabi  # noqa: F401
 from ._cabi import Context, Matrix, MfbError, default_context  # noqa: F401
-from .backends import (AlsSession, HostRng, als_nmf, als_replicate, genericFactorization,  # noqa: F401
-                       genericFit, nnls, otsuHelper, threshold)
+from .backends import (AlsSession, BiclusterExperiment, BiclusterStrategy, HostRng, addStrat,  # noqa: F401
+                       als_nmf, als_replicate, auto_bcv, bcv, bcvGivenKs, cell_range, clean, draw_folds,
+                       genericFactorization, genericFit, kLimiter, nipals, nipals_pca, nipals_pca_nocatch, nnls,
+                       otsuHelper, pseudovalues, shard_cells, svd_pca, threshold, thresholdHelper, validateKM)

@@ -231,3 +231,393 @@ def threshold(m, th, MARGIN=2, ctx=None):
     check(lib().mfb_threshold(ctx.handle, dptr(M), M.shape[0], M.shape[1], dptr(th), int(MARGIN),
                               out.ctypes.data_as(C.POINTER(C.c_int32))))
     return out.astype(bool)
+
+
+# ---------------------------------------------------------------------------
+# svd_pca / nipals_pca
+# ---------------------------------------------------------------------------
+def svd_pca(A, k, ctx=None, **_):
+    """``svd_pca(A, k, ...)`` (``R/bicluster.R:528-539``): ``prcomp(t(A), rank. = k, retx = TRUE,
+    center = FALSE)``; W = rotation (m x k'), H = t(x) (k' x n), k' = min(k, dim(A)).
+
+    The sign of a component is the one the device eigen-solver returns (LAPACK's is equally arbitrary);
+    W[:, j] and H[j, :] always flip together."""
+    ctx = ctx or _cabi.default_context()
+    own = not isinstance(A, _cabi.Matrix)
+    Ad = _cabi.Matrix(ctx, host=A) if own else A
+    try:
+        m, n = Ad.shape
+        kk = min(int(k), m, n)
+        W = np.zeros((m, kk), order="F")
+        H = np.zeros((kk, n), order="F")
+        kout = C.c_int(0)
+        check(lib().mfb_svd_pca(ctx.handle, Ad.handle, int(k), dptr(W), dptr(H), C.byref(kout)))
+        assert kout.value == kk
+    finally:
+        if own:
+            Ad.free()
+    return genericFit(genericFactorization(W=W, H=H), "svd-pca")
+
+
+def clean(obj, cleanParam=0.0, dimsRemain=True):
+    """``clean(object, cleanParam, dimsRemain)`` (``R/helperFunctions.R:89-109``): host-side pre-step."""
+    if not (0 <= cleanParam <= 1):
+        raise ValueError('Arg "cleanParam" must be in the range of 0 to 1.')
+    obj = np.asarray(obj, dtype=np.float64)
+    max_na_row = np.floor((1 - cleanParam) * obj.shape[1] + 0.5)
+    max_na_col = np.floor((1 - cleanParam) * obj.shape[0] + 0.5)
+    bad = np.isnan(obj) | (obj == 0)
+    good_rows = bad.sum(axis=1) < max_na_row
+    good_cols = bad.sum(axis=0) < max_na_col
+    out = obj[np.ix_(good_rows, good_cols)]
+    return (out, [good_rows, good_cols]) if dimsRemain else out
+
+
+def nipals(x, ncomp, center=True, scale=True, maxiter=500, tol=1e-6, gramschmidt=True, ctx=None):
+    """``nipals::nipals(x, ncomp, center, scale, maxiter, tol, gramschmidt)`` for complete data ->
+    ``dict(eig, scores, loadings, iter)``; the call site is ``R/bicluster.R:226``."""
+    ctx = ctx or _cabi.default_context()
+    own = not isinstance(x, _cabi.Matrix)
+    xd = _cabi.Matrix(ctx, host=x) if own else x
+    try:
+        m, n = xd.shape
+        ncomp = int(ncomp)
+        scores = np.zeros((m, ncomp), order="F")
+        loadings = np.zeros((n, ncomp), order="F")
+        eig = np.zeros(ncomp)
+        iters = np.zeros(ncomp, dtype=np.int32)
+        st = check(lib().mfb_nipals(ctx.handle, xd.handle, ncomp, int(bool(center)), int(bool(scale)), int(maxiter),
+                                    float(tol), int(bool(gramschmidt)), dptr(scores), dptr(loadings), dptr(eig),
+                                    iters.ctypes.data_as(C.POINTER(C.c_int))))
+        if st == _cabi.MFB_NOT_CONVERGED:
+            warnings.warn("Stopping after %d iterations for a principal component" % int(maxiter))
+    finally:
+        if own:
+            xd.free()
+    return dict(eig=eig, scores=scores, loadings=loadings, iter=iters)
+
+
+def nipals_pca_nocatch(A, k, ctx=None, **kwargs):
+    """``nipals_pca_nocatch(A, k, ...)`` (``R/bicluster.R:218-242``): forwards scale / center / maxiter /
+    gramschmidt when given (``tol`` is fixed at 1e-6 by the call) -> genericFit."""
+    fwd = {key: kwargs[key] for key in ("scale", "center", "maxiter", "gramschmidt") if kwargs.get(key) is not None}
+    np_res = nipals(A, k, tol=1e-6, ctx=ctx, **fwd)
+    return genericFit(genericFactorization(W=np_res["scores"], H=np.asfortranarray(np_res["loadings"].T)),
+                      "nipals-pca")
+
+
+def nipals_pca(A, k, cleanParam=0, verbose=True, ctx=None, **kwargs):
+    """``nipals_pca(A, k, cleanParam = 0, verbose = TRUE, ...)`` (``R/bicluster.R:269-289``) ->
+    ``dict(m, genericFit, indexRemaining)``."""
+    mClean, indexRem = clean(A, cleanParam, dimsRemain=True)
+    if np.isnan(mClean).any():
+        raise NotImplementedError("nipals_pca: matrices with NA entries are not supported yet")
+    return dict(m=mClean, genericFit=nipals_pca_nocatch(mClean, k, ctx=ctx, **kwargs), indexRemaining=indexRem)
+
+
+# ---------------------------------------------------------------------------
+# bcv / auto_bcv
+# ---------------------------------------------------------------------------
+def kLimiter(holdouts, dim, ks):
+    """``kLimiter`` (``R/bcv.R:241-251``)."""
+    ks = np.asarray(ks)
+    kLimit = np.floor((holdouts - 1) / holdouts * dim)
+    if (ks < kLimit).sum() < len(ks):
+        warnings.warn("Due to the number of holdouts, not all ks can be tested. A higher number of holdouts can "
+                      "be specified to test higher values of k, but the author does not recommend doing so.\n")
+    return ks[ks < kLimit]
+
+
+def draw_folds(rng, n, p, holdouts):
+    """``sample((seq_len(n) %% holdouts) + 1L)`` for rows and columns (``R/bcv.R:170-174``)."""
+    rf = ((np.arange(1, n + 1) % holdouts) + 1)[np.asarray(rng.permutation(n))]
+    cf = ((np.arange(1, p + 1) % holdouts) + 1)[np.asarray(rng.permutation(p))]
+    return rf.astype(np.int32), cf.astype(np.int32)
+
+
+def _dist_info(group):
+    """(rank, world, dist module or None) of the process group the cells are sharded over."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return 0, 1, None
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1, None
+    return dist.get_rank(group), dist.get_world_size(group), dist
+
+
+def cell_range(ncell, rank, world):
+    """Contiguous block of (row-fold, col-fold) cells owned by ``rank``."""
+    return (ncell * rank) // world, (ncell * (rank + 1)) // world
+
+
+def _bcast_folds(rf, cf, ctx_device, dist, group):
+    """Every rank must hold rank 0's fold vectors."""
+    import torch
+    n = rf.size
+    t = torch.from_numpy(np.concatenate([rf, cf]).astype(np.int32))
+    dev = torch.device("cuda", ctx_device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = t.to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    t = t.cpu().numpy()
+    return np.ascontiguousarray(t[:n]), np.ascontiguousarray(t[n:])
+
+
+def shard_cells(ncell, nks, compute, ctx_device=0, group=None):
+    """Run ``compute(cell_begin, cell_end) -> (cells x nks) array`` on this rank's contiguous block of the
+    ``ncell`` bcv cells and exchange the results: one all-reduce of a zero-padded ``ncell x nks`` array.  Each
+    entry has exactly one non-zero contributor, so the gathered array is exact and does not depend on the
+    number of ranks.  Without ``torch.distributed`` (or world size 1) all cells run here."""
+    rank, world, dist = _dist_info(group)
+    c0, c1 = cell_range(ncell, rank, world)
+    err = np.zeros((ncell, nks))
+    if c1 > c0:
+        err[c0:c1] = compute(c0, c1)
+    if dist is not None and world > 1:
+        import torch
+        dev = torch.device("cuda", ctx_device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(err).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        err = t.cpu().numpy()
+    return err
+
+
+def bcvGivenKs(Y, ks, holdouts=10, folds=None, rng=None, ctx=None, group=None, cell_errors=False):
+    """``bcvGivenKs(Y, ks, holdouts)`` (``R/bcv.R:164-239``) on a resident matrix.
+
+    The ``holdouts^2`` cells are independent given the fold vectors: under ``torch.distributed`` every rank
+    computes a contiguous block of cells on its own GPU and only the per-cell error vectors are exchanged
+    (:func:`shard_cells`)."""
+    ctx = ctx or _cabi.default_context()
+    rank, world, dist = _dist_info(group)
+    own = not isinstance(Y, _cabi.Matrix)
+    Yd = _cabi.Matrix(ctx, host=Y) if own else Y
+    try:
+        n, p = Yd.shape
+        ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
+        if folds is None:
+            rf, cf = draw_folds(rng or HostRng(), n, p, holdouts)
+        else:
+            rf, cf = (np.ascontiguousarray(np.asarray(f, dtype=np.int32)) for f in folds)
+        if dist is not None and world > 1:
+            rf, cf = _bcast_folds(rf, cf, ctx.device, dist, group)
+
+        def compute(c0, c1):
+            loc = np.zeros((c1 - c0, len(ks)))
+            check(lib().mfb_bcv_cells(ctx.handle, Yd.handle, rf.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      cf.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
+                                      ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), c0, c1, dptr(loc)))
+            return loc
+        err = shard_cells(holdouts * holdouts, len(ks), compute, ctx.device, group)
+    finally:
+        if own:
+            Yd.free()
+    rcvs = err.sum(axis=0)            # rowSums over row folds of rowSums over column folds (:231-233)
+    return (rcvs, err) if cell_errors else rcvs
+
+
+def bcv(Y, ks=None, holdouts=10, interactive=True, rng=None, folds=None, ctx=None, group=None):
+    """``bcv(Y, ks = seq_len(min(dim(Y)) - 1), holdouts = 10L, interactive = TRUE)`` (``R/bcv.R:124-159``)
+    -> dict ``{k: bcv value}`` (R: named numeric vector)."""
+    shape = Y.shape
+    if not isinstance(Y, _cabi.Matrix):
+        Y = np.asarray(Y, dtype=np.float64)
+        if np.isnan(Y).any():
+            raise NotImplementedError("bcv: matrices with NA entries need the NIPALS branch (not supported yet)")
+    minDim = min(shape)
+    if ks is None:
+        ks = np.arange(1, minDim)
+    ks = kLimiter(holdouts, minDim, ks)
+    ks = np.asarray(ks)
+    if ks.size == 0 or (ks < 1).any() or (ks != np.floor(ks)).any():
+        raise ValueError("ks must be a vector of positive whole numbers")
+    if holdouts > minDim:
+        holdouts = minDim
+        warnings.warn(f"Using {holdouts} holdouts to ensure non-zero holdout size.")
+    res = bcvGivenKs(Y, ks, holdouts, folds=folds, rng=rng, ctx=ctx, group=group)
+    return {int(k): float(v) for k, v in zip(ks, res)}
+
+
+def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verbose=False, interactive=True,
+             rng=None, ctx=None, group=None):
+    """``auto_bcv(Y, ks, holdouts = 3L, maxIter = 100L, tol = 1e-4, bestOnly = FALSE, verbose = FALSE,
+    interactive = TRUE)`` (``R/bcv.R:31-98``).  Y is uploaded once and stays resident for every ``bcv`` call."""
+    ctx = ctx or _cabi.default_context()
+    rng = rng or HostRng()
+    own = not isinstance(Y, _cabi.Matrix)
+    if own:
+        Y = np.asarray(Y, dtype=np.float64)
+        if np.isnan(Y).any():
+            raise NotImplementedError("auto_bcv: matrices with NA entries are not supported yet")
+    Yd = _cabi.Matrix(ctx, host=Y) if own else Y
+    try:
+        minDim = min(Yd.shape)
+        if ks is None:
+            ks = np.arange(1, minDim)
+        ks = kLimiter(holdouts, minDim, ks)                                   # :48
+        distr = {int(k): 1 for k in ks}
+        distrOld = dict(distr)
+        i = 0
+        converged = False
+        while not converged and i < maxIter:                                   # :56
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = bcv(Yd, list(distr.keys()), holdouts=holdouts, interactive=False, rng=rng, ctx=ctx,
+                          group=group)                                         # :58
+            best = min(res, key=lambda kk: (res[kk], list(res).index(kk)))     # names(which.min(res))
+            distr[best] += 1
+            if len(distr) > len(res):                                          # :64-66
+                distr = {kk: distr[kk] for kk in res}
+                distrOld = {kk: distrOld[kk] for kk in res}
+            sd, so = sum(distr.values()), sum(distrOld.values())
+            resid = [(distr[kk] / sd - distrOld[kk] / so) ** 2 for kk in distr]
+            if verbose:
+                cur = max(distr, key=lambda kk: (distr[kk], -list(distr).index(kk)))
+                print(f"Iteration {i + 1} ")
+                print(f"Current best: {cur} ")
+                print("BCV result distribution:")
+                print("\t".join(str(kk) for kk in distr) + "\n" + "\t".join(str(v - 1) for v in distr.values()))
+            converged = all(r < tol for r in resid)                            # :84
+            distrOld = dict(distr)
+            i += 1
+        if i == maxIter:
+            warnings.warn(f"BCV results did not converge after{maxIter}iterations")
+    finally:
+        if own:
+            Yd.free()
+    counts = {kk: v - 1 for kk, v in distr.items()}                            # :93
+    med = max(counts, key=lambda kk: (counts[kk], -list(counts).index(kk)))    # which.max: first maximum
+    if bestOnly:
+        return med
+    return dict(best=med, counts=counts, iterations=i)
+
+
+# ---------------------------------------------------------------------------
+# BiclusterStrategy / addStrat (the callers either side of the path; R/BiclusterStrategy.R:61-163,
+# 475-502 and R/addStrat.R:49-97) -- glue only, no arithmetic of their own
+# ---------------------------------------------------------------------------
+def pseudovalues(m):
+    """``pseudovalues`` (``R/helperFunctions.R:270-278``)."""
+    m = np.asarray(m, dtype=np.float64)
+    if (m < 0).any():
+        return m + abs(m.min())
+    return m
+
+
+def validateKM(k, m, method):
+    """``validateKM`` (``R/helperFunctions.R:400-412``) including its ``"method" == "svd-pca"`` literal."""
+    if not float(k) > 0:
+        raise ValueError('Argument "k" must be positive.')
+    k = int(np.floor(float(k) + 0.5))
+    if method in ("als-nmf", "nipals-pca", "snmf") and k > min(m.shape):
+        warnings.warn("Initializing k to the size of the smaller matrix dimension.")
+        return min(m.shape)
+    return k
+
+
+@dataclass
+class BiclustResult:
+    """The slots of ``biclust::BiclustResult`` the strategy fills (``R/BiclusterStrategy.R:150``)."""
+    RowxNumber: np.ndarray
+    NumberxCol: np.ndarray
+    Number: int
+
+
+@dataclass
+class BiclusterStrategyResult:
+    factors: genericFit
+    featureThresh: np.ndarray
+    sampleThresh: np.ndarray
+    threshAlgo: str
+    k: int
+    biclust: BiclustResult
+    name: str
+
+
+def thresholdHelper(W, H, k, featureThresh="otsu", sampleThresh="otsu", threshAlgo="otsu", ctx=None):
+    """``thresholdHelper`` (``R/BiclusterStrategy.R:475-502``) -> (threshAlgo, featureThresh, sampleThresh,
+    RowxNumber, NumberxCol)."""
+    if k <= 0:
+        warnings.warn("Biclustering did not find valid results. No samples or features are biclustered.")
+        return threshAlgo, featureThresh, sampleThresh, np.zeros((W.shape[0], 0), bool), np.zeros((0, H.shape[1]), bool)
+    if not isinstance(featureThresh, str) and not isinstance(sampleThresh, str):
+        featureThresh, sampleThresh = np.asarray(featureThresh, float), np.asarray(sampleThresh, float)
+        if featureThresh.size != k or sampleThresh.size != k:
+            raise ValueError('Length of "featureThresh" and "sampleThresh" must equal "k"')
+        threshAlgo = "user"
+    elif threshAlgo == "otsu":
+        featureThresh = otsuHelper(W, ctx=ctx)                        # :485
+        sampleThresh = otsuHelper(np.asfortranarray(H.T), ctx=ctx)    # :486
+    else:
+        raise ValueError('Currently "otsu" is the only implemented thresholding algorithm')
+    return (threshAlgo, featureThresh, sampleThresh, threshold(W, featureThresh, 2, ctx=ctx),
+            threshold(H, sampleThresh, 1, ctx=ctx))
+
+
+_METHODS = {"als-nmf": "als_nmf", "svd-pca": "svd_pca", "nipals-pca": "nipals_pca"}
+
+
+def BiclusterStrategy(obj, k, method="als-nmf", threshAlgo="otsu", featureThresh=None, sampleThresh=None, ctx=None,
+                      **kwargs):
+    """``BiclusterStrategy(obj, k, method, ...)`` for a matrix or a genericFit
+    (``R/BiclusterStrategy.R:61-100, 134-163``)."""
+    featureThresh = threshAlgo if featureThresh is None else featureThresh
+    sampleThresh = threshAlgo if sampleThresh is None else sampleThresh
+    if not isinstance(obj, genericFit):
+        if method not in _METHODS:
+            raise ValueError(f"method '{method}' is outside the GPU hot path (als-nmf | svd-pca | nipals-pca)")
+        obj = np.asarray(obj, dtype=np.float64)
+        if method == "als-nmf":
+            obj = pseudovalues(obj)                                    # :79
+        try:
+            if method == "nipals-pca":
+                fit = nipals_pca(obj, k, ctx=ctx, **kwargs)["genericFit"]
+            else:
+                fit = globals()[_METHODS[method]](obj, k, ctx=ctx, **kwargs)   # do.call(get(method), ...) :82-87
+        except (_cabi.MfbError, np.linalg.LinAlgError, ValueError) as e:       # :88-94
+            warnings.warn(str(e))
+            warnings.warn(f"{_METHODS[method]} failed, switching to PCA.")
+            fit = svd_pca(obj, k, ctx=ctx)
+            method = "svd-pca"
+    else:
+        fit = obj
+    W, H = fit.fit.W, fit.fit.H
+    k = min(int(k), W.shape[1])                                        # :138
+    algo, fth, sth, rn, nc = thresholdHelper(W, H, W.shape[1], featureThresh, sampleThresh, threshAlgo, ctx=ctx)
+    pretty = {"als-nmf": "ALS-NMF", "svd-pca": "SVD-PCA", "nipals-pca": "NIPALS-PCA"}.get(method, method)
+    name = " | ".join([pretty, algo.capitalize() if algo != "user" else "User", str(k)])
+    return BiclusterStrategyResult(factors=fit, featureThresh=np.asarray(fth), sampleThresh=np.asarray(sth),
+                                   threshAlgo=algo, k=k, biclust=BiclustResult(rn, nc, W.shape[1]), name=name)
+
+
+class BiclusterExperiment:
+    """Minimal carrier of the ``abund`` assay matrix and the strategies list
+    (``R/BiclusterExperiment.R:36-38, 118-145``)."""
+
+    def __init__(self, m):
+        self.abund = np.asfortranarray(np.asarray(m, dtype=np.float64))
+        self.strategies = {}
+
+    def as_matrix(self):
+        return self.abund
+
+
+def addStrat(bce, k, method="als-nmf", silent=False, ctx=None, **kwargs):
+    """``addStrat(bce, k, method, silent = FALSE, ...)`` (``R/addStrat.R:49-97``)."""
+    m = bce.as_matrix()
+    k = validateKM(k, m, method)
+    if method == "nipals-pca" or np.isnan(m).any():
+        if method != "nipals-pca":
+            warnings.warn("Since some data is NA, the NIPALS-PCA algorithm must be used.")
+        res = nipals_pca(m, k, cleanParam=0, center=False, ctx=ctx)                  # :72
+        bcs = BiclusterStrategy(res["genericFit"], k, method="nipals-pca", ctx=ctx)
+        rows, cols = res["indexRemaining"]
+        if not (rows.all() and cols.all()):
+            warnings.warn("Some samples or features with too much missing data were removed.")
+            bce.abund = np.asfortranarray(m[np.ix_(rows, cols)])
+    else:
+        bcs = BiclusterStrategy(m, k, method=method, ctx=ctx, verbose=not silent, **kwargs)
+    bce.strategies[bcs.name] = bcs
+    if not silent:
+        print(f"Added BiclusterStrategy named {bcs.name}")
+    return bce

@@ -1,0 +1,433 @@
+// Dense FP64 building blocks for svd_pca and the bcv cells (see linalg.cuh).
+#include <cooperative_groups.h>
+
+#include "linalg.cuh"
+
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------
+// C = A' B  (dot products of contiguous columns), FP64 tensor cores
+// ---------------------------------------------------------------------------
+// One warp owns a 32 x 32 tile of C: 4 x 4 m8n8k4 blocks, accumulators in registers; per 16-deep k step a lane
+// reads 4 consecutive k of one column per block (A-operand [M = column of A][K], B-operand [K][N = column of B]).
+__global__ void __launch_bounds__(128) gemm_tn_kernel(const double *__restrict__ A, int64_t lda,
+                                                      const double *__restrict__ B, int64_t ldb,
+                                                      double *__restrict__ C, int64_t ldc, int64_t M, int64_t N,
+                                                      int64_t K, int64_t kz, int vec_ok) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t m0 = ((int64_t)blockIdx.x * 2 + (warp & 1)) * 32;
+    const int64_t n0 = ((int64_t)blockIdx.y * 2 + (warp >> 1)) * 32;
+    if (m0 >= M || n0 >= N) return;
+    const int64_t kbeg = (int64_t)blockIdx.z * kz, kend = (kbeg + kz < K) ? kbeg + kz : K;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double *ap[4], *bp[4];
+    bool av[4], bv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t mc = m0 + 8 * i + g, nc = n0 + 8 * i + g;
+        av[i] = mc < M;
+        bv[i] = nc < N;
+        ap[i] = A + (av[i] ? mc : 0) * lda;
+        bp[i] = B + (bv[i] ? nc : 0) * ldb;
+    }
+    for (int64_t k0 = kbeg; k0 < kend; k0 += 16) {
+        double a[4][4], b[4][4];
+        const int64_t kk = k0 + 4 * t;
+        if (vec_ok && k0 + 16 <= kend) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 a0 = *(const double2 *)(ap[i] + kk), a1 = *(const double2 *)(ap[i] + kk + 2);
+                const double2 b0 = *(const double2 *)(bp[i] + kk), b1 = *(const double2 *)(bp[i] + kk + 2);
+                a[i][0] = av[i] ? a0.x : 0.0; a[i][1] = av[i] ? a0.y : 0.0; a[i][2] = av[i] ? a1.x : 0.0; a[i][3] = av[i] ? a1.y : 0.0;
+                b[i][0] = bv[i] ? b0.x : 0.0; b[i][1] = bv[i] ? b0.y : 0.0; b[i][2] = bv[i] ? b1.x : 0.0; b[i][3] = bv[i] ? b1.y : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const bool in = (kk + s) < kend;
+                    a[i][s] = (in && av[i]) ? ap[i][kk + s] : 0.0;
+                    b[i][s] = (in && bv[i]) ? bp[i][kk + s] : 0.0;
+                }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i][s], b[j][s]);
+    }
+    double *Cz = C + (size_t)blockIdx.z * (size_t)ldc * (size_t)N;   // split-K partial z (ldc * N doubles apart)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t mr = m0 + 8 * i + g;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t nc = n0 + 8 * j + 2 * t + e;
+                if (mr < M && nc < N) Cz[mr + nc * ldc] = acc[i][j][e];
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double *__restrict__ part, int Z, int64_t M,
+                                                            int64_t N, int64_t ldp, double *__restrict__ C,
+                                                            int64_t ldc) {
+    const int64_t total = M * N;
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t n = e / M, m = e - n * M;
+        double s = 0.0;
+        for (int z = 0; z < Z; ++z) s += part[(size_t)z * ldp * N + m + n * ldp];
+        C[m + n * ldc] = s;
+    }
+}
+
+static int splitk_factor(int64_t M, int64_t N, int64_t K, int sm_count) {
+    const int64_t tiles = ((M + 63) / 64) * ((N + 63) / 64);
+    int Z = 1;
+    if (tiles < 2 * sm_count) {
+        Z = (int)((2 * sm_count + tiles - 1) / tiles);
+        const int64_t maxz = (K + 255) / 256;
+        if (Z > maxz) Z = (int)maxz;
+        if (Z < 1) Z = 1;
+        if (Z > 64) Z = 64;
+    }
+    return Z;
+}
+
+size_t gemm_tn_workspace(int64_t M, int64_t N, int64_t K, int sm_count) {
+    const int Z = splitk_factor(M, N, K, sm_count);
+    return Z > 1 ? (size_t)Z * M * N : 0;
+}
+
+int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+            int64_t M, int64_t N, int64_t K, double *work) {
+    const int Z = splitk_factor(M, N, K, ctx->sm_count);
+    int64_t kz = (K + Z - 1) / Z;
+    kz = (kz + 15) / 16 * 16;
+    const int vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A) % 32 == 0) && (((uintptr_t)B) % 32 == 0);
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)Z);
+    if (Z == 1) {
+        gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, kz, vec_ok);
+    } else {
+        MFB_ARG(work != nullptr, "gemm_tn: split-K needs a workspace");
+        gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, work, M, M, N, K, kz, vec_ok);
+        int nb = (int)((M * N + 255) / 256);
+        if (nb > 4 * ctx->sm_count) nb = 4 * ctx->sm_count;
+        splitk_reduce_kernel<<<nb, 256, 0, ctx->stream>>>(work, Z, M, N, M, C, ldc);
+    }
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C = A V  for a tall A and a thin V (kk <= 64): one thread per row
+// ---------------------------------------------------------------------------
+template <int KK>
+__global__ void __launch_bounds__(128) tall_times_small_kernel(const double *__restrict__ A, int64_t lda,
+                                                               const double *__restrict__ V, int64_t ldv,
+                                                               double *__restrict__ C, int64_t ldc, int64_t rows,
+                                                               int64_t inner, int kk,
+                                                               const double *__restrict__ colscale) {
+    __shared__ double sv[32 * KK];
+    const int64_t i = blockIdx.x * 128ll + threadIdx.x;
+    double acc[KK];
+#pragma unroll
+    for (int j = 0; j < KK; ++j) acc[j] = 0.0;
+    for (int64_t c0 = 0; c0 < inner; c0 += 32) {
+        const int cn = (int)((inner - c0 < 32) ? inner - c0 : 32);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * KK; e += 128) {
+            const int c = e / KK, j = e - c * KK;
+            sv[e] = (c < cn && j < kk) ? V[(c0 + c) + (int64_t)j * ldv] : 0.0;
+        }
+        __syncthreads();
+        if (i < rows) {
+            for (int c = 0; c < cn; ++c) {
+                const double a = A[i + (c0 + c) * lda];
+#pragma unroll
+                for (int j = 0; j < KK; ++j) acc[j] += a * sv[c * KK + j];
+            }
+        }
+    }
+    if (i < rows) {
+#pragma unroll
+        for (int j = 0; j < KK; ++j)
+            if (j < kk) C[i + (int64_t)j * ldc] = colscale ? acc[j] * colscale[j] : acc[j];
+    }
+}
+
+int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv, double *C,
+                     int64_t ldc, int64_t rows, int64_t inner, int kk, const double *colscale) {
+    MFB_ARG(kk >= 1 && kk <= 64, "tall_times_small: kk must be in 1..64");
+    const unsigned nb = (unsigned)((rows + 127) / 128);
+    cudaStream_t st = ctx->stream;
+    if (kk <= 8) tall_times_small_kernel<8><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    else if (kk <= 16) tall_times_small_kernel<16><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    else if (kk <= 32) tall_times_small_kernel<32><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    else tall_times_small_kernel<64><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// symmetric eigen-solver, top-k
+// ---------------------------------------------------------------------------
+#define TRI_THREADS 256
+
+__device__ __forceinline__ double tri_block_sum(double v, double *sh) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < TRI_THREADS / 32; ++i) s += sh[i];
+    return s;
+}
+
+// Householder reduction to tridiagonal form (LAPACK dsytd2, lower): A = Q T Q', reflector i stored in A[i+2:N, i]
+// (v[i+1] = 1 implicit), tau[i], T = (d, e).  Rows of the trailing block are dealt to the blocks every step.
+__global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t N, double *d, double *e,
+                                                              double *tau, double *vbuf, double *pbuf,
+                                                              double *part) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[TRI_THREADS / 32];
+    const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    for (int64_t i = 0; i + 1 < N; ++i) {
+        // phase 0 (redundant per block): reflector from column i
+        const double alpha = A[(i + 1) + i * N];
+        double q = 0.0;
+        for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) { const double v = A[r + i * N]; q += v * v; }
+        const double xnorm = sqrt(tri_block_sum(q, sh));
+        double beta, tq, scale;
+        if (xnorm == 0.0) {
+            beta = alpha; tq = 0.0; scale = 0.0;
+        } else {
+            beta = -copysign(hypot(alpha, xnorm), alpha);
+            tq = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) vbuf[r] = (r == i + 1) ? 1.0 : A[r + i * N] * scale;
+        if (b == 0 && tid == 0) { d[i] = A[i + i * N]; e[i] = beta; tau[i] = tq; }
+        __syncthreads();
+        // columns i+1 .. N-1 of the (symmetric, fully stored) trailing block are dealt to the warps of the grid;
+        // a warp walks a column with coalesced loads (row r of A22 equals column r)
+        const int warp = tid >> 5, lane = tid & 31;
+        const int64_t gw = (int64_t)b * (TRI_THREADS / 32) + warp, tw = (int64_t)nb * (TRI_THREADS / 32);
+        // phase 1: p = tau * A22 v
+        double pvs = 0.0;
+        for (int64_t c = i + 1 + gw; c < N; c += tw) {
+            const double *col = A + c * N;
+            double s0 = 0.0;
+            for (int64_t r = i + 1 + lane; r < N; r += 32) s0 += col[r] * vbuf[r];
+            s0 = warp_sum(s0);
+            const double pc = tq * s0;
+            if (lane == 0) { pbuf[c] = pc; pvs += pc * vbuf[c]; }
+        }
+        pvs = tri_block_sum(pvs, sh);
+        if (tid == 0) part[b] = pvs;
+        grid.sync();
+        // phase 2: w = p - (tau/2)(p'v) v ;  A22 -= v w' + w v'
+        double pv = 0.0;
+        for (int bb = 0; bb < nb; ++bb) pv += part[bb];
+        const double alpha2 = -0.5 * tq * pv;
+        for (int64_t c = i + 1 + gw; c < N; c += tw) {
+            double *col = A + c * N;
+            const double vc = vbuf[c], wc = pbuf[c] + alpha2 * vc;
+            for (int64_t r = i + 1 + lane; r < N; r += 32) {
+                const double vr = vbuf[r], wr = pbuf[r] + alpha2 * vr;
+                col[r] -= vr * wc + wr * vc;
+            }
+        }
+        if (b == 0)   // keep the reflector for the back-transformation
+            for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) A[r + i * N] = vbuf[r];
+        grid.sync();
+    }
+    if (b == 0 && tid == 0) {
+        d[N - 1] = A[(N - 1) + (N - 1) * N];
+        if (N >= 1) { e[N - 1] = 0.0; tau[N - 1] = 0.0; }
+    }
+}
+
+// number of eigenvalues of the symmetric tridiagonal (d, e) that are < x  (Sturm sequence, LAPACK dlaebz style)
+__device__ int sturm_count(const double *d, const double *e, int64_t N, double x, double pivmin) {
+    int cnt = 0;
+    double q = d[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    if (q < 0.0) ++cnt;
+    for (int64_t i = 1; i < N; ++i) {
+        q = d[i] - x - e[i - 1] * e[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        if (q < 0.0) ++cnt;
+    }
+    return cnt;
+}
+
+// Top-k eigenpairs of the tridiagonal matrix: bisection (one thread per eigenvalue) then inverse iteration
+// (one thread per eigenvector for the tridiagonal solves, the whole block for the Gram-Schmidt sweeps).
+// work: k * 5 * N doubles.  Z: N x k.
+__global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double *d, const double *e, int64_t N, int k,
+                                                                   double *evals, double *Z, double *work) {
+    __shared__ double sh[TRI_THREADS / 32];
+    __shared__ double s_lo, s_hi, s_pivmin, s_norm;
+    __shared__ double s_lam[64];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        double lo = INFINITY, hi = -INFINITY, emax = 0.0;
+        for (int64_t i = 0; i < N; ++i) {
+            const double el = (i > 0) ? fabs(e[i - 1]) : 0.0, er = (i + 1 < N) ? fabs(e[i]) : 0.0;
+            lo = fmin(lo, d[i] - el - er);
+            hi = fmax(hi, d[i] + el + er);
+            emax = fmax(emax, er * er);
+        }
+        const double nrm = fmax(fabs(lo), fabs(hi));
+        s_lo = lo - 2.0 * nrm * 2.3e-16 * N - 1e-300;
+        s_hi = hi + 2.0 * nrm * 2.3e-16 * N + 1e-300;
+        s_pivmin = fmax(2.3e-308 * fmax(1.0, emax), 1e-300);
+        s_norm = nrm;
+    }
+    __syncthreads();
+    if (tid < k) {
+        // eigenvalue with index N-1-tid (0-based ascending): smallest x with count(x) >= N - tid
+        const int target = (int)(N - tid);
+        double lo = s_lo, hi = s_hi;
+        for (int it = 0; it < 200; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if (mid <= lo || mid >= hi) break;
+            if (sturm_count(d, e, N, mid, s_pivmin) >= target) hi = mid; else lo = mid;
+            if (hi - lo <= 4.0 * 2.3e-16 * fmax(fabs(lo), fabs(hi))) break;
+        }
+        s_lam[tid] = 0.5 * (lo + hi);
+        evals[tid] = s_lam[tid];
+    }
+    __syncthreads();
+    // separate eigenvalues that coincide to working precision (dstein-style perturbation) so the LU factors differ
+    if (tid == 0) {
+        const double sep = 10.0 * 2.3e-16 * s_norm;
+        for (int j = 1; j < k; ++j)
+            if (s_lam[j - 1] - s_lam[j] < sep) s_lam[j] = s_lam[j - 1] - sep;
+    }
+    __syncthreads();
+    for (int iter = 0; iter < 4; ++iter) {
+        if (tid < k) {
+            // solve (T - lam I) z = b by Gaussian elimination with partial pivoting (tridiagonal)
+            double *du = work + (size_t)tid * 5 * N, *du2 = du + N, *dd = du2 + N, *dl = dd + N;
+            double *z = Z + (size_t)tid * N;
+            const double lam = s_lam[tid];
+            for (int64_t i = 0; i < N; ++i) {
+                dd[i] = d[i] - lam;
+                du[i] = (i + 1 < N) ? e[i] : 0.0;
+                dl[i] = (i + 1 < N) ? e[i] : 0.0;
+                du2[i] = 0.0;
+                if (iter == 0) z[i] = 1.0 / sqrt((double)N) * (1.0 + 0.01 * (double)((i * 2654435761u + tid * 40503u) % 97) / 97.0);
+            }
+            const double tiny = 2.3e-16 * s_norm + 1e-300;
+            // forward elimination applied to the right-hand side on the fly
+            for (int64_t i = 0; i + 1 < N; ++i) {
+                if (fabs(dd[i]) >= fabs(dl[i])) {
+                    if (fabs(dd[i]) < tiny) dd[i] = copysign(tiny, dd[i] == 0.0 ? 1.0 : dd[i]);
+                    const double f = dl[i] / dd[i];
+                    dd[i + 1] -= f * du[i];
+                    z[i + 1] -= f * z[i];
+                    du2[i] = 0.0;
+                } else {
+                    // swap rows i and i+1
+                    const double f = dd[i] / dl[i];
+                    const double t0 = dd[i + 1];
+                    dd[i] = dl[i];
+                    dd[i + 1] = du[i] - f * t0;
+                    du[i] = t0;
+                    if (i + 2 < N) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+                    const double zt = z[i];
+                    z[i] = z[i + 1];
+                    z[i + 1] = zt - f * z[i + 1];
+                }
+            }
+            if (fabs(dd[N - 1]) < tiny) dd[N - 1] = copysign(tiny, dd[N - 1] == 0.0 ? 1.0 : dd[N - 1]);
+            // back substitution with the two super-diagonals
+            z[N - 1] /= dd[N - 1];
+            if (N >= 2) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) / dd[N - 2];
+            for (int64_t i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) / dd[i];
+            // crude normalisation against overflow
+            double mx = 0.0;
+            for (int64_t i = 0; i < N; ++i) mx = fmax(mx, fabs(z[i]));
+            const double inv = 1.0 / mx;
+            for (int64_t i = 0; i < N; ++i) z[i] *= inv;
+        }
+        __syncthreads();
+        // modified Gram-Schmidt in eigenvalue order (all previous vectors: cheap, and exact for clusters)
+        for (int j = 0; j < k; ++j) {
+            double *zj = Z + (size_t)j * N;
+            for (int l = 0; l < j; ++l) {
+                if (fabs(s_lam[l] - s_lam[j]) > 1e-3 * s_norm) continue;
+                const double *zl = Z + (size_t)l * N;
+                double s = 0.0;
+                for (int64_t i = tid; i < N; i += TRI_THREADS) s += zl[i] * zj[i];
+                s = tri_block_sum(s, sh);
+                for (int64_t i = tid; i < N; i += TRI_THREADS) zj[i] -= s * zl[i];
+                __syncthreads();
+            }
+            double s = 0.0;
+            for (int64_t i = tid; i < N; i += TRI_THREADS) s += zj[i] * zj[i];
+            s = tri_block_sum(s, sh);
+            const double inv = 1.0 / sqrt(s);
+            for (int64_t i = tid; i < N; i += TRI_THREADS) zj[i] *= inv;
+            __syncthreads();
+        }
+    }
+}
+
+// z <- H(0) H(1) ... H(N-2) z, one block per eigenvector column
+__global__ void __launch_bounds__(TRI_THREADS) backtransform_kernel(const double *A, int64_t N, const double *tau,
+                                                                    double *Z) {
+    __shared__ double sh[TRI_THREADS / 32];
+    double *z = Z + (size_t)blockIdx.x * N;
+    const int tid = threadIdx.x;
+    for (int64_t i = N - 2; i >= 0; --i) {
+        const double tq = tau[i];
+        if (tq == 0.0) continue;
+        double s = 0.0;
+        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) s += ((r == i + 1) ? 1.0 : A[r + i * N]) * z[r];
+        s = tq * tri_block_sum(s, sh);
+        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) z[r] -= s * ((r == i + 1) ? 1.0 : A[r + i * N]);
+        __syncthreads();
+    }
+}
+
+int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, double *evecs) {
+    MFB_ARG(N >= 1 && k >= 1 && k <= 64 && k <= N, "sym_eig_topk: need 1 <= k <= min(N, 64)");
+    cudaStream_t st = ctx->stream;
+    double *wk = nullptr;
+    const size_t nwork = (size_t)5 * N + (size_t)ctx->sm_count + (size_t)k * 5 * N + 16;
+    MFB_CUDA(cudaMalloc(&wk, nwork * sizeof(double)));
+    double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + N, *part = pbuf + N;
+    double *work = part + ctx->sm_count;
+    if (N == 1) {
+        MFB_CUDA(cudaMemcpyAsync(evals, G, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        const double one = 1.0;
+        MFB_CUDA(cudaMemcpyAsync(evecs, &one, sizeof(double), cudaMemcpyHostToDevice, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(wk);
+        return MFB_OK;
+    }
+    int nb = (int)((N + 7) / 8);          // one warp per column of the trailing block, 8 warps per block
+    if (nb > ctx->sm_count) nb = ctx->sm_count;
+    if (nb < 1) nb = 1;
+    void *args[] = {&G, &N, &d, &e, &tau, &vbuf, &pbuf, &part};
+    MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_kernel, dim3(nb), dim3(TRI_THREADS), args, 0, st));
+    tridiag_topk_kernel<<<1, TRI_THREADS, 0, st>>>(d, e, N, k, evals, evecs, work);
+    backtransform_kernel<<<k, TRI_THREADS, 0, st>>>(G, N, tau, evecs);
+    MFB_CUDA(cudaGetLastError());
+    MFB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(wk);
+    return MFB_OK;
+}

@@ -1,0 +1,20 @@
+// Dense FP64 building blocks shared by svd_pca and the bcv cells (device pointers, column-major).
+#pragma once
+#include "common.cuh"
+
+// C[M x N] (ldc) = A' B with A = [K x M] (lda), B = [K x N] (ldb): every entry is a dot product of two
+// contiguous columns.  FP64 tensor cores (DMMA.8x8x4), 32 x 32 tile per warp, deterministic split-K.
+// `work` must hold at least gemm_tn_workspace(M, N, K) doubles (may be NULL when that is 0).
+size_t gemm_tn_workspace(int64_t M, int64_t N, int64_t K, int sm_count);
+int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+            int64_t M, int64_t N, int64_t K, double *work);
+
+// C[rows x kk] (ldc) = A[rows x inner] (lda) * V[inner x kk] (ldv), kk <= 64: one thread per row of A.
+// Optional per-column scale: C[:, j] *= colscale[j].
+int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv, double *C,
+                     int64_t ldc, int64_t rows, int64_t inner, int kk, const double *colscale);
+
+// Top-`k` eigenpairs (largest first) of the symmetric N x N matrix G (column-major, ld = N, destroyed):
+// Householder tridiagonalisation (cooperative persistent kernel), Sturm bisection, inverse iteration with
+// modified Gram-Schmidt, reflector back-transformation.  evals: k, evecs: N x k (ld = N), device pointers.
+int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, double *evecs);

@@ -1,0 +1,117 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/mfbiclust.h declares, the
+host-side mirror of the reference's pre-steps, and the multi-rank cell sharding over gloo (world size 2)."""
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mfbiclust_b200._cabi as cabi
+    L = cabi.lib()                       # raises if the .so is missing or a prototype is not exported
+    hdr = open(os.path.join(ROOT, "include", "mfbiclust.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mfb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/mfbiclust.h but not exported"
+    assert declared == set(cabi.PROTOTYPES), declared ^ set(cabi.PROTOTYPES)
+    assert L.mfb_version() >= 100
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import mfbiclust_b200 as mfb
+    with pytest.raises(mfb.MfbError, match="no CUDA device|no CPU fallback"):
+        mfb.Context(0)
+    with pytest.raises(mfb.MfbError):
+        mfb.otsuHelper(np.arange(12.0).reshape(4, 3))
+
+
+def test_klimiter_and_cell_ranges():
+    import mfbiclust_b200 as mfb
+    with pytest.warns(UserWarning):
+        assert list(mfb.kLimiter(3, 18, np.arange(1, 18))) == list(range(1, 12))      # R/bcv.R:241-251
+    for ncell in (9, 100, 4):
+        for world in (1, 2, 3, 8):
+            got = [mfb.cell_range(ncell, r, world) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == ncell
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            sizes = [b - a for a, b in got]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_draw_folds_balanced():
+    import mfbiclust_b200 as mfb
+    rf, cf = mfb.draw_folds(mfb.HostRng(1), 1099, 18, 3)
+    assert sorted(np.bincount(rf)[1:]) == [366, 366, 367] and sorted(np.bincount(cf)[1:]) == [6, 6, 6]
+
+
+def test_validate_km_clean_pseudovalues():
+    import mfbiclust_b200 as mfb
+    from oracle import helpers as Hh
+    m = np.arange(12.0).reshape(4, 3) - 3
+    with pytest.warns(UserWarning):
+        assert mfb.validateKM(7, m, "als-nmf") == 3
+    assert mfb.validateKM(7, m, "svd-pca") == 7          # R/helperFunctions.R:402 quirk
+    assert np.array_equal(mfb.pseudovalues(m), Hh.pseudovalues(m))
+    x = m.copy()
+    x[1, :] = 0
+    x[:, 2] = np.nan
+    got, idx = mfb.clean(x, 0)
+    ref, gr, gc = Hh.clean(x, 0)
+    assert np.array_equal(idx[0], gr) and np.array_equal(idx[1], gc) and got.shape == ref.shape
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    import mfbiclust_b200 as mfb
+    from oracle import bcv as B
+    z = np.load(os.path.join({root!r}, "tests", "golden", "yeast_benchmark.npz"))
+    Y = np.asfortranarray(z["y06"])
+    h = 3
+    ks = B.k_limiter(h, min(Y.shape), np.arange(1, 7))
+    rs = np.random.default_rng(5)
+    rf = B.make_folds(Y.shape[0], h, rs.permutation(Y.shape[0]))
+    cf = B.make_folds(Y.shape[1], h, rs.permutation(Y.shape[1]))
+    calls = []
+    def compute(c0, c1):      # stands in for mfb_bcv_cells (no GPU here): same cell numbering, cell = (x-1)*h + (y-1)
+        calls.append((c0, c1))
+        return np.stack([B.bcv_cell_errors(Y, list(ks), rf == (c // h + 1), cf == (c % h + 1)) for c in range(c0, c1)])
+    err = mfb.shard_cells(h * h, len(ks), compute)
+    full = np.stack([B.bcv_cell_errors(Y, list(ks), rf == (c // h + 1), cf == (c % h + 1)) for c in range(h * h)])
+    assert calls == [mfb.cell_range(h * h, dist.get_rank(), 2)], calls
+    assert np.array_equal(err, full), np.abs(err - full).max()
+    assert np.array_equal(err.sum(axis=0), full.sum(axis=0))
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", sys.argv[1], "ok")
+""")
+
+
+def test_bcv_cell_sharding_gloo_world2(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
