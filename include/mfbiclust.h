@@ -96,6 +96,12 @@ int  mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k,
 int  mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters,
                      int *iters_total, int *converged);
 int  mfb_als_restart(mfb_als *s, const double *Wnew);
+/*
+ * Measurement aid for bench.py: runs `iters` further fixed iterations with a CUDA event recorded (on the
+ * context's stream) after every kernel, and returns the mean duration in ms of the four launches of an
+ * iteration: ms[0] H-step stream, ms[1] H-step solve, ms[2] W-step stream, ms[3] W-step solve.
+ */
+int  mfb_als_profile(mfb_als *s, int iters, double ms[4]);
 /* trace: iters_total x 3 row-major (residNorm, rms dW, rms dH) per completed iteration (NaN rows for failed ones). */
 int  mfb_als_result(mfb_als *s, double *W, double *H, double *resid, double *trace);
 void mfb_als_end(mfb_als *s);

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "mfb_als_begin": (C.c_int, [_vp, _vp, C.c_int, _dp, _dp, C.c_double, C.POINTER(_vp)]),
     "mfb_als_iterate": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip]),
     "mfb_als_restart": (C.c_int, [_vp, _dp]),
+    "mfb_als_profile": (C.c_int, [_vp, C.c_int, _dp]),
     "mfb_als_result": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "mfb_als_end": (None, [_vp]),
     "mfb_als_run": (C.c_int, [_vp, _vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_double, C.c_int,

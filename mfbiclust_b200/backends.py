@@ -80,6 +80,14 @@ class AlsSession:
         self.iters = it.value
         return st, it.value, bool(conv.value)
 
+    def profile(self, iters):
+        """Mean duration (ms) of the four kernel launches of an iteration over ``iters`` further fixed
+        iterations: ``[H stream, H solve, W stream, W solve]`` (``mfb_als_profile``)."""
+        ms = np.zeros(4)
+        check(lib().mfb_als_profile(self._h, int(iters), dptr(ms)))
+        self.iters += int(iters)
+        return ms
+
     def restart(self, Wnew):
         Wnew = as_f(Wnew)
         check(lib().mfb_als_restart(self._h, dptr(Wnew)))

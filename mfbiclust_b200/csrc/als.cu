@@ -1,24 +1,23 @@
 // ALS-NMF hot loop on B200 (sm_100a): replaces als_nmf's `while (i < maxIter)` body
 // (R/bicluster.R:119-203) and the two NMF::.fcnnls calls inside it (:123, :150).
 //
-// One ALS iteration = two launches of one templated kernel:
-//   H-step  (WSTEP = false): R = W'A  (k x n), then exact NNLS per column of A   -> H
-//   W-step  (WSTEP = true):  R = A H' (m x k), then exact NNLS per row of A      -> W,
-//                            plus residNorm / rms(dW) / rms(dH) and the convergence test.
-// A (m x n, column-major, FP64) is streamed from HBM exactly once per half-step:
-//   * a producer warp moves 16-row x 128-col (H-step) or 128-row x 32-col (W-step) boxes of A
-//     into a shared-memory ring with TMA (cp.async.bulk.tensor, SWIZZLE_128B) signalled on
-//     mbarriers;
-//   * eight consumer warps read the m8n8k4 FP64 tensor-core fragments straight out of the
-//     swizzled ring (conflict-free by construction, see frag_* below) and accumulate with
-//     DMMA.8x8x4; the k-row fragments of the fixed factor come through L1 from global memory;
-//   * work is cut stream-K style: the (tile, reduction-stage) space is split into 148 equal
-//     contiguous ranges, one persistent CTA per SM; a CTA writes one k x 128 partial per tile it
-//     touches and the LAST CTA to arrive at a tile (atomic counter) sums the partials in slot
-//     order (deterministic) and runs the NNLS epilogue for the tile's 128 columns / rows, one
-//     thread per problem (nnls.cuh);
-//   * the last tile epilogue of the launch reduces the per-tile Gram partials of the factor just
-//     produced, inverts the k x k Gram for the next half-step, and folds the iteration scalars.
+// One ALS iteration = two half-steps, each a STREAM launch followed by a SOLVE launch:
+//   H-step:  R = W'A  (k x n), then exact NNLS per column of A   -> H
+//   W-step:  R = A H' (m x k), then exact NNLS per row of A      -> W,
+//            plus residNorm / rms(dW) / rms(dH) and the convergence test.
+// Stream kernel (als_stream_kernel): A (m x n, column-major, FP64) is read from HBM exactly once per half-step:
+//   * a producer warp moves 16-row x 128-col (H-step) or 128-row x 32-col (W-step) boxes of A, and the matching
+//     slab of the fixed factor, into a shared-memory ring with TMA (cp.async.bulk.tensor, SWIZZLE_128B)
+//     signalled on mbarriers;
+//   * two groups of four consumer warps, one stage out of phase, read the m8n8k4 FP64 tensor-core fragments
+//     straight out of the swizzled ring (conflict-free by construction) and accumulate with DMMA.8x8x4;
+//   * work is cut stream-K style: the (tile, reduction-stage) space is split into 148 equal contiguous
+//     ranges, one persistent CTA per SM; a consumer group writes one k x 128 partial per tile it touches.
+// Solve kernel (als_solve_kernel): thousands of warps sum the partials in slot order (deterministic) and run
+// the exact NNLS for 16 units per CTA, write the factor, and fold the Gram of the new factor, its inverse and
+// the iteration scalars in two fixed-order levels.  Splitting the launches exposes one launch gap per
+// half-step but replaces a tail of ~40 (H) / ~100-200 (W) us during which 8 warps per SM ran the NNLS of a whole
+// 128-unit tile with a ~15 us kernel at full occupancy (profiles/r01_*).
 // Nothing but A's two passes touches HBM in bulk: factors, partials and Grams stay in L2.
 #include "common.cuh"
 #include "nnls.cuh"
@@ -26,7 +25,6 @@
 #define ALS_THREADS 384           // 2 consumer warpgroups (8 warps) + 1 producer warpgroup (one elected lane)
 #define ALS_CONSUMERS 256
 #define TILE_UNITS 128            // columns (H-step) or rows (W-step) per tile
-#define XS_LD 129
 
 // ---------------------------------------------------------------------------
 // device control block (lives in global memory, mirrored to the host after a batch)
@@ -36,7 +34,7 @@ struct AlsCtrl {
     int reason;                // 0 none, 1 converged, 2 zero row in H, 3 singular W'W, 4 singular HH'
     int iters_done;            // completed (successful) iterations in this batch epoch
     int fixed;                 // 1: no convergence break
-    int tiles_done[2];         // per half-step tile completion counters
+    int groups_done[2];        // per half-step completion counters of the solve kernel's CTA groups
     int max_trace;
     int pad0;
     unsigned long long nzmask; // bit c set when row c of H has a non-zero entry
@@ -54,14 +52,14 @@ struct HalfParams {
     const double *G; const double *Minv;  // Gram of Fin and its inverse, KP x KP
     double *Gout; double *Minvout;        // Gram of Fout (+ inverse), written by the last epilogue
     double *P; int maxslots;              // partials [tile][slot][KP][128]
-    int *tile_counter;                    // [T]
-    double *gpart;                        // [T][KP*KP]
-    double *spart;                        // [T][4]
+    int *group_counter;                   // [solve groups]
+    double *gpart, *gpart2;               // Gram partials per solve CTA / per group, [..][KP*KP]
+    double *spart, *spart2;               // scalar partials per solve CTA / per group, [..][4]
     AlsCtrl *ctrl; double *trace;
     int k, T, SPT;
     long long U;                          // T * SPT
     long long nvalid;                     // number of real units (n for H-step, m for W-step)
-    int debug;                            // development aid: bit 0 = skip tile epilogues
+    int Gstream;                          // grid size of the stream kernel (stream-K partition)
 };
 
 // ---------------------------------------------------------------------------
@@ -92,9 +90,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // bounded wait: a protocol bug must never hang the GPU.  On a time-out the first waiter records who / where
 // in a global debug record, raises a global abort flag (every later wait returns at once) and the launch
 // drains; the host reports MFB_ERR_CUDA with the record.
-__device__ unsigned long long g_dbg_times[148 * 8];
-__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ unsigned long long g_dbg_marks[8];
 __device__ int g_mbar_abort = 0;
 __device__ int g_mbar_record[8];
 __device__ __noinline__ void mbar_timeout(int code, int a, int b, int c) {
@@ -150,238 +145,254 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
     return v;
 }
 
-// Tile epilogue (cold path, kept out of line so that the streaming loop's registers stay clean):
-// sums the partials of a finished tile, solves its 128 NNLS problems, writes the factor, and -- for the last
-// tile of the launch -- folds the Gram / inverse / iteration scalars.
-template <int KB, bool WSTEP>
-__device__ __noinline__ void tile_epilogue(const HalfParams &p, const int tile, const int expected, double *sG,
-                                           double *sM, double *xs, double *sred, int *sflag) {
-    constexpr int KP = KB * 8;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-        // ---------------- tile epilogue: NNLS for 128 units ----------------
-        if ((p.debug & 16) && tid == 0 && tile == 3) { g_mark_block = (int)blockIdx.x; g_dbg_marks[0] = gtimer(); }
-        const long long unit = (long long)tile * TILE_UNITS + tid;
-        const bool valid = (tid < TILE_UNITS) && (unit < p.nvalid);
-        double d2 = 0.0, t1 = 0.0, t2 = 0.0;
-        unsigned long long nz = 0ull;
-        if constexpr (KP <= 32) {
-            // (a) right-hand sides: sum the partials in slot order; thread = (unit, half of the ranks)
-            {
-                constexpr int HK = KP / 2;
-                const int u = tid & (TILE_UNITS - 1), c0 = (tid >> 7) * HK;
-                const bool uvalid = ((long long)tile * TILE_UNITS + u) < p.nvalid;
-                double r[HK];
-#pragma unroll
-                for (int c = 0; c < HK; ++c) r[c] = 0.0;
-                for (int s = 0; s < expected; ++s) {
-                    const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + u;
-#pragma unroll
-                    for (int c = 0; c < HK; ++c)
-                        if (c0 + c < p.k) r[c] += ldcg(Ps + (size_t)(c0 + c) * TILE_UNITS);
-                }
-#pragma unroll
-                for (int c = 0; c < HK; ++c) xs[(c0 + c) * XS_LD + u] = uvalid ? r[c] : 0.0;
-            }
-            consumer_bar();
-        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[1] = gtimer();
-            // (b) lane-distributed principal-pivoting NNLS, 16 units per warp
-            t1 = nnls_tile_lanes<KP, XS_LD>(sM, p.k, xs, warp, lane, 8);
-            consumer_bar();
-        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[2] = gtimer();
-            // (c) write-back and statistics, one thread per unit
-            if (tid < TILE_UNITS) {
-                double x[KP];
-#pragma unroll
-                for (int c = 0; c < KP; ++c) x[c] = (c < p.k) ? xs[c * XS_LD + tid] : 0.0;
-#pragma unroll
-                for (int c = 0; c < KP; ++c) {
-                    if (c < p.k) {
-                        const size_t off = (size_t)c * p.ldout + unit;
-                        if (valid) {
-                            const double o = p.Fold[off];
-                            d2 += (x[c] - o) * (x[c] - o);
-                            if (x[c] != 0.0) nz |= (1ull << c);
-                        }
-                        p.Fout[off] = x[c];
-                    }
-                }
-                if (WSTEP && valid) {
-#pragma unroll
-                    for (int c = 0; c < KP; ++c) {
-                        double gx = 0.0;
-#pragma unroll
-                        for (int j = 0; j < KP; ++j) gx += sG[c * KP + j] * x[j];
-                        t2 += x[c] * gx;
-                    }
-                }
-            }
-        } else {
-            if (tid < TILE_UNITS) {
-                double r[KP], x[KP];
-#pragma unroll
-                for (int c = 0; c < KP; ++c) r[c] = 0.0;
-                for (int s = 0; s < expected; ++s) {
-                    const double *Ps = p.P + ((size_t)tile * p.maxslots + s) * (size_t)(KP * TILE_UNITS) + tid;
-#pragma unroll
-                    for (int c = 0; c < KP; ++c)
-                        if (c < p.k) r[c] += ldcg(Ps + (size_t)c * TILE_UNITS);
-                }
-#pragma unroll
-                for (int c = 0; c < KP; ++c) x[c] = 0.0;
-                if (valid) nnls_thread<KP>(sG, sM, p.k, r, x);
-#pragma unroll
-                for (int c = 0; c < KP; ++c) {
-                    if (c < p.k) {
-                        const size_t off = (size_t)c * p.ldout + unit;
-                        if (valid) {
-                            const double o = p.Fold[off];
-                            d2 += (x[c] - o) * (x[c] - o);
-                            if (x[c] != 0.0) nz |= (1ull << c);
-                        }
-                        p.Fout[off] = x[c];
-                        xs[c * XS_LD + tid] = x[c];
-                    }
-                }
-                if (WSTEP && valid) {
-                    for (int c = 0; c < p.k; ++c) {
-                        t1 += x[c] * r[c];
-                        double gx = 0.0;
-                        for (int j = 0; j < p.k; ++j) gx += sG[c * KP + j] * x[j];
-                        t2 += x[c] * gx;
-                    }
-                }
-            }
-        }
-        // block reduction of the scalars
-        d2 = warp_sum(d2);
-        t1 = warp_sum(t1);
-        t2 = warp_sum(t2);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nz |= __shfl_xor_sync(0xffffffffu, nz, o);
-        if (lane == 0) {
-            sred[warp * 3 + 0] = d2;
-            sred[warp * 3 + 1] = t1;
-            sred[warp * 3 + 2] = t2;
-            ((unsigned long long *)(sred + 24))[warp] = nz;
-        }
-        consumer_bar();
-        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[3] = gtimer();
-        // Gram partial of the produced factor over this tile's units
-        for (int e = tid; e < p.k * p.k; e += ALS_CONSUMERS) {
-            const int c1 = e / p.k, c2 = e - c1 * p.k;
-            double s = 0.0;
-            for (int uu = 0; uu < TILE_UNITS; ++uu) s += xs[c1 * XS_LD + uu] * xs[c2 * XS_LD + uu];
-            p.gpart[(size_t)tile * (KP * KP) + c1 * KP + c2] = s;
-        }
-        if (tid == 0) {
-            double a = 0, b = 0, c = 0;
-            unsigned long long m = 0;
-            for (int w = 0; w < 8; ++w) {
-                a += sred[w * 3 + 0];
-                b += sred[w * 3 + 1];
-                c += sred[w * 3 + 2];
-                m |= ((unsigned long long *)(sred + 24))[w];
-            }
-            p.spart[tile * 4 + 0] = a;
-            p.spart[tile * 4 + 1] = b;
-            p.spart[tile * 4 + 2] = c;
-            if (!WSTEP) atomicOr(&p.ctrl->nzmask, m);
-        }
-        __threadfence();
-        consumer_bar();
-        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[4] = gtimer();
-        if (tid == 0) {
-            int prev = atomicAdd(&p.ctrl->tiles_done[WSTEP ? 1 : 0], 1);
-            sflag[1] = (prev == p.T - 1);
-        }
-        consumer_bar();
-        if ((p.debug & 16) && tid == 0 && tile == 3) g_dbg_marks[5] = gtimer();
-        if (!sflag[1]) return;
-        __threadfence();
+// ---------------------------------------------------------------------------
+// the solve kernel: second launch of a half-step
+// ---------------------------------------------------------------------------
+// Every CTA owns SU consecutive units (columns of H / rows of W): it sums the stream-K partials of its units
+// in slot order (deterministic), solves the SU exact NNLS problems (one round of the lane-distributed
+// principal-pivoting solver per warp: 2500 / 10000 warps in flight at 20000 x 5000 instead of the 8 per SM a
+// fused tile epilogue could use), writes the factor and leaves per-CTA partials of the iteration scalars
+// and of the Gram matrix of the factor just produced.  Partials are folded in two levels, each in a fixed
+// order: the last CTA of a group of SOLVE_GROUP CTAs sums the group, the last group sums the groups, inverts the
+// k x k Gram (one warp, rows in registers) for the next half-step and updates the control block.
+#define SOLVE_THREADS 256
+#define SOLVE_GROUP 32
 
-        // ---------------- launch finalisation (one CTA, once per half-step) ----------------
-        if ((p.debug & 16) && tid == 0) g_nnls_marks[8] = gtimer();
-        // Gram of the new factor: sum the per-tile partials with eight independent chains per entry (fixed
-        // association, so the result does not depend on which CTA runs this)
-        for (int e = tid; e < KP * KP; e += ALS_CONSUMERS) {
-            const int c1 = e / KP, c2 = e - c1 * KP;
-            double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (c1 < p.k && c2 < p.k) {
-                for (int t0 = 0; t0 < p.T; t0 += 8) {
+template <int KB>
+struct SolveCfg {
+    static constexpr int KP = KB * 8;
+    static constexpr bool LANES = KP <= 32;
+    static constexpr int LP = (KP <= 16) ? 16 : 32;
+    static constexpr int SU = LANES ? 8 * (32 / LP) : 64;      // units per CTA
+    static constexpr int XS = SU + 1;
+    static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + 48) * sizeof(double) + 16;
+};
+
+template <int KB, bool WSTEP>
+__global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfParams p) {
+    using Cfg = SolveCfg<KB>;
+    constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS;
+    if (*(volatile int *)&p.ctrl->stop) return;
+    extern __shared__ __align__(16) unsigned char solve_smem[];
+    double *sG = (double *)solve_smem;
+    double *sM = sG + KP * KP;
+    double *xs = sM + KP * KP;
+    double *sred = xs + KP * XS;            // 48 doubles
+    int *sflag = (int *)(sred + 48);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = p.k;
+
+    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
+        sG[e] = p.G[e];
+        sM[e] = p.Minv[e];
+    }
+    const long long unit0 = (long long)blockIdx.x * SU;
+    const int tile = (int)(unit0 / TILE_UNITS), uoff = (int)(unit0 - (long long)tile * TILE_UNITS);
+    const int nvalid_local = (int)((p.nvalid - unit0 < SU) ? (p.nvalid - unit0) : SU);
+    // number of partial slots the stream kernel filled for this tile (see its flush())
+    int expected;
+    {
+        const long long tb = (long long)tile * p.SPT;
+        if (p.U >= p.Gstream)
+            expected = 2 * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
+        else
+            expected = 2 * p.SPT;
+    }
+    // (a) right-hand sides: sum the partials in slot order
+    for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
+        const int u = e % SU, c = e / SU;
+        double r = 0.0;
+        if (c < k && u < nvalid_local) {
+            const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + uoff + u;
+#pragma unroll 4
+            for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
+        }
+        xs[c * XS + u] = r;
+    }
+    __syncthreads();
+    // (b) exact NNLS
+    double t1 = 0.0;
+    if constexpr (Cfg::LANES) {
+        constexpr int UPW = SU / (SOLVE_THREADS / 32);
+        t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane);
+    } else {
+        if (tid < SU) {
+            double r[KP], x[KP];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (t0 + j < p.T) a8[j] += ldcg(&p.gpart[(size_t)(t0 + j) * (KP * KP) + e]);
+            for (int c = 0; c < KP; ++c) { r[c] = (c < k) ? xs[c * XS + tid] : 0.0; x[c] = 0.0; }
+            if (tid < nvalid_local) nnls_thread<KP>(sG, sM, k, r, x);
+            for (int c = 0; c < k; ++c) { t1 += x[c] * r[c]; xs[c * XS + tid] = x[c]; }
+        }
+    }
+    __syncthreads();
+    // (c) write-back and statistics
+    double d2 = 0.0, t2 = 0.0;
+    unsigned long long nz = 0ull;
+    for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
+        const int u = e % SU, c = e / SU;
+        if (c < k) {
+            const double x = xs[c * XS + u];
+            const size_t off = (size_t)c * p.ldout + (size_t)(unit0 + u);
+            if (u < nvalid_local) {
+                const double o = p.Fold[off];
+                d2 += (x - o) * (x - o);
+                if (x != 0.0) nz |= (1ull << c);
+                if (WSTEP) {
+                    double gx = 0.0;
+                    for (int j = 0; j < k; ++j) gx += sG[c * KP + j] * xs[j * XS + u];
+                    t2 += x * gx;
                 }
             }
-            const double s = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-            sG[e] = s;
-            p.Gout[e] = s;
+            p.Fout[off] = x;
         }
-        // iteration scalars: warp 0 sums the per-tile partials, lane = tile mod 32, then a fixed butterfly
+    }
+    d2 = warp_sum(d2);
+    t1 = warp_sum(t1);
+    t2 = warp_sum(t2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nz |= __shfl_xor_sync(0xffffffffu, nz, o);
+    if (lane == 0) {
+        sred[warp * 3 + 0] = d2;
+        sred[warp * 3 + 1] = t1;
+        sred[warp * 3 + 2] = t2;
+        ((unsigned long long *)(sred + 24))[warp] = nz;
+    }
+    // Gram partial of the produced factor over this CTA's units
+    for (int e = tid; e < k * k; e += SOLVE_THREADS) {
+        const int c1 = e / k, c2 = e - c1 * k;
+        double s = 0.0;
+#pragma unroll 8
+        for (int uu = 0; uu < SU; ++uu) s += xs[c1 * XS + uu] * xs[c2 * XS + uu];
+        p.gpart[(size_t)blockIdx.x * (KP * KP) + c1 * KP + c2] = s;
+    }
+    __syncthreads();
+    const int grp = (int)blockIdx.x / SOLVE_GROUP;
+    if (tid == 0) {
+        double a = 0, b = 0, c = 0;
+        unsigned long long m = 0;
+        for (int w = 0; w < SOLVE_THREADS / 32; ++w) {
+            a += sred[w * 3 + 0];
+            b += sred[w * 3 + 1];
+            c += sred[w * 3 + 2];
+            m |= ((unsigned long long *)(sred + 24))[w];
+        }
+        p.spart[(size_t)blockIdx.x * 4 + 0] = a;
+        p.spart[(size_t)blockIdx.x * 4 + 1] = b;
+        p.spart[(size_t)blockIdx.x * 4 + 2] = c;
+        if (!WSTEP) atomicOr(&p.ctrl->nzmask, m);
+    }
+    __threadfence();
+    __syncthreads();
+    const int ngroups = ((int)gridDim.x + SOLVE_GROUP - 1) / SOLVE_GROUP;
+    const int gfirst = grp * SOLVE_GROUP;
+    const int gsize = ((int)gridDim.x - gfirst < SOLVE_GROUP) ? (int)gridDim.x - gfirst : SOLVE_GROUP;
+    if (tid == 0) {
+        const int prev = atomicAdd(&p.group_counter[grp], 1);
+        const int lastone = (prev == gsize - 1);
+        if (lastone) p.group_counter[grp] = 0;
+        sflag[0] = lastone;
+    }
+    __syncthreads();
+    if (!sflag[0]) return;
+    __threadfence();
+    // ---- level 1: fold this group's CTA partials (fixed order) ----
+    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        double s = 0.0;
+        if (c1 < k && c2 < k) {
+#pragma unroll 8
+            for (int b = 0; b < gsize; ++b) s += ldcg(&p.gpart[(size_t)(gfirst + b) * (KP * KP) + e]);
+        }
+        p.gpart2[(size_t)grp * (KP * KP) + e] = s;
+    }
+    if (tid < 3) {
+        double s = 0.0;
+        for (int b = 0; b < gsize; ++b) s += ldcg(&p.spart[(size_t)(gfirst + b) * 4 + tid]);
+        p.spart2[(size_t)grp * 4 + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int prev = atomicAdd(&p.ctrl->groups_done[WSTEP ? 1 : 0], 1);
+        sflag[1] = (prev == ngroups - 1);
+    }
+    __syncthreads();
+    if (!sflag[1]) return;
+    __threadfence();
+    // ---- level 2 (one CTA, once per half-step): Gram of the new factor, its inverse, iteration scalars ----
+    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        double s = 0.0;
+        if (c1 < k && c2 < k) {
+#pragma unroll 8
+            for (int g = 0; g < ngroups; ++g) s += ldcg(&p.gpart2[(size_t)g * (KP * KP) + e]);
+        }
+        sG[e] = s;
+        p.Gout[e] = s;
+    }
+    if (tid < 3) {
+        double s = 0.0;
+        for (int g = 0; g < ngroups; ++g) s += ldcg(&p.spart2[(size_t)g * 4 + tid]);
+        sred[32 + tid] = s;
+    }
+    __syncthreads();
+    int sing;
+    if constexpr (KP <= 32) {
         if (warp == 0) {
-            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-            for (int tt = lane; tt < p.T; tt += 32) {
-                v0 += ldcg(&p.spart[tt * 4 + 0]);
-                v1 += ldcg(&p.spart[tt * 4 + 1]);
-                v2 += ldcg(&p.spart[tt * 4 + 2]);
+            const int sg = warp_gauss_jordan_inverse<KP>(sG, k, KP, lane);
+            if (lane == 0) sflag[1] = sg;
+        }
+        __syncthreads();
+        sing = sflag[1];
+    } else {
+        sing = gauss_jordan_inverse(sG, k, KP, tid, SOLVE_THREADS, sred + 36, [] { __syncthreads(); });
+    }
+    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        p.Minvout[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
+    }
+    if (tid == 0) {
+        AlsCtrl *c = p.ctrl;
+        const double sd2 = sred[32], st1 = sred[33], st2 = sred[34];
+        c->groups_done[WSTEP ? 1 : 0] = 0;
+        if (!WSTEP) {
+            c->dH2 = sd2;
+            const unsigned long long fullm = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
+            const unsigned long long m = c->nzmask;
+            c->nzmask = 0ull;
+            if ((m & fullm) != fullm) { c->stop = 1; c->reason = 2; }
+            else if (sing) { c->stop = 1; c->reason = 4; }
+        } else {
+            double r2 = (c->normA2 - 2.0 * st1 + st2) / c->mn;
+            const double resid = sqrt(r2 > 0.0 ? r2 : 0.0);
+            const double dW = sqrt(sd2 / c->mk);
+            const double dH = sqrt(c->dH2 / c->kn);
+            const int it = c->iters_done;
+            if (it < c->max_trace) {
+                p.trace[it * 3 + 0] = resid;
+                p.trace[it * 3 + 1] = dW;
+                p.trace[it * 3 + 2] = dH;
             }
-            v0 = warp_sum(v0);
-            v1 = warp_sum(v1);
-            v2 = warp_sum(v2);
-            if (lane == 0) { sred[32] = v0; sred[33] = v1; sred[34] = v2; }
-        }
-        consumer_bar();
-        if ((p.debug & 16) && tid == 0) g_nnls_marks[9] = gtimer();
-        const int sing = gauss_jordan_inverse(sG, p.k, KP, tid, ALS_CONSUMERS, sred, [] { consumer_bar(); });
-        if ((p.debug & 16) && tid == 0) g_nnls_marks[10] = gtimer();
-        for (int e = tid; e < KP * KP; e += ALS_CONSUMERS) {
-            const int c1 = e / KP, c2 = e - c1 * KP;
-            p.Minvout[e] = (c1 < p.k && c2 < p.k) ? sG[e] : 0.0;
-        }
-        if (tid == 0) {
-            AlsCtrl *c = p.ctrl;
-            const double sd2 = sred[32], st1 = sred[33], st2 = sred[34];
-            c->tiles_done[WSTEP ? 1 : 0] = 0;
-            if (!WSTEP) {
-                c->dH2 = sd2;
-                const unsigned long long fullm = (p.k >= 64) ? ~0ull : ((1ull << p.k) - 1ull);
-                const unsigned long long m = c->nzmask;
-                c->nzmask = 0ull;
-                if ((m & fullm) != fullm) { c->stop = 1; c->reason = 2; }
-                else if (sing) { c->stop = 1; c->reason = 4; }
+            c->resid = resid;
+            c->dW = dW;
+            c->dH = dH;
+            c->iters_done = it + 1;
+            if (!c->fixed && (fabs(c->resid_old - resid) <= c->eps || (dW <= c->eps && dH <= c->eps))) {
+                c->stop = 1;
+                c->reason = 1;
             } else {
-                double r2 = (c->normA2 - 2.0 * st1 + st2) / c->mn;
-                const double resid = sqrt(r2 > 0.0 ? r2 : 0.0);
-                const double dW = sqrt(sd2 / c->mk);
-                const double dH = sqrt(c->dH2 / c->kn);
-                const int it = c->iters_done;
-                if (it < c->max_trace) {
-                    p.trace[it * 3 + 0] = resid;
-                    p.trace[it * 3 + 1] = dW;
-                    p.trace[it * 3 + 2] = dH;
-                }
-                c->resid = resid;
-                c->dW = dW;
-                c->dH = dH;
-                c->iters_done = it + 1;
-                if (!c->fixed && (fabs(c->resid_old - resid) <= c->eps || (dW <= c->eps && dH <= c->eps))) {
-                    c->stop = 1;
-                    c->reason = 1;
-                } else {
-                    c->resid_old = resid;
-                    if (sing) { c->stop = 1; c->reason = 3; }
-                }
+                c->resid_old = resid;
+                if (sing) { c->stop = 1; c->reason = 3; }
             }
-            __threadfence();
-            if (p.debug & 16) g_nnls_marks[11] = gtimer();
         }
+        __threadfence();
+    }
 }
 
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(ALS_THREADS, 1)
-als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmF, const HalfParams p,
-                const int nstage) {
+als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmF, const HalfParams p,
+                  const int nstage) {
     constexpr int KP = KB * 8;
     constexpr int A_BYTES = WSTEP ? 32768 : 16384;       // A box(es) of one stage
     constexpr int F_BOX = KP * 128;                      // one 16-unit box of the fixed factor: [KP][16] doubles
@@ -391,15 +402,10 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (*(volatile int *)&p.ctrl->stop) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: ring | barriers | G | Minv | xs | misc
+    // carve: ring | barriers
     unsigned char *ring = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = (uint64_t *)(ring + (size_t)nstage * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + nstage;
-    double *sG = (double *)(empty_bar + nstage);
-    double *sM = sG + KP * KP;
-    double *xs = sM + KP * KP;
-    double *sred = xs + KP * XS_LD;          // 40 doubles of reduction scratch
-    int *sflag = (int *)(sred + 40);
     const uint32_t ring_s = smem_u32(ring);
 
     const int tid = threadIdx.x;
@@ -416,13 +422,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // Gram of the fixed factor and its inverse (for the epilogues of this CTA)
-    for (int e = tid; e < KP * KP; e += ALS_THREADS) {
-        sG[e] = p.G[e];
-        sM[e] = p.Minv[e];
-    }
     __syncthreads();
-    if ((p.debug & 16) && tid == 0) g_dbg_times[blockIdx.x * 8 + 0] = gtimer();
     if (u0 >= u1) return;
     const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
     const int nunits = (int)(u1 - u0);
@@ -442,13 +442,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_load_2d(dst + A_BYTES, &tmF, st * 16, 0, &full_bar[stage]);
                 } else {
                     // one 3-D box {16 rows, 32 columns, 8 row groups}: lands as [row group][column][16 rows]
-                    if (p.debug & 2) {
-#pragma unroll
-                        for (int rg = 0; rg < 8; ++rg)
-                            tma_load_2d(dst + rg * 4096, &tmA, tile * TILE_UNITS + rg * 16, st * 32, &full_bar[stage]);
-                    } else {
-                        tma_load_3d(dst, &tmA, 0, st * 32, tile * 8, &full_bar[stage]);
-                    }
+                    tma_load_3d(dst, &tmA, 0, st * 32, tile * 8, &full_bar[stage]);
                     tma_load_2d(dst + A_BYTES, &tmF, st * 32, 0, &full_bar[stage]);
                     tma_load_2d(dst + A_BYTES + F_BOX, &tmF, st * 32 + 16, 0, &full_bar[stage]);
                 }
@@ -474,16 +468,11 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     auto flush = [&](int tile) {
         const long long tb = (long long)tile * p.SPT;
-        int expected, slot;
-        if (p.U >= G) {          // every CTA owns >= 1 unit: contributors to a tile are contiguous CTAs
-            const int first = cta_of_unit(tb, p.U, G);
-            const int last = cta_of_unit(tb + p.SPT - 1, p.U, G);
-            expected = last - first + 1;                       // CTAs contributing to this tile
-            slot = NG * ((int)blockIdx.x - first) + grp;       // one partial per consumer group of each CTA
-        } else {                 // fewer units than CTAs: each non-empty CTA owns exactly one unit
-            expected = p.SPT;
+        int slot;
+        if (p.U >= G)            // every CTA owns >= 1 unit: contributors to a tile are contiguous CTAs
+            slot = NG * ((int)blockIdx.x - cta_of_unit(tb, p.U, G)) + grp;   // one partial per consumer group of each CTA
+        else                     // fewer units than CTAs: each non-empty CTA owns exactly one unit
             slot = NG * (int)(u0 - tb) + grp;
-        }
         double *Pb = p.P + ((size_t)tile * p.maxslots + slot) * (size_t)(KP * TILE_UNITS);
 #pragma unroll
         for (int cb = 0; cb < KB; ++cb) {
@@ -505,20 +494,6 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int a = 0; a < 4; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
         }
-        __threadfence();
-        consumer_bar();
-        if (tid == 0) {
-            int prev = atomicAdd(&p.tile_counter[tile], 1);
-            int lastone = (prev == expected - 1);
-            if (lastone) p.tile_counter[tile] = 0;
-            sflag[0] = lastone;
-        }
-        consumer_bar();
-        if (!sflag[0]) return;
-        __threadfence();
-        if (p.debug & 1) return;
-
-        tile_epilogue<KB, WSTEP>(p, tile, NG * expected, sG, sM, xs, sred, sflag);
     };
 
     // Main loop.  One stage = one unit: an A box plus the matching 16- (H-step) or 32-wide (W-step) slab of
@@ -543,10 +518,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if ((it % NG) == grp) {
             const uint32_t sb = ring_s + (uint32_t)stage * STAGE_BYTES;
             mbar_wait(&full_bar[stage], phase, 2, it, stage);
-            if (p.debug & 4) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[stage]);
-            } else if (!WSTEP) {
+            if (!WSTEP) {
                 // m8n8k4: A-operand = W fragment [M = rank 8cb+g][K = row 4t+s], B-operand = A fragment [K = row 4t+s][N = column g]
                 double2 b[4][2], f[KB][2];
 #pragma unroll
@@ -612,11 +584,7 @@ als_half_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (stage >= nst_r) { stage -= nst_r; phase ^= 1; }
         }
         const bool last_of_tile = (st + 1 == spt_r) || (it + 1 == nunits);
-        if (last_of_tile && !(p.debug & 8)) {
-            if ((p.debug & 16) && tid == 0) { if (it + 1 == nunits) g_dbg_times[blockIdx.x * 8 + 2] = gtimer(); else g_dbg_times[blockIdx.x * 8 + 1] = gtimer(); }
-            flush(tile);
-            if ((p.debug & 16) && tid == 0) { if (it + 1 == nunits) g_dbg_times[blockIdx.x * 8 + 4] = gtimer(); else g_dbg_times[blockIdx.x * 8 + 3] = gtimer(); }
-        }
+        if (last_of_tile) flush(tile);
         if (++st == spt_r) { st = 0; ++tile; }
     }
 }
@@ -737,14 +705,17 @@ struct mfb_als {
     int64_t m, n, ldw, ldh;
     double *Wb[2], *Wr, *Hb[2];          // factor buffers [KP][ld]
     double *G_W, *Minv_W, *G_H, *Minv_H; // Grams (+ inverses)
-    double *P_h, *P_w, *gpart, *spart;
+    double *P_h, *P_w, *gpart, *spart, *gpart2, *spart2;
     int *counters;
+    int nsolve_h, nsolve_w;       // solve-kernel grids
+    bool attr_set = false;
+    std::vector<cudaEvent_t> *prof = nullptr;   // mfb_als_profile: one event after every kernel
     AlsCtrl *ctrl;
     double *trace_dev;
     int maxslots_h, maxslots_w, T_h, T_w, SPT_h, SPT_w;
     int nstage_h, nstage_w;
     size_t smem_h, smem_w;
-    CUtensorMap tm_h, tm_w, tm_w2d;
+    CUtensorMap tm_h, tm_w;
     CUtensorMap tm_W[3], tm_H[2];   // factor slabs: Wb[0], Wb[1], Wr / Hb[0], Hb[1]
     int cur;              // index of the buffer holding the last accepted W / H
     bool restart_pending; // next H-step reads Wr instead of Wb[cur]
@@ -805,19 +776,64 @@ static int encode_map_rowgroups(CUtensorMap *tm, double *base, int64_t cols, int
     return MFB_OK;
 }
 
+#define MFB_TRY(expr) do { int _r = (expr); if (_r != MFB_OK) return _r; } while (0)
+
+static int prof_mark(mfb_als *s) {
+    if (!s->prof) return MFB_OK;
+    cudaEvent_t e;
+    MFB_CUDA(cudaEventCreate(&e));
+    MFB_CUDA(cudaEventRecord(e, s->ctx->stream));
+    s->prof->push_back(e);
+    return MFB_OK;
+}
+
 template <int KB>
 static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
     cudaStream_t st = s->ctx->stream;
-    const int G = s->ctx->sm_count;
+    const int G = hp.Gstream;
+    const int nsolve = wstep ? s->nsolve_w : s->nsolve_h;
     if (wstep) {
-        MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
-        als_half_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>((hp.debug & 2) ? s->tm_w2d : s->tm_w, tmF, hp, s->nstage_w);
+        if (!s->attr_set) {
+            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
+            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
+            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+            s->attr_set = true;
+        }
+        als_stream_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>(s->tm_w, tmF, hp, s->nstage_w);
+        MFB_TRY(prof_mark(s));
+        als_solve_kernel<KB, true><<<nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st>>>(hp);
+        MFB_TRY(prof_mark(s));
     } else {
-        MFB_CUDA(cudaFuncSetAttribute(als_half_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
-        als_half_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, tmF, hp, s->nstage_h);
+        if (!s->attr_set) {
+            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
+            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
+            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+            s->attr_set = true;
+        }
+        als_stream_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, tmF, hp, s->nstage_h);
+        MFB_TRY(prof_mark(s));
+        als_solve_kernel<KB, false><<<nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st>>>(hp);
+        MFB_TRY(prof_mark(s));
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
+}
+
+template <int KB>
+static int solve_units(void) { return SolveCfg<KB>::SU; }
+
+static int solve_units_dispatch(int KB) {
+    switch (KB) {
+        case 1: return solve_units<1>();
+        case 2: return solve_units<2>();
+        case 3: return solve_units<3>();
+        case 4: return solve_units<4>();
+        case 6: return solve_units<6>();
+        case 8: return solve_units<8>();
+    }
+    return 0;
 }
 
 static int check_mbar_abort(const char *where) {
@@ -868,8 +884,6 @@ static int dev_alloc(mfb_als *s, T **p, size_t count, bool zero = true) {
     if (zero) MFB_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), s->ctx->stream));
     return MFB_OK;
 }
-
-#define MFB_TRY(expr) do { int _r = (expr); if (_r != MFB_OK) return _r; } while (0)
 
 extern "C" {
 
@@ -933,8 +947,7 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->maxslots_h = 2 * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
     s->maxslots_w = 2 * max_slots(s->T_w, s->SPT_w, G);
     const size_t KP = s->KP;
-    const size_t epi = (2 * KP * KP + KP * XS_LD + 40 + 8) * sizeof(double);   // sred has 40 doubles
-    const size_t budget = 227 * 1024 - 1024 /*align*/ - epi - 2 * 16 * sizeof(uint64_t);
+    const size_t budget = 227 * 1024 - 1024 /*align*/ - 2 * 16 * sizeof(uint64_t);
     const size_t stage_h = 16384 + KP * 128, stage_w = 32768 + 2 * KP * 128;
     s->nstage_h = (int)(budget / stage_h); if (s->nstage_h > 12) s->nstage_h = 12;
     s->nstage_w = (int)(budget / stage_w); if (s->nstage_w > 6) s->nstage_w = 6;
@@ -948,8 +961,11 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
         mfb_set_error("rank %d leaves no shared memory for the streaming ring", k);
         return MFB_ERR_UNSUPPORTED;
     }
-    s->smem_h = 1024 + (size_t)s->nstage_h * stage_h + 2 * s->nstage_h * sizeof(uint64_t) + epi;
-    s->smem_w = 1024 + (size_t)s->nstage_w * stage_w + 2 * s->nstage_w * sizeof(uint64_t) + epi;
+    s->smem_h = 1024 + (size_t)s->nstage_h * stage_h + 2 * s->nstage_h * sizeof(uint64_t);
+    s->smem_w = 1024 + (size_t)s->nstage_w * stage_w + 2 * s->nstage_w * sizeof(uint64_t);
+    const int SU = solve_units_dispatch(s->KB);
+    s->nsolve_h = (int)((s->n + SU - 1) / SU);
+    s->nsolve_w = (int)((s->m + SU - 1) / SU);
 
     int rc;
 #define ALLOC(ptr, cnt) if ((rc = dev_alloc(s, &(ptr), (cnt))) != MFB_OK) { mfb_als_end(s); return rc; }
@@ -958,9 +974,11 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     ALLOC(s->G_W, KP * KP) ALLOC(s->Minv_W, KP * KP) ALLOC(s->G_H, KP * KP) ALLOC(s->Minv_H, KP * KP)
     ALLOC(s->P_h, (size_t)s->T_h * s->maxslots_h * KP * TILE_UNITS)
     ALLOC(s->P_w, (size_t)s->T_w * s->maxslots_w * KP * TILE_UNITS)
-    const size_t Tmax = (size_t)(s->T_h > s->T_w ? s->T_h : s->T_w);
-    ALLOC(s->gpart, Tmax * KP * KP) ALLOC(s->spart, Tmax * 4)
-    ALLOC(s->counters, Tmax * 2)
+    const size_t Smax = (size_t)(s->nsolve_h > s->nsolve_w ? s->nsolve_h : s->nsolve_w);
+    const size_t Gmax = (Smax + SOLVE_GROUP - 1) / SOLVE_GROUP;
+    ALLOC(s->gpart, Smax * KP * KP) ALLOC(s->spart, Smax * 4)
+    ALLOC(s->gpart2, Gmax * KP * KP) ALLOC(s->spart2, Gmax * 4)
+    ALLOC(s->counters, Gmax)
     ALLOC(s->ctrl, 1)
     s->max_trace = 4096;
     ALLOC(s->trace_dev, (size_t)s->max_trace * 3)
@@ -969,8 +987,7 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
 #undef ALLOC
     // tensor maps over A: dims {m rows (contiguous), n cols}
     if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, 16, 128)) != MFB_OK ||
-        (rc = encode_map_rowgroups(&s->tm_w, A->d, A->n, A->lda)) != MFB_OK ||
-        (rc = encode_map(&s->tm_w2d, A->d, A->m, A->n, A->lda, 16, 32)) != MFB_OK) {
+        (rc = encode_map_rowgroups(&s->tm_w, A->d, A->n, A->lda)) != MFB_OK) {
         mfb_als_end(s);
         return rc;
     }
@@ -1022,9 +1039,11 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.Fin = use_restart_w ? s->Wr : s->Wb[cur]; h.ldin = s->ldw;
     h.Fout = s->Hb[nxt]; h.Fold = s->Hb[cur]; h.ldout = s->ldh;
     h.G = s->G_W; h.Minv = s->Minv_W; h.Gout = s->G_H; h.Minvout = s->Minv_H;
-    h.P = s->P_h; h.maxslots = s->maxslots_h; h.tile_counter = s->counters;
-    h.gpart = s->gpart; h.spart = s->spart; h.ctrl = s->ctrl; h.trace = s->trace_dev;
+    h.P = s->P_h; h.maxslots = s->maxslots_h; h.group_counter = s->counters;
+    h.gpart = s->gpart; h.spart = s->spart; h.gpart2 = s->gpart2; h.spart2 = s->spart2;
+    h.ctrl = s->ctrl; h.trace = s->trace_dev;
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
+    h.Gstream = s->ctx->sm_count;
     MFB_TRY(launch_half_dispatch(s, false, h, use_restart_w ? s->tm_W[2] : s->tm_W[cur]));
     HalfParams w = h;
     w.Fin = s->Hb[nxt]; w.ldin = s->ldh;
@@ -1051,7 +1070,7 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
         MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
         MFB_CUDA(cudaStreamSynchronize(st));
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = fixed_iters ? 1 : 0; hc->eps = eps_conv;
-        hc->tiles_done[0] = hc->tiles_done[1] = 0; hc->nzmask = 0ull;
+        hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
         if (batch > s->max_trace) { mfb_set_error("too many iterations in one batch"); return MFB_ERR_ARG; }
         MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
         int cur = s->cur;
@@ -1093,51 +1112,31 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
     return status;
 }
 
-// development aid (not in the public header): relaunch one half-step `count` times on unchanged inputs
-int mfb_als_debug_repeat(mfb_als *s, int which, int count) {
-    const int dbg = which >> 4;
-    which &= 15;
+int mfb_als_profile(mfb_als *s, int iters, double ms[4]) {
+    MFB_ARG(s && ms && iters >= 1, "bad argument");
     MFB_CUDA(cudaSetDevice(s->ctx->device));
-    cudaStream_t st = s->ctx->stream;
-    AlsCtrl *hc = (AlsCtrl *)s->ctx->pinned;
-    for (int i = 0; i < count; ++i) {
-        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
-        hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = 1; hc->eps = 1e-4;
-        hc->tiles_done[0] = hc->tiles_done[1] = 0; hc->nzmask = 0ull;
-        MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
-        HalfParams h;
-        memset(&h, 0, sizeof(h));
-        const int cur = s->cur, nxt = cur ^ 1;
-        h.Fin = s->Wb[cur]; h.ldin = s->ldw;
-        h.Fout = s->Hb[nxt]; h.Fold = s->Hb[cur]; h.ldout = s->ldh;
-        h.G = s->G_W; h.Minv = s->Minv_W; h.Gout = s->G_H; h.Minvout = s->Minv_H;
-        h.P = s->P_h; h.maxslots = s->maxslots_h; h.tile_counter = s->counters;
-        h.gpart = s->gpart; h.spart = s->spart; h.ctrl = s->ctrl; h.trace = s->trace_dev;
-        h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
-        h.debug = dbg;
-        if (which == 0) {
-            MFB_TRY(launch_half_dispatch(s, false, h, s->tm_W[cur]));
-        } else {
-            HalfParams w = h;
-            w.Fin = s->Hb[cur]; w.ldin = s->ldh;
-            w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
-            w.G = s->G_H; w.Minv = s->Minv_H; w.Gout = s->gram_scratch; w.Minvout = s->gram_scratch + 4096;
-            w.P = s->P_w; w.maxslots = s->maxslots_w;
-            w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
-            MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[cur]));
-        }
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { mfb_set_error("debug repeat %d of kind %d failed: %s", i, which, cudaGetErrorString(e)); return MFB_ERR_CUDA; }
-        MFB_TRY(check_mbar_abort("debug repeat"));
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t e0;
+    MFB_CUDA(cudaEventCreate(&e0));
+    MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    MFB_CUDA(cudaEventRecord(e0, s->ctx->stream));
+    ev.push_back(e0);
+    s->prof = &ev;
+    int it = 0, conv = 0;
+    const int rc = mfb_als_iterate(s, iters, 1e-4, 1, &it, &conv);
+    s->prof = nullptr;
+    MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    double acc[4] = {0, 0, 0, 0};
+    const size_t nk = ev.size() - 1;
+    for (size_t i = 0; i < nk; ++i) {
+        float t = 0.f;
+        MFB_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        acc[i & 3] += t;
     }
-    return MFB_OK;
-}
-
-int mfb_als_debug_times(unsigned long long *out) {
-    MFB_CUDA(cudaMemcpyFromSymbol(out, g_dbg_times, sizeof(unsigned long long) * 148 * 8));
-    MFB_CUDA(cudaMemcpyFromSymbol(out + 148 * 8, g_dbg_marks, sizeof(unsigned long long) * 8));
-    MFB_CUDA(cudaMemcpyFromSymbol(out + 148 * 8 + 8, g_nnls_marks, sizeof(unsigned long long) * 16));
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (rc != MFB_OK) return rc;
+    if (nk != (size_t)4 * iters) { mfb_set_error("mfb_als_profile: expected %d kernel launches, saw %zu", 4 * iters, nk); return MFB_ERR_CUDA; }
+    for (int q = 0; q < 4; ++q) ms[q] = acc[q] / iters;
     return MFB_OK;
 }
 

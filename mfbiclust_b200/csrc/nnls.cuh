@@ -191,7 +191,53 @@ __device__ int nnls_thread(const double *__restrict__ G, const double *__restric
 
 
 // ---------------------------------------------------------------------------
-// Warp-cooperative NNLS for a tile of 128 problems (rank padded to KP <= 32).
+// Warp-level in-place inversion of the SPD k x k matrix `a` (shared memory, ld, k <= 32): lane i owns row i in
+// registers, Gauss-Jordan without pivoting, pivot rows broadcast by shuffles (no barriers).  Same acceptance rule
+// as gauss_jordan_inverse.  Must be called by one full warp; returns 1 (to all lanes) if singular.
+// ---------------------------------------------------------------------------
+template <int KP>
+__device__ int warp_gauss_jordan_inverse(double *a, int k, int ld, int lane) {
+    static_assert(KP <= 32, "one lane per row");
+    const unsigned FULL = 0xffffffffu;
+    double r[KP];
+    double an = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        r[j] = (lane < k && j < k) ? a[lane * ld + j] : ((lane == j) ? 1.0 : 0.0);   // identity padding
+        if (lane < k && j < k) an += fabs(r[j]);
+    }
+    an = warp_max(an);                       // 1-norm (symmetric: max absolute row sum)
+    int sing = 0;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+        if (p < k) {
+            double piv = __shfl_sync(FULL, r[p], p);
+            if (!(piv > 0.0) || !isfinite(piv)) { sing = 1; piv = 1.0; }
+            const double ipiv = 1.0 / piv;
+            const double f = r[p] * ipiv;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                const double rp = __shfl_sync(FULL, r[j], p);
+                if (j != p) r[j] = (lane == p) ? rp * ipiv : r[j] - f * rp;
+            }
+            r[p] = (lane == p) ? ipiv : -f;
+        }
+    }
+    double in = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        if (lane < k && j < k) {
+            in += fabs(r[j]);
+            a[lane * ld + j] = r[j];
+        }
+    }
+    in = warp_max(in);
+    if (!isfinite(in) || an * in * 2.220446049250313e-16 > 1.0) sing = 1;
+    return sing;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative NNLS (rank padded to KP <= 32).
 //
 // Same pivot rules as nnls_thread / one column of .fcnnls, but carried as a principal-pivoting
 // tableau  z_B = q + T z_NB  (basic variables: x_i on the passive set S, the gradient
@@ -201,25 +247,28 @@ __device__ int nnls_thread(const double *__restrict__ G, const double *__restric
 // for free after every pivot: no refactorisation, no local memory, no per-pivot division chain
 // beyond one reciprocal.  LP = 16 for KP <= 16 (two problems per warp), 32 otherwise.
 //
-// xs: shared [KP][XS] -- right-hand sides r on entry, solutions x on exit (column = problem).
+// xs: shared [KP][XS] -- right-hand sides r on entry, solutions x on exit (column = problem).  The warp solves
+// the problems [first, first + count) of xs, 32 / LP at a time; problems >= nvalid are skipped (x = 0).
 // sM: shared G^-1 (ld KP, symmetric).  Returns this lane's partial of sum_i x_i r_i.
 // ---------------------------------------------------------------------------
-__device__ unsigned long long g_nnls_marks[16];
-__device__ int g_mark_block = -1;
 template <int KP, int XS>
-__device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *xs, int warp, int lane, int nwarps) {
+__device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, int first, int count, int nvalid,
+                             int lane) {
     constexpr int LP = (KP <= 16) ? 16 : 32;
     constexpr int PPW = 32 / LP;
     const unsigned FULL = 0xffffffffu;
     const int sub = lane / LP, i = lane % LP, base = sub * LP;
     const bool rowvalid = i < k;
-    const int units_per_warp = 128 / nwarps;
     const unsigned gmask = (LP == 32) ? 0xffffffffu : (0xffffu << base);
     double t1 = 0.0;
-    for (int rd = 0; rd < units_per_warp / PPW; ++rd) {
-        if (threadIdx.x == 0 && (int)blockIdx.x == g_mark_block) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); g_nnls_marks[rd] = tt; }
-        const int unit = warp * units_per_warp + rd * PPW + sub;
-        const double ri = rowvalid ? xs[i * XS + unit] : 0.0;
+    for (int rd = 0; rd < count; rd += PPW) {
+        const int unit = first + rd + sub;
+        const bool uvalid = (rd + sub < count) && (unit < nvalid);
+        if (!__any_sync(FULL, uvalid)) {
+            if (rowvalid && rd + sub < count) xs[i * XS + unit] = 0.0;
+            continue;
+        }
+        const double ri = (rowvalid && uvalid) ? xs[i * XS + unit] : 0.0;
         double T[KP];
         double qv = 0.0;
 #pragma unroll
@@ -231,8 +280,9 @@ __device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *
         }
         bool inS = rowvalid;
         double dv = qv > 0.0 ? qv : 0.0;
-        unsigned pend = (__ballot_sync(FULL, rowvalid && !(qv > 0.0)) & gmask) >> base;
-        bool done = false;
+        const unsigned negs = __ballot_sync(FULL, rowvalid && !(qv > 0.0));
+        unsigned pend = uvalid ? ((negs & gmask) >> base) : 0u;
+        bool done = !uvalid;
         int iters = 0;
         const int cap = 6 * k + 16;
         while (true) {
@@ -281,33 +331,28 @@ __device__ double nnls_tile_lanes(const double *__restrict__ sM, int k, double *
             // exchange x_piv <-> w_piv (predicated per problem)
             const int pq = piv >= 0 ? piv : 0;
             const int src = base + pq;
-            double rowq[KP];
             double tiq = 0.0;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                rowq[j] = __shfl_sync(FULL, T[j], src);
-                tiq = (j == pq) ? T[j] : tiq;
-            }
+            for (int j = 0; j < KP; ++j) tiq = (j == pq) ? T[j] : tiq;
             const double qq = __shfl_sync(FULL, qv, src);
             const double pp = __shfl_sync(FULL, tiq, src);
-            if (piv >= 0) {
-                const double ip = 1.0 / pp;
-                if (i != piv) {
-                    const double f = tiq * ip;
-                    qv -= f * qq;
+            const double ip = 1.0 / pp;
+            const bool act = piv >= 0, isrow = act && (i == piv);
+            const double f = tiq * ip;
 #pragma unroll
-                    for (int j = 0; j < KP; ++j) T[j] = (j == piv) ? f : (T[j] - f * rowq[j]);
-                } else {
-                    qv = -qq * ip;
-#pragma unroll
-                    for (int j = 0; j < KP; ++j) T[j] = (j == piv) ? ip : (-rowq[j] * ip);
-                    inS = !inS;
-                }
+            for (int j = 0; j < KP; ++j) {
+                const double rq = __shfl_sync(FULL, T[j], src);
+                const double upd = (j == pq) ? (isrow ? ip : f) : (isrow ? -rq * ip : T[j] - f * rq);
+                T[j] = act ? upd : T[j];
+            }
+            if (act) {
+                qv = isrow ? -qq * ip : qv - f * qq;
+                if (isrow) inS = !inS;
             }
         }
-        const double x = (inS && rowvalid && qv > 0.0) ? qv : 0.0;
+        const double x = (inS && rowvalid && uvalid && qv > 0.0) ? qv : 0.0;
         t1 += x * ri;
-        if (rowvalid) xs[i * XS + unit] = x;
+        if (rowvalid && rd + sub < count) xs[i * XS + unit] = x;
     }
     return t1;
 }
