@@ -155,7 +155,10 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 // and of the Gram matrix of the factor just produced.  Partials are folded in two levels, each in a fixed
 // order: the last CTA of a group of SOLVE_GROUP CTAs sums the group, the last group sums the groups, inverts the
 // k x k Gram (one warp, rows in registers) for the next half-step and updates the control block.
+#ifndef SOLVE_THREADS
 #define SOLVE_THREADS 256
+#endif
+#define SOLVE_WARPS (SOLVE_THREADS / 32)
 #define SOLVE_GROUP 32
 
 template <int KB>
@@ -163,13 +166,14 @@ struct SolveCfg {
     static constexpr int KP = KB * 8;
     static constexpr bool LANES = KP <= 32;
     static constexpr int LP = (KP <= 16) ? 16 : 32;
-    static constexpr int SU = LANES ? 8 * (32 / LP) : 64;      // units per CTA
+    static constexpr int UPW = 2;                                // units per warp (lane path)
+    static constexpr int SU = LANES ? SOLVE_WARPS * UPW : 64;    // units per CTA
     static constexpr int XS = SU + 1;
     static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + 48) * sizeof(double) + 16;
 };
 
 template <int KB, bool WSTEP>
-__global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfParams p) {
+__global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : 1) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
     constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS;
     if (*(volatile int *)&p.ctrl->stop) return;
@@ -210,11 +214,33 @@ __global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfPara
         xs[c * XS + u] = r;
     }
     __syncthreads();
-    // (b) exact NNLS
-    double t1 = 0.0;
+    double t1 = 0.0, d2 = 0.0, t2 = 0.0;
+    unsigned long long nz = 0ull;
     if constexpr (Cfg::LANES) {
-        constexpr int UPW = SU / (SOLVE_THREADS / 32);
+        // (b) exact NNLS, (c) write-back and statistics: both warp-local (lane = (unit, rank) as in nnls_lanes)
+        constexpr int LP = Cfg::LP, UPW = Cfg::UPW;
         t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane);
+        __syncwarp();
+        const int i = lane % LP;
+        for (int uu = lane / LP; uu < UPW; uu += 32 / LP) {
+            const int u = warp * UPW + uu;
+            if (i < k) {
+                const double x = xs[i * XS + u];
+                const size_t off = (size_t)i * p.ldout + (size_t)(unit0 + u);
+                if (u < nvalid_local) {
+                    const double o = p.Fold[off];
+                    d2 += (x - o) * (x - o);
+                    if (x != 0.0) nz |= (1ull << i);
+                    if (WSTEP) {
+                        double gx = 0.0;
+#pragma unroll 4
+                        for (int j = 0; j < k; ++j) gx += sG[j * KP + i] * xs[j * XS + u];   // G symmetric: conflict-free
+                        t2 += x * gx;
+                    }
+                }
+                p.Fout[off] = x;
+            }
+        }
     } else {
         if (tid < SU) {
             double r[KP], x[KP];
@@ -223,27 +249,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfPara
             if (tid < nvalid_local) nnls_thread<KP>(sG, sM, k, r, x);
             for (int c = 0; c < k; ++c) { t1 += x[c] * r[c]; xs[c * XS + tid] = x[c]; }
         }
-    }
-    __syncthreads();
-    // (c) write-back and statistics
-    double d2 = 0.0, t2 = 0.0;
-    unsigned long long nz = 0ull;
-    for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
-        const int u = e % SU, c = e / SU;
-        if (c < k) {
-            const double x = xs[c * XS + u];
-            const size_t off = (size_t)c * p.ldout + (size_t)(unit0 + u);
-            if (u < nvalid_local) {
-                const double o = p.Fold[off];
-                d2 += (x - o) * (x - o);
-                if (x != 0.0) nz |= (1ull << c);
-                if (WSTEP) {
-                    double gx = 0.0;
-                    for (int j = 0; j < k; ++j) gx += sG[c * KP + j] * xs[j * XS + u];
-                    t2 += x * gx;
+        __syncthreads();
+        for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
+            const int u = e % SU, c = e / SU;
+            if (c < k) {
+                const double x = xs[c * XS + u];
+                const size_t off = (size_t)c * p.ldout + (size_t)(unit0 + u);
+                if (u < nvalid_local) {
+                    const double o = p.Fold[off];
+                    d2 += (x - o) * (x - o);
+                    if (x != 0.0) nz |= (1ull << c);
+                    if (WSTEP) {
+                        double gx = 0.0;
+                        for (int j = 0; j < k; ++j) gx += sG[c * KP + j] * xs[j * XS + u];
+                        t2 += x * gx;
+                    }
                 }
+                p.Fout[off] = x;
             }
-            p.Fout[off] = x;
         }
     }
     d2 = warp_sum(d2);
@@ -257,6 +280,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfPara
         sred[warp * 3 + 2] = t2;
         ((unsigned long long *)(sred + 24))[warp] = nz;
     }
+    __syncthreads();
     // Gram partial of the produced factor over this CTA's units
     for (int e = tid; e < k * k; e += SOLVE_THREADS) {
         const int c1 = e / k, c2 = e - c1 * k;
@@ -265,12 +289,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfPara
         for (int uu = 0; uu < SU; ++uu) s += xs[c1 * XS + uu] * xs[c2 * XS + uu];
         p.gpart[(size_t)blockIdx.x * (KP * KP) + c1 * KP + c2] = s;
     }
-    __syncthreads();
     const int grp = (int)blockIdx.x / SOLVE_GROUP;
     if (tid == 0) {
         double a = 0, b = 0, c = 0;
         unsigned long long m = 0;
-        for (int w = 0; w < SOLVE_THREADS / 32; ++w) {
+        for (int w = 0; w < SOLVE_WARPS; ++w) {
             a += sred[w * 3 + 0];
             b += sred[w * 3 + 1];
             c += sred[w * 3 + 2];
@@ -300,8 +323,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfPara
         const int c1 = e / KP, c2 = e - c1 * KP;
         double s = 0.0;
         if (c1 < k && c2 < k) {
-#pragma unroll 8
-            for (int b = 0; b < gsize; ++b) s += ldcg(&p.gpart[(size_t)(gfirst + b) * (KP * KP) + e]);
+#pragma unroll
+            for (int b = 0; b < SOLVE_GROUP; ++b)
+                if (b < gsize) s += ldcg(&p.gpart[(size_t)(gfirst + b) * (KP * KP) + e]);
         }
         p.gpart2[(size_t)grp * (KP * KP) + e] = s;
     }
@@ -324,7 +348,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) als_solve_kernel(const HalfPara
         const int c1 = e / KP, c2 = e - c1 * KP;
         double s = 0.0;
         if (c1 < k && c2 < k) {
-#pragma unroll 8
+#pragma unroll 16
             for (int g = 0; g < ngroups; ++g) s += ldcg(&p.gpart2[(size_t)g * (KP * KP) + e]);
         }
         sG[e] = s;

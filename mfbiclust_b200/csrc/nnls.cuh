@@ -253,7 +253,7 @@ __device__ int warp_gauss_jordan_inverse(double *a, int k, int ld, int lane) {
 // ---------------------------------------------------------------------------
 template <int KP, int XS>
 __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, int first, int count, int nvalid,
-                             int lane) {
+                             int lane) {   // (each lane leaves x_i of its problem in xs; see the callers)
     constexpr int LP = (KP <= 16) ? 16 : 32;
     constexpr int PPW = 32 / LP;
     const unsigned FULL = 0xffffffffu;
@@ -328,7 +328,8 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
                 if (++iters > cap) { done = true; piv = -1; }
             }
             if (!__any_sync(FULL, piv >= 0)) break;
-            // exchange x_piv <-> w_piv (predicated per problem)
+            // exchange x_piv <-> w_piv: every row becomes a * row + b * (pivot row), then column piv is patched;
+            // a problem that does not pivot in this pass runs with (a, b) = (1, 0)
             const int pq = piv >= 0 ? piv : 0;
             const int src = base + pq;
             double tiq = 0.0;
@@ -339,16 +340,18 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
             const double ip = 1.0 / pp;
             const bool act = piv >= 0, isrow = act && (i == piv);
             const double f = tiq * ip;
+            const double a = isrow ? 0.0 : 1.0;
+            const double b = act ? (isrow ? -ip : -f) : 0.0;
+            const double fix = isrow ? ip : f;
+            const int pfix = act ? pq : -1;
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 const double rq = __shfl_sync(FULL, T[j], src);
-                const double upd = (j == pq) ? (isrow ? ip : f) : (isrow ? -rq * ip : T[j] - f * rq);
-                T[j] = act ? upd : T[j];
+                const double t = fma(b, rq, a * T[j]);
+                T[j] = (j == pfix) ? fix : t;
             }
-            if (act) {
-                qv = isrow ? -qq * ip : qv - f * qq;
-                if (isrow) inS = !inS;
-            }
+            qv = fma(b, qq, a * qv);
+            if (isrow) inS = !inS;
         }
         const double x = (inS && rowvalid && uvalid && qv > 0.0) ? qv : 0.0;
         t1 += x * ri;
