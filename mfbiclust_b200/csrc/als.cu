@@ -48,13 +48,14 @@ struct AlsCtrl {
 
 struct HalfParams {
     const double *Fin;  int64_t ldin;     // fixed factor, [KP][ldin]
+    long long nfix;                       // valid units of the fixed factor (m for the H-step, n for the W-step)
     double *Fout; const double *Fold; int64_t ldout;   // factor being solved / its previous value
-    const double *G; const double *Minv;  // Gram of Fin and its inverse, KP x KP
-    double *Gout; double *Minvout;        // Gram of Fout (+ inverse), written by the last epilogue
+    double *G; double *Minv;              // Gram of Fin and its inverse, KP x KP: written by the stream kernel's side job
+    double *gram_part, *gram_part2;       // [stream CTA][KP*KP] / [group][KP*KP] partial Grams of Fin
+    int *gram_counter;                    // [1 + groups] arrival counters
     double *P; int maxslots;              // partials [tile][slot][KP][128]
     int *group_counter;                   // [solve groups]
-    double *gpart, *gpart2;               // Gram partials per solve CTA / per group, [..][KP*KP]
-    double *spart, *spart2;               // scalar partials per solve CTA / per group, [..][4]
+    double *spart, *spart2;               // scalar partials per solve warp / per group, [..][4]
     AlsCtrl *ctrl; double *trace;
     int k, T, SPT;
     long long U;                          // T * SPT
@@ -148,41 +149,39 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 // ---------------------------------------------------------------------------
 // the solve kernel: second launch of a half-step
 // ---------------------------------------------------------------------------
-// Every CTA owns SU consecutive units (columns of H / rows of W): it sums the stream-K partials of its units
-// in slot order (deterministic), solves the SU exact NNLS problems (one round of the lane-distributed
-// principal-pivoting solver per warp: 2500 / 10000 warps in flight at 20000 x 5000 instead of the 8 per SM a
-// fused tile epilogue could use), writes the factor and leaves per-CTA partials of the iteration scalars
-// and of the Gram matrix of the factor just produced.  Partials are folded in two levels, each in a fixed
-// order: the last CTA of a group of SOLVE_GROUP CTAs sums the group, the last group sums the groups, inverts the
-// k x k Gram (one warp, rows in registers) for the next half-step and updates the control block.
+// A CTA owns SU consecutive units (columns of H / rows of W) and, after one barrier, its warps are independent:
+// the CTA sums the stream-K partials of its units in slot order (deterministic, coalesced), then every warp solves
+// its UPW exact NNLS problems (lane-distributed principal pivoting, nnls.cuh), writes its slice of the factor and
+// leaves one partial of the iteration scalars.  Thousands of warps are in flight (10000 at 20000 x 5000, k = 16)
+// instead of the 8 per SM a fused tile epilogue could use.  The scalars are folded in two fixed-order levels by the
+// last warp of a group of SOLVE_GROUP warps and then by the last group, which also updates the control block.
+// (The Gram matrix of the factor produced here is formed by the NEXT stream kernel's side job.)
 #ifndef SOLVE_THREADS
-#define SOLVE_THREADS 256
+#define SOLVE_THREADS 128
 #endif
 #define SOLVE_WARPS (SOLVE_THREADS / 32)
-#define SOLVE_GROUP 32
+#define SOLVE_GROUP 128          // warps per fold group
 
 template <int KB>
 struct SolveCfg {
     static constexpr int KP = KB * 8;
     static constexpr bool LANES = KP <= 32;
     static constexpr int LP = (KP <= 16) ? 16 : 32;
-    static constexpr int UPW = 2;                                // units per warp (lane path)
-    static constexpr int SU = LANES ? SOLVE_WARPS * UPW : 64;    // units per CTA
+    static constexpr int UPW = LANES ? 2 : 32;                   // units per warp
+    static constexpr int SU = SOLVE_WARPS * UPW;                 // units per CTA
     static constexpr int XS = SU + 1;
-    static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + 48) * sizeof(double) + 16;
+    static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + 8) * sizeof(double);
 };
 
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : 1) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
-    constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS;
+    constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW;
     if (*(volatile int *)&p.ctrl->stop) return;
     extern __shared__ __align__(16) unsigned char solve_smem[];
     double *sG = (double *)solve_smem;
     double *sM = sG + KP * KP;
     double *xs = sM + KP * KP;
-    double *sred = xs + KP * XS;            // 48 doubles
-    int *sflag = (int *)(sred + 48);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = p.k;
 
@@ -214,11 +213,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         xs[c * XS + u] = r;
     }
     __syncthreads();
+    // ---- from here on the warps of the CTA are independent ----
     double t1 = 0.0, d2 = 0.0, t2 = 0.0;
     unsigned long long nz = 0ull;
     if constexpr (Cfg::LANES) {
-        // (b) exact NNLS, (c) write-back and statistics: both warp-local (lane = (unit, rank) as in nnls_lanes)
-        constexpr int LP = Cfg::LP, UPW = Cfg::UPW;
+        // (b) exact NNLS, (c) write-back and statistics (lane = (unit, rank) as in nnls_lanes)
+        constexpr int LP = Cfg::LP;
         t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane);
         __syncwarp();
         const int i = lane % LP;
@@ -242,31 +242,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
             }
         }
     } else {
-        if (tid < SU) {
-            double r[KP], x[KP];
+        // one problem per lane (k > 32): Schur-complement active-set solver with per-thread scratch
+        const int u = warp * UPW + lane;
+        double r[KP], x[KP];
 #pragma unroll
-            for (int c = 0; c < KP; ++c) { r[c] = (c < k) ? xs[c * XS + tid] : 0.0; x[c] = 0.0; }
-            if (tid < nvalid_local) nnls_thread<KP>(sG, sM, k, r, x);
-            for (int c = 0; c < k; ++c) { t1 += x[c] * r[c]; xs[c * XS + tid] = x[c]; }
-        }
-        __syncthreads();
-        for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
-            const int u = e % SU, c = e / SU;
-            if (c < k) {
-                const double x = xs[c * XS + u];
-                const size_t off = (size_t)c * p.ldout + (size_t)(unit0 + u);
-                if (u < nvalid_local) {
-                    const double o = p.Fold[off];
-                    d2 += (x - o) * (x - o);
-                    if (x != 0.0) nz |= (1ull << c);
-                    if (WSTEP) {
-                        double gx = 0.0;
-                        for (int j = 0; j < k; ++j) gx += sG[c * KP + j] * xs[j * XS + u];
-                        t2 += x * gx;
-                    }
+        for (int c = 0; c < KP; ++c) { r[c] = (c < k) ? xs[c * XS + u] : 0.0; x[c] = 0.0; }
+        if (u < nvalid_local) nnls_thread<KP>(sG, sM, k, r, x);
+        for (int c = 0; c < k; ++c) {
+            const size_t off = (size_t)c * p.ldout + (size_t)(unit0 + u);
+            if (u < nvalid_local) {
+                t1 += x[c] * r[c];
+                const double o = p.Fold[off];
+                d2 += (x[c] - o) * (x[c] - o);
+                if (x[c] != 0.0) nz |= (1ull << c);
+                if (WSTEP) {
+                    double gx = 0.0;
+                    for (int j = 0; j < k; ++j) gx += sG[c * KP + j] * x[j];
+                    t2 += x[c] * gx;
                 }
-                p.Fout[off] = x;
             }
+            p.Fout[off] = x[c];
         }
     }
     d2 = warp_sum(d2);
@@ -274,110 +269,60 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     t2 = warp_sum(t2);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nz |= __shfl_xor_sync(0xffffffffu, nz, o);
+    const int gw = (int)blockIdx.x * SOLVE_WARPS + warp;            // global warp index
+    const int nwarps = (int)gridDim.x * SOLVE_WARPS;
+    const int grp = gw / SOLVE_GROUP, gfirst = grp * SOLVE_GROUP;
+    const int gsize = (nwarps - gfirst < SOLVE_GROUP) ? nwarps - gfirst : SOLVE_GROUP;
+    const int ngroups = (nwarps + SOLVE_GROUP - 1) / SOLVE_GROUP;
+    int last = 0;
     if (lane == 0) {
-        sred[warp * 3 + 0] = d2;
-        sred[warp * 3 + 1] = t1;
-        sred[warp * 3 + 2] = t2;
-        ((unsigned long long *)(sred + 24))[warp] = nz;
-    }
-    __syncthreads();
-    // Gram partial of the produced factor over this CTA's units
-    for (int e = tid; e < k * k; e += SOLVE_THREADS) {
-        const int c1 = e / k, c2 = e - c1 * k;
-        double s = 0.0;
-#pragma unroll 8
-        for (int uu = 0; uu < SU; ++uu) s += xs[c1 * XS + uu] * xs[c2 * XS + uu];
-        p.gpart[(size_t)blockIdx.x * (KP * KP) + c1 * KP + c2] = s;
-    }
-    const int grp = (int)blockIdx.x / SOLVE_GROUP;
-    if (tid == 0) {
-        double a = 0, b = 0, c = 0;
-        unsigned long long m = 0;
-        for (int w = 0; w < SOLVE_WARPS; ++w) {
-            a += sred[w * 3 + 0];
-            b += sred[w * 3 + 1];
-            c += sred[w * 3 + 2];
-            m |= ((unsigned long long *)(sred + 24))[w];
-        }
-        p.spart[(size_t)blockIdx.x * 4 + 0] = a;
-        p.spart[(size_t)blockIdx.x * 4 + 1] = b;
-        p.spart[(size_t)blockIdx.x * 4 + 2] = c;
-        if (!WSTEP) atomicOr(&p.ctrl->nzmask, m);
-    }
-    __threadfence();
-    __syncthreads();
-    const int ngroups = ((int)gridDim.x + SOLVE_GROUP - 1) / SOLVE_GROUP;
-    const int gfirst = grp * SOLVE_GROUP;
-    const int gsize = ((int)gridDim.x - gfirst < SOLVE_GROUP) ? (int)gridDim.x - gfirst : SOLVE_GROUP;
-    if (tid == 0) {
+        p.spart[(size_t)gw * 4 + 0] = d2;
+        p.spart[(size_t)gw * 4 + 1] = t1;
+        p.spart[(size_t)gw * 4 + 2] = t2;
+        if (!WSTEP) atomicOr(&p.ctrl->nzmask, nz);
+        __threadfence();
         const int prev = atomicAdd(&p.group_counter[grp], 1);
-        const int lastone = (prev == gsize - 1);
-        if (lastone) p.group_counter[grp] = 0;
-        sflag[0] = lastone;
+        last = (prev == gsize - 1);
+        if (last) p.group_counter[grp] = 0;
     }
-    __syncthreads();
-    if (!sflag[0]) return;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
     __threadfence();
-    // ---- level 1: fold this group's CTA partials (fixed order) ----
-    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        double s = 0.0;
-        if (c1 < k && c2 < k) {
+    // ---- level 1: this warp arrived last in its group: fold the group's warp partials in a fixed order ----
+    {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
-            for (int b = 0; b < SOLVE_GROUP; ++b)
-                if (b < gsize) s += ldcg(&p.gpart[(size_t)(gfirst + b) * (KP * KP) + e]);
+        for (int q = 0; q < SOLVE_GROUP / 32; ++q) {
+            const int w = q * 32 + lane;
+            if (w < gsize) {
+                a0 += ldcg(&p.spart[(size_t)(gfirst + w) * 4 + 0]);
+                a1 += ldcg(&p.spart[(size_t)(gfirst + w) * 4 + 1]);
+                a2 += ldcg(&p.spart[(size_t)(gfirst + w) * 4 + 2]);
+            }
         }
-        p.gpart2[(size_t)grp * (KP * KP) + e] = s;
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == 0) {
+            p.spart2[(size_t)grp * 4 + 0] = a0;
+            p.spart2[(size_t)grp * 4 + 1] = a1;
+            p.spart2[(size_t)grp * 4 + 2] = a2;
+            __threadfence();
+            const int prev = atomicAdd(&p.ctrl->groups_done[WSTEP ? 1 : 0], 1);
+            last = (prev == ngroups - 1);
+        }
     }
-    if (tid < 3) {
-        double s = 0.0;
-        for (int b = 0; b < gsize; ++b) s += ldcg(&p.spart[(size_t)(gfirst + b) * 4 + tid]);
-        p.spart2[(size_t)grp * 4 + tid] = s;
-    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
     __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int prev = atomicAdd(&p.ctrl->groups_done[WSTEP ? 1 : 0], 1);
-        sflag[1] = (prev == ngroups - 1);
+    // ---- level 2 (one warp, once per half-step): iteration scalars and the control block ----
+    double sd2 = 0.0, st1 = 0.0, st2 = 0.0;
+    for (int g = lane; g < ngroups; g += 32) {
+        sd2 += ldcg(&p.spart2[(size_t)g * 4 + 0]);
+        st1 += ldcg(&p.spart2[(size_t)g * 4 + 1]);
+        st2 += ldcg(&p.spart2[(size_t)g * 4 + 2]);
     }
-    __syncthreads();
-    if (!sflag[1]) return;
-    __threadfence();
-    // ---- level 2 (one CTA, once per half-step): Gram of the new factor, its inverse, iteration scalars ----
-    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        double s = 0.0;
-        if (c1 < k && c2 < k) {
-#pragma unroll 16
-            for (int g = 0; g < ngroups; ++g) s += ldcg(&p.gpart2[(size_t)g * (KP * KP) + e]);
-        }
-        sG[e] = s;
-        p.Gout[e] = s;
-    }
-    if (tid < 3) {
-        double s = 0.0;
-        for (int g = 0; g < ngroups; ++g) s += ldcg(&p.spart2[(size_t)g * 4 + tid]);
-        sred[32 + tid] = s;
-    }
-    __syncthreads();
-    int sing;
-    if constexpr (KP <= 32) {
-        if (warp == 0) {
-            const int sg = warp_gauss_jordan_inverse<KP>(sG, k, KP, lane);
-            if (lane == 0) sflag[1] = sg;
-        }
-        __syncthreads();
-        sing = sflag[1];
-    } else {
-        sing = gauss_jordan_inverse(sG, k, KP, tid, SOLVE_THREADS, sred + 36, [] { __syncthreads(); });
-    }
-    for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        p.Minvout[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
-    }
-    if (tid == 0) {
+    sd2 = warp_sum(sd2); st1 = warp_sum(st1); st2 = warp_sum(st2);
+    if (lane == 0) {
         AlsCtrl *c = p.ctrl;
-        const double sd2 = sred[32], st1 = sred[33], st2 = sred[34];
         c->groups_done[WSTEP ? 1 : 0] = 0;
         if (!WSTEP) {
             c->dH2 = sd2;
@@ -385,7 +330,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
             const unsigned long long m = c->nzmask;
             c->nzmask = 0ull;
             if ((m & fullm) != fullm) { c->stop = 1; c->reason = 2; }
-            else if (sing) { c->stop = 1; c->reason = 4; }
         } else {
             double r2 = (c->normA2 - 2.0 * st1 + st2) / c->mn;
             const double resid = sqrt(r2 > 0.0 ? r2 : 0.0);
@@ -406,11 +350,146 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
                 c->reason = 1;
             } else {
                 c->resid_old = resid;
-                if (sing) { c->stop = 1; c->reason = 3; }
             }
         }
         __threadfence();
     }
+}
+
+// ---------------------------------------------------------------------------
+// side job of the stream kernel: Gram matrix of the FIXED factor and its inverse
+// ---------------------------------------------------------------------------
+// Run by the three idle warps of the producer warpgroup (96 threads, named barrier 2) of every stream CTA while the
+// other warps stream A: CTA b forms the partial Gram of its slice of the fixed factor's units, the last CTA to
+// arrive folds the 148 partials in CTA order and inverts the k x k matrix in shared memory.  The solve kernel of the
+// same half-step reads G and G^-1; nothing on the critical path waits for them.  R's solve() failure ("system is
+// computationally singular") is raised here: reason 3 = W'W (H-step), 4 = HH' (W-step).
+#define GRAM_THREADS 96
+#define GRAM_GROUP 16            // stream CTAs per fold group
+__device__ __forceinline__ void gram_bar() { asm volatile("bar.sync 2, 96;" ::: "memory"); }
+
+template <int KB, bool WSTEP>
+__device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, double *sGm, int *gflag) {
+    constexpr int KP = KB * 8;
+    constexpr int NBLK = KB * KB, NGRP = (NBLK + 3) / 4;
+    const int k = p.k, G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int w = t >> 5, lane = t & 31, g = lane >> 2, tt = lane & 3;
+    // --- partial Gram of this CTA's slice of units; each warp takes a third of the slice, FP64 tensor cores:
+    //     D(8x8 block i,j) += F[8i+g][u + tt] * F[8j+g][u + tt], 4 units per DMMA, loads of 2 k-steps in flight ---
+    const long long lo = (long long)b * p.nfix / G, hi = (long long)(b + 1) * p.nfix / G;
+    const long long wlo = lo + (hi - lo) * w / 3, whi = lo + (hi - lo) * (w + 1) / 3;
+    for (int e = t; e < KP * KP; e += GRAM_THREADS) sGm[e] = 0.0;
+    gram_bar();
+    for (int q = 0; q < NGRP; ++q) {
+        double acc[4][2];
+        const double *ra[4], *rb[4];
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+            const int bidx = (4 * q + blk < NBLK) ? 4 * q + blk : NBLK - 1;
+            acc[blk][0] = acc[blk][1] = 0.0;
+            ra[blk] = p.Fin + (size_t)(8 * (bidx / KB) + g) * p.ldin + tt;
+            rb[blk] = p.Fin + (size_t)(8 * (bidx % KB) + g) * p.ldin + tt;
+        }
+        for (long long u = wlo; u < whi; u += 8) {
+            double av[4][2], bv[4][2];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const long long uu = u + 4 * s2;
+                const bool ok = uu + tt < whi;
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) {
+                    av[blk][s2] = ok ? ra[blk][uu] : 0.0;
+                    bv[blk][s2] = ok ? rb[blk][uu] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) dmma884(acc[blk][0], acc[blk][1], av[blk][s2], bv[blk][s2]);
+        }
+        // the three warps add their thirds into the shared matrix one after the other (fixed order)
+        for (int turn = 0; turn < 3; ++turn) {
+            if (turn == w) {
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) {
+                    const int bidx = 4 * q + blk;
+                    if (bidx < NBLK) {
+                        const int row = 8 * (bidx / KB) + g, col = 8 * (bidx % KB) + 2 * tt;
+                        sGm[row * KP + col] += acc[blk][0];
+                        sGm[row * KP + col + 1] += acc[blk][1];
+                    }
+                }
+            }
+            gram_bar();
+        }
+    }
+    for (int e = t; e < KP * KP; e += GRAM_THREADS) p.gram_part[(size_t)b * (KP * KP) + e] = sGm[e];
+    __threadfence();
+    gram_bar();
+    // --- level 1: the last CTA of a group of GRAM_GROUP folds the group (CTA order) ---
+    const int grp = b / GRAM_GROUP, gfirst = grp * GRAM_GROUP;
+    const int gsize = (G - gfirst < GRAM_GROUP) ? G - gfirst : GRAM_GROUP;
+    const int ngroups = (G + GRAM_GROUP - 1) / GRAM_GROUP;
+    if (t == 0) {
+        const int prev = atomicAdd(&p.gram_counter[1 + grp], 1);
+        const int lastone = (prev == gsize - 1);
+        if (lastone) p.gram_counter[1 + grp] = 0;
+        *gflag = lastone;
+    }
+    gram_bar();
+    if (!*gflag) return;
+    __threadfence();
+    for (int e = t; e < KP * KP; e += GRAM_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < GRAM_GROUP; ++bb)
+            if (bb < gsize) s += ldcg(&p.gram_part[(size_t)(gfirst + bb) * (KP * KP) + e]);
+        p.gram_part2[(size_t)grp * (KP * KP) + e] = s;
+    }
+    __threadfence();
+    gram_bar();
+    if (t == 0) {
+        const int prev = atomicAdd(&p.gram_counter[0], 1);
+        const int lastone = (prev == ngroups - 1);
+        if (lastone) p.gram_counter[0] = 0;
+        *gflag = lastone;
+    }
+    gram_bar();
+    if (!*gflag) return;
+    __threadfence();
+    // --- level 2 (one CTA per launch): fold the groups, publish G, invert ---
+    for (int e = t; e < KP * KP; e += GRAM_THREADS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        double s = 0.0;
+        if (c1 < k && c2 < k) {
+#pragma unroll 10
+            for (int gg = 0; gg < ngroups; ++gg) s += ldcg(&p.gram_part2[(size_t)gg * (KP * KP) + e]);
+        }
+        sGm[e] = s;
+        p.G[e] = s;
+    }
+    gram_bar();
+    int sing;
+    if constexpr (KP <= 16) {
+        if (w == 0) {
+            const int sg = warp_gauss_jordan_inverse<KP>(sGm, k, KP, lane);
+            if (lane == 0) *gflag = sg;
+        }
+        gram_bar();
+        sing = *gflag;
+    } else {
+        sing = gauss_jordan_inverse(sGm, k, KP, t, GRAM_THREADS, sGm + KP * KP, [] { gram_bar(); });
+    }
+    for (int e = t; e < KP * KP; e += GRAM_THREADS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        p.Minv[e] = (c1 < k && c2 < k) ? sGm[e] : 0.0;
+    }
+    if (t == 0 && sing) {
+        p.ctrl->reason = WSTEP ? 4 : 3;
+        __threadfence();
+        p.ctrl->stop = 1;
+    }
+    __threadfence();
 }
 
 template <int KB, bool WSTEP>
@@ -430,6 +509,8 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     unsigned char *ring = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = (uint64_t *)(ring + (size_t)nstage * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + nstage;
+    double *sGm = (double *)(empty_bar + nstage);        // KP*KP + 2 doubles: Gram side job
+    int *gflag = (int *)(sGm + KP * KP + 2);
     const uint32_t ring_s = smem_u32(ring);
 
     const int tid = threadIdx.x;
@@ -447,14 +528,16 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (u0 >= u1) return;
+    const bool has_work = u0 < u1;
     const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
     const int nunits = (int)(u1 - u0);
 
     if (warp >= 8) {
-        // ===================== TMA producer (warpgroup 2 hands its registers to the consumers) =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 8 && lane == 0) {
+        // ===== warpgroup 2: TMA producer (warp 8) + Gram side job (warps 9-11); hands registers to the consumers =====
+        if (has_work) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        if (warp > 8) {
+            gram_side_job<KB, WSTEP>(p, tid - 288, sGm, gflag);
+        } else if (has_work && lane == 0) {
             int stage = 0, tile = tile0, st = st0;
             uint32_t phase = 0;
             for (int it = 0; it < nunits; ++it) {
@@ -480,7 +563,8 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== consumers: NG groups of 4 warps (one warp per SM sub-partition) =====================
     // Group `grp` owns the units it == grp (mod NG) of this CTA's range, so the two warps that share a
     // sub-partition are one stage out of phase: one issues DMMAs while the other waits / loads fragments.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (!has_work) return;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     constexpr int NG = 2;
     const int grp = warp >> 2, wg = warp & 3;
     const int g = lane >> 2, t = lane & 3;
@@ -729,8 +813,8 @@ struct mfb_als {
     int64_t m, n, ldw, ldh;
     double *Wb[2], *Wr, *Hb[2];          // factor buffers [KP][ld]
     double *G_W, *Minv_W, *G_H, *Minv_H; // Grams (+ inverses)
-    double *P_h, *P_w, *gpart, *spart, *gpart2, *spart2;
-    int *counters;
+    double *P_h, *P_w, *spart, *spart2, *gram_part, *gram_part2;
+    int *counters, *gram_counter;
     int nsolve_h, nsolve_w;       // solve-kernel grids
     bool attr_set = false;
     std::vector<cudaEvent_t> *prof = nullptr;   // mfb_als_profile: one event after every kernel
@@ -747,8 +831,6 @@ struct mfb_als {
     int max_trace;
     std::vector<double> trace;   // host copy: iters_total x 3
     double resid;
-    int *sing_dev;
-    double *gram_scratch;
     std::vector<void *> allocs;
 };
 
@@ -885,18 +967,6 @@ static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, co
     return MFB_ERR_UNSUPPORTED;
 }
 
-static int gram_of_factor(mfb_als *s, const double *F, int64_t ld, int64_t len, double *Gout, double *Minvout) {
-    cudaStream_t st = s->ctx->stream;
-    int nb = (int)((len + 2047) / 2048);
-    if (nb > 64) nb = 64;
-    if (nb < 1) nb = 1;
-    gram_partial_kernel<<<nb, 256, (size_t)s->k * 65 * sizeof(double), st>>>(F, ld, len, s->k, s->KP, s->gram_scratch);
-    gram_finalize_kernel<<<1, 256, (size_t)(s->KP * s->KP + 2) * sizeof(double), st>>>(s->gram_scratch, nb, s->k, s->KP,
-                                                                                     Gout, Minvout, s->sing_dev);
-    MFB_CUDA(cudaGetLastError());
-    return MFB_OK;
-}
-
 template <typename T>
 static int dev_alloc(mfb_als *s, T **p, size_t count, bool zero = true) {
     cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
@@ -971,7 +1041,8 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->maxslots_h = 2 * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
     s->maxslots_w = 2 * max_slots(s->T_w, s->SPT_w, G);
     const size_t KP = s->KP;
-    const size_t budget = 227 * 1024 - 1024 /*align*/ - 2 * 16 * sizeof(uint64_t);
+    const size_t side = (KP * KP + 2) * sizeof(double) + 16;            // Gram side job scratch
+    const size_t budget = 227 * 1024 - 1024 /*align*/ - 2 * 16 * sizeof(uint64_t) - side;
     const size_t stage_h = 16384 + KP * 128, stage_w = 32768 + 2 * KP * 128;
     s->nstage_h = (int)(budget / stage_h); if (s->nstage_h > 12) s->nstage_h = 12;
     s->nstage_w = (int)(budget / stage_w); if (s->nstage_w > 6) s->nstage_w = 6;
@@ -985,8 +1056,8 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
         mfb_set_error("rank %d leaves no shared memory for the streaming ring", k);
         return MFB_ERR_UNSUPPORTED;
     }
-    s->smem_h = 1024 + (size_t)s->nstage_h * stage_h + 2 * s->nstage_h * sizeof(uint64_t);
-    s->smem_w = 1024 + (size_t)s->nstage_w * stage_w + 2 * s->nstage_w * sizeof(uint64_t);
+    s->smem_h = 1024 + (size_t)s->nstage_h * stage_h + 2 * s->nstage_h * sizeof(uint64_t) + side;
+    s->smem_w = 1024 + (size_t)s->nstage_w * stage_w + 2 * s->nstage_w * sizeof(uint64_t) + side;
     const int SU = solve_units_dispatch(s->KB);
     s->nsolve_h = (int)((s->n + SU - 1) / SU);
     s->nsolve_w = (int)((s->m + SU - 1) / SU);
@@ -998,16 +1069,15 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     ALLOC(s->G_W, KP * KP) ALLOC(s->Minv_W, KP * KP) ALLOC(s->G_H, KP * KP) ALLOC(s->Minv_H, KP * KP)
     ALLOC(s->P_h, (size_t)s->T_h * s->maxslots_h * KP * TILE_UNITS)
     ALLOC(s->P_w, (size_t)s->T_w * s->maxslots_w * KP * TILE_UNITS)
-    const size_t Smax = (size_t)(s->nsolve_h > s->nsolve_w ? s->nsolve_h : s->nsolve_w);
-    const size_t Gmax = (Smax + SOLVE_GROUP - 1) / SOLVE_GROUP;
-    ALLOC(s->gpart, Smax * KP * KP) ALLOC(s->spart, Smax * 4)
-    ALLOC(s->gpart2, Gmax * KP * KP) ALLOC(s->spart2, Gmax * 4)
+    const size_t Wmax = (size_t)(s->nsolve_h > s->nsolve_w ? s->nsolve_h : s->nsolve_w) * SOLVE_WARPS;   // solve warps
+    const size_t Gmax = (Wmax + SOLVE_GROUP - 1) / SOLVE_GROUP;
+    ALLOC(s->spart, Wmax * 4) ALLOC(s->spart2, Gmax * 4)
     ALLOC(s->counters, Gmax)
+    ALLOC(s->gram_part, (size_t)G * KP * KP) ALLOC(s->gram_part2, (size_t)(G / GRAM_GROUP + 1) * KP * KP)
+    ALLOC(s->gram_counter, (size_t)(G / GRAM_GROUP + 2))
     ALLOC(s->ctrl, 1)
     s->max_trace = 4096;
     ALLOC(s->trace_dev, (size_t)s->max_trace * 3)
-    ALLOC(s->sing_dev, 1)
-    ALLOC(s->gram_scratch, (size_t)64 * KP * KP)
 #undef ALLOC
     // tensor maps over A: dims {m rows (contiguous), n cols}
     if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, 16, 128)) != MFB_OK ||
@@ -1037,7 +1107,6 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     c.kn = (double)k * s->n;
     c.max_trace = s->max_trace;
     MFB_CUDA(cudaMemcpyAsync(s->ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
-    if ((rc = gram_of_factor(s, s->Wb[0], s->ldw, s->m, s->G_W, s->Minv_W)) != MFB_OK) { mfb_als_end(s); return rc; }
     MFB_CUDA(cudaStreamSynchronize(st));
     *out = s;
     return MFB_OK;
@@ -1049,7 +1118,6 @@ int mfb_als_restart(mfb_als *s, const double *Wnew) {
     cudaStream_t st = s->ctx->stream;
     MFB_CUDA(cudaMemcpy2DAsync(s->Wr, s->ldw * sizeof(double), Wnew, s->m * sizeof(double), s->m * sizeof(double), s->k,
                                cudaMemcpyHostToDevice, st));
-    MFB_TRY(gram_of_factor(s, s->Wr, s->ldw, s->m, s->G_W, s->Minv_W));
     MFB_CUDA(cudaStreamSynchronize(st));
     s->restart_pending = true;
     return MFB_OK;
@@ -1060,19 +1128,19 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     memset(&h, 0, sizeof(h));
     const int nxt = cur ^ 1;
     // H-step: fixed W (or the restart draw), solve H
-    h.Fin = use_restart_w ? s->Wr : s->Wb[cur]; h.ldin = s->ldw;
+    h.Fin = use_restart_w ? s->Wr : s->Wb[cur]; h.ldin = s->ldw; h.nfix = s->m;
     h.Fout = s->Hb[nxt]; h.Fold = s->Hb[cur]; h.ldout = s->ldh;
-    h.G = s->G_W; h.Minv = s->Minv_W; h.Gout = s->G_H; h.Minvout = s->Minv_H;
+    h.G = s->G_W; h.Minv = s->Minv_W; h.gram_part = s->gram_part; h.gram_part2 = s->gram_part2; h.gram_counter = s->gram_counter;
     h.P = s->P_h; h.maxslots = s->maxslots_h; h.group_counter = s->counters;
-    h.gpart = s->gpart; h.spart = s->spart; h.gpart2 = s->gpart2; h.spart2 = s->spart2;
+    h.spart = s->spart; h.spart2 = s->spart2;
     h.ctrl = s->ctrl; h.trace = s->trace_dev;
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
     h.Gstream = s->ctx->sm_count;
     MFB_TRY(launch_half_dispatch(s, false, h, use_restart_w ? s->tm_W[2] : s->tm_W[cur]));
     HalfParams w = h;
-    w.Fin = s->Hb[nxt]; w.ldin = s->ldh;
+    w.Fin = s->Hb[nxt]; w.ldin = s->ldh; w.nfix = s->n;
     w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
-    w.G = s->G_H; w.Minv = s->Minv_H; w.Gout = s->G_W; w.Minvout = s->Minv_W;
+    w.G = s->G_H; w.Minv = s->Minv_H;
     w.P = s->P_w; w.maxslots = s->maxslots_w;
     w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
     MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt]));
