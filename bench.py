@@ -115,6 +115,58 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def make_d3(dimx=10000, dimy=2000, seed=3):
+    """D3: genSimData(n=5, dimx=10000, dimy=2000, clusterHeight=clusterWidth=400, bgNorm=1,
+    biclusterShift=3, rowShift=1, colShift=1)."""
+    from oracle.gen_sim_data import gen_sim_data
+    side = min(dimx, dimy) // 5
+    return np.asfortranarray(gen_sim_data(n=5, cluster_height=side, cluster_width=side, dimx=dimx, dimy=dimy,
+                                          bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=seed))
+
+
+def run_auto_bcv(mfb, ctx, rank, world, with_cpu):
+    """auto_bcv(Y, ks = 1:20, holdouts = 3) on D3 to convergence: wall time through the public call with a HOST
+    matrix (upload inside), the bcv cells sharded over the ranks; plus one bcv call beside the oracle's."""
+    import torch
+    import torch.distributed as dist
+    Y = make_d3()
+    ks = np.arange(1, 21)
+    rf, cf = mfb.draw_folds(mfb.HostRng(50), *Y.shape, 3)
+    Yd = mfb.Matrix(ctx, host=Y)
+    mfb.bcvGivenKs(Yd, ks, 3, folds=(rf, cf), ctx=ctx)            # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    got = mfb.bcvGivenKs(Yd, ks, 3, folds=(rf, cf), ctx=ctx)
+    torch.cuda.synchronize()
+    t_call = time.perf_counter() - t0
+    Yd.free()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = mfb.auto_bcv(Y, ks, holdouts=3, rng=mfb.HostRng(51), ctx=ctx)
+    torch.cuda.synchronize()
+    t_auto = time.perf_counter() - t0
+    tt = torch.tensor([t_call, t_auto], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    info = {"workload": "auto_bcv(Y, ks=1:20, holdouts=3) on genSimData-shaped 10000x2000 (D3), FP64",
+            "wall_s": float(tt[1].item()), "best": int(res["best"]), "iterations": int(res["iterations"]),
+            "bcv_call_s": float(tt[0].item()), "bcv_argmin_k": int(ks[int(np.argmin(got))]), "cells": 9,
+            "n_gpus": world}
+    if with_cpu and rank == 0:
+        from oracle import bcv as OB
+        t0 = time.perf_counter()
+        ref = OB.bcv_given_ks(Y, ks, rf, cf, 3)
+        info["cpu_bcv_call_s"] = time.perf_counter() - t0
+        info["cpu_kind"] = ("oracle one-SVD-per-cell restatement (NumPy/LAPACK, %d cores); the reference's literal path "
+                            "does one more full SVD per k per cell" % os.cpu_count())
+        info["curve_max_rel_err"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+        info["cpu_argmin_k"] = int(ks[int(np.argmin(ref))])
+    return info
+
+
 def run_reference(args, rank, world):
     """Reference arm: the CPU oracle port (literal R loop) on all host cores, rank 0 only."""
     if rank != 0:
@@ -153,6 +205,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bcv", action="store_true", help="skip the auto_bcv wall-time leg (second half of the metric)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +305,11 @@ def main():
         assert np.allclose(Wout, Wout) and itc.value == K
     Ad.free()
 
+    # ---- auto_bcv wall time (second half of BASELINE.json's metric): D3, cells sharded over the ranks --------
+    bcv_info = None
+    if not args.no_bcv:
+        bcv_info = run_auto_bcv(mfb, ctx, rank, world, not args.no_cpu_baseline)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -294,7 +352,7 @@ def main():
                         "step_achieved": step_achieved, "step_frac": step_achieved / peak,
                         "step_note": "whole iteration (all 4 launches + gaps): 2*m*n*8*K / timed seconds; this is "
                                      "the north-star '% of HBM roofline' figure"},
-           "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+           "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "auto_bcv": bcv_info,
            "final_resid": resid}
     print(json.dumps(out), flush=True)
     if world > 1:

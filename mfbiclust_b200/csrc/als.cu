@@ -19,11 +19,18 @@
 // half-step but replaces a tail of ~40 (H) / ~100-200 (W) us during which 8 warps per SM ran the NNLS of a whole
 // 128-unit tile with a ~15 us kernel at full occupancy (profiles/r01_*).
 // Nothing but A's two passes touches HBM in bulk: factors, partials and Grams stay in L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "nnls.cuh"
 
-#define ALS_THREADS 384           // 2 consumer warpgroups (8 warps) + 1 producer warpgroup (one elected lane)
-#define ALS_CONSUMERS 256
+#ifndef ALS_NG
+#define ALS_NG 2                  // consumer groups of 4 warps, one stage out of phase with each other
+#endif
+#define ALS_CONSUMERS (ALS_NG * 128)
+#define ALS_THREADS (ALS_CONSUMERS + 128)   // + the producer warpgroup (TMA lane, Gram side job)
+#define ALS_STR2(x) #x
+#define ALS_STR(x) ALS_STR2(x)
 #define TILE_UNITS 128            // columns (H-step) or rows (W-step) per tile
 
 // ---------------------------------------------------------------------------
@@ -128,7 +135,15 @@ __device__ __forceinline__ int pin_reg(int v) {
     asm volatile("mov.u32 %0, %0;" : "+r"(v));
     return v;
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Programmatic dependent launch: let the next kernel of the stream be scheduled as soon as this grid's CTAs have
+// started (its CTAs only become resident as ours retire), then wait until the previous grid has completed and its
+// writes are visible before touching anything it produced.  Hides the launch latency between the four kernels of
+// an iteration; a no-op when the launch does not carry the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, " ALS_STR(ALS_CONSUMERS) ";" ::: "memory"); }
 
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 
@@ -177,6 +192,7 @@ template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : 1) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
     constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW;
+    pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     extern __shared__ __align__(16) unsigned char solve_smem[];
     double *sG = (double *)solve_smem;
@@ -197,9 +213,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     {
         const long long tb = (long long)tile * p.SPT;
         if (p.U >= p.Gstream)
-            expected = 2 * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
+            expected = ALS_NG * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
         else
-            expected = 2 * p.SPT;
+            expected = ALS_NG * p.SPT;
     }
     // (a) right-hand sides: sum the partials in slot order
     for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
@@ -502,6 +518,7 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int NFB = WSTEP ? 2 : 1;                   // factor boxes per stage (32 columns / 16 rows of reduction)
     constexpr int STAGE_BYTES = A_BYTES + NFB * F_BOX;
     constexpr int NF = WSTEP ? 4 : 2;                    // double2 fragments of the fixed factor per rank block and unit
+    pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -532,11 +549,13 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tile0 = (int)(u0 / p.SPT), st0 = (int)(u0 - (long long)tile0 * p.SPT);
     const int nunits = (int)(u1 - u0);
 
-    if (warp >= 8) {
+    if (warp >= 4 * ALS_NG) {
         // ===== warpgroup 2: TMA producer (warp 8) + Gram side job (warps 9-11); hands registers to the consumers =====
+#if ALS_NG == 2
         if (has_work) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-        if (warp > 8) {
-            gram_side_job<KB, WSTEP>(p, tid - 288, sGm, gflag);
+#endif
+        if (warp > 4 * ALS_NG) {
+            gram_side_job<KB, WSTEP>(p, tid - (ALS_CONSUMERS + 32), sGm, gflag);
         } else if (has_work && lane == 0) {
             int stage = 0, tile = tile0, st = st0;
             uint32_t phase = 0;
@@ -564,8 +583,10 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Group `grp` owns the units it == grp (mod NG) of this CTA's range, so the two warps that share a
     // sub-partition are one stage out of phase: one issues DMMAs while the other waits / loads fragments.
     if (!has_work) return;
+#if ALS_NG == 2
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    constexpr int NG = 2;
+#endif
+    constexpr int NG = ALS_NG;
     const int grp = warp >> 2, wg = warp & 3;
     const int g = lane >> 2, t = lane & 3;
     double acc[KB][4][2];                        // [rank block][v (H-step: column block) or 2*rg+s (W-step: row)][2]
@@ -893,11 +914,29 @@ static int prof_mark(mfb_als *s) {
     return MFB_OK;
 }
 
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                              Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int KB>
 static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
     cudaStream_t st = s->ctx->stream;
     const int G = hp.Gstream;
     const int nsolve = wstep ? s->nsolve_w : s->nsolve_h;
+    const bool pdl = (s->prof == nullptr) && !getenv("MFB_NO_PDL");   // events between launches serialise anyway
     if (wstep) {
         if (!s->attr_set) {
             MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
@@ -906,9 +945,9 @@ static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUten
             MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
             s->attr_set = true;
         }
-        als_stream_kernel<KB, true><<<G, ALS_THREADS, s->smem_w, st>>>(s->tm_w, tmF, hp, s->nstage_w);
+        MFB_CUDA(launch_pdl(als_stream_kernel<KB, true>, G, ALS_THREADS, s->smem_w, st, pdl, s->tm_w, tmF, hp, s->nstage_w));
         MFB_TRY(prof_mark(s));
-        als_solve_kernel<KB, true><<<nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st>>>(hp);
+        MFB_CUDA(launch_pdl(als_solve_kernel<KB, true>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
         MFB_TRY(prof_mark(s));
     } else {
         if (!s->attr_set) {
@@ -918,9 +957,9 @@ static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUten
             MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
             s->attr_set = true;
         }
-        als_stream_kernel<KB, false><<<G, ALS_THREADS, s->smem_h, st>>>(s->tm_h, tmF, hp, s->nstage_h);
+        MFB_CUDA(launch_pdl(als_stream_kernel<KB, false>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
         MFB_TRY(prof_mark(s));
-        als_solve_kernel<KB, false><<<nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st>>>(hp);
+        MFB_CUDA(launch_pdl(als_solve_kernel<KB, false>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
         MFB_TRY(prof_mark(s));
     }
     MFB_CUDA(cudaGetLastError());
@@ -1038,8 +1077,8 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->SPT_h = (int)((s->m + 15) / 16);
     s->T_w = (int)((s->m + 127) / 128);
     s->SPT_w = (int)((s->n + 31) / 32);
-    s->maxslots_h = 2 * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
-    s->maxslots_w = 2 * max_slots(s->T_w, s->SPT_w, G);
+    s->maxslots_h = ALS_NG * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
+    s->maxslots_w = ALS_NG * max_slots(s->T_w, s->SPT_w, G);
     const size_t KP = s->KP;
     const size_t side = (KP * KP + 2) * sizeof(double) + 16;            // Gram side job scratch
     const size_t budget = 227 * 1024 - 1024 /*align*/ - 2 * 16 * sizeof(uint64_t) - side;
@@ -1049,8 +1088,8 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     // The ring depth must be a multiple of the number of consumer groups (2): a stage is then always drained by
     // the same group, which therefore waits on EVERY phase of that stage's full-barrier.  With an odd depth a
     // group skips every other phase and the parity wait aliases (returns on a phase two fills old).
-    s->nstage_h &= ~1;
-    s->nstage_w &= ~1;
+    s->nstage_h -= s->nstage_h % ALS_NG;
+    s->nstage_w -= s->nstage_w % ALS_NG;
     if (s->nstage_h < 2 || s->nstage_w < 2) {
         mfb_als_end(s);
         mfb_set_error("rank %d leaves no shared memory for the streaming ring", k);
