@@ -40,6 +40,8 @@ M_ROWS, N_COLS, RANK = 20000, 5000, 16
 TRAFFIC_BYTES_PER_LAUNCH = None
 METRIC = "ALS-NMF iters/s @20kx5k k=16 (FP64)"
 UNIT = "iter/s"
+WORKLOAD = ("ALS-NMF 20000x5000 k=16 FP64, genSimData-shaped (D4, BASELINE configs[3]), fixed iterations, "
+            "given W0/Hold0")
 
 
 def make_workload(m=M_ROWS, n=N_COLS, k=RANK, seed=4):
@@ -187,7 +189,7 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "ALS-NMF 20000x5000 k=16 FP64, genSimData-shaped (D4), fixed iterations",
+           "config": {"workload": WORKLOAD,
                       "note": "R absent and NMF::.fcnnls un-vendored: oracle port (NumPy/OpenBLAS, literal R loop)"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{steps} literal ALS iterations of the full 20000x5000 k=16 workload "
@@ -206,6 +208,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bcv", action="store_true", help="skip the auto_bcv wall-time leg (second half of the metric)")
+    ap.add_argument("--k", type=int, default=RANK, help="rank (default 16 = the headline; 64 = BASELINE configs[3]'s "
+                                                        "compute-bound variant, reported against the FP64 pipe)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -228,12 +232,13 @@ def main():
     ctx = mfb.Context(local_rank)
     K, W = max(1, args.steps), max(3, args.warmup)
 
-    A, W0, H0 = make_workload()
+    RANK_ = args.k
+    A, W0, H0 = make_workload(k=RANK_)
     m, n = A.shape
     # ---- resident-input timing -------------------------------------------------------------
     Ad = mfb.Matrix(ctx, host=A)
     stats = Ad.stats()
-    sess = mfb.AlsSession(Ad, RANK, W0, H0, stats["max"])
+    sess = mfb.AlsSession(Ad, RANK_, W0, H0, stats["max"])
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     st, _, _ = sess.iterate(W, fixed_iters=True)          # warm-up iterations (untimed)
     assert st == 0, f"warm-up failed with status {st}"
@@ -273,13 +278,13 @@ def main():
         assert Ah.flags["F_CONTIGUOUS"]
         import ctypes as C
         from mfbiclust_b200._cabi import dptr, lib, check
-        Wout = np.zeros((m, RANK), order="F")
-        Hout = np.zeros((RANK, n), order="F")
+        Wout = np.zeros((m, RANK_), order="F")
+        Hout = np.zeros((RANK_, n), order="F")
         residc, itc, convc = C.c_double(0), C.c_int(0), C.c_int(0)
         tr = np.zeros((K, 3))
 
         def one_call():
-            check(lib().mfb_als_run_host(ctx.handle, dptr(Ah), m, n, RANK, dptr(W0), dptr(H0), K, 1e-4, 1,
+            check(lib().mfb_als_run_host(ctx.handle, dptr(Ah), m, n, RANK_, dptr(W0), dptr(H0), K, 1e-4, 1,
                                          dptr(Wout), dptr(Hout), C.byref(residc), C.byref(itc), C.byref(convc),
                                          dptr(tr)))
         one_call()                                  # warm-up call
@@ -335,11 +340,11 @@ def main():
                "sample": f"{nit} literal ALS iterations (oracle/als_nmf.py, NumPy/OpenBLAS) of the same "
                          f"20000x5000 k=16 workload"}
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+    flops_per_iter = 4.0 * m * n * RANK_ + 2.0 * (m + n) * RANK_ * RANK_
+    out = {"metric": METRIC if RANK_ == RANK else METRIC.replace("k=16", f"k={RANK_}"), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "ALS-NMF 20000x5000 k=16 FP64, genSimData-shaped (D4, BASELINE configs[3]), "
-                                  "fixed iterations, given W0/Hold0",
+           "config": {"workload": WORKLOAD if RANK_ == RANK else WORKLOAD.replace("k=16", f"k={RANK_}"),
                       "l2": "input (800 MB) larger than L2 (126 MB); no flush needed",
                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicates (als_nmf reps axis)"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -350,6 +355,9 @@ def main():
                                       "w_solve": kern_ms[3]},
                         "stream_share_of_step": (kern_ms[0] + kern_ms[2]) / float(sum(kern_ms)),
                         "step_achieved": step_achieved, "step_frac": step_achieved / peak,
+                        "fp64_tflops_step": flops_per_iter * K / (ms_max * 1e-3) / 1e12,
+                        "fp64_tflops_stream": 2.0 * m * n * RANK_ / (stream_ms * 1e-3) / 1e12,
+                        "fp64_peak_tflops_measured": 37.1,
                         "step_note": "whole iteration (all 4 launches + gaps): 2*m*n*8*K / timed seconds; this is "
                                      "the north-star '% of HBM roofline' figure"},
            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "auto_bcv": bcv_info,

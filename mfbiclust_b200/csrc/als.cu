@@ -180,24 +180,25 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 template <int KB>
 struct SolveCfg {
     static constexpr int KP = KB * 8;
-    static constexpr bool LANES = KP <= 32;
-    static constexpr int LP = (KP <= 16) ? 16 : 32;
-    static constexpr int UPW = LANES ? 2 : 32;                   // units per warp
+    static constexpr int LP = NnlsCfg<KP>::LP;
+    static constexpr int R = NnlsCfg<KP>::R;
+    static constexpr int UPW = 2;                                // units per warp
     static constexpr int SU = SOLVE_WARPS * UPW;                 // units per CTA
     static constexpr int XS = SU + 1;
-    static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + 8) * sizeof(double);
+    static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + SOLVE_WARPS * NnlsCfg<KP>::SCR + 8) * sizeof(double);
 };
 
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : 1) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
-    constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW;
+    constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW, LP = Cfg::LP, R = Cfg::R;
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     extern __shared__ __align__(16) unsigned char solve_smem[];
     double *sG = (double *)solve_smem;
     double *sM = sG + KP * KP;
     double *xs = sM + KP * KP;
+    double *scr = xs + KP * XS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = p.k;
 
@@ -230,54 +231,39 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     }
     __syncthreads();
     // ---- from here on the warps of the CTA are independent ----
-    double t1 = 0.0, d2 = 0.0, t2 = 0.0;
+    // (b) exact NNLS, (c) write-back and statistics (lane = (unit, variables) as in nnls_warp)
+    double d2 = 0.0, t2 = 0.0;
     unsigned long long nz = 0ull;
-    if constexpr (Cfg::LANES) {
-        // (b) exact NNLS, (c) write-back and statistics (lane = (unit, rank) as in nnls_lanes)
-        constexpr int LP = Cfg::LP;
+    double t1;
+    if constexpr (KP <= 32)      // tableau in registers, one lane per row
         t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane);
-        __syncwarp();
+    else                         // compressed active-set solves, two variables per lane
+        t1 = nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * UPW, UPW, nvalid_local, lane);
+    __syncwarp();
+    {
         const int i = lane % LP;
         for (int uu = lane / LP; uu < UPW; uu += 32 / LP) {
             const int u = warp * UPW + uu;
-            if (i < k) {
-                const double x = xs[i * XS + u];
-                const size_t off = (size_t)i * p.ldout + (size_t)(unit0 + u);
-                if (u < nvalid_local) {
-                    const double o = p.Fold[off];
-                    d2 += (x - o) * (x - o);
-                    if (x != 0.0) nz |= (1ull << i);
-                    if (WSTEP) {
-                        double gx = 0.0;
-#pragma unroll 4
-                        for (int j = 0; j < k; ++j) gx += sG[j * KP + i] * xs[j * XS + u];   // G symmetric: conflict-free
-                        t2 += x * gx;
-                    }
-                }
-                p.Fout[off] = x;
-            }
-        }
-    } else {
-        // one problem per lane (k > 32): Schur-complement active-set solver with per-thread scratch
-        const int u = warp * UPW + lane;
-        double r[KP], x[KP];
 #pragma unroll
-        for (int c = 0; c < KP; ++c) { r[c] = (c < k) ? xs[c * XS + u] : 0.0; x[c] = 0.0; }
-        if (u < nvalid_local) nnls_thread<KP>(sG, sM, k, r, x);
-        for (int c = 0; c < k; ++c) {
-            const size_t off = (size_t)c * p.ldout + (size_t)(unit0 + u);
-            if (u < nvalid_local) {
-                t1 += x[c] * r[c];
-                const double o = p.Fold[off];
-                d2 += (x[c] - o) * (x[c] - o);
-                if (x[c] != 0.0) nz |= (1ull << c);
-                if (WSTEP) {
-                    double gx = 0.0;
-                    for (int j = 0; j < k; ++j) gx += sG[c * KP + j] * x[j];
-                    t2 += x[c] * gx;
+            for (int q = 0; q < R; ++q) {
+                const int v = i + LP * q;
+                if (v < k) {
+                    const double x = xs[v * XS + u];
+                    const size_t off = (size_t)v * p.ldout + (size_t)(unit0 + u);
+                    if (u < nvalid_local) {
+                        const double o = p.Fold[off];
+                        d2 += (x - o) * (x - o);
+                        if (x != 0.0) nz |= (1ull << v);
+                        if (WSTEP) {
+                            double gx = 0.0;
+#pragma unroll 4
+                            for (int j = 0; j < k; ++j) gx += sG[j * KP + v] * xs[j * XS + u];   // G symmetric: conflict-free
+                            t2 += x * gx;
+                        }
+                    }
+                    p.Fout[off] = x;
                 }
             }
-            p.Fout[off] = x[c];
         }
     }
     d2 = warp_sum(d2);
@@ -802,26 +788,45 @@ __global__ void __launch_bounds__(256) small_crossprod_kernel(const double *__re
     }
 }
 
-template <int KP>
+// mfb_nnls: the product solver (nnls_warp) on given normal equations, 8 columns per CTA
+template <int KB>
 __global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restrict__ G, const double *__restrict__ Minv,
                                                            const double *__restrict__ R, int k, int64_t pcols,
                                                            double *__restrict__ K) {
+    constexpr int KP = KB * 8, SU = 8, XS = SU + 1;
     extern __shared__ double nn_sh[];
-    double *sG = nn_sh, *sM = nn_sh + KP * KP;
-    for (int e = threadIdx.x; e < KP * KP; e += 128) {
-        sG[e] = G[e];
-        sM[e] = Minv[e];
+    double *sG = nn_sh, *sM = sG + KP * KP, *xs = sM + KP * KP, *scr = xs + KP * XS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < KP * KP; e += 128) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        sG[e] = (c1 < k && c2 < k) ? G[c1 * KP + c2] : 0.0;
+        sM[e] = (c1 < k && c2 < k) ? Minv[c1 * KP + c2] : 0.0;
+    }
+    const int64_t j0 = blockIdx.x * (int64_t)SU;
+    const int nvalid = (int)((pcols - j0 < SU) ? pcols - j0 : SU);
+    for (int e = tid; e < SU * KP; e += 128) {
+        const int u = e % SU, c = e / SU;
+        xs[c * XS + u] = (c < k && u < nvalid) ? R[(j0 + u) * k + c] : 0.0;
     }
     __syncthreads();
-    const int64_t j = blockIdx.x * 128ll + threadIdx.x;
-    if (j >= pcols) return;
-    double r[KP], x[KP];
-    for (int c = 0; c < KP; ++c) {
-        r[c] = (c < k) ? R[j * k + c] : 0.0;
-        x[c] = 0.0;
+    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sM, k, xs, warp * 2, 2, nvalid, lane);
+    else nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * 2, 2, nvalid, lane);
+    __syncthreads();
+    for (int e = tid; e < SU * KP; e += 128) {
+        const int u = e % SU, c = e / SU;
+        if (c < k && u < nvalid) K[(j0 + u) * k + c] = xs[c * XS + u];
     }
-    nnls_thread<KP>(sG, sM, k, r, x);
-    for (int c = 0; c < k; ++c) K[j * k + c] = x[c];
+}
+
+template <int KB>
+static int launch_nnls_columns(const double *G, const double *Minv, const double *R, int k, int64_t pcols, double *K,
+                               cudaStream_t st) {
+    constexpr int KP = KB * 8;
+    const size_t smem = (size_t)(2 * KP * KP + KP * 9 + 4 * NnlsCfg<KP>::SCR) * sizeof(double);
+    MFB_CUDA(cudaFuncSetAttribute(nnls_columns_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nnls_columns_kernel<KB><<<(unsigned)((pcols + 7) / 8), 128, smem, st>>>(G, Minv, R, k, pcols, K);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -1328,7 +1333,10 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     MFB_ARG(k >= 1 && k <= 64 && r >= 1 && pcols >= 1, "bad sizes");
     MFB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int KP = (k <= 16) ? 16 : 64;
+    int KB = (k + 7) / 8;
+    if (KB == 5) KB = 6;
+    if (KB == 7) KB = 8;
+    const int KP = KB * 8;
     double *dC, *dB, *dR, *dG, *dM, *dK, *part;
     int *dsing;
     MFB_CUDA(cudaMalloc(&dC, sizeof(double) * r * k));
@@ -1346,11 +1354,17 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     gram_partial_kernel<<<nb, 256, (size_t)k * 65 * sizeof(double), st>>>(dC, r, r, k, KP, part);
     gram_finalize_kernel<<<1, 256, (size_t)(KP * KP + 2) * sizeof(double), st>>>(part, nb, k, KP, dG, dM, dsing);
     small_crossprod_kernel<<<(unsigned)pcols, 256, 0, st>>>(dC, dB, r, k, pcols, dR);
-    if (KP == 16) {
-        nnls_columns_kernel<16><<<(unsigned)((pcols + 127) / 128), 128, 2 * 16 * 16 * sizeof(double), st>>>(dG, dM, dR, k, pcols, dK);
-    } else {
-        MFB_CUDA(cudaFuncSetAttribute(nnls_columns_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * (int)sizeof(double)));
-        nnls_columns_kernel<64><<<(unsigned)((pcols + 127) / 128), 128, 2 * 64 * 64 * sizeof(double), st>>>(dG, dM, dR, k, pcols, dK);
+    {
+        int rc = MFB_ERR_UNSUPPORTED;
+        switch (KB) {
+            case 1: rc = launch_nnls_columns<1>(dG, dM, dR, k, pcols, dK, st); break;
+            case 2: rc = launch_nnls_columns<2>(dG, dM, dR, k, pcols, dK, st); break;
+            case 3: rc = launch_nnls_columns<3>(dG, dM, dR, k, pcols, dK, st); break;
+            case 4: rc = launch_nnls_columns<4>(dG, dM, dR, k, pcols, dK, st); break;
+            case 6: rc = launch_nnls_columns<6>(dG, dM, dR, k, pcols, dK, st); break;
+            case 8: rc = launch_nnls_columns<8>(dG, dM, dR, k, pcols, dK, st); break;
+        }
+        if (rc != MFB_OK) return rc;
     }
     MFB_CUDA(cudaGetLastError());
     int sing = 0;

@@ -1,18 +1,10 @@
-// Per-problem exact NNLS on the normal equations and the k x k Gram inverse it shares.
+// Exact NNLS on the normal equations and the k x k Gram inverse it shares.
 //
-// Replaces NMF::.fcnnls / .cssls (NMF 0.21.0; call sites R/bicluster.R:123,150).  The R code
-// groups columns by passive set and calls solve() per group; here every column (H-step) or
-// row (W-step) of the factor is one thread running the same pivot rules on its own problem
+// Replaces NMF::.fcnnls / .cssls (NMF 0.21.0; call sites R/bicluster.R:123,150).  The R code groups columns by
+// passive set and calls solve() per group; here every column (H-step) or row (W-step) of the factor is solved by
+// a group of 16 or 32 lanes running the same pivot rules on its own problem
 //     min_x 1/2 x'Gx - r'x,  x >= 0        (G = C'C, r = C'a)
-//   * first guess: unconstrained solution xu = solve(G) %*% r, passive set P = {xu > 0}
-//   * inner loop (Lawson-Hanson): while the solution on P has a negative entry, step from the
-//     last feasible point d towards it until the first entry hits zero, drop that entry
-//   * outer loop: gradient w = r - G x on the active set; optimal when no w > 0, else add
-//     argmax w to P.
-// The solve on a passive set P uses the SHARED inverse M = G^-1 (one k x k inversion per
-// half-step for all columns) through the Schur complement on the ACTIVE set N = ~P:
-//     x_P = xu_P - M_PN y,   y = (M_NN)^-1 xu_N,   x_N = 0
-// which costs O(|N|^3 + k|N|) per pivot instead of O(|P|^3), and |N| is small in practice.
+// against the SHARED inverse M = G^-1 (one k x k inversion per half-step for all problems): see nnls_warp below.
 #pragma once
 #include "common.cuh"
 
@@ -70,125 +62,6 @@ __device__ int gauss_jordan_inverse(double *a, int k, int ld, int tid, int nthre
     bar();
     return scratch[1] != 0.0;
 }
-
-// One NNLS problem per thread.  G, M: shared memory, leading dimension KP (KP = padded rank).
-// r: right-hand side (k entries used).  x: result.  Returns the number of pivots taken.
-template <int KP>
-__device__ int nnls_thread(const double *__restrict__ G, const double *__restrict__ M, int k, const double *r,
-                           double *x) {
-    double xu[KP], d[KP], y[KP];
-    int idx[KP];
-    double L[KP * (KP + 1) / 2];
-    uint64_t P = 0;
-    const uint64_t full = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
-    for (int i = 0; i < k; ++i) {
-        double s = 0.0;
-        for (int j = 0; j < k; ++j) s += M[i * KP + j] * r[j];
-        xu[i] = s;
-        if (s > 0.0) P |= (1ull << i);
-    }
-    if (P == full) {
-        for (int i = 0; i < k; ++i) x[i] = xu[i];
-        return 0;
-    }
-    for (int i = 0; i < k; ++i) {
-        x[i] = (xu[i] > 0.0) ? xu[i] : 0.0;
-        d[i] = x[i];
-    }
-    int pivots = 0;
-    const int cap = 4 * k + 8;
-
-    auto solve_on_P = [&]() {
-        // active list
-        int nn = 0;
-        for (int i = 0; i < k; ++i)
-            if (!((P >> i) & 1ull)) idx[nn++] = i;
-        if (nn == 0) {
-            for (int i = 0; i < k; ++i) x[i] = xu[i];
-            return;
-        }
-        if (nn == k) {
-            for (int i = 0; i < k; ++i) x[i] = 0.0;
-            return;
-        }
-        // Cholesky of M[N,N] (row-packed lower triangle), forward/back substitution
-        for (int a = 0; a < nn; ++a) {
-            for (int b = 0; b <= a; ++b) {
-                double s = M[idx[a] * KP + idx[b]];
-                for (int c = 0; c < b; ++c) s -= L[a * (a + 1) / 2 + c] * L[b * (b + 1) / 2 + c];
-                if (a == b)
-                    L[a * (a + 1) / 2 + a] = sqrt(fmax(s, 1e-300));
-                else
-                    L[a * (a + 1) / 2 + b] = s / L[b * (b + 1) / 2 + b];
-            }
-        }
-        for (int a = 0; a < nn; ++a) {
-            double s = xu[idx[a]];
-            for (int c = 0; c < a; ++c) s -= L[a * (a + 1) / 2 + c] * y[c];
-            y[a] = s / L[a * (a + 1) / 2 + a];
-        }
-        for (int a = nn - 1; a >= 0; --a) {
-            double s = y[a];
-            for (int c = a + 1; c < nn; ++c) s -= L[c * (c + 1) / 2 + a] * y[c];
-            y[a] = s / L[a * (a + 1) / 2 + a];
-        }
-        for (int i = 0; i < k; ++i) {
-            if ((P >> i) & 1ull) {
-                double s = xu[i];
-                for (int a = 0; a < nn; ++a) s -= M[i * KP + idx[a]] * y[a];
-                x[i] = s;
-            } else {
-                x[i] = 0.0;
-            }
-        }
-    };
-
-    while (pivots < cap) {
-        solve_on_P();
-        // inner loop: restore feasibility
-        while (pivots < cap) {
-            double amin = INFINITY;
-            int imin = -1;
-            for (int i = 0; i < k; ++i) {
-                if (((P >> i) & 1ull) && x[i] < 0.0) {
-                    double al = d[i] / (d[i] - x[i]);
-                    if (al < amin) {
-                        amin = al;
-                        imin = i;
-                    }
-                }
-            }
-            if (imin < 0) break;
-            for (int i = 0; i < k; ++i) d[i] = d[i] - amin * (d[i] - x[i]);
-            d[imin] = 0.0;
-            P &= ~(1ull << imin);
-            ++pivots;
-            solve_on_P();
-        }
-        // optimality on the active set: w = r - G x
-        double wmax = 0.0;
-        int imax = -1;
-        for (int i = 0; i < k; ++i) {
-            if (!((P >> i) & 1ull)) {
-                double w = r[i];
-                for (int j = 0; j < k; ++j) w -= G[i * KP + j] * x[j];
-                if (w > wmax) {
-                    wmax = w;
-                    imax = i;
-                }
-            }
-        }
-        if (imax < 0) break;
-        P |= (1ull << imax);
-        for (int i = 0; i < k; ++i) d[i] = x[i];
-        ++pivots;
-    }
-    // guard: whatever the path, never return a negative entry
-    for (int i = 0; i < k; ++i)
-        if (!(x[i] > 0.0)) x[i] = 0.0;
-    return pivots;
-}
-
 
 // ---------------------------------------------------------------------------
 // Warp-level in-place inversion of the SPD k x k matrix `a` (shared memory, ld, k <= 32): lane i owns row i in
@@ -356,6 +229,231 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
         const double x = (inS && rowvalid && uvalid && qv > 0.0) ? qv : 0.0;
         t1 += x * ri;
         if (rowvalid && rd + sub < count) xs[i * XS + unit] = x;
+    }
+    return t1;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative exact NNLS for any rank up to 64 (used for k > 32, where a tableau row no longer fits the
+// registers of one lane): active-set iteration with a COMPRESSED solve.
+//
+// Same pivot rules as one column of .fcnnls (first passive set = {xu > 0}; while the solve on the passive set
+// goes negative step back along d -> x and drop the blocking variable; when feasible add the variable with the
+// largest positive gradient; stop when there is none).  A group of LP lanes owns one problem, lane i owning the
+// variables i (+ LP): instead of exchanging variables one at a time, every iteration solves the current
+// partition directly on its SMALLER side S (|S| <= k/2):
+//   S = N (active set):   y = (M_NN)^-1 xu_N,  x_P = xu_P - M_PN y,  w_N = y          (M = G^-1, xu = M r)
+//   S = P (passive set):  y = (G_PP)^-1 r_P,   x_P = y,              w_N = r_N - G_NP y
+// The |S| x |S| system is gathered into registers (lane l = compressed row l), eliminated without pivoting (SPD)
+// with the pivot rows broadcast by shuffles, and back-substituted so that every lane ends up holding all of y.
+// The initial clamp guess therefore costs ONE small solve instead of one tableau exchange per clamped variable.
+//
+// xs: shared [KP][XS] -- right-hand sides r on entry, solutions x on exit (column = problem).  The warp solves the
+// problems [first, first + count) of xs, 32 / LP at a time; problems >= nvalid are skipped (x = 0).
+// scr: per-warp shared scratch of nnls_scratch_doubles<KP>() doubles.  Returns this lane's partial of sum x_i r_i.
+// ---------------------------------------------------------------------------
+template <int KP>
+struct NnlsCfg {
+    static constexpr int LP = (KP <= 16) ? 16 : 32;
+    static constexpr int R = (KP + LP - 1) / LP;           // variables per lane
+    static constexpr int NS = (KP / 2 < 1) ? 1 : KP / 2;   // largest compressed system
+    static constexpr int PPW = 32 / LP;                    // problems per warp and round
+    static constexpr int SCR = PPW * (KP + NS + (NS + 1) / 2);   // doubles: xu[KP], y[NS], idx[NS] (ints) per problem
+};
+
+template <int KP, int XS>
+__device__ double nnls_warp(const double *__restrict__ sG, const double *__restrict__ sM, int k, double *xs,
+                            double *scr, int first, int count, int nvalid, int lane) {
+    using C = NnlsCfg<KP>;
+    constexpr int LP = C::LP, R = C::R, NS = C::NS, PPW = C::PPW;
+    const unsigned FULL = 0xffffffffu;
+    const int grp = lane / LP, i = lane % LP, base = grp * LP;
+    const unsigned long long fullk = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
+    double *xu_s = scr + grp * (KP + NS + (NS + 1) / 2);
+    double *y_s = xu_s + KP;
+    int *idx_s = (int *)(y_s + NS);
+    double t1 = 0.0;
+    for (int rd = 0; rd < count; rd += PPW) {
+        const int unit = first + rd + grp;
+        const bool inrange = rd + grp < count;
+        const bool uvalid = inrange && (unit < nvalid);
+        if (!__any_sync(FULL, uvalid)) {
+            if (inrange)
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (i + LP * q < k) xs[(i + LP * q) * XS + unit] = 0.0;
+            continue;
+        }
+        const int ucol = inrange ? unit : first;           // a readable column for lanes without a problem
+        double r_[R], xu_[R], d_[R], x_[R], w_[R];
+        bool inN_[R], val_[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int v = i + LP * q;
+            val_[q] = uvalid && (v < k);
+            r_[q] = val_[q] ? xs[v * XS + ucol] : 0.0;
+            double acc = 0.0;
+            if (v < k)
+                for (int j = 0; j < k; ++j) acc += sM[j * KP + v] * xs[j * XS + ucol];
+            xu_[q] = val_[q] ? acc : 0.0;
+            if (v < KP) xu_s[v] = xu_[q];
+            inN_[q] = val_[q] && !(xu_[q] > 0.0);
+            d_[q] = xu_[q] > 0.0 ? xu_[q] : 0.0;
+            x_[q] = d_[q];
+            w_[q] = 0.0;
+        }
+        bool done = !uvalid;
+        int iters = 0;
+        const int cap = 6 * k + 16;
+        while (true) {
+            // ---- partition of this group's problem ----
+            unsigned long long maskN = 0ull;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const unsigned bal = __ballot_sync(FULL, inN_[q]);
+                const unsigned long long gb = (LP == 32) ? (unsigned long long)bal : (unsigned long long)((bal >> base) & 0xffffu);
+                maskN |= gb << (LP * q);
+            }
+            const int na = __popcll(maskN), np = k - na;
+            const bool useN = na <= np;
+            const unsigned long long smask = useN ? maskN : (~maskN & fullk);
+            const int ns = done ? 0 : (useN ? na : np);
+            int ns_max = ns;
+#pragma unroll
+            for (int o = 16; o >= LP; o >>= 1) ns_max = max(ns_max, __shfl_xor_sync(FULL, ns_max, o));
+            if (!__any_sync(FULL, !done)) break;
+            const double *Msrc = useN ? sM : sG;
+            int pos_[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int v = i + LP * q;
+                pos_[q] = __popcll(smask & ((1ull << v) - 1ull));
+                if (!done && ((smask >> v) & 1ull)) idx_s[pos_[q]] = v;
+            }
+            __syncwarp();
+            // ---- gather the compressed system: lane i < ns owns row i ----
+            double A[NS], yv[NS];
+            const bool rowok = i < ns;
+            const int my = rowok ? idx_s[i] : 0;
+#pragma unroll
+            for (int b = 0; b < NS; ++b) {
+                A[b] = (b == i) ? 1.0 : 0.0;                 // identity padding outside the ns x ns block
+                yv[b] = 0.0;
+                if (b < ns_max) {
+                    const int ib = (b < ns) ? idx_s[b] : 0;
+                    if (rowok && b < ns) A[b] = Msrc[ib * KP + my];
+                }
+            }
+            double rhs = rowok ? (useN ? xu_s[my] : xs[my * XS + ucol]) : 0.0;
+            // ---- forward elimination (no pivoting: principal sub-matrix of an SPD matrix) ----
+#pragma unroll
+            for (int a = 0; a < NS; ++a) {
+                if (a < ns_max) {
+                    const double pa = __shfl_sync(FULL, A[a], base + a);
+                    const double ip = 1.0 / pa;
+                    yv[a] = ip;
+                    const double f = (i > a) ? A[a] * ip : 0.0;
+#pragma unroll
+                    for (int b = a + 1; b < NS; ++b)
+                        if (b < ns_max) A[b] -= f * __shfl_sync(FULL, A[b], base + a);
+                    rhs -= f * __shfl_sync(FULL, rhs, base + a);
+                }
+            }
+            // ---- back substitution: every lane learns every y_a ----
+#pragma unroll
+            for (int a = NS - 1; a >= 0; --a) {
+                if (a < ns_max) {
+                    const double ya = __shfl_sync(FULL, rhs, base + a) * yv[a];
+                    yv[a] = ya;
+                    if (i < a) rhs -= A[a] * ya;
+                    if (i == 0 && a < ns) y_s[a] = ya;
+                }
+            }
+            __syncwarp();
+            // ---- primal values on P, gradient on N ----
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int v = i + LP * q;
+                if (val_[q] && !done) {
+                    const bool inS = (smask >> v) & 1ull;
+                    if (inS) {
+                        const double ys = y_s[pos_[q]];
+                        x_[q] = useN ? 0.0 : ys;
+                        w_[q] = useN ? ys : 0.0;
+                    } else {
+                        double acc = useN ? xu_[q] : r_[q];
+#pragma unroll
+                        for (int b = 0; b < NS; ++b)
+                            if (b < ns) acc -= Msrc[idx_s[b] * KP + v] * yv[b];
+                        x_[q] = useN ? acc : 0.0;
+                        w_[q] = useN ? 0.0 : acc;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- pivot rules ----
+            if (!done) {
+                const unsigned gm = (LP == 32) ? FULL : (0xffffu << base);
+                bool anyneg = false;
+                double al = INFINITY;
+                int av = 1 << 20;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const bool neg = val_[q] && !inN_[q] && x_[q] < 0.0;
+                    anyneg |= neg;
+                    const double a1 = neg ? d_[q] / (d_[q] - x_[q]) : INFINITY;
+                    if (a1 < al) { al = a1; av = i + LP * q; }
+                }
+                if (__ballot_sync(gm, anyneg) != 0u) {
+                    // Lawson-Hanson step back: the first passive variable to hit zero leaves the passive set
+#pragma unroll
+                    for (int o = LP / 2; o > 0; o >>= 1) {
+                        const double oa = __shfl_xor_sync(gm, al, o);
+                        const int ov = __shfl_xor_sync(gm, av, o);
+                        if (oa < al || (oa == al && ov < av)) { al = oa; av = ov; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        d_[q] = d_[q] - al * (d_[q] - x_[q]);
+                        if (i + LP * q == av) { d_[q] = 0.0; inN_[q] = true; }
+                    }
+                } else {
+                    bool anypos = false;
+                    double wm = -1.0;
+                    int wv = 1 << 20;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const bool pos = val_[q] && inN_[q] && w_[q] > 0.0;
+                        anypos |= pos;
+                        if (pos && w_[q] > wm) { wm = w_[q]; wv = i + LP * q; }
+                    }
+                    if (__ballot_sync(gm, anypos) != 0u) {
+#pragma unroll
+                        for (int o = LP / 2; o > 0; o >>= 1) {
+                            const double ow = __shfl_xor_sync(gm, wm, o);
+                            const int ov = __shfl_xor_sync(gm, wv, o);
+                            if (ow > wm || (ow == wm && ov < wv)) { wm = ow; wv = ov; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            d_[q] = x_[q];
+                            if (i + LP * q == wv) inN_[q] = false;
+                        }
+                    } else {
+                        done = true;
+                    }
+                }
+                if (++iters > cap) done = true;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int v = i + LP * q;
+            const double x = (val_[q] && !inN_[q] && x_[q] > 0.0) ? x_[q] : 0.0;
+            t1 += x * r_[q];
+            if (inrange && v < k) xs[v * XS + unit] = x;
+        }
+        __syncwarp();
     }
     return t1;
 }

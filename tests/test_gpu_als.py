@@ -22,7 +22,8 @@ def make_init(m, n, k, seed):
     return np.asfortranarray(W0), np.asfortranarray(rs.random((k, n)))
 
 
-@pytest.mark.parametrize("k,r,p", [(1, 50, 7), (3, 200, 33), (8, 300, 500), (16, 257, 129), (20, 100, 40)])
+@pytest.mark.parametrize("k,r,p", [(1, 50, 7), (3, 200, 33), (8, 300, 500), (16, 257, 129), (20, 100, 40), (33, 150, 90),
+                                   (48, 200, 130), (64, 300, 257)])
 def test_nnls_matches_fcnnls(k, r, p):
     import mfbiclust_b200 as mfb
     rs = np.random.default_rng(k * 100 + p)
@@ -96,7 +97,7 @@ def test_als_yeast_k3(yeast):
     _check_replicate(A, 3, 10, seed=42)
 
 
-@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1500, 700, 10), (640, 1030, 24)])
+@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1500, 700, 10), (640, 1030, 24), (900, 600, 40), (600, 400, 64)])
 def test_als_synthetic(m, n, k):
     A = pseudovalues(gen_sim_data(n=4, cluster_height=min(m, n) // 5, cluster_width=min(m, n) // 5, dimx=m, dimy=n,
                                   bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=m + n))
@@ -113,3 +114,25 @@ def test_als_convergence_matches_oracle(yeast):
     assert got["iters"] == ref["iters"]
     assert rel_fro(got["W"], ref["W"]) < 1e-8 and rel_fro(got["H"], ref["H"]) < 1e-8
     assert abs(got["obj"] - ref["obj"]) < 1e-10
+
+
+def test_nnls_is_optimal_where_the_reference_hits_its_sweep_cap():
+    """NMF::.fcnnls caps its inner loop with a sweep counter that is cumulative over ALL columns (maxiter = 3k,
+    SURVEY.md App. A.1): on a large enough problem at k = 64 the reference (and the literal oracle) stops early and
+    returns a K that violates the KKT conditions.  The GPU solver has no such cap across problems: it must return
+    the optimum, i.e. agree with an independent exact NNLS and satisfy KKT.  (Knowing divergence, DESIGN.md.)"""
+    import scipy.optimize as so
+    import mfbiclust_b200 as mfb
+    m, n, k = 1200, 800, 64
+    A = pseudovalues(gen_sim_data(n=4, cluster_height=160, cluster_width=160, dimx=m, dimy=n, bg_norm=1.0,
+                                  bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=m + n))
+    W0, _ = make_init(m, n, k, 43)
+    K = mfb.nnls(W0, A)
+    G, R = W0.T @ W0, W0.T @ A
+    w = R - G @ K
+    assert (K >= 0).all()
+    assert (w[K == 0] <= 1e-8 * np.abs(R).max()).all()            # no positive gradient left on the active set
+    assert np.abs(w[K > 0]).max() <= 1e-8 * np.abs(R).max()       # stationarity on the passive set
+    for j in range(0, n, 80):
+        x, _ = so.nnls(W0, A[:, j])
+        assert np.abs(x - K[:, j]).max() < 1e-8 * max(1.0, np.abs(x).max())
