@@ -446,12 +446,54 @@ def bcv(Y, ks=None, holdouts=10, interactive=True, rng=None, folds=None, ctx=Non
     return {int(k): float(v) for k, v in zip(ks, res)}
 
 
+def bcv_batch(Yd, ks, holdouts, folds_list, ctx=None, group=None):
+    """``bcvGivenKs`` for several fold draws at once: the ``len(folds_list) * holdouts^2`` cells are one flat work
+    list sharded over the ranks (:func:`shard_cells`).  Returns ``(len(folds_list), len(ks))`` BCV values."""
+    ctx = ctx or _cabi.default_context()
+    rank, world, dist = _dist_info(group)
+    ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
+    h2 = holdouts * holdouts
+    n = Yd.shape[0]
+    if dist is not None and world > 1:
+        flat = [_bcast_folds(np.ascontiguousarray(rf, dtype=np.int32), np.ascontiguousarray(cf, dtype=np.int32),
+                             ctx.device, dist, group) for rf, cf in folds_list]
+    else:
+        flat = [(np.ascontiguousarray(rf, dtype=np.int32), np.ascontiguousarray(cf, dtype=np.int32))
+                for rf, cf in folds_list]
+
+    def compute(c0, c1):
+        out = np.zeros((c1 - c0, len(ks)))
+        c = c0
+        while c < c1:
+            it, lo = divmod(c, h2)
+            hi = min(h2, lo + (c1 - c))
+            rf, cf = flat[it]
+            loc = np.zeros((hi - lo, len(ks)))
+            check(lib().mfb_bcv_cells(ctx.handle, Yd.handle, rf.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      cf.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
+                                      ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), lo, hi, dptr(loc)))
+            out[c - c0:c - c0 + (hi - lo)] = loc
+            c += hi - lo
+        return out
+    err = shard_cells(len(flat) * h2, len(ks), compute, ctx.device, group)
+    return err.reshape(len(flat), h2, len(ks)).sum(axis=1)
+
+
 def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verbose=False, interactive=True,
-             rng=None, ctx=None, group=None):
+             rng=None, ctx=None, group=None, speculate=None):
     """``auto_bcv(Y, ks, holdouts = 3L, maxIter = 100L, tol = 1e-4, bestOnly = FALSE, verbose = FALSE,
-    interactive = TRUE)`` (``R/bcv.R:31-98``).  Y is uploaded once and stays resident for every ``bcv`` call."""
+    interactive = TRUE)`` (``R/bcv.R:31-98``).  Y is uploaded once and stays resident for every ``bcv`` call.
+
+    The outer loop is sequential only through its stopping rule; the fold draws do not depend on the data.  With
+    ``speculate = B`` (default: the number of ranks, i.e. 1 on a single GPU) the folds of the next B outer
+    iterations are drawn in order, their ``B * holdouts^2`` cells are computed as one sharded batch, and the
+    stopping rule is then applied iteration by iteration exactly as in R; iterations computed past the one that
+    converges are discarded.  ``best``, ``counts`` and the iteration count are therefore identical for every B and
+    every number of GPUs; only the number of uniforms consumed from ``rng`` after convergence differs."""
     ctx = ctx or _cabi.default_context()
     rng = rng or HostRng()
+    rank, world, _ = _dist_info(group)
+    B = max(1, int(speculate if speculate is not None else world))
     own = not isinstance(Y, _cabi.Matrix)
     if own:
         Y = np.asarray(Y, dtype=np.float64)
@@ -459,42 +501,50 @@ def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verb
             raise NotImplementedError("auto_bcv: matrices with NA entries are not supported yet")
     Yd = _cabi.Matrix(ctx, host=Y) if own else Y
     try:
-        minDim = min(Yd.shape)
+        n, p = Yd.shape
+        minDim = min(n, p)
         if ks is None:
             ks = np.arange(1, minDim)
         ks = kLimiter(holdouts, minDim, ks)                                   # :48
-        distr = {int(k): 1 for k in ks}
+        ks = np.asarray(ks)
+        if ks.size == 0 or (ks < 1).any() or (ks != np.floor(ks)).any():
+            raise ValueError("ks must be a vector of positive whole numbers")
+        if holdouts > minDim:                                                  # bcv(): :146-150
+            holdouts = minDim
+            warnings.warn(f"Using {holdouts} holdouts to ensure non-zero holdout size.")
+        keys = [int(k) for k in ks]
+        distr = {k: 1 for k in keys}
         distrOld = dict(distr)
         i = 0
         converged = False
         while not converged and i < maxIter:                                   # :56
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                res = bcv(Yd, list(distr.keys()), holdouts=holdouts, interactive=False, rng=rng, ctx=ctx,
-                          group=group)                                         # :58
-            best = min(res, key=lambda kk: (res[kk], list(res).index(kk)))     # names(which.min(res))
-            distr[best] += 1
-            if len(distr) > len(res):                                          # :64-66
-                distr = {kk: distr[kk] for kk in res}
-                distrOld = {kk: distrOld[kk] for kk in res}
-            sd, so = sum(distr.values()), sum(distrOld.values())
-            resid = [(distr[kk] / sd - distrOld[kk] / so) ** 2 for kk in distr]
-            if verbose:
-                cur = max(distr, key=lambda kk: (distr[kk], -list(distr).index(kk)))
-                print(f"Iteration {i + 1} ")
-                print(f"Current best: {cur} ")
-                print("BCV result distribution:")
-                print("\t".join(str(kk) for kk in distr) + "\n" + "\t".join(str(v - 1) for v in distr.values()))
-            converged = all(r < tol for r in resid)                            # :84
-            distrOld = dict(distr)
-            i += 1
+            nb = min(B, maxIter - i)
+            folds = [draw_folds(rng, n, p, holdouts) for _ in range(nb)]       # in order: the stream R would consume
+            vals = bcv_batch(Yd, keys, holdouts, folds, ctx=ctx, group=group)  # :58, nb calls of bcv()
+            for j in range(nb):
+                res = dict(zip(keys, vals[j]))
+                best = min(keys, key=lambda kk: (res[kk], keys.index(kk)))     # names(which.min(res))
+                distr[best] += 1
+                sd, so = sum(distr.values()), sum(distrOld.values())
+                resid = [(distr[kk] / sd - distrOld[kk] / so) ** 2 for kk in keys]   # :69-71
+                if verbose:
+                    cur = max(keys, key=lambda kk: (distr[kk], -keys.index(kk)))
+                    print(f"Iteration {i + 1} ")
+                    print(f"Current best: {cur} ")
+                    print("BCV result distribution:")
+                    print("\t".join(str(kk) for kk in keys) + "\n" + "\t".join(str(distr[kk] - 1) for kk in keys))
+                converged = all(r < tol for r in resid)                        # :84
+                distrOld = dict(distr)
+                i += 1
+                if converged:
+                    break
         if i == maxIter:
             warnings.warn(f"BCV results did not converge after{maxIter}iterations")
     finally:
         if own:
             Yd.free()
     counts = {kk: v - 1 for kk, v in distr.items()}                            # :93
-    med = max(counts, key=lambda kk: (counts[kk], -list(counts).index(kk)))    # which.max: first maximum
+    med = max(keys, key=lambda kk: (counts[kk], -keys.index(kk)))              # which.max: first maximum
     if bestOnly:
         return med
     return dict(best=med, counts=counts, iterations=i)

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     using Cfg = SolveCfg<KB>;
     constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW, LP = Cfg::LP, R = Cfg::R;
     pdl_prologue();
-    if (*(volatile int *)&p.ctrl->stop) return;
+    const int stopped = *(volatile int *)&p.ctrl->stop;     // consumed after the loads below are in flight
     extern __shared__ __align__(16) unsigned char solve_smem[];
     double *sG = (double *)solve_smem;
     double *sM = sG + KP * KP;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     const int k = p.k;
 
     for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
-        sG[e] = p.G[e];
+        if (WSTEP || KP > 32) sG[e] = p.G[e];               // the H-step tableau solver only needs G^-1
         sM[e] = p.Minv[e];
     }
     const long long unit0 = (long long)blockIdx.x * SU;
@@ -224,11 +224,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         double r = 0.0;
         if (c < k && u < nvalid_local) {
             const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + uoff + u;
+            if (expected <= 12) {                            // all slots in flight at once, summed in slot order
+                double v[12];
+#pragma unroll
+                for (int s = 0; s < 12; ++s) v[s] = (s < expected) ? ldcg(Pt + (size_t)s * (KP * TILE_UNITS)) : 0.0;
+#pragma unroll
+                for (int s = 0; s < 12; ++s) r += v[s];
+            } else {
 #pragma unroll 4
-            for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
+                for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
+            }
         }
         xs[c * XS + u] = r;
     }
+    if (stopped) return;
     __syncthreads();
     // ---- from here on the warps of the CTA are independent ----
     // (b) exact NNLS, (c) write-back and statistics (lane = (unit, variables) as in nnls_warp)

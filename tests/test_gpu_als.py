@@ -136,3 +136,39 @@ def test_nnls_is_optimal_where_the_reference_hits_its_sweep_cap():
     for j in range(0, n, 80):
         x, _ = so.nnls(W0, A[:, j])
         assert np.abs(x - K[:, j]).max() < 1e-8 * max(1.0, np.abs(x).max())
+
+
+def test_fixture_w_halfstep_k1(ref_bces):
+    # tests/testdata/ref_bces.rda pins the W half-step arithmetic: stored W == NNLS(t(H), t(A))  (R/bicluster.R:150)
+    import mfbiclust_b200 as mfb
+    g = ref_bces["bce.als_nmf"]
+    A = np.array(ref_bces["input"])
+    W, H = np.array(g["W"]), np.array(g["H"])
+    Wt = mfb.nnls(H.T, A.T)
+    assert np.abs(Wt.T - W).max() < 1e-14
+    bcs = mfb.BiclusterStrategy(mfb.genericFit(mfb.genericFactorization(W, H), "als-nmf"), 1, method="als-nmf")
+    assert np.array_equal(bcs.featureThresh, np.array(g["featureThresh"]))
+    assert np.array_equal(bcs.sampleThresh, np.array(g["sampleThresh"]))
+    assert np.array_equal(bcs.biclust.RowxNumber.astype(int), np.array(g["RowxNumber"]))
+    assert np.array_equal(bcs.biclust.NumberxCol.astype(int), np.array(g["NumberxCol"]))
+
+
+@pytest.mark.parametrize("m,n,k", [(6, 6, 1), (17, 5, 2), (5, 40, 3), (130, 33, 7), (33, 300, 4)])
+def test_als_tiny_and_ragged(m, n, k):
+    # fewer work units than CTAs, single tiles, dimensions that are not multiples of any tile size
+    rs = np.random.default_rng(m * 1000 + n)
+    A = np.asfortranarray(rs.random((m, n)) + 0.05)
+    _check_replicate(A, k, 6, seed=m + n)
+
+
+def test_als_rejects_negative_and_bad_eps():
+    import mfbiclust_b200 as mfb
+    A = np.ones((8, 8))
+    A[2, 3] = -1.0
+    W0, H0 = make_init(8, 8, 2, 1)
+    with pytest.raises(ValueError, match="Negative values are not allowed"):          # R/bicluster.R:76
+        mfb.als_nmf(A, 2)
+    with pytest.raises(ValueError, match="eps_conv"):                                 # R/bicluster.R:86
+        mfb.als_nmf(np.abs(A), 2, eps_conv=0.0)
+    with pytest.raises(mfb.MfbError, match="Negative values are not allowed"):
+        mfb.AlsSession(mfb.Matrix(mfb.default_context(), host=A), 2, W0, H0, 1.0)

@@ -80,3 +80,12 @@ def test_auto_bcv_vignette(yeast, vignette):
     best, counts, iters = B.auto_bcv(Y, np.arange(1, min(Y.shape)), 3, draw)
     assert best == res["best"] and iters == res["iterations"]
     assert list(counts) == [res["counts"][k] for k in sorted(res["counts"])]
+
+
+def test_auto_bcv_speculation_is_invisible(yeast):
+    # computing several outer iterations per batch must not change best / counts / iteration count
+    import mfbiclust_b200 as mfb
+    Y = yeast[2]
+    a = mfb.auto_bcv(Y, rng=mfb.HostRng(7), speculate=1)
+    b = mfb.auto_bcv(Y, rng=mfb.HostRng(7), speculate=5)
+    assert a == b
