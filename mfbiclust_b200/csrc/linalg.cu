@@ -195,18 +195,25 @@ __device__ __forceinline__ double tri_block_sum(double v, double *sh) {
 }
 
 // Householder reduction to tridiagonal form (LAPACK dsytd2, lower): A = Q T Q', reflector i stored in A[i+2:N, i]
-// (v[i+1] = 1 implicit), tau[i], T = (d, e).  Rows of the trailing block are dealt to the blocks every step.
+// (v[i+1] = 1 implicit), tau[i], T = (d, e).  One cooperative launch, two grid-wide barriers per column.  Block b
+// owns the columns c with c % gridDim.x == b of the (symmetric, fully stored) trailing block for both the
+// matrix-vector product p = tau A22 v and the rank-2 update A22 -= v w' + w v'; it works on four columns at a time
+// so that every thread has ~20 independent loads in flight (the sweep is latency-, not bandwidth-bound).
 __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t N, double *d, double *e,
                                                               double *tau, double *vbuf, double *pbuf,
                                                               double *part) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[TRI_THREADS / 32];
+    __shared__ double shq[TRI_THREADS / 32][4];
+    __shared__ double spv[4];
     const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     for (int64_t i = 0; i + 1 < N; ++i) {
         // phase 0 (redundant per block): reflector from column i
-        const double alpha = A[(i + 1) + i * N];
+        // (column i was last written by its owner block before the grid barrier: read it through L2)
+        const double alpha = __ldcg(&A[(i + 1) + i * N]);
         double q = 0.0;
-        for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) { const double v = A[r + i * N]; q += v * v; }
+        for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) { const double v = __ldcg(&A[r + i * N]); q += v * v; }
         const double xnorm = sqrt(tri_block_sum(q, sh));
         double beta, tq, scale;
         if (xnorm == 0.0) {
@@ -216,36 +223,87 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
             tq = (beta - alpha) / beta;
             scale = 1.0 / (alpha - beta);
         }
-        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) vbuf[r] = (r == i + 1) ? 1.0 : A[r + i * N] * scale;
-        if (b == 0 && tid == 0) { d[i] = A[i + i * N]; e[i] = beta; tau[i] = tq; }
+        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) vbuf[r] = (r == i + 1) ? 1.0 : __ldcg(&A[r + i * N]) * scale;
+        if (b == 0 && tid == 0) { d[i] = __ldcg(&A[i + i * N]); e[i] = beta; tau[i] = tq; }
         __syncthreads();
-        // columns i+1 .. N-1 of the (symmetric, fully stored) trailing block are dealt to the warps of the grid;
-        // a warp walks a column with coalesced loads (row r of A22 equals column r)
-        const int warp = tid >> 5, lane = tid & 31;
-        const int64_t gw = (int64_t)b * (TRI_THREADS / 32) + warp, tw = (int64_t)nb * (TRI_THREADS / 32);
-        // phase 1: p = tau * A22 v
+        const double *v = vbuf;      // (no __restrict__ / read-only path: these buffers are rewritten inside the kernel)
+        // first owned column >= i + 1
+        const int64_t cfirst = (i + 1) + (((int64_t)b - (i + 1)) % nb + nb) % nb;
+        // phase 1: p = tau * A22 v on the owned columns
         double pvs = 0.0;
-        for (int64_t c = i + 1 + gw; c < N; c += tw) {
-            const double *col = A + c * N;
-            double s0 = 0.0;
-            for (int64_t r = i + 1 + lane; r < N; r += 32) s0 += col[r] * vbuf[r];
-            s0 = warp_sum(s0);
-            const double pc = tq * s0;
-            if (lane == 0) { pbuf[c] = pc; pvs += pc * vbuf[c]; }
+        for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
+            const double *col[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int64_t cq = c0 + qq * (int64_t)nb;
+                col[qq] = A + ((cq < N) ? cq : c0) * N;
+            }
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+            for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) {
+                const double vr = v[r];
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) s4[qq] += col[qq][r] * vr;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const double t = warp_sum(s4[qq]);
+                if (lane == 0) shq[warp][qq] = t;
+            }
+            __syncthreads();
+            if (tid < 4) {
+                const int64_t cq = c0 + tid * (int64_t)nb;
+                if (cq < N) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < TRI_THREADS / 32; ++w) t += shq[w][tid];
+                    const double pc = tq * t;
+                    pbuf[cq] = pc;
+                    pvs += pc * v[cq];
+                }
+            }
+            __syncthreads();
         }
-        pvs = tri_block_sum(pvs, sh);
-        if (tid == 0) part[b] = pvs;
+        if (tid < 4) spv[tid] = pvs;
+        __syncthreads();
+        if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
         grid.sync();
-        // phase 2: w = p - (tau/2)(p'v) v ;  A22 -= v w' + w v'
+        // phase 2: w = p - (tau/2)(p'v) v ;  A22 -= v w' + w v' on the owned columns
         double pv = 0.0;
-        for (int bb = 0; bb < nb; ++bb) pv += part[bb];
+        for (int bb = tid; bb < nb; bb += TRI_THREADS) pv += __ldcg(&part[bb]);
+        pv = tri_block_sum(pv, sh);
         const double alpha2 = -0.5 * tq * pv;
-        for (int64_t c = i + 1 + gw; c < N; c += tw) {
-            double *col = A + c * N;
-            const double vc = vbuf[c], wc = pbuf[c] + alpha2 * vc;
-            for (int64_t r = i + 1 + lane; r < N; r += 32) {
-                const double vr = vbuf[r], wr = pbuf[r] + alpha2 * vr;
-                col[r] -= vr * wc + wr * vc;
+        const double *pb = pbuf;
+        for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
+            double *col[4];
+            double vc[4], wc[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int64_t cq = c0 + qq * (int64_t)nb;
+                const bool ok = cq < N;
+                col[qq] = ok ? A + cq * N : nullptr;
+                vc[qq] = ok ? __ldcg(&vbuf[cq]) : 0.0;
+                wc[qq] = ok ? __ldcg(&pbuf[cq]) + alpha2 * vc[qq] : 0.0;
+            }
+            // two rows per trip, all loads before the stores (the compiler cannot reorder them itself)
+            for (int64_t r = i + 1 + tid; r < N; r += 2 * TRI_THREADS) {
+                const int64_t r2 = r + TRI_THREADS;
+                const bool ok2 = r2 < N;
+                const double vr = v[r], wr = __ldcg(&pb[r]) + alpha2 * vr;
+                const double vr2 = ok2 ? v[r2] : 0.0, wr2 = ok2 ? __ldcg(&pb[r2]) + alpha2 * vr2 : 0.0;
+                double a1[4], a2[4];
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    a1[qq] = col[qq] ? col[qq][r] : 0.0;
+                    a2[qq] = (col[qq] && ok2) ? col[qq][r2] : 0.0;
+                }
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    if (col[qq]) {
+                        col[qq][r] = a1[qq] - (vr * wc[qq] + wr * vc[qq]);
+                        if (ok2) col[qq][r2] = a2[qq] - (vr2 * wc[qq] + wr2 * vc[qq]);
+                    }
+                }
             }
         }
         if (b == 0)   // keep the reflector for the back-transformation
@@ -272,66 +330,101 @@ __device__ int sturm_count(const double *d, const double *e, int64_t N, double x
     return cnt;
 }
 
-// Top-k eigenpairs of the tridiagonal matrix: bisection (one thread per eigenvalue) then inverse iteration
-// (one thread per eigenvector for the tridiagonal solves, the whole block for the Gram-Schmidt sweeps).
-// work: k * 5 * N doubles.  Z: N x k.
+// Top-k eigenpairs of the tridiagonal matrix, one block per eigenpair (cooperative launch, k blocks):
+//   * eigenvalue j by 256-way multisection on the Sturm count (7 rounds instead of 55 bisection steps),
+//   * inverse iteration: the block's thread 0 runs the pivoted tridiagonal solve in SHARED memory (or in the global
+//     workspace when 7 N doubles do not fit), then block 0 re-orthogonalises clustered vectors (dstein's rule:
+//     eigenvalues closer than 1e-3 ||T||) by modified Gram-Schmidt in eigenvalue order.
+// work: k * 5 * N doubles (only used by the global fall-back).  Z: N x k.
 __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double *d, const double *e, int64_t N, int k,
-                                                                   double *evals, double *Z, double *work) {
+                                                                   double *evals, double *Z, double *work,
+                                                                   int use_smem) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double tsm[];
     __shared__ double sh[TRI_THREADS / 32];
     __shared__ double s_lo, s_hi, s_pivmin, s_norm;
+    __shared__ int s_cnt[TRI_THREADS];
     __shared__ double s_lam[64];
-    const int tid = threadIdx.x;
-    if (tid == 0) {
+    const int tid = threadIdx.x, j = blockIdx.x;
+    // tridiagonal in shared memory when it fits
+    const double *dd0 = d, *ee0 = e;
+    if (use_smem) {
+        for (int64_t i = tid; i < N; i += TRI_THREADS) { tsm[i] = d[i]; tsm[N + i] = e[i]; }
+        dd0 = tsm; ee0 = tsm + N;
+    }
+    // Gershgorin bounds
+    {
         double lo = INFINITY, hi = -INFINITY, emax = 0.0;
-        for (int64_t i = 0; i < N; ++i) {
+        for (int64_t i = tid; i < N; i += TRI_THREADS) {
             const double el = (i > 0) ? fabs(e[i - 1]) : 0.0, er = (i + 1 < N) ? fabs(e[i]) : 0.0;
             lo = fmin(lo, d[i] - el - er);
             hi = fmax(hi, d[i] + el + er);
             emax = fmax(emax, er * er);
         }
-        const double nrm = fmax(fabs(lo), fabs(hi));
-        s_lo = lo - 2.0 * nrm * 2.3e-16 * N - 1e-300;
-        s_hi = hi + 2.0 * nrm * 2.3e-16 * N + 1e-300;
-        s_pivmin = fmax(2.3e-308 * fmax(1.0, emax), 1e-300);
-        s_norm = nrm;
-    }
-    __syncthreads();
-    if (tid < k) {
-        // eigenvalue with index N-1-tid (0-based ascending): smallest x with count(x) >= N - tid
-        const int target = (int)(N - tid);
-        double lo = s_lo, hi = s_hi;
-        for (int it = 0; it < 200; ++it) {
-            const double mid = 0.5 * (lo + hi);
-            if (mid <= lo || mid >= hi) break;
-            if (sturm_count(d, e, N, mid, s_pivmin) >= target) hi = mid; else lo = mid;
-            if (hi - lo <= 4.0 * 2.3e-16 * fmax(fabs(lo), fabs(hi))) break;
+        lo = warp_min(lo); hi = warp_max(hi); emax = warp_max(emax);
+        __shared__ double sb[3][TRI_THREADS / 32];
+        if ((tid & 31) == 0) { sb[0][tid >> 5] = lo; sb[1][tid >> 5] = hi; sb[2][tid >> 5] = emax; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < TRI_THREADS / 32; ++w) { lo = fmin(lo, sb[0][w]); hi = fmax(hi, sb[1][w]); emax = fmax(emax, sb[2][w]); }
+            const double nrm = fmax(fabs(lo), fabs(hi));
+            s_lo = lo - 2.0 * nrm * 2.3e-16 * N - 1e-300;
+            s_hi = hi + 2.0 * nrm * 2.3e-16 * N + 1e-300;
+            s_pivmin = fmax(2.3e-308 * fmax(1.0, emax), 1e-300);
+            s_norm = nrm;
         }
-        s_lam[tid] = 0.5 * (lo + hi);
-        evals[tid] = s_lam[tid];
+        __syncthreads();
     }
-    __syncthreads();
-    // separate eigenvalues that coincide to working precision (dstein-style perturbation) so the LU factors differ
+    // eigenvalue with index N-1-j (0-based ascending): smallest x with count(x) >= N - j
+    {
+        const int target = (int)(N - j);
+        double lo = s_lo, hi = s_hi;
+        for (int round = 0; round < 12; ++round) {
+            const double step = (hi - lo) / (TRI_THREADS + 1);
+            const double x = lo + step * (tid + 1);
+            s_cnt[tid] = (x > lo && x < hi) ? sturm_count(dd0, ee0, N, x, s_pivmin) : -1;
+            __syncthreads();
+            // first sample whose count reaches the target: every thread scans the (tiny) table in shared memory
+            int first = TRI_THREADS;
+            for (int t = 0; t < TRI_THREADS; ++t)
+                if (s_cnt[t] >= target) { first = t; break; }
+            const double nlo = (first == 0) ? lo : lo + step * first;            // sample first-1 (or lo)
+            const double nhi = (first == TRI_THREADS) ? hi : lo + step * (first + 1);
+            __syncthreads();
+            const bool stalled = !(nhi - nlo < hi - lo);
+            lo = fmax(lo, nlo); hi = fmin(hi, nhi);
+            if (stalled || hi - lo <= 4.0 * 2.3e-16 * fmax(fabs(lo), fabs(hi))) break;
+        }
+        if (tid == 0) evals[j] = 0.5 * (lo + hi);
+    }
+    grid.sync();
+    // all blocks apply the same separation of coincident eigenvalues (dstein-style perturbation)
     if (tid == 0) {
         const double sep = 10.0 * 2.3e-16 * s_norm;
-        for (int j = 1; j < k; ++j)
-            if (s_lam[j - 1] - s_lam[j] < sep) s_lam[j] = s_lam[j - 1] - sep;
+        for (int q = 0; q < k; ++q) s_lam[q] = __ldcg(&evals[q]);
+        for (int q = 1; q < k; ++q)
+            if (s_lam[q - 1] - s_lam[q] < sep) s_lam[q] = s_lam[q - 1] - sep;
     }
     __syncthreads();
+    double *du, *du2, *dd, *dl, *zl;
+    if (use_smem) { du = tsm + 2 * N; du2 = du + N; dd = du2 + N; dl = dd + N; zl = dl + N; }
+    else { du = work + (size_t)j * 5 * N; du2 = du + N; dd = du2 + N; dl = dd + N; zl = Z + (size_t)j * N; }
+    double *zg = Z + (size_t)j * N;
     for (int iter = 0; iter < 4; ++iter) {
-        if (tid < k) {
+        const double lam = s_lam[j];
+        for (int64_t i = tid; i < N; i += TRI_THREADS) {
+            dd[i] = dd0[i] - lam;
+            du[i] = (i + 1 < N) ? ee0[i] : 0.0;
+            dl[i] = (i + 1 < N) ? ee0[i] : 0.0;
+            du2[i] = 0.0;
+            zl[i] = (iter == 0) ? 1.0 / sqrt((double)N) * (1.0 + 0.01 * (double)((i * 2654435761u + j * 40503u) % 97) / 97.0)
+                                : __ldcg(&zg[i]);
+        }
+        __syncthreads();
+        if (tid == 0) {
             // solve (T - lam I) z = b by Gaussian elimination with partial pivoting (tridiagonal)
-            double *du = work + (size_t)tid * 5 * N, *du2 = du + N, *dd = du2 + N, *dl = dd + N;
-            double *z = Z + (size_t)tid * N;
-            const double lam = s_lam[tid];
-            for (int64_t i = 0; i < N; ++i) {
-                dd[i] = d[i] - lam;
-                du[i] = (i + 1 < N) ? e[i] : 0.0;
-                dl[i] = (i + 1 < N) ? e[i] : 0.0;
-                du2[i] = 0.0;
-                if (iter == 0) z[i] = 1.0 / sqrt((double)N) * (1.0 + 0.01 * (double)((i * 2654435761u + tid * 40503u) % 97) / 97.0);
-            }
+            double *z = zl;
             const double tiny = 2.3e-16 * s_norm + 1e-300;
-            // forward elimination applied to the right-hand side on the fly
             for (int64_t i = 0; i + 1 < N; ++i) {
                 if (fabs(dd[i]) >= fabs(dl[i])) {
                     if (fabs(dd[i]) < tiny) dd[i] = copysign(tiny, dd[i] == 0.0 ? 1.0 : dd[i]);
@@ -340,7 +433,6 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
                     z[i + 1] -= f * z[i];
                     du2[i] = 0.0;
                 } else {
-                    // swap rows i and i+1
                     const double f = dd[i] / dl[i];
                     const double t0 = dd[i + 1];
                     dd[i] = dl[i];
@@ -353,36 +445,47 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
                 }
             }
             if (fabs(dd[N - 1]) < tiny) dd[N - 1] = copysign(tiny, dd[N - 1] == 0.0 ? 1.0 : dd[N - 1]);
-            // back substitution with the two super-diagonals
             z[N - 1] /= dd[N - 1];
             if (N >= 2) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) / dd[N - 2];
             for (int64_t i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) / dd[i];
-            // crude normalisation against overflow
-            double mx = 0.0;
-            for (int64_t i = 0; i < N; ++i) mx = fmax(mx, fabs(z[i]));
-            const double inv = 1.0 / mx;
-            for (int64_t i = 0; i < N; ++i) z[i] *= inv;
         }
         __syncthreads();
-        // modified Gram-Schmidt in eigenvalue order (all previous vectors: cheap, and exact for clusters)
-        for (int j = 0; j < k; ++j) {
-            double *zj = Z + (size_t)j * N;
-            for (int l = 0; l < j; ++l) {
-                if (fabs(s_lam[l] - s_lam[j]) > 1e-3 * s_norm) continue;
-                const double *zl = Z + (size_t)l * N;
+        // crude normalisation against overflow, publish
+        double mx = 0.0;
+        for (int64_t i = tid; i < N; i += TRI_THREADS) mx = fmax(mx, fabs(zl[i]));
+        mx = warp_max(mx);
+        __syncthreads();
+        if ((tid & 31) == 0) sh[tid >> 5] = mx;
+        __syncthreads();
+        mx = sh[0];
+        for (int w = 1; w < TRI_THREADS / 32; ++w) mx = fmax(mx, sh[w]);
+        const double inv = 1.0 / mx;
+        for (int64_t i = tid; i < N; i += TRI_THREADS) zg[i] = zl[i] * inv;
+        __threadfence();
+        grid.sync();
+        // block 0: modified Gram-Schmidt in eigenvalue order inside clusters, then normalise every vector
+        if (j == 0) {
+            for (int q = 0; q < k; ++q) {
+                double *zq = Z + (size_t)q * N;
+                for (int l = 0; l < q; ++l) {
+                    if (fabs(s_lam[l] - s_lam[q]) > 1e-3 * s_norm) continue;
+                    const double *zp = Z + (size_t)l * N;       // (other blocks' vectors: read through L2)
+                    double s = 0.0;
+                    for (int64_t i = tid; i < N; i += TRI_THREADS) s += __ldcg(&zp[i]) * __ldcg(&zq[i]);
+                    s = tri_block_sum(s, sh);
+                    for (int64_t i = tid; i < N; i += TRI_THREADS) zq[i] = __ldcg(&zq[i]) - s * __ldcg(&zp[i]);
+                    __syncthreads();
+                }
                 double s = 0.0;
-                for (int64_t i = tid; i < N; i += TRI_THREADS) s += zl[i] * zj[i];
+                for (int64_t i = tid; i < N; i += TRI_THREADS) { const double t = __ldcg(&zq[i]); s += t * t; }
                 s = tri_block_sum(s, sh);
-                for (int64_t i = tid; i < N; i += TRI_THREADS) zj[i] -= s * zl[i];
+                const double inv2 = 1.0 / sqrt(s);
+                for (int64_t i = tid; i < N; i += TRI_THREADS) zq[i] = __ldcg(&zq[i]) * inv2;
                 __syncthreads();
             }
-            double s = 0.0;
-            for (int64_t i = tid; i < N; i += TRI_THREADS) s += zj[i] * zj[i];
-            s = tri_block_sum(s, sh);
-            const double inv = 1.0 / sqrt(s);
-            for (int64_t i = tid; i < N; i += TRI_THREADS) zj[i] *= inv;
-            __syncthreads();
+            __threadfence();
         }
+        grid.sync();
     }
 }
 
@@ -424,7 +527,15 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
     if (nb < 1) nb = 1;
     void *args[] = {&G, &N, &d, &e, &tau, &vbuf, &pbuf, &part};
     MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_kernel, dim3(nb), dim3(TRI_THREADS), args, 0, st));
-    tridiag_topk_kernel<<<1, TRI_THREADS, 0, st>>>(d, e, N, k, evals, evecs, work);
+    {
+        size_t tsm = (size_t)7 * N * sizeof(double);
+        int use_smem = tsm <= 200 * 1024;
+        if (!use_smem) tsm = 0;
+        MFB_CUDA(cudaFuncSetAttribute(tridiag_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int kk = k;
+        void *targs[] = {&d, &e, &N, &kk, &evals, &evecs, &work, &use_smem};
+        MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_topk_kernel, dim3(k), dim3(TRI_THREADS), targs, tsm, st));
+    }
     backtransform_kernel<<<k, TRI_THREADS, 0, st>>>(G, N, tau, evecs);
     MFB_CUDA(cudaGetLastError());
     MFB_CUDA(cudaStreamSynchronize(st));
