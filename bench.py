@@ -126,6 +126,40 @@ def make_d3(dimx=10000, dimy=2000, seed=3):
                                           bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=seed))
 
 
+def run_secondary(mfb, ctx, Ad, m, n):
+    """The other kernels of the path on the same resident D4 matrix (wall time of the C-ABI call, second run):
+    NIPALS (2 passes over x per inner iteration + one read/write deflation pass per component), svd_pca k = 16,
+    Otsu + threshold on a 20000 x 16 factor."""
+    import warnings
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            res = mfb.nipals(Ad, 3, center=False, scale=True, maxiter=40, tol=1e-6, ctx=ctx)
+            dt = time.perf_counter() - t0
+    passes = 1 + 3 + 1 + sum(int(i) * 2 + 2 for i in res["iter"])   # copy, sd scaling (3), |.| sums, 2/iteration, deflation r+w
+    peak, _ = peaks()
+    out["nipals"] = {"workload": "nipals(x = D4, ncomp = 3, center = FALSE, scale = TRUE, maxiter = 40)",
+                     "wall_s": dt, "inner_iterations": [int(i) for i in res["iter"]], "passes_over_x": passes,
+                     "achieved_GBps": passes * m * n * 8 / dt / 1e9, "frac_of_hbm": passes * m * n * 8 / dt / 1e9 / peak,
+                     "note": "wall time of mfb_nipals incl. the working copy of x and result download"}
+    for _ in range(2):
+        t0 = time.perf_counter()
+        mfb.svd_pca(Ad, 16, ctx=ctx)
+        dt = time.perf_counter() - t0
+    out["svd_pca"] = {"workload": "svd_pca(D4, k = 16)", "wall_s": dt,
+                      "gram_tflops": 2.0 * m * n * n / dt / 1e12}
+    Wf = np.asfortranarray(np.abs(np.random.default_rng(1).standard_normal((m, 16))))
+    for _ in range(2):
+        t0 = time.perf_counter()
+        th = mfb.otsuHelper(Wf, ctx=ctx)
+        mfb.threshold(Wf, th, 2, ctx=ctx)
+        dt = time.perf_counter() - t0
+    out["otsu_threshold"] = {"workload": "otsuHelper + threshold on a 20000 x 16 factor (host buffers)", "wall_s": dt}
+    return out
+
+
 def run_auto_bcv(mfb, ctx, rank, world, with_cpu):
     """auto_bcv(Y, ks = 1:20, holdouts = 3) on D3 to convergence: wall time through the public call with a HOST
     matrix (upload inside), the bcv cells sharded over the ranks; plus one bcv call beside the oracle's."""
@@ -208,6 +242,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bcv", action="store_true", help="skip the auto_bcv wall-time leg (second half of the metric)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the NIPALS / svd_pca / Otsu timings on D4")
     ap.add_argument("--k", type=int, default=RANK, help="rank (default 16 = the headline; 64 = BASELINE configs[3]'s "
                                                         "compute-bound variant, reported against the FP64 pipe)")
     args = ap.parse_args()
@@ -308,6 +343,9 @@ def main():
                "note": f"mfb_als_run_host: upload A from pinned host memory + {K} iterations + download W,H; "
                        f"one call = {K} steps"}
         assert np.allclose(Wout, Wout) and itc.value == K
+    secondary = None
+    if not args.no_secondary and rank == 0:
+        secondary = run_secondary(mfb, ctx, Ad, m, n)
     Ad.free()
 
     # ---- auto_bcv wall time (second half of BASELINE.json's metric): D3, cells sharded over the ranks --------
@@ -361,6 +399,7 @@ def main():
                         "step_note": "whole iteration (all 4 launches + gaps): 2*m*n*8*K / timed seconds; this is "
                                      "the north-star '% of HBM roofline' figure"},
            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "auto_bcv": bcv_info,
+           "secondary": secondary,
            "final_resid": resid}
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -27,6 +27,7 @@ struct NipalsParams {
     double *th, *th_old;  // m
     double *ph;           // n  (raw x'th, then the normalised loading)
     double *colabs;       // n
+    double *phn;          // [nblocks][n] block-private normalised loading
     double *part;         // [nblocks][ncomp + 4] per-block partials
     int *status;          // 0 ok, 1 maxiter reached on some component, 2 constant column under scale
 };
@@ -43,64 +44,123 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
     return s;
 }
 
+// ---- warp-level column helpers: a warp owns whole columns and keeps 4 columns x 4 rows of loads in flight ----
+#define NIP_WARPS (NIP_THREADS / 32)
+
+// dot products of up to four columns with the vector t (lane partials; caller reduces)
+__device__ __forceinline__ void cols_dot4(const double *c0, const double *c1, const double *c2, const double *c3,
+                                          const double *t, int64_t m, int lane, double s[4]) {
+    s[0] = s[1] = s[2] = s[3] = 0.0;
+    int64_t i = lane;
+    for (; i + 96 < m; i += 128) {
+        double tv[4], a[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            tv[u] = __ldcg(&t[i + 32 * u]);
+            a[0][u] = c0[i + 32 * u]; a[1][u] = c1[i + 32 * u]; a[2][u] = c2[i + 32 * u]; a[3][u] = c3[i + 32 * u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s[0] += a[0][u] * tv[u]; s[1] += a[1][u] * tv[u]; s[2] += a[2][u] * tv[u]; s[3] += a[3][u] * tv[u];
+        }
+    }
+    for (; i < m; i += 32) {
+        const double tv = __ldcg(&t[i]);
+        s[0] += c0[i] * tv; s[1] += c1[i] * tv; s[2] += c2[i] * tv; s[3] += c3[i] * tv;
+    }
+}
+
 __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ double nsm[];          // [NIP_WARPS][256] partial scores of one 256-row pass
     __shared__ double sh[NIP_THREADS / 32];
     __shared__ double scoef[64];
     const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int64_t m = p.m, n = p.n, ld = p.ld;
     const int PW = p.ncomp + 4;      // width of a block's partial record
+    const int64_t gw = (int64_t)b * NIP_WARPS + warp, tw = (int64_t)nb * NIP_WARPS;   // global warp index / count
 
-    // ---- pre-processing: per column mean / sd (about the mean, n-1 denominator), one block per column ----
+    // ---- pre-processing: per column mean / sd (about the mean, n-1 denominator), one warp per column ----
     if (p.center || p.scale) {
-        for (int64_t j = b; j < n; j += nb) {
+        for (int64_t j = gw; j < n; j += tw) {
             double *col = p.x + j * ld;
-            double s = 0.0;
-            for (int64_t i = tid; i < m; i += NIP_THREADS) s += col[i];
-            const double mean = block_sum(s, sh) / (double)m;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int64_t i = lane;
+            for (; i + 96 < m; i += 128) { s0 += col[i]; s1 += col[i + 32]; s2 += col[i + 64]; s3 += col[i + 96]; }
+            for (; i < m; i += 32) s0 += col[i];
+            const double mean = warp_sum((s0 + s1) + (s2 + s3)) / (double)m;
             double sd = 1.0;
             if (p.scale) {
-                double q = 0.0;
-                for (int64_t i = tid; i < m; i += NIP_THREADS) { const double d = col[i] - mean; q += d * d; }
-                sd = sqrt(block_sum(q, sh) / (double)(m - 1));
-                if (!(sd > 0.0) && tid == 0) atomicExch(p.status, 2);
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+                i = lane;
+                for (; i + 96 < m; i += 128) {
+                    const double d0 = col[i] - mean, d1 = col[i + 32] - mean, d2 = col[i + 64] - mean, d3 = col[i + 96] - mean;
+                    q0 += d0 * d0; q1 += d1 * d1; q2 += d2 * d2; q3 += d3 * d3;
+                }
+                for (; i < m; i += 32) { const double d0 = col[i] - mean; q0 += d0 * d0; }
+                sd = sqrt(warp_sum((q0 + q1) + (q2 + q3)) / (double)(m - 1));
+                if (!(sd > 0.0) && lane == 0) atomicExch(p.status, 2);
             }
-            for (int64_t i = tid; i < m; i += NIP_THREADS) {
+            double ab = 0.0;
+            for (i = lane; i < m; i += 32) {
                 double v = col[i];
                 if (p.center) v -= mean;
                 if (p.scale) v /= sd;
                 col[i] = v;
+                ab += fabs(v);
             }
+            ab = warp_sum(ab);
+            if (lane == 0) p.colabs[j] = ab;
         }
-        grid.sync();
-    }
-    // column |.| sums of the starting matrix
-    for (int64_t j = b; j < n; j += nb) {
-        const double *col = p.x + j * ld;
-        double s = 0.0;
-        for (int64_t i = tid; i < m; i += NIP_THREADS) s += fabs(col[i]);
-        s = block_sum(s, sh);
-        if (tid == 0) p.colabs[j] = s;
+    } else {
+        // column |.| sums of the starting matrix
+        for (int64_t j = gw; j < n; j += tw) {
+            const double *col = p.x + j * ld;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int64_t i = lane;
+            for (; i + 96 < m; i += 128) { s0 += fabs(col[i]); s1 += fabs(col[i + 32]); s2 += fabs(col[i + 64]); s3 += fabs(col[i + 96]); }
+            for (; i < m; i += 32) s0 += fabs(col[i]);
+            const double ab = warp_sum((s0 + s1) + (s2 + s3));
+            if (lane == 0) p.colabs[j] = ab;
+        }
     }
     grid.sync();
 
-    const int64_t rows_per = (m + nb - 1) / nb;
-    const int64_t r0 = b * rows_per, r1 = (r0 + rows_per < m) ? r0 + rows_per : m;
+    // rows of the scores owned by this block: a multiple of 32 so that a warp always reads 256 contiguous bytes
+    const int64_t rows_per = ((m + nb - 1) / nb + 31) / 32 * 32;
+    const int64_t r0 = (b * rows_per < m) ? b * rows_per : m, r1 = (r0 + rows_per < m) ? r0 + rows_per : m;
 
     for (int h = 0; h < p.ncomp; ++h) {
         // start column: which.max(colSums(abs(x))) -- first maximum; every block finds it redundantly
         int64_t scol = 0;
         {
             double best = -1.0;
-            for (int64_t j = 0; j < n; ++j) {
-                const double v = p.colabs[j];
-                if (v > best) { best = v; scol = j; }
+            int64_t bj = 0;
+            for (int64_t j = tid; j < n; j += NIP_THREADS) {
+                const double v = __ldcg(&p.colabs[j]);
+                if (v > best) { best = v; bj = j; }
             }
+            // block arg-max, ties -> smallest index
+            __shared__ double sbv[NIP_THREADS];
+            __shared__ long long sbj[NIP_THREADS];
+            sbv[tid] = best; sbj[tid] = bj;
+            __syncthreads();
+            for (int o = NIP_THREADS / 2; o > 0; o >>= 1) {
+                if (tid < o) {
+                    const double ov = sbv[tid + o];
+                    const long long oj = sbj[tid + o];
+                    if (ov > sbv[tid] || (ov == sbv[tid] && oj < sbj[tid])) { sbv[tid] = ov; sbj[tid] = oj; }
+                }
+                __syncthreads();
+            }
+            scol = sbj[0];
+            __syncthreads();
         }
         // th = x[, scol]; tt = sum(th^2)
         double tts = 0.0;
         for (int64_t i = r0 + tid; i < r1; i += NIP_THREADS) {
-            const double v = p.x[scol * ld + i];
+            const double v = __ldcg(&p.x[scol * ld + i]);
             p.th[i] = v;
             tts += v * v;
         }
@@ -108,72 +168,101 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
         if (tid == 0) p.part[(size_t)b * PW + 0] = tts;
         grid.sync();
         double tt = 0.0;
-        for (int bb = 0; bb < nb; ++bb) tt += p.part[(size_t)bb * PW + 0];
+        for (int bb = 0; bb < nb; ++bb) tt += __ldcg(&p.part[(size_t)bb * PW + 0]);
 
         int pciter = 1;
+        const double *phn = p.phn + (size_t)b * n;
         while (true) {
-            // S1: ph_raw[j] = sum_i x[i,j] th[i], one block per column
-            for (int64_t j = b; j < n; j += nb) {
-                const double *col = p.x + j * ld;
-                double s = 0.0;
-                for (int64_t i = tid; i < m; i += NIP_THREADS) s += col[i] * p.th[i];
-                s = block_sum(s, sh);
-                if (tid == 0) p.ph[j] = s;
+            // S1: ph_raw[j] = sum_i x[i,j] th[i]: a warp owns columns, four at a time
+            for (int64_t j0 = gw * 4; j0 < n; j0 += tw * 4) {
+                const double *c0 = p.x + j0 * ld;
+                const double *c1 = p.x + ((j0 + 1 < n) ? j0 + 1 : j0) * ld;
+                const double *c2 = p.x + ((j0 + 2 < n) ? j0 + 2 : j0) * ld;
+                const double *c3 = p.x + ((j0 + 3 < n) ? j0 + 3 : j0) * ld;
+                double s4[4];
+                cols_dot4(c0, c1, c2, c3, p.th, m, lane, s4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s4[q] = warp_sum(s4[q]);
+                if (lane < 4 && j0 + lane < n) p.ph[j0 + lane] = s4[lane];
             }
             grid.sync();
             // S2 (redundant per block): ph = ph_raw / tt; Gram-Schmidt against P[, 0..h); normalise
             double pp_inv;   // 1 / (ph'ph) after normalisation
+            const int nh = (p.gramschmidt && h > 0) ? h : 0;
             {
-                // coefficients c_l = sum_j P[j,l] * ph[j] / tt
-                const int nh = (p.gramschmidt && h > 0) ? h : 0;
                 for (int l = 0; l < nh; ++l) {
                     double s = 0.0;
-                    for (int64_t j = tid; j < n; j += NIP_THREADS) s += p.P[(size_t)l * n + j] * (p.ph[j] / tt);
+                    for (int64_t j = tid; j < n; j += NIP_THREADS) s += p.P[(size_t)l * n + j] * (__ldcg(&p.ph[j]) / tt);
                     s = block_sum(s, sh);
                     if (tid == 0) scoef[l] = s;
                 }
                 __syncthreads();
                 double nrm = 0.0;
                 for (int64_t j = tid; j < n; j += NIP_THREADS) {
-                    double v = p.ph[j] / tt;
+                    double v = __ldcg(&p.ph[j]) / tt;
                     double corr = 0.0;
                     for (int l = 0; l < nh; ++l) corr += p.P[(size_t)l * n + j] * scoef[l];
                     v -= corr;
                     nrm += v * v;
                 }
                 nrm = sqrt(block_sum(nrm, sh));
-                // th_new[i] for this block's rows needs the normalised ph: recompute it on the fly per column
-                // (ph[j] final value is written by block 0 only, after everybody has finished reading ph_raw)
                 double p2 = 0.0;
                 for (int64_t j = tid; j < n; j += NIP_THREADS) {
-                    double v = p.ph[j] / tt;
+                    double v = __ldcg(&p.ph[j]) / tt;
                     double corr = 0.0;
                     for (int l = 0; l < nh; ++l) corr += p.P[(size_t)l * n + j] * scoef[l];
                     v = (v - corr) / nrm;
                     p2 += v * v;
-                    p.colabs[j] = v;    // every block writes the same value: colabs doubles as the ph scratch
+                    p.phn[(size_t)b * n + j] = v;   // block-private copy of the normalised loading (no extra barrier)
                 }
                 p2 = block_sum(p2, sh);
                 pp_inv = 1.0 / p2;
                 __syncthreads();
             }
-            grid.sync();   // colabs (= normalised ph) visible everywhere; ph_raw no longer needed
-            // S3: th_new = x ph / (ph'ph) for this block's rows; partials of t_l' th_new for Gram-Schmidt
-            const int nh = (p.gramschmidt && h > 0) ? h : 0;
-            for (int64_t i = r0 + tid; i < r1; i += NIP_THREADS) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int64_t j = 0;
-                for (; j + 3 < n; j += 4) {
-                    s0 += p.x[j * ld + i] * p.colabs[j];
-                    s1 += p.x[(j + 1) * ld + i] * p.colabs[j + 1];
-                    s2 += p.x[(j + 2) * ld + i] * p.colabs[j + 2];
-                    s3 += p.x[(j + 3) * ld + i] * p.colabs[j + 3];
+            // S3: th_new = x ph / (ph'ph) for this block's rows, 256 rows per pass: warp w sums its eighth of the
+            // columns for all eight 32-row groups of the pass (two columns x eight row groups of loads in flight)
+            for (int64_t rb = r0; rb < r1; rb += 256) {
+                const int64_t jlo = n * warp / NIP_WARPS, jhi = n * (warp + 1) / NIP_WARPS;
+                double acc[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) acc[g] = 0.0;
+                const int ngr = (int)((r1 - rb + 31) / 32 < 8 ? (r1 - rb + 31) / 32 : 8);
+                int64_t j = jlo;
+                for (; j + 1 < jhi; j += 2) {
+                    const double pj0 = phn[j], pj1 = phn[j + 1];
+                    const double *ca = p.x + j * ld + rb + lane, *cb2 = ca + ld;
+                    double va[8], vb[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const bool ok = g < ngr && rb + 32 * g + lane < r1;
+                        va[g] = ok ? __ldcg(&ca[32 * g]) : 0.0;      // (x is deflated by other blocks: read through L2)
+                        vb[g] = ok ? __ldcg(&cb2[32 * g]) : 0.0;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) acc[g] += va[g] * pj0 + vb[g] * pj1;
                 }
-                for (; j < n; ++j) s0 += p.x[j * ld + i] * p.colabs[j];
-                p.th_old[i] = p.th[i];
-                p.th[i] = ((s0 + s1) + (s2 + s3)) * pp_inv;
+                for (; j < jhi; ++j) {
+                    const double pj0 = phn[j];
+                    const double *ca = p.x + j * ld + rb + lane;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if (g < ngr && rb + 32 * g + lane < r1) acc[g] += __ldcg(&ca[32 * g]) * pj0;
+                }
+#pragma unroll
+                for (int g = 0; g < 8; ++g) nsm[warp * 256 + 32 * g + lane] = acc[g];
+                __syncthreads();
+                {
+                    const int64_t i = rb + tid;
+                    if (i < r1) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int w = 0; w < NIP_WARPS; ++w) sacc += nsm[w * 256 + tid];
+                        p.th_old[i] = p.th[i];
+                        p.th[i] = sacc * pp_inv;
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
             for (int l = 0; l < nh; ++l) {
                 double s = 0.0;
                 for (int64_t i = r0 + tid; i < r1; i += NIP_THREADS) s += p.T[(size_t)l * m + i] * p.th[i];
@@ -184,8 +273,8 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                 grid.sync();
                 for (int l = tid; l < nh; l += NIP_THREADS) {
                     double s = 0.0;
-                    for (int bb = 0; bb < nb; ++bb) s += p.part[(size_t)bb * PW + 4 + l];
-                    scoef[l] = s / p.eig[l];
+                    for (int bb = 0; bb < nb; ++bb) s += __ldcg(&p.part[(size_t)bb * PW + 4 + l]);
+                    scoef[l] = s / __ldcg(&p.eig[l]);
                 }
                 __syncthreads();
             }
@@ -211,8 +300,8 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
             double diff = 0.0;
             tt = 0.0;
             for (int bb = 0; bb < nb; ++bb) {
-                diff += p.part[(size_t)bb * PW + 1];
-                tt += p.part[(size_t)bb * PW + 2];
+                diff += __ldcg(&p.part[(size_t)bb * PW + 1]);
+                tt += __ldcg(&p.part[(size_t)bb * PW + 2]);
             }
             if (diff < p.tol) break;
             ++pciter;
@@ -224,27 +313,34 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
         // component done: record, then deflate x -= th ph' fused with the next start-column search
         for (int64_t i = r0 + tid; i < r1; i += NIP_THREADS) p.T[(size_t)h * m + i] = p.th[i];
         if (b == 0) {
-            for (int64_t j = tid; j < n; j += NIP_THREADS) p.P[(size_t)h * n + j] = p.colabs[j];
+            for (int64_t j = tid; j < n; j += NIP_THREADS) p.P[(size_t)h * n + j] = phn[j];
             if (tid == 0) { p.eig[h] = tt; p.iters[h] = pciter; }
         }
-        grid.sync();   // everybody is done reading colabs as ph before it is overwritten below... (P holds ph now)
-        for (int64_t j = b; j < n; j += nb) {
+        for (int64_t j = gw; j < n; j += tw) {
             double *col = p.x + j * ld;
-            const double pj = p.P[(size_t)h * n + j];
-            double s = 0.0;
-            for (int64_t i = tid; i < m; i += NIP_THREADS) {
-                const double v = col[i] - p.th[i] * pj;
-                col[i] = v;
-                s += fabs(v);
+            const double pj = phn[j];
+            double s0 = 0.0, s1 = 0.0;
+            int64_t i = lane;
+            for (; i + 96 < m; i += 128) {
+                const double t0 = __ldcg(&p.th[i]), t1 = __ldcg(&p.th[i + 32]), t2 = __ldcg(&p.th[i + 64]), t3 = __ldcg(&p.th[i + 96]);
+                const double v0 = col[i] - t0 * pj, v1 = col[i + 32] - t1 * pj, v2 = col[i + 64] - t2 * pj, v3 = col[i + 96] - t3 * pj;
+                col[i] = v0; col[i + 32] = v1; col[i + 64] = v2; col[i + 96] = v3;
+                s0 += fabs(v0) + fabs(v2);
+                s1 += fabs(v1) + fabs(v3);
             }
-            s = block_sum(s, sh);
-            if (tid == 0) p.colabs[j] = s;
+            for (; i < m; i += 32) {
+                const double v0 = col[i] - __ldcg(&p.th[i]) * pj;
+                col[i] = v0;
+                s0 += fabs(v0);
+            }
+            const double ab = warp_sum(s0 + s1);
+            if (lane == 0) p.colabs[j] = ab;
         }
         grid.sync();
     }
     // eig <- sqrt(eig); scores <- sweep(scores, 2, eig, "/")  (unit-norm score columns)
     for (int h = 0; h < p.ncomp; ++h) {
-        const double e = sqrt(p.eig[h]);
+        const double e = sqrt(__ldcg(&p.eig[h]));
         for (int64_t i = r0 + tid; i < r1; i += NIP_THREADS) p.T[(size_t)h * m + i] /= e;
         if (b == 0 && tid == 0) p.part[h] = e;     // part[] is free now: reuse for the sqrt(eig) output
     }
@@ -269,13 +365,15 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     }
     const int64_t m = x->m, n = x->n, ld = x->lda;
     int nb_max = 0;
-    MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, nipals_kernel, NIP_THREADS, 0));
+    MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, nipals_kernel, NIP_THREADS,
+                                                           NIP_WARPS * 256 * sizeof(double)));
     int nb = nb_max * ctx->sm_count;
     if (nb > ctx->sm_count) nb = ctx->sm_count;               // one block per SM is plenty; keeps grid.sync cheap
     const int64_t want = (m + NIP_THREADS - 1) / NIP_THREADS > n ? (m + NIP_THREADS - 1) / NIP_THREADS : n;
     if (want < nb) nb = (int)(want < 1 ? 1 : want);
     const size_t PW = ncomp + 4;
-    size_t nd = (size_t)ld * n + (size_t)m * ncomp + (size_t)n * ncomp + ncomp + 2 * (size_t)m + 2 * (size_t)n + (size_t)nb * PW;
+    size_t nd = (size_t)ld * n + (size_t)m * ncomp + (size_t)n * ncomp + ncomp + 2 * (size_t)m + 2 * (size_t)n + (size_t)nb * PW +
+                (size_t)nb * n;
     double *buf = nullptr;
     int *ibuf = nullptr;
     MFB_CUDA(cudaMalloc(&buf, nd * sizeof(double)));
@@ -292,6 +390,7 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     p.ph = p.th_old + m;
     p.colabs = p.ph + n;
     p.part = p.colabs + n;
+    p.phn = p.part + (size_t)nb * PW;
     p.iters = ibuf;
     p.status = ibuf + ncomp;
     p.m = m; p.n = n; p.ld = ld;
@@ -299,7 +398,8 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     p.tol = tol;
     MFB_CUDA(cudaMemcpyAsync(p.x, x->d, (size_t)ld * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     void *args[] = {&p};
-    MFB_CUDA(cudaLaunchCooperativeKernel((void *)nipals_kernel, dim3(nb), dim3(NIP_THREADS), args, 0, st));
+    MFB_CUDA(cudaLaunchCooperativeKernel((void *)nipals_kernel, dim3(nb), dim3(NIP_THREADS), args,
+                                         NIP_WARPS * 256 * sizeof(double), st));
     std::vector<double> hE(ncomp);
     std::vector<int> hI(ncomp + 1);
     MFB_CUDA(cudaMemcpyAsync(scores, p.T, (size_t)m * ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));

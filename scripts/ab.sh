@@ -6,7 +6,7 @@ for v in "$@"; do
 import mfbiclust_b200._cabi as c
 c.LIB_PATH = "/tmp/cur.so"
 import sys, json
-sys.argv = ["bench.py", "--no-cpu-baseline", "--no-e2e", "--steps", "40"]
+sys.argv = ["bench.py", "--no-cpu-baseline", "--no-e2e", "--no-bcv", "--no-secondary", "--steps", "40"]
 import runpy, io, contextlib
 buf = io.StringIO()
 with contextlib.redirect_stdout(buf):
