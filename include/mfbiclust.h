@@ -56,6 +56,8 @@ void mfb_context_destroy(mfb_context *ctx);
 int  mfb_context_sync(mfb_context *ctx);
 /* CUDA stream (cudaStream_t) every kernel of this context is launched on; for callers that time with CUDA events. */
 void *mfb_context_stream(mfb_context *ctx);
+/* Device buffers are recycled through a per-context pool; this returns the cached ones to the driver. */
+int  mfb_context_trim(mfb_context *ctx);
 
 /* ---- resident matrix ---------------------------------------------------- */
 /* Upload a column-major host matrix (the `A` / `Y` argument of every back-end). */

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "mfb_context_destroy": (None, [_vp]),
     "mfb_context_sync": (C.c_int, [_vp]),
     "mfb_context_stream": (_vp, [_vp]),
+    "mfb_context_trim": (C.c_int, [_vp]),
     "mfb_matrix_upload": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_wrap_dev": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_free": (None, [_vp]),
@@ -116,6 +117,10 @@ class Context:
 
     def stream(self) -> int:
         return int(lib().mfb_context_stream(self._h) or 0)
+
+    def trim(self):
+        """Return the cached device buffers of the workspace pool to the driver."""
+        check(lib().mfb_context_trim(self._h))
 
     def close(self):
         if self._h:

@@ -1022,11 +1022,7 @@ static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, co
 
 template <typename T>
 static int dev_alloc(mfb_als *s, T **p, size_t count, bool zero = true) {
-    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
-    if (e != cudaSuccess) {
-        mfb_set_error("cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-        return MFB_ERR_ALLOC;
-    }
+    if (mfb_pool_alloc(s->ctx, (void **)p, count * sizeof(T)) != MFB_OK) return MFB_ERR_ALLOC;
     s->allocs.push_back((void *)*p);
     if (zero) MFB_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), s->ctx->stream));
     return MFB_OK;
@@ -1038,7 +1034,7 @@ void mfb_als_end(mfb_als *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    for (void *p : s->allocs) cudaFree(p);
+    for (void *p : s->allocs) mfb_pool_free(s->ctx, p);
     delete s;
 }
 
@@ -1348,14 +1344,18 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     const int KP = KB * 8;
     double *dC, *dB, *dR, *dG, *dM, *dK, *part;
     int *dsing;
-    MFB_CUDA(cudaMalloc(&dC, sizeof(double) * r * k));
-    MFB_CUDA(cudaMalloc(&dB, sizeof(double) * r * pcols));
-    MFB_CUDA(cudaMalloc(&dR, sizeof(double) * k * pcols));
-    MFB_CUDA(cudaMalloc(&dK, sizeof(double) * k * pcols));
-    MFB_CUDA(cudaMalloc(&dG, sizeof(double) * KP * KP));
-    MFB_CUDA(cudaMalloc(&dM, sizeof(double) * KP * KP));
-    MFB_CUDA(cudaMalloc(&part, sizeof(double) * 64 * KP * KP));
-    MFB_CUDA(cudaMalloc(&dsing, sizeof(int)));
+    DevBuf buf(ctx);
+    {
+        int rc = buf.alloc(&dC, (size_t)r * k);
+        if (rc == MFB_OK) rc = buf.alloc(&dB, (size_t)r * pcols);
+        if (rc == MFB_OK) rc = buf.alloc(&dR, (size_t)k * pcols);
+        if (rc == MFB_OK) rc = buf.alloc(&dK, (size_t)k * pcols);
+        if (rc == MFB_OK) rc = buf.alloc(&dG, (size_t)KP * KP);
+        if (rc == MFB_OK) rc = buf.alloc(&dM, (size_t)KP * KP);
+        if (rc == MFB_OK) rc = buf.alloc(&part, (size_t)64 * KP * KP);
+        if (rc == MFB_OK) rc = buf.alloc(&dsing, 1);
+        if (rc != MFB_OK) return rc;
+    }
     MFB_CUDA(cudaMemcpyAsync(dC, C, sizeof(double) * r * k, cudaMemcpyHostToDevice, st));
     MFB_CUDA(cudaMemcpyAsync(dB, B, sizeof(double) * r * pcols, cudaMemcpyHostToDevice, st));
     int nb = (int)((r + 2047) / 2048);
@@ -1380,7 +1380,6 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     MFB_CUDA(cudaMemcpyAsync(K, dK, sizeof(double) * k * pcols, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaMemcpyAsync(&sing, dsing, sizeof(int), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dC); cudaFree(dB); cudaFree(dR); cudaFree(dK); cudaFree(dG); cudaFree(dM); cudaFree(part); cudaFree(dsing);
     return sing ? MFB_SINGULAR : MFB_OK;
 }
 

@@ -5,7 +5,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mfbiclust.h"
@@ -43,6 +45,29 @@ struct mfb_context {
     // small pinned mailbox for control blocks / scalars
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // device workspace pool: blocks are recycled by rounded size instead of going back to cudaFree (which
+    // synchronises the device and unmaps); safe because every kernel and copy of a context runs on its one stream
+    std::multimap<size_t, void *> pool_free;
+    std::unordered_map<void *, size_t> pool_live;
+    size_t pool_cached_bytes = 0;
+};
+
+// pooled device allocations (context.cu).  mfb_pool_alloc returns MFB_OK / MFB_ERR_ALLOC.
+int mfb_pool_alloc(mfb_context *ctx, void **p, size_t bytes);
+void mfb_pool_free(mfb_context *ctx, void *p);
+void mfb_pool_release(mfb_context *ctx);      // cudaFree every cached block
+
+// RAII bundle of pooled buffers
+struct DevBuf {
+    mfb_context *ctx;
+    std::vector<void *> ptrs;
+    explicit DevBuf(mfb_context *c) : ctx(c) {}
+    ~DevBuf() { for (void *q : ptrs) mfb_pool_free(ctx, q); }
+    template <typename T> int alloc(T **p, size_t count) {
+        int rc = mfb_pool_alloc(ctx, (void **)p, (count ? count : 1) * sizeof(T));
+        if (rc == MFB_OK) ptrs.push_back((void *)*p);
+        return rc;
+    }
 };
 
 struct mfb_matrix {

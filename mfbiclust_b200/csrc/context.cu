@@ -24,6 +24,60 @@ mfb_encode_tiled_fn mfb_get_encode_tiled() {
     return fn;
 }
 
+static size_t pool_round(size_t bytes) {
+    if (bytes <= 512) return 512;
+    if (bytes <= ((size_t)1 << 20)) {
+        size_t r = 512;
+        while (r < bytes) r <<= 1;
+        return r;
+    }
+    const size_t q = (size_t)2 << 20;
+    return (bytes + q - 1) / q * q;
+}
+
+int mfb_pool_alloc(mfb_context *ctx, void **p, size_t bytes) {
+    const size_t r = pool_round(bytes);
+    auto it = ctx->pool_free.find(r);
+    if (it != ctx->pool_free.end()) {
+        *p = it->second;
+        ctx->pool_free.erase(it);
+        ctx->pool_cached_bytes -= r;
+        ctx->pool_live[*p] = r;
+        return MFB_OK;
+    }
+    cudaError_t e = cudaMalloc(p, r);
+    if (e != cudaSuccess) {                    // give the cached blocks back to the driver and try once more
+        cudaGetLastError();
+        mfb_pool_release(ctx);
+        e = cudaMalloc(p, r);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        mfb_set_error("cudaMalloc(%zu) failed: %s", r, cudaGetErrorString(e));
+        *p = nullptr;
+        return MFB_ERR_ALLOC;
+    }
+    ctx->pool_live[*p] = r;
+    return MFB_OK;
+}
+
+void mfb_pool_free(mfb_context *ctx, void *p) {
+    if (!p) return;
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) { cudaFree(p); return; }
+    ctx->pool_free.emplace(it->second, p);
+    ctx->pool_cached_bytes += it->second;
+    ctx->pool_live.erase(it);
+}
+
+void mfb_pool_release(mfb_context *ctx) {
+    if (ctx->pool_free.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pool_free) cudaFree(kv.second);
+    ctx->pool_free.clear();
+    ctx->pool_cached_bytes = 0;
+}
+
 extern "C" {
 
 int mfb_version(void) { return 100; }
@@ -75,10 +129,11 @@ int mfb_context_create(int device, mfb_context **out) {
 void mfb_context_destroy(mfb_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
-    }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    mfb_pool_release(ctx);
+    for (auto &kv : ctx->pool_live) cudaFree(kv.first);     // handles the caller forgot to release
+    ctx->pool_live.clear();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
 }
@@ -91,6 +146,13 @@ int mfb_context_sync(mfb_context *ctx) {
 }
 
 void *mfb_context_stream(mfb_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int mfb_context_trim(mfb_context *ctx) {
+    MFB_ARG(ctx, "ctx is NULL");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    mfb_pool_release(ctx);
+    return MFB_OK;
+}
 
 }  // extern "C"
 
@@ -181,10 +243,8 @@ int mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t n
     A->lda = round_up(m, 16);   // 128-byte aligned columns: TMA strides, 32-byte vector loads
     A->owned = true;
     size_t bytes = (size_t)A->lda * (size_t)n * sizeof(double) + 256;
-    cudaError_t e = cudaMalloc(&A->d, bytes);
-    if (e != cudaSuccess) {
+    if (mfb_pool_alloc(ctx, (void **)&A->d, bytes) != MFB_OK) {
         delete A;
-        mfb_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
         return MFB_ERR_ALLOC;
     }
     if (A->lda != m) MFB_CUDA(cudaMemsetAsync(A->d, 0, bytes, ctx->stream));
@@ -214,8 +274,7 @@ void mfb_matrix_free(mfb_matrix *A) {
     if (!A) return;
     if (A->owned && A->d) {
         cudaSetDevice(A->ctx->device);
-        cudaStreamSynchronize(A->ctx->stream);
-        cudaFree(A->d);
+        mfb_pool_free(A->ctx, A->d);
     }
     delete A;
 }
@@ -228,16 +287,21 @@ int mfb_matrix_stats(mfb_matrix *A, double stats[5]) {
     MFB_CUDA(cudaSetDevice(ctx->device));
     if (!A->stats_valid) {
         int nb = (int)(A->n < 4 * ctx->sm_count ? A->n : 4 * ctx->sm_count);
+        DevBuf buf(ctx);
         Stat5 *part = nullptr;
         double *dout = nullptr;
-        MFB_CUDA(cudaMalloc(&part, sizeof(Stat5) * nb + 5 * sizeof(double)));
+        {
+            unsigned char *raw = nullptr;
+            int rc = buf.alloc(&raw, sizeof(Stat5) * nb + 5 * sizeof(double));
+            if (rc != MFB_OK) return rc;
+            part = (Stat5 *)raw;
+        }
         dout = (double *)(part + nb);
         stats_partial_kernel<<<nb, 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, part);
         stats_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, dout);
         MFB_CUDA(cudaGetLastError());
         MFB_CUDA(cudaMemcpyAsync(A->stats, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));
-        MFB_CUDA(cudaFree(part));
         A->stats_valid = true;
     }
     memcpy(stats, A->stats, 5 * sizeof(double));

@@ -509,9 +509,13 @@ __global__ void __launch_bounds__(TRI_THREADS) backtransform_kernel(const double
 int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, double *evecs) {
     MFB_ARG(N >= 1 && k >= 1 && k <= 64 && k <= N, "sym_eig_topk: need 1 <= k <= min(N, 64)");
     cudaStream_t st = ctx->stream;
+    DevBuf buf(ctx);
     double *wk = nullptr;
     const size_t nwork = (size_t)5 * N + (size_t)ctx->sm_count + (size_t)k * 5 * N + 16;
-    MFB_CUDA(cudaMalloc(&wk, nwork * sizeof(double)));
+    {
+        int rc = buf.alloc(&wk, nwork);
+        if (rc != MFB_OK) return rc;
+    }
     double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + N, *part = pbuf + N;
     double *work = part + ctx->sm_count;
     if (N == 1) {
@@ -519,7 +523,6 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
         const double one = 1.0;
         MFB_CUDA(cudaMemcpyAsync(evecs, &one, sizeof(double), cudaMemcpyHostToDevice, st));
         MFB_CUDA(cudaStreamSynchronize(st));
-        cudaFree(wk);
         return MFB_OK;
     }
     int nb = (int)((N + 7) / 8);          // one warp per column of the trailing block, 8 warps per block
@@ -539,6 +542,5 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
     backtransform_kernel<<<k, TRI_THREADS, 0, st>>>(G, N, tau, evecs);
     MFB_CUDA(cudaGetLastError());
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(wk);
     return MFB_OK;
 }

@@ -374,10 +374,14 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     const size_t PW = ncomp + 4;
     size_t nd = (size_t)ld * n + (size_t)m * ncomp + (size_t)n * ncomp + ncomp + 2 * (size_t)m + 2 * (size_t)n + (size_t)nb * PW +
                 (size_t)nb * n;
+    DevBuf pool(ctx);
     double *buf = nullptr;
     int *ibuf = nullptr;
-    MFB_CUDA(cudaMalloc(&buf, nd * sizeof(double)));
-    MFB_CUDA(cudaMalloc(&ibuf, (ncomp + 1) * sizeof(int)));
+    {
+        int rc2 = pool.alloc(&buf, nd);
+        if (rc2 == MFB_OK) rc2 = pool.alloc(&ibuf, (size_t)ncomp + 1);
+        if (rc2 != MFB_OK) return rc2;
+    }
     MFB_CUDA(cudaMemsetAsync(buf, 0, nd * sizeof(double), st));
     MFB_CUDA(cudaMemsetAsync(ibuf, 0, (ncomp + 1) * sizeof(int), st));
     NipalsParams p;
@@ -407,8 +411,6 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     MFB_CUDA(cudaMemcpyAsync(hE.data(), p.part, ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaMemcpyAsync(hI.data(), ibuf, (ncomp + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(buf);
-    cudaFree(ibuf);
     for (int h = 0; h < ncomp; ++h) {
         if (eig) eig[h] = hE[h];
         if (iters) iters[h] = hI[h];

@@ -100,15 +100,17 @@ int mfb_otsu(mfb_context *ctx, const double *M, int64_t rows, int64_t cols, doub
     MFB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     double *dM = nullptr, *dth = nullptr;
-    MFB_CUDA(cudaMalloc(&dM, sizeof(double) * rows * cols));
-    MFB_CUDA(cudaMalloc(&dth, sizeof(double) * cols));
+    DevBuf buf(ctx);
+    {
+        int rc = buf.alloc(&dM, (size_t)rows * cols);
+        if (rc == MFB_OK) rc = buf.alloc(&dth, (size_t)cols);
+        if (rc != MFB_OK) return rc;
+    }
     MFB_CUDA(cudaMemcpyAsync(dM, M, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, st));
     otsu_kernel<<<(unsigned)cols, 512, 0, st>>>(dM, rows, rows, dth);
     MFB_CUDA(cudaGetLastError());
     MFB_CUDA(cudaMemcpyAsync(th, dth, sizeof(double) * cols, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dM);
-    cudaFree(dth);
     return MFB_OK;
 }
 
@@ -122,9 +124,13 @@ int mfb_threshold(mfb_context *ctx, const double *M, int64_t rows, int64_t cols,
     const int64_t nth = (margin == 1) ? rows : cols;
     double *dM = nullptr, *dth = nullptr;
     int32_t *dout = nullptr;
-    MFB_CUDA(cudaMalloc(&dM, sizeof(double) * rows * cols));
-    MFB_CUDA(cudaMalloc(&dth, sizeof(double) * nth));
-    MFB_CUDA(cudaMalloc(&dout, sizeof(int32_t) * rows * cols));
+    DevBuf buf(ctx);
+    {
+        int rc = buf.alloc(&dM, (size_t)rows * cols);
+        if (rc == MFB_OK) rc = buf.alloc(&dth, (size_t)nth);
+        if (rc == MFB_OK) rc = buf.alloc(&dout, (size_t)rows * cols);
+        if (rc != MFB_OK) return rc;
+    }
     MFB_CUDA(cudaMemcpyAsync(dM, M, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, st));
     MFB_CUDA(cudaMemcpyAsync(dth, th, sizeof(double) * nth, cudaMemcpyHostToDevice, st));
     int64_t nb = (rows * cols + 255) / 256;
@@ -133,9 +139,6 @@ int mfb_threshold(mfb_context *ctx, const double *M, int64_t rows, int64_t cols,
     MFB_CUDA(cudaGetLastError());
     MFB_CUDA(cudaMemcpyAsync(out, dout, sizeof(int32_t) * rows * cols, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dM);
-    cudaFree(dth);
-    cudaFree(dout);
     return MFB_OK;
 }
 

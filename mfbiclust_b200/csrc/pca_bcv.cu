@@ -19,21 +19,6 @@
 
 namespace {
 
-struct DevBuf {
-    std::vector<void *> ptrs;
-    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
-    template <typename T> int alloc(T **p, size_t count) {
-        if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
-        if (e != cudaSuccess) {
-            mfb_set_error("cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-            return MFB_ERR_ALLOC;
-        }
-        ptrs.push_back((void *)*p);
-        return MFB_OK;
-    }
-};
-
 // dst (cols x rows, ld = ldd) = src' (src rows x cols, ld = lds): 32 x 32 shared-memory tiles
 __global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src, int64_t rows, int64_t cols,
                                                         int64_t lds, double *__restrict__ dst, int64_t ldd) {
@@ -180,7 +165,7 @@ int launch_transpose(mfb_context *ctx, const double *src, int64_t rows, int64_t 
 int topk_svd(mfb_context *ctx, const double *X, int64_t rows, int64_t cols, int64_t ldx, double *Xt, int64_t ldxt,
              int kk, double rel_tol, double *sigma, double *colscale, double *U, int64_t ldu, double *V,
              int64_t ldv) {
-    DevBuf buf;
+    DevBuf buf(ctx);
     const bool tall = rows >= cols;
     const int64_t N = tall ? cols : rows, K = tall ? rows : cols;
     double *G = nullptr, *evals = nullptr, *evecs = nullptr, *work = nullptr;
@@ -233,7 +218,7 @@ int mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, in
     if (kk > n) kk = (int)n;
     MFB_ARG(kk <= 64, "svd_pca: at most 64 components are supported");
     if (kout) *kout = kk;
-    DevBuf buf;
+    DevBuf buf(ctx);
     double *sigma, *colscale, *dW, *dH, *At = nullptr, *work = nullptr;
     const int64_t ldw = round_up(m, 4), ldat = round_up(n, 4);
     MFB_TRY(buf.alloc(&sigma, 64));
@@ -291,7 +276,7 @@ int mfb_bcv_cells(mfb_context *ctx, mfb_matrix *Y, const int32_t *row_fold, cons
     }
     const int ncell = cell_end - cell_begin;
     if (ncell == 0) return MFB_OK;
-    DevBuf buf;
+    DevBuf buf(ctx);
     int32_t *d_rin, *d_rout, *d_cin, *d_cout, *d_ks;
     double *D, *Dt = nullptr, *R1, *R2, *mu, *sigma, *colscale, *U, *V, *B, *C, *part, *d_err, *work = nullptr;
     const int64_t ldD = round_up(maxr_in, 4), ldDt = round_up(maxc_in, 4), ldR1 = round_up(maxr_out, 4);
