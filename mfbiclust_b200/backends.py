@@ -479,6 +479,21 @@ def bcv_batch(Yd, ks, holdouts, folds_list, ctx=None, group=None):
     return err.reshape(len(flat), h2, len(ks)).sum(axis=1)
 
 
+def _iters_until_stable(distr, distrOld, tol, winner, keys, limit):
+    """Number of further outer iterations after which ``auto_bcv``'s stopping rule fires if ``winner`` wins every
+    one of them (at least 1, at most ``limit``): used to size the speculative batches."""
+    if winner is None:
+        return limit
+    d, dold = dict(distr), dict(distrOld)
+    for t in range(1, limit + 1):
+        d[winner] += 1
+        sd, so = sum(d.values()), sum(dold.values())
+        if all((d[kk] / sd - dold[kk] / so) ** 2 < tol for kk in keys):
+            return t
+        dold = dict(d)
+    return limit
+
+
 def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verbose=False, interactive=True,
              rng=None, ctx=None, group=None, speculate=None):
     """``auto_bcv(Y, ks, holdouts = 3L, maxIter = 100L, tol = 1e-4, bestOnly = FALSE, verbose = FALSE,
@@ -517,13 +532,17 @@ def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verb
         distrOld = dict(distr)
         i = 0
         converged = False
+        last_best = None
         while not converged and i < maxIter:                                   # :56
-            nb = min(B, maxIter - i)
+            # batch size: never more than B, and no more than the stopping rule can use if the current winner
+            # keeps winning (it cannot fire earlier on that path; any other path is simply continued next batch)
+            nb = min(B, maxIter - i, _iters_until_stable(distr, distrOld, tol, last_best, keys, B))
             folds = [draw_folds(rng, n, p, holdouts) for _ in range(nb)]       # in order: the stream R would consume
             vals = bcv_batch(Yd, keys, holdouts, folds, ctx=ctx, group=group)  # :58, nb calls of bcv()
             for j in range(nb):
                 res = dict(zip(keys, vals[j]))
                 best = min(keys, key=lambda kk: (res[kk], keys.index(kk)))     # names(which.min(res))
+                last_best = best
                 distr[best] += 1
                 sd, so = sum(distr.values()), sum(distrOld.values())
                 resid = [(distr[kk] / sd - distrOld[kk] / so) ** 2 for kk in keys]   # :69-71
