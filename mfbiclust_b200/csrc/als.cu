@@ -642,7 +642,53 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if ((it % NG) == grp) {
             const uint32_t sb = ring_s + (uint32_t)stage * STAGE_BYTES;
             mbar_wait(&full_bar[stage], phase, 2, it, stage);
-            if (!WSTEP) {
+            if (!WSTEP && KB >= 6) {
+                // large ranks: the 16 KB accumulator tile leaves no room for all factor fragments at once, so they
+                // are fetched rank block by rank block (same accumulation order per accumulator as below)
+                double2 b[4][2];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    b[v][0] = lds128(sb + offA + v * 1024);
+                    b[v][1] = lds128(sb + (offA ^ 16) + v * 1024);
+                }
+#pragma unroll
+                for (int cb = 0; cb < KB; ++cb) {
+                    const double2 f0 = lds128(sb + offF + cb * 1024), f1 = lds128(sb + (offF ^ 16) + cb * 1024);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f0.x, b[v][0].x);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f0.y, b[v][0].y);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f1.x, b[v][1].x);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f1.y, b[v][1].y);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            } else if (WSTEP && KB >= 6) {
+#pragma unroll
+                for (int rg = 0; rg < 2; ++rg) {
+                    double2 a[4][2];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        a[q][0] = lds128(sb + offA + rg * 4096 + q * 1024);
+                        a[q][1] = lds128(sb + ((offA + 128) ^ 16) + rg * 4096 + q * 1024);
+                    }
+#pragma unroll
+                    for (int cb = 0; cb < KB; ++cb) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 fq = lds128(sb + (q >> 1) * F_BOX + ((offF + cb * 1024) ^ ((q & 1) << 6)));
+                            dmma884(acc[cb][2 * rg][0], acc[cb][2 * rg][1], a[q][0].x, fq.x);
+                            dmma884(acc[cb][2 * rg + 1][0], acc[cb][2 * rg + 1][1], a[q][0].y, fq.x);
+                            dmma884(acc[cb][2 * rg][0], acc[cb][2 * rg][1], a[q][1].x, fq.y);
+                            dmma884(acc[cb][2 * rg + 1][0], acc[cb][2 * rg + 1][1], a[q][1].y, fq.y);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            } else if (!WSTEP) {
                 // m8n8k4: A-operand = W fragment [M = rank 8cb+g][K = row 4t+s], B-operand = A fragment [K = row 4t+s][N = column g]
                 double2 b[4][2], f[KB][2];
 #pragma unroll
