@@ -138,7 +138,7 @@ int  mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, i
 
 /* ---- nipals_pca (R/bicluster.R:218-242 -> nipals::nipals, call site :226) -- */
 /* scores: m x ncomp (unit-norm columns), loadings: n x ncomp, eig: ncomp, iters: ncomp.
- * Complete data only (NA support is SURVEY.md 8f "next").  x is not modified. */
+ * NaN entries are treated as NA (nipals' has.na branch: sums over observed cells only).  x is not modified. */
 int  mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale,
                 int maxiter, double tol, int gramschmidt,
                 double *scores, double *loadings, double *eig, int *iters);

@@ -318,8 +318,9 @@ def nipals_pca(A, k, cleanParam=0, verbose=True, ctx=None, **kwargs):
     """``nipals_pca(A, k, cleanParam = 0, verbose = TRUE, ...)`` (``R/bicluster.R:269-289``) ->
     ``dict(m, genericFit, indexRemaining)``."""
     mClean, indexRem = clean(A, cleanParam, dimsRemain=True)
-    if np.isnan(mClean).any():
-        raise NotImplementedError("nipals_pca: matrices with NA entries are not supported yet")
+    miss = np.isnan(mClean)
+    if miss.any() and (miss.all(axis=0).any() or miss.all(axis=1).any()):
+        raise ValueError("At least one column or row is all NAs")          # nipals::nipals' own check
     return dict(m=mClean, genericFit=nipals_pca_nocatch(mClean, k, ctx=ctx, **kwargs), indexRemaining=indexRem)
 
 

@@ -1,4 +1,6 @@
-// NIPALS PCA on the GPU: replaces nipals::nipals (nipals 0.5; call site R/bicluster.R:226) for complete data.
+// NIPALS PCA on the GPU: replaces nipals::nipals (nipals 0.5; call site R/bicluster.R:226), complete data and the
+// missing-value branch (NaN = NA: every sum skips missing cells and the regression denominators t't / p'p become
+// per-column / per-row sums over the observed cells, nipals' `has.na` path).
 //
 // The whole algorithm -- optional centring / sd scaling, and for every component the start-column search, the
 // deflated power iteration (two passes over x per iteration: p = x't / t't and t = x p / p'p), Gram-Schmidt
@@ -18,7 +20,7 @@ namespace cg = cooperative_groups;
 struct NipalsParams {
     double *x;            // working copy, m x n, column-major, leading dimension ld (deflated in place)
     int64_t m, n, ld;
-    int ncomp, center, scale, maxiter, gramschmidt;
+    int ncomp, center, scale, maxiter, gramschmidt, has_na;
     double tol;
     double *T;            // m x ncomp unnormalised scores
     double *P;            // n x ncomp loadings
@@ -72,7 +74,7 @@ __device__ __forceinline__ void cols_dot4(const double *c0, const double *c1, co
 
 __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ double nsm[];          // [NIP_WARPS][256] partial scores of one 256-row pass
+    extern __shared__ double nsm[];          // [2][NIP_WARPS][256] partial scores (and denominators) of a 256-row pass
     __shared__ double sh[NIP_THREADS / 32];
     __shared__ double scoef[64];
     const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
@@ -85,6 +87,30 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
     if (p.center || p.scale) {
         for (int64_t j = gw; j < n; j += tw) {
             double *col = p.x + j * ld;
+            if (p.has_na) {      // colMeans(na.rm = TRUE) / sd(na.rm = TRUE): plain loops, missing cells skipped
+                double s = 0.0, cnt = 0.0;
+                for (int64_t i = lane; i < m; i += 32) { const double v = col[i]; if (v == v) { s += v; cnt += 1.0; } }
+                s = warp_sum(s); cnt = warp_sum(cnt);
+                const double mean = s / cnt;
+                double sd = 1.0;
+                if (p.scale) {
+                    double q = 0.0;
+                    for (int64_t i = lane; i < m; i += 32) { const double v = col[i]; if (v == v) q += (v - mean) * (v - mean); }
+                    sd = sqrt(warp_sum(q) / (cnt - 1.0));
+                    if (!(sd > 0.0) && lane == 0) atomicExch(p.status, 2);
+                }
+                double ab = 0.0;
+                for (int64_t i = lane; i < m; i += 32) {
+                    double v = col[i];
+                    if (p.center) v -= mean;
+                    if (p.scale) v /= sd;
+                    col[i] = v;
+                    if (v == v) ab += fabs(v);
+                }
+                ab = warp_sum(ab);
+                if (lane == 0) p.colabs[j] = ab;
+                continue;
+            }
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int64_t i = lane;
             for (; i + 96 < m; i += 128) { s0 += col[i]; s1 += col[i + 32]; s2 += col[i + 64]; s3 += col[i + 96]; }
@@ -119,6 +145,9 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
             const double *col = p.x + j * ld;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int64_t i = lane;
+            if (p.has_na) {
+                for (; i < m; i += 32) { const double v = col[i]; if (v == v) s0 += fabs(v); }
+            }
             for (; i + 96 < m; i += 128) { s0 += fabs(col[i]); s1 += fabs(col[i + 32]); s2 += fabs(col[i + 64]); s3 += fabs(col[i + 96]); }
             for (; i < m; i += 32) s0 += fabs(col[i]);
             const double ab = warp_sum((s0 + s1) + (s2 + s3));
@@ -160,7 +189,8 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
         // th = x[, scol]; tt = sum(th^2)
         double tts = 0.0;
         for (int64_t i = r0 + tid; i < r1; i += NIP_THREADS) {
-            const double v = __ldcg(&p.x[scol * ld + i]);
+            double v = __ldcg(&p.x[scol * ld + i]);
+            if (!(v == v)) v = 0.0;                      // x0: missing cells count as zero
             p.th[i] = v;
             tts += v * v;
         }
@@ -179,27 +209,41 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                 const double *c1 = p.x + ((j0 + 1 < n) ? j0 + 1 : j0) * ld;
                 const double *c2 = p.x + ((j0 + 2 < n) ? j0 + 2 : j0) * ld;
                 const double *c3 = p.x + ((j0 + 3 < n) ? j0 + 3 : j0) * ld;
-                double s4[4];
-                cols_dot4(c0, c1, c2, c3, p.th, m, lane, s4);
+                double s4[4], den4[4] = {tt, tt, tt, tt};
+                if (p.has_na) {      // crossprod(x0, th) / colSums(T2): numerator and denominator over observed cells
+                    const double *cc[4] = {c0, c1, c2, c3};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) s4[q] = warp_sum(s4[q]);
+                    for (int q = 0; q < 4; ++q) {
+                        double sn = 0.0, sd2 = 0.0;
+                        for (int64_t i = lane; i < m; i += 32) {
+                            const double v = cc[q][i], t = __ldcg(&p.th[i]);
+                            if (v == v) { sn += v * t; sd2 += t * t; }
+                        }
+                        s4[q] = sn;
+                        den4[q] = warp_sum(sd2);
+                    }
+                } else {
+                    cols_dot4(c0, c1, c2, c3, p.th, m, lane, s4);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s4[q] = warp_sum(s4[q]) / den4[q];
                 if (lane < 4 && j0 + lane < n) p.ph[j0 + lane] = s4[lane];
             }
             grid.sync();
             // S2 (redundant per block): ph = ph_raw / tt; Gram-Schmidt against P[, 0..h); normalise
-            double pp_inv;   // 1 / (ph'ph) after normalisation
+            double pp_den;   // ph'ph after normalisation
             const int nh = (p.gramschmidt && h > 0) ? h : 0;
             {
                 for (int l = 0; l < nh; ++l) {
                     double s = 0.0;
-                    for (int64_t j = tid; j < n; j += NIP_THREADS) s += p.P[(size_t)l * n + j] * (__ldcg(&p.ph[j]) / tt);
+                    for (int64_t j = tid; j < n; j += NIP_THREADS) s += p.P[(size_t)l * n + j] * __ldcg(&p.ph[j]);
                     s = block_sum(s, sh);
                     if (tid == 0) scoef[l] = s;
                 }
                 __syncthreads();
                 double nrm = 0.0;
                 for (int64_t j = tid; j < n; j += NIP_THREADS) {
-                    double v = __ldcg(&p.ph[j]) / tt;
+                    double v = __ldcg(&p.ph[j]);
                     double corr = 0.0;
                     for (int l = 0; l < nh; ++l) corr += p.P[(size_t)l * n + j] * scoef[l];
                     v -= corr;
@@ -208,7 +252,7 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                 nrm = sqrt(block_sum(nrm, sh));
                 double p2 = 0.0;
                 for (int64_t j = tid; j < n; j += NIP_THREADS) {
-                    double v = __ldcg(&p.ph[j]) / tt;
+                    double v = __ldcg(&p.ph[j]);
                     double corr = 0.0;
                     for (int l = 0; l < nh; ++l) corr += p.P[(size_t)l * n + j] * scoef[l];
                     v = (v - corr) / nrm;
@@ -216,18 +260,30 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                     p.phn[(size_t)b * n + j] = v;   // block-private copy of the normalised loading (no extra barrier)
                 }
                 p2 = block_sum(p2, sh);
-                pp_inv = 1.0 / p2;
+                pp_den = p2;
                 __syncthreads();
             }
             // S3: th_new = x ph / (ph'ph) for this block's rows, 256 rows per pass: warp w sums its eighth of the
             // columns for all eight 32-row groups of the pass (two columns x eight row groups of loads in flight)
             for (int64_t rb = r0; rb < r1; rb += 256) {
                 const int64_t jlo = n * warp / NIP_WARPS, jhi = n * (warp + 1) / NIP_WARPS;
-                double acc[8];
+                double acc[8], dacc[8];
 #pragma unroll
-                for (int g = 0; g < 8; ++g) acc[g] = 0.0;
+                for (int g = 0; g < 8; ++g) acc[g] = dacc[g] = 0.0;
                 const int ngr = (int)((r1 - rb + 31) / 32 < 8 ? (r1 - rb + 31) / 32 : 8);
                 int64_t j = jlo;
+                if (p.has_na) {      // x0 %*% ph / colSums(P2): observed cells only
+                    for (; j < jhi; ++j) {
+                        const double pj0 = phn[j];
+                        const double *ca = p.x + j * ld + rb + lane;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            if (g < ngr && rb + 32 * g + lane < r1) {
+                                const double v = __ldcg(&ca[32 * g]);
+                                if (v == v) { acc[g] += v * pj0; dacc[g] += pj0 * pj0; }
+                            }
+                    }
+                }
                 for (; j + 1 < jhi; j += 2) {
                     const double pj0 = phn[j], pj1 = phn[j + 1];
                     const double *ca = p.x + j * ld + rb + lane, *cb2 = ca + ld;
@@ -249,16 +305,19 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                         if (g < ngr && rb + 32 * g + lane < r1) acc[g] += __ldcg(&ca[32 * g]) * pj0;
                 }
 #pragma unroll
-                for (int g = 0; g < 8; ++g) nsm[warp * 256 + 32 * g + lane] = acc[g];
+                for (int g = 0; g < 8; ++g) {
+                    nsm[warp * 256 + 32 * g + lane] = acc[g];
+                    nsm[(NIP_WARPS + warp) * 256 + 32 * g + lane] = dacc[g];
+                }
                 __syncthreads();
                 {
                     const int64_t i = rb + tid;
                     if (i < r1) {
-                        double sacc = 0.0;
+                        double sacc = 0.0, sden = 0.0;
 #pragma unroll
-                        for (int w = 0; w < NIP_WARPS; ++w) sacc += nsm[w * 256 + tid];
+                        for (int w = 0; w < NIP_WARPS; ++w) { sacc += nsm[w * 256 + tid]; sden += nsm[(NIP_WARPS + w) * 256 + tid]; }
                         p.th_old[i] = p.th[i];
-                        p.th[i] = sacc * pp_inv;
+                        p.th[i] = sacc / (p.has_na ? sden : pp_den);
                     }
                 }
                 __syncthreads();
@@ -325,13 +384,13 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                 const double t0 = __ldcg(&p.th[i]), t1 = __ldcg(&p.th[i + 32]), t2 = __ldcg(&p.th[i + 64]), t3 = __ldcg(&p.th[i + 96]);
                 const double v0 = col[i] - t0 * pj, v1 = col[i + 32] - t1 * pj, v2 = col[i + 64] - t2 * pj, v3 = col[i + 96] - t3 * pj;
                 col[i] = v0; col[i + 32] = v1; col[i + 64] = v2; col[i + 96] = v3;
-                s0 += fabs(v0) + fabs(v2);
-                s1 += fabs(v1) + fabs(v3);
+                s0 += ((v0 == v0) ? fabs(v0) : 0.0) + ((v2 == v2) ? fabs(v2) : 0.0);
+                s1 += ((v1 == v1) ? fabs(v1) : 0.0) + ((v3 == v3) ? fabs(v3) : 0.0);
             }
             for (; i < m; i += 32) {
                 const double v0 = col[i] - __ldcg(&p.th[i]) * pj;
                 col[i] = v0;
-                s0 += fabs(v0);
+                s0 += (v0 == v0) ? fabs(v0) : 0.0;
             }
             const double ab = warp_sum(s0 + s1);
             if (lane == 0) p.colabs[j] = ab;
@@ -359,14 +418,11 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     double stats[5];
     int rc = mfb_matrix_stats(x, stats);
     if (rc != MFB_OK) return rc;
-    if (stats[3] > 0) {
-        mfb_set_error("mfb_nipals: NA values are not supported yet (SURVEY.md 8f)");
-        return MFB_ERR_UNSUPPORTED;
-    }
+    const int has_na = stats[3] > 0;
     const int64_t m = x->m, n = x->n, ld = x->lda;
     int nb_max = 0;
     MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, nipals_kernel, NIP_THREADS,
-                                                           NIP_WARPS * 256 * sizeof(double)));
+                                                           2 * NIP_WARPS * 256 * sizeof(double)));
     int nb = nb_max * ctx->sm_count;
     if (nb > ctx->sm_count) nb = ctx->sm_count;               // one block per SM is plenty; keeps grid.sync cheap
     const int64_t want = (m + NIP_THREADS - 1) / NIP_THREADS > n ? (m + NIP_THREADS - 1) / NIP_THREADS : n;
@@ -400,10 +456,11 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     p.m = m; p.n = n; p.ld = ld;
     p.ncomp = ncomp; p.center = center; p.scale = scale; p.maxiter = maxiter; p.gramschmidt = gramschmidt;
     p.tol = tol;
+    p.has_na = has_na;
     MFB_CUDA(cudaMemcpyAsync(p.x, x->d, (size_t)ld * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     void *args[] = {&p};
     MFB_CUDA(cudaLaunchCooperativeKernel((void *)nipals_kernel, dim3(nb), dim3(NIP_THREADS), args,
-                                         NIP_WARPS * 256 * sizeof(double), st));
+                                         2 * NIP_WARPS * 256 * sizeof(double), st));
     std::vector<double> hE(ncomp);
     std::vector<int> hI(ncomp + 1);
     MFB_CUDA(cudaMemcpyAsync(scores, p.T, (size_t)m * ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -40,16 +40,22 @@ def svd_pca(A: np.ndarray, k: int):
 
 def nipals(x: np.ndarray, ncomp: int, center=True, scale=True, maxiter=500, tol=1e-6,
            gramschmidt=True):
-    """``nipals::nipals`` (complete-data branch; ``startcol = 0``, ``fitted = FALSE``).
+    """``nipals::nipals`` (``startcol = 0``, ``fitted = FALSE``), complete data and the ``has.na`` branch
+    (NaN = NA; SURVEY.md App. A.3: ``ph = x0't / colSums(T2)``, ``th = x0 p / colSums(P2)`` with the squared
+    vectors zeroed at the missing cells).  The NA branch and ncomp > 1 are parity unpinned.
 
     Returns ``dict(eig, scores, loadings, iters)``; scores have unit-norm columns.
     """
     x = np.array(x, dtype=np.float64)
     nobs, nvar = x.shape
+    miss = np.isnan(x)
+    has_na = bool(miss.any())
+    if has_na and (miss.all(axis=0).any() or miss.all(axis=1).any()):
+        raise ValueError("At least one column or row is all NAs")
     if center:
-        x = x - x.mean(axis=0, keepdims=True)
+        x = x - np.nanmean(x, axis=0, keepdims=True)
     if scale:
-        x = x / x.std(axis=0, ddof=1, keepdims=True)      # apply(x, 2, sd)
+        x = x / np.nanstd(x, axis=0, ddof=1, keepdims=True)      # apply(x, 2, sd, na.rm = TRUE)
     PPp = np.zeros((nvar, nvar))
     TTp = np.zeros((nobs, nobs)) if nobs <= 4096 else None
     Ts = []
@@ -57,17 +63,25 @@ def nipals(x: np.ndarray, ncomp: int, center=True, scale=True, maxiter=500, tol=
     loadings = np.zeros((nvar, ncomp))
     scores = np.zeros((nobs, ncomp))
     iters = np.zeros(ncomp, dtype=np.int64)
+    obs = (~miss).astype(np.float64)
     for h in range(ncomp):
-        scol = int(np.argmax(np.abs(x).sum(axis=0)))
-        th = x[:, scol].copy()
+        scol = int(np.argmax(np.nansum(np.abs(x), axis=0)))
+        x0 = np.where(miss, 0.0, x)
+        th = x0[:, scol].copy()
         pciter = 1
         while True:
-            ph = x.T @ th / float(th @ th)
+            if has_na:
+                ph = (x0.T @ th) / (obs.T @ (th * th))
+            else:
+                ph = x.T @ th / float(th @ th)
             if gramschmidt and h > 0:
                 ph = ph - PPp @ ph
             ph = ph / np.sqrt(float(ph @ ph))
             th_old = th
-            th = x @ ph / float(ph @ ph)
+            if has_na:
+                th = (x0 @ ph) / (obs @ (ph * ph))
+            else:
+                th = x @ ph / float(ph @ ph)
             if gramschmidt and h > 0:
                 if TTp is not None:
                     th = th - TTp @ th

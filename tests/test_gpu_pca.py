@@ -126,3 +126,20 @@ def test_addstrat_svd_and_als(simdata):
     s = bce.strategies["ALS-NMF | Otsu | 5"]
     assert s.biclust.RowxNumber.shape == (80, 5) and s.biclust.NumberxCol.shape == (5, 80)
     assert (s.factors.fit.W >= 0).all() and (s.factors.fit.H >= 0).all()
+
+
+def test_nipals_missing_values():
+    # nipals' has.na branch (NaN = NA), as addStrat routes any matrix with NA (R/addStrat.R:67-84)
+    import mfbiclust_b200 as mfb
+    rs = np.random.default_rng(33)
+    x = rs.standard_normal((400, 3)) @ rs.standard_normal((3, 30)) * 2 + rs.standard_normal((400, 30)) + 1.0
+    x[rs.random(x.shape) < 0.05] = np.nan
+    for center, scale in ((False, True), (True, False)):
+        got = mfb.nipals(x, 3, center=center, scale=scale, tol=1e-9)
+        ref = P.nipals(x, 3, center=center, scale=scale, tol=1e-9)
+        assert np.array_equal(got["iter"], ref["iters"])
+        assert rel_fro(got["scores"], ref["scores"]) < 1e-8
+        assert rel_fro(got["loadings"], ref["loadings"]) < 1e-8
+    with pytest.warns(UserWarning, match="NIPALS-PCA algorithm must be used"):
+        bce = mfb.addStrat(mfb.BiclusterExperiment(x), 2, method="svd-pca", silent=True)
+    assert "NIPALS-PCA | Otsu | 2" in bce.strategies
