@@ -128,53 +128,81 @@ int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int
 }
 
 // ---------------------------------------------------------------------------
-// C = A V  for a tall A and a thin V (kk <= 64): one thread per row
+// C = A V  for a tall A and a thin V (kk <= 64)
 // ---------------------------------------------------------------------------
+// Block = 32 rows x 8 column slices: warp w walks the columns c = w, w + 8, ... of A (a warp reads 256 contiguous
+// bytes per column, four columns of loads in flight), V is staged through shared memory 32 columns at a time, and
+// the eight slices are summed in shared memory in a fixed order.
 template <int KK>
-__global__ void __launch_bounds__(128) tall_times_small_kernel(const double *__restrict__ A, int64_t lda,
+__global__ void __launch_bounds__(256) tall_times_small_kernel(const double *__restrict__ A, int64_t lda,
                                                                const double *__restrict__ V, int64_t ldv,
                                                                double *__restrict__ C, int64_t ldc, int64_t rows,
                                                                int64_t inner, int kk,
                                                                const double *__restrict__ colscale) {
     __shared__ double sv[32 * KK];
-    const int64_t i = blockIdx.x * 128ll + threadIdx.x;
+    extern __shared__ double red[];            // [8][32][KK + 1]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = blockIdx.x * 32ll + lane;
+    const bool rowok = i < rows;
     double acc[KK];
 #pragma unroll
     for (int j = 0; j < KK; ++j) acc[j] = 0.0;
     for (int64_t c0 = 0; c0 < inner; c0 += 32) {
         const int cn = (int)((inner - c0 < 32) ? inner - c0 : 32);
         __syncthreads();
-        for (int e = threadIdx.x; e < 32 * KK; e += 128) {
+        for (int e = threadIdx.x; e < 32 * KK; e += 256) {
             const int c = e / KK, j = e - c * KK;
             sv[e] = (c < cn && j < kk) ? V[(c0 + c) + (int64_t)j * ldv] : 0.0;
         }
         __syncthreads();
-        if (i < rows) {
-            for (int c = 0; c < cn; ++c) {
-                const double a = A[i + (c0 + c) * lda];
+        // this warp's four columns of the chunk: c = w, w + 8, w + 16, w + 24
+        double a4[4];
 #pragma unroll
-                for (int j = 0; j < KK; ++j) acc[j] += a * sv[c * KK + j];
-            }
+        for (int q = 0; q < 4; ++q) {
+            const int c = w + 8 * q;
+            a4[q] = (rowok && c < cn) ? A[i + (c0 + c) * lda] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = w + 8 * q;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) acc[j] += a4[q] * sv[c * KK + j];
         }
     }
-    if (i < rows) {
 #pragma unroll
-        for (int j = 0; j < KK; ++j)
-            if (j < kk) C[i + (int64_t)j * ldc] = colscale ? acc[j] * colscale[j] : acc[j];
+    for (int j = 0; j < KK; ++j) red[(w * 32 + lane) * (KK + 1) + j] = acc[j];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * KK; e += 256) {
+        const int r = e % 32, j = e / 32;
+        const int64_t ir = blockIdx.x * 32ll + r;
+        if (ir < rows && j < kk) {
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) s += red[(ww * 32 + r) * (KK + 1) + j];
+            C[ir + (int64_t)j * ldc] = colscale ? s * colscale[j] : s;
+        }
     }
+}
+
+template <int KK>
+static int launch_tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv,
+                                   double *C, int64_t ldc, int64_t rows, int64_t inner, int kk,
+                                   const double *colscale) {
+    const size_t smem = (size_t)8 * 32 * (KK + 1) * sizeof(double);
+    MFB_CUDA(cudaFuncSetAttribute(tall_times_small_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tall_times_small_kernel<KK><<<(unsigned)((rows + 31) / 32), 256, smem, ctx->stream>>>(A, lda, V, ldv, C, ldc, rows,
+                                                                                         inner, kk, colscale);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
 }
 
 int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv, double *C,
                      int64_t ldc, int64_t rows, int64_t inner, int kk, const double *colscale) {
     MFB_ARG(kk >= 1 && kk <= 64, "tall_times_small: kk must be in 1..64");
-    const unsigned nb = (unsigned)((rows + 127) / 128);
-    cudaStream_t st = ctx->stream;
-    if (kk <= 8) tall_times_small_kernel<8><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
-    else if (kk <= 16) tall_times_small_kernel<16><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
-    else if (kk <= 32) tall_times_small_kernel<32><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
-    else tall_times_small_kernel<64><<<nb, 128, 0, st>>>(A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
-    MFB_CUDA(cudaGetLastError());
-    return MFB_OK;
+    if (kk <= 8) return launch_tall_times_small<8>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    if (kk <= 16) return launch_tall_times_small<16>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    if (kk <= 32) return launch_tall_times_small<32>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
+    return launch_tall_times_small<64>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
 }
 
 // ---------------------------------------------------------------------------

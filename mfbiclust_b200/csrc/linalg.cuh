@@ -9,7 +9,7 @@ size_t gemm_tn_workspace(int64_t M, int64_t N, int64_t K, int sm_count);
 int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
             int64_t M, int64_t N, int64_t K, double *work);
 
-// C[rows x kk] (ldc) = A[rows x inner] (lda) * V[inner x kk] (ldv), kk <= 64: one thread per row of A.
+// C[rows x kk] (ldc) = A[rows x inner] (lda) * V[inner x kk] (ldv), kk <= 64: 32 rows x 8 column slices per block.
 // Optional per-column scale: C[:, j] *= colscale[j].
 int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv, double *C,
                      int64_t ldc, int64_t rows, int64_t inner, int kk, const double *colscale);
