@@ -237,10 +237,13 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
 // Warp-cooperative exact NNLS for any rank up to 64 (used for k > 32, where a tableau row no longer fits the
 // registers of one lane): active-set iteration with a COMPRESSED solve.
 //
-// Same pivot rules as one column of .fcnnls (first passive set = {xu > 0}; while the solve on the passive set
-// goes negative step back along d -> x and drop the blocking variable; when feasible add the variable with the
-// largest positive gradient; stop when there is none).  A group of LP lanes owns one problem, lane i owning the
-// variables i (+ LP): instead of exchanging variables one at a time, every iteration solves the current
+// First passive set = {xu > 0} as in .fcnnls; then BLOCK principal pivoting (Judice & Pires / Kim & Park): every
+// iteration solves the current partition exactly and exchanges ALL infeasible variables at once (negative primal
+// values leave the passive set, positive gradients enter it); when the number of infeasibilities has not
+// decreased for three iterations only the infeasible variable with the largest index is exchanged (Murty's rule,
+// which cannot cycle).  The optimum of the strictly convex problem is unique, so this reaches the same solution as
+// the reference's one-variable-at-a-time Lawson-Hanson path in ~4 solves instead of one per exchanged variable.
+// A group of LP lanes owns one problem, lane i owning the variables i (+ LP); every iteration solves the current
 // partition directly on its SMALLER side S (|S| <= k/2):
 //   S = N (active set):   y = (M_NN)^-1 xu_N,  x_P = xu_P - M_PN y,  w_N = y          (M = G^-1, xu = M r)
 //   S = P (passive set):  y = (G_PP)^-1 r_P,   x_P = y,              w_N = r_N - G_NP y
@@ -252,6 +255,17 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
 // problems [first, first + count) of xs, 32 / LP at a time; problems >= nvalid are skipped (x = 0).
 // scr: per-warp shared scratch of nnls_scratch_doubles<KP>() doubles.  Returns this lane's partial of sum x_i r_i.
 // ---------------------------------------------------------------------------
+// 1/x to full double precision from the single-precision estimate and two Newton steps (x well inside the float
+// range, as Gram pivots are); falls back to the division otherwise
+__device__ __forceinline__ double fast_rcp(double x) {
+    const float xf = (float)x;
+    double r = (double)(1.0f / xf);
+    if (!(fabsf(xf) > 1e-30f && fabsf(xf) < 1e30f)) return 1.0 / x;
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
 template <int KP>
 struct NnlsCfg {
     static constexpr int LP = (KP <= 16) ? 16 : 32;
@@ -285,7 +299,7 @@ __device__ double nnls_warp(const double *__restrict__ sG, const double *__restr
             continue;
         }
         const int ucol = inrange ? unit : first;           // a readable column for lanes without a problem
-        double r_[R], xu_[R], d_[R], x_[R], w_[R];
+        double r_[R], xu_[R], x_[R], w_[R];
         bool inN_[R], val_[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
@@ -298,12 +312,11 @@ __device__ double nnls_warp(const double *__restrict__ sG, const double *__restr
             xu_[q] = val_[q] ? acc : 0.0;
             if (v < KP) xu_s[v] = xu_[q];
             inN_[q] = val_[q] && !(xu_[q] > 0.0);
-            d_[q] = xu_[q] > 0.0 ? xu_[q] : 0.0;
-            x_[q] = d_[q];
+            x_[q] = xu_[q] > 0.0 ? xu_[q] : 0.0;
             w_[q] = 0.0;
         }
         bool done = !uvalid;
-        int iters = 0;
+        int iters = 0, best_inf = k + 1, patience = 3;
         const int cap = 6 * k + 16;
         while (true) {
             // ---- partition of this group's problem ----
@@ -350,7 +363,7 @@ __device__ double nnls_warp(const double *__restrict__ sG, const double *__restr
             for (int a = 0; a < NS; ++a) {
                 if (a < ns_max) {
                     const double pa = __shfl_sync(FULL, A[a], base + a);
-                    const double ip = 1.0 / pa;
+                    const double ip = fast_rcp(pa);
                     yv[a] = ip;
                     const double f = (i > a) ? A[a] * ip : 0.0;
 #pragma unroll
@@ -391,57 +404,29 @@ __device__ double nnls_warp(const double *__restrict__ sG, const double *__restr
                 }
             }
             __syncwarp();
-            // ---- pivot rules ----
+            // ---- block principal pivoting ----
             if (!done) {
                 const unsigned gm = (LP == 32) ? FULL : (0xffffu << base);
-                bool anyneg = false;
-                double al = INFINITY;
-                int av = 1 << 20;
+                bool bad_[R];
+                int ninf = 0, top = -1;
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
-                    const bool neg = val_[q] && !inN_[q] && x_[q] < 0.0;
-                    anyneg |= neg;
-                    const double a1 = neg ? d_[q] / (d_[q] - x_[q]) : INFINITY;
-                    if (a1 < al) { al = a1; av = i + LP * q; }
+                    bad_[q] = val_[q] && (inN_[q] ? (w_[q] > 0.0) : (x_[q] < 0.0));
+                    const unsigned bal = __ballot_sync(gm, bad_[q]);
+                    const unsigned gb = (LP == 32) ? bal : ((bal >> base) & 0xffffu);
+                    ninf += __popc(gb);
+                    if (gb) top = max(top, LP * q + 31 - __clz(gb));     // largest infeasible variable index
                 }
-                if (__ballot_sync(gm, anyneg) != 0u) {
-                    // Lawson-Hanson step back: the first passive variable to hit zero leaves the passive set
-#pragma unroll
-                    for (int o = LP / 2; o > 0; o >>= 1) {
-                        const double oa = __shfl_xor_sync(gm, al, o);
-                        const int ov = __shfl_xor_sync(gm, av, o);
-                        if (oa < al || (oa == al && ov < av)) { al = oa; av = ov; }
-                    }
-#pragma unroll
-                    for (int q = 0; q < R; ++q) {
-                        d_[q] = d_[q] - al * (d_[q] - x_[q]);
-                        if (i + LP * q == av) { d_[q] = 0.0; inN_[q] = true; }
-                    }
+                if (ninf == 0) {
+                    done = true;
                 } else {
-                    bool anypos = false;
-                    double wm = -1.0;
-                    int wv = 1 << 20;
+                    bool all;
+                    if (ninf < best_inf) { best_inf = ninf; patience = 3; all = true; }
+                    else if (patience > 0) { --patience; all = true; }
+                    else all = false;
 #pragma unroll
-                    for (int q = 0; q < R; ++q) {
-                        const bool pos = val_[q] && inN_[q] && w_[q] > 0.0;
-                        anypos |= pos;
-                        if (pos && w_[q] > wm) { wm = w_[q]; wv = i + LP * q; }
-                    }
-                    if (__ballot_sync(gm, anypos) != 0u) {
-#pragma unroll
-                        for (int o = LP / 2; o > 0; o >>= 1) {
-                            const double ow = __shfl_xor_sync(gm, wm, o);
-                            const int ov = __shfl_xor_sync(gm, wv, o);
-                            if (ow > wm || (ow == wm && ov < wv)) { wm = ow; wv = ov; }
-                        }
-#pragma unroll
-                        for (int q = 0; q < R; ++q) {
-                            d_[q] = x_[q];
-                            if (i + LP * q == wv) inN_[q] = false;
-                        }
-                    } else {
-                        done = true;
-                    }
+                    for (int q = 0; q < R; ++q)
+                        if (bad_[q] && (all || i + LP * q == top)) inN_[q] = !inN_[q];
                 }
                 if (++iters > cap) done = true;
             }

@@ -115,3 +115,34 @@ def test_bcv_cell_sharding_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_auto_bcv_batch_sizing_matches_the_stopping_rule():
+    # R/bcv.R:56-87: with one k winning every time the rule fires at iteration 22 on an 11-candidate grid
+    # (vignettes/my-vignette.html:408-413: counts = 22); the batch sizing must predict exactly that
+    from mfbiclust_b200.backends import _iters_until_stable
+    keys = list(range(1, 12))
+    distr = {k: 1 for k in keys}
+    old = dict(distr)
+    done = 0
+    while True:
+        nb = _iters_until_stable(distr, old, 1e-4, 11 if done else None, keys, 8)
+        assert 1 <= nb <= 8
+        conv = False
+        for _ in range(nb):
+            distr[11] += 1
+            sd, so = sum(distr.values()), sum(old.values())
+            conv = all((distr[k] / sd - old[k] / so) ** 2 < 1e-4 for k in keys)
+            old = dict(distr)
+            done += 1
+            if conv:
+                break
+        if conv:
+            break
+    assert done == 22 and distr[11] - 1 == 22
+    # the last batch must not overshoot: after 19 identical winners exactly 3 more iterations are needed
+    d = {k: 1 for k in keys}
+    o = dict(d)
+    d[11] += 19
+    o[11] += 18
+    assert _iters_until_stable(d, o, 1e-4, 11, keys, 8) == 3
