@@ -172,3 +172,34 @@ def test_als_rejects_negative_and_bad_eps():
         mfb.als_nmf(np.abs(A), 2, eps_conv=0.0)
     with pytest.raises(mfb.MfbError, match="Negative values are not allowed"):
         mfb.AlsSession(mfb.Matrix(mfb.default_context(), host=A), 2, W0, H0, 1.0)
+
+
+def test_als_full_size_properties():
+    """BASELINE.json configs[3] at full size (20000 x 5000, k = 16), where the oracle is too slow to run:
+    size-independent properties instead -- the reported residual equals ||A - WH|| computed independently, the
+    final W satisfies the KKT conditions of its NNLS problem given the final H, factors are non-negative, the
+    residual trace never increases, and two runs are bit-identical."""
+    import mfbiclust_b200 as mfb
+    m, n, k = 20000, 5000, 16
+    A = np.asfortranarray(pseudovalues(gen_sim_data(n=5, cluster_height=1000, cluster_width=1000, dimx=m, dimy=n,
+                                                    bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0,
+                                                    seed=4)))
+    W0, H0 = make_init(m, n, k, 40)
+    ctx = mfb.default_context()
+    Ad = mfb.Matrix(ctx, host=A)
+    try:
+        a = mfb.als_replicate(Ad, k, W0, H0, maxIter=6, fixed_iters=True)
+        b = mfb.als_replicate(Ad, k, W0, H0, maxIter=6, fixed_iters=True)
+    finally:
+        Ad.free()
+    W, H = a["W"], a["H"]
+    assert np.array_equal(W, b["W"]) and np.array_equal(H, b["H"]) and np.array_equal(a["trace"], b["trace"])
+    assert (W >= 0).all() and (H >= 0).all()
+    resid = np.sqrt(np.mean((A - W @ H) ** 2))
+    assert abs(a["trace"][-1, 0] - resid) <= 1e-10 * resid            # no third pass over A, same number
+    assert (np.diff(a["trace"][:, 0]) <= 1e-12).all()
+    G, R = H @ H.T, A @ H.T                                           # W-step problem of the last iteration
+    grad = R - W @ G
+    scale = np.abs(R).max()
+    assert np.abs(grad[W > 0]).max() <= 1e-9 * scale                  # stationarity on the passive set
+    assert grad[W == 0].max() <= 1e-9 * scale                         # no positive gradient left on the active set
