@@ -62,6 +62,9 @@ int  mfb_context_trim(mfb_context *ctx);
 /* ---- resident matrix ---------------------------------------------------- */
 /* Upload a column-major host matrix (the `A` / `Y` argument of every back-end). */
 int  mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t n, mfb_matrix **out);
+/* Same, but the resident copy is kept in SINGLE precision (half the HBM traffic of the ALS stream kernels; the
+ * factors, the tensor-core accumulation and the NNLS stay FP64).  Accepted by the mfb_als_* entry points only. */
+int  mfb_matrix_upload_f32(mfb_context *ctx, const double *host, int64_t m, int64_t n, mfb_matrix **out);
 /* Wrap an existing device buffer (column-major, ld = m); not owned. */
 int  mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb_matrix **out);
 void mfb_matrix_free(mfb_matrix *A);

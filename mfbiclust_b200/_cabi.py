@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mfb_context_stream": (_vp, [_vp]),
     "mfb_context_trim": (C.c_int, [_vp]),
     "mfb_matrix_upload": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
+    "mfb_matrix_upload_f32": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_wrap_dev": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_free": (None, [_vp]),
     "mfb_matrix_stats": (C.c_int, [_vp, _dp]),
@@ -151,13 +152,16 @@ def default_context(device: int | None = None) -> Context:
 class Matrix:
     """``mfb_matrix``: an FP64 matrix resident in HBM."""
 
-    def __init__(self, ctx: Context, host: np.ndarray | None = None, dev_ptr: int | None = None, shape=None):
+    def __init__(self, ctx: Context, host: np.ndarray | None = None, dev_ptr: int | None = None, shape=None,
+                 precision: str = "f64"):
         self.ctx = ctx
         self._h = _vp()
+        self.precision = precision
         if host is not None:
             a = as_f(host)
             self.shape = a.shape
-            check(lib().mfb_matrix_upload(ctx.handle, dptr(a), a.shape[0], a.shape[1], C.byref(self._h)))
+            up = lib().mfb_matrix_upload_f32 if precision == "f32" else lib().mfb_matrix_upload
+            check(up(ctx.handle, dptr(a), a.shape[0], a.shape[1], C.byref(self._h)))
         else:
             self.shape = tuple(shape)
             check(lib().mfb_matrix_wrap_dev(ctx.handle, _vp(dev_ptr), shape[0], shape[1], C.byref(self._h)))

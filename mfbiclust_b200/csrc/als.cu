@@ -503,16 +503,24 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
     __threadfence();
 }
 
-template <int KB, bool WSTEP>
+// F32 = the resident matrix is stored in single precision (half the HBM traffic): a stage then covers 32 rows
+// (H-step) / a 128 x 32 tile of floats (W-step), the fragments are widened to FP64 in registers and everything
+// downstream (FP64 tensor-core accumulation, partials, factors, NNLS) is unchanged.
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int KB, bool WSTEP, bool F32>
 __global__ void __launch_bounds__(ALS_THREADS, 1)
 als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmF, const HalfParams p,
                   const int nstage) {
     constexpr int KP = KB * 8;
-    constexpr int A_BYTES = WSTEP ? 32768 : 16384;       // A box(es) of one stage
+    constexpr int A_BYTES = (WSTEP && !F32) ? 32768 : 16384;   // A box(es) of one stage
     constexpr int F_BOX = KP * 128;                      // one 16-unit box of the fixed factor: [KP][16] doubles
-    constexpr int NFB = WSTEP ? 2 : 1;                   // factor boxes per stage (32 columns / 16 rows of reduction)
+    constexpr int NFB = (WSTEP || F32) ? 2 : 1;          // factor boxes per stage (32 columns / 32 or 16 rows of reduction)
     constexpr int STAGE_BYTES = A_BYTES + NFB * F_BOX;
-    constexpr int NF = WSTEP ? 4 : 2;                    // double2 fragments of the fixed factor per rank block and unit
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
 
@@ -558,12 +566,18 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&empty_bar[stage], phase ^ 1, 1, it, stage);
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                 unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
-                if (!WSTEP) {
+                if (!WSTEP && !F32) {
                     tma_load_2d(dst, &tmA, st * 16, tile * TILE_UNITS, &full_bar[stage]);
                     tma_load_2d(dst + A_BYTES, &tmF, st * 16, 0, &full_bar[stage]);
+                } else if (!WSTEP) {
+                    // 32 rows of floats per column = the same 128-byte smem rows; two 16-row slabs of W
+                    tma_load_2d(dst, &tmA, st * 32, tile * TILE_UNITS, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES, &tmF, st * 32, 0, &full_bar[stage]);
+                    tma_load_2d(dst + A_BYTES + F_BOX, &tmF, st * 32 + 16, 0, &full_bar[stage]);
                 } else {
-                    // one 3-D box {16 rows, 32 columns, 8 row groups}: lands as [row group][column][16 rows]
-                    tma_load_3d(dst, &tmA, 0, st * 32, tile * 8, &full_bar[stage]);
+                    // one 3-D box {16 rows, 32 columns, 8 row groups} (FP32: {32 rows, 32 columns, 4 row groups}):
+                    // lands as [row group][column][128 bytes of rows]
+                    tma_load_3d(dst, &tmA, 0, st * 32, tile * (F32 ? 4 : 8), &full_bar[stage]);
                     tma_load_2d(dst + A_BYTES, &tmF, st * 32, 0, &full_bar[stage]);
                     tma_load_2d(dst + A_BYTES + F_BOX, &tmF, st * 32 + 16, 0, &full_bar[stage]);
                 }
@@ -606,7 +620,7 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int v = 0; v < 4; ++v)
                     *(double2 *)&Pb[(size_t)(8 * cb + g) * TILE_UNITS + 32 * wg + 8 * v + 2 * t] =
                         make_double2(acc[cb][v][0], acc[cb][v][1]);
-            } else {
+            } else if (!F32) {
                 // acc[cb][2rg+s][e] = R[row 32wg + 16rg + 2g + s][c = 8cb + t + 4e]   (rank index permuted, see the W-step loop)
 #pragma unroll
                 for (int rg = 0; rg < 2; ++rg)
@@ -614,6 +628,14 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int e = 0; e < 2; ++e)
                         *(double2 *)&Pb[(size_t)(8 * cb + t + 4 * e) * TILE_UNITS + 32 * wg + 16 * rg + 2 * g] =
                             make_double2(acc[cb][2 * rg][e], acc[cb][2 * rg + 1][e]);
+            } else {
+                // FP32 tiles: acc[cb][s][e] = R[row 32wg + 4g + s][c = 8cb + t + 4e]
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        *(double2 *)&Pb[(size_t)(8 * cb + t + 4 * e) * TILE_UNITS + 32 * wg + 4 * g + 2 * s2] =
+                            make_double2(acc[cb][2 * s2][e], acc[cb][2 * s2 + 1][e]);
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a) acc[cb][a][0] = acc[cb][a][1] = 0.0;
@@ -630,7 +652,11 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t offA, offF;
     if (!WSTEP) {
         offA = (uint32_t)((32 * wg + g) * 128 + (((2 * t) ^ g) << 4));      // column 32wg + g (+8v), chunk 2t (^1 for rows 4t+2..)
-        offF = (uint32_t)(A_BYTES + g * 128 + (((2 * t) ^ g) << 4));        // rank g (+8cb)
+        offF = F32 ? (uint32_t)(A_BYTES + (t >> 1) * F_BOX + g * 128)       // FP32: rows 8t..8t+7 = slab t>>1, chunks 4(t&1)+e
+                   : (uint32_t)(A_BYTES + g * 128 + (((2 * t) ^ g) << 4));  // rank g (+8cb)
+    } else if (F32) {
+        offA = (uint32_t)(wg * 4096 + (2 * t) * 128 + ((g ^ (2 * t)) << 4));       // row group wg, column 2t (+e +8q), chunk g = rows 4g..4g+3
+        offF = (uint32_t)(A_BYTES + pg * 128 + ((t ^ pg) << 4));
     } else {
         offA = (uint32_t)(2 * wg * 4096 + (2 * t) * 128 + ((g ^ (2 * t)) << 4));   // row group 2wg (+rg), column 2t (+e +8q), chunk g
         offF = (uint32_t)(A_BYTES + pg * 128 + ((t ^ pg) << 4));                   // rank pi(g) (+8cb), chunk t (+4(q&1)) ^ pi(g)
@@ -642,7 +668,69 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if ((it % NG) == grp) {
             const uint32_t sb = ring_s + (uint32_t)stage * STAGE_BYTES;
             mbar_wait(&full_bar[stage], phase, 2, it, stage);
-            if (!WSTEP && KB >= 6) {
+            if (!WSTEP && F32) {
+                // stage = 32 rows x 128 columns of floats; lane (g, t) owns rows 8t..8t+7 of the columns g (+8v) of its
+                // 32-column slice: the same two 16-byte chunks per column as in FP64, four rows each
+                float4 b4[4][2];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    b4[v][0] = lds128f(sb + offA + v * 1024);
+                    b4[v][1] = lds128f(sb + (offA ^ 16) + v * 1024);
+                }
+#pragma unroll
+                for (int cb = 0; cb < KB; ++cb) {
+                    double2 f2[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        f2[e] = lds128(sb + offF + cb * 1024 + ((((t & 1) * 4 + e) ^ g) << 4));   // rows 8t+2e, 8t+2e+1 of rank 8cb+g
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 q4 = b4[v][e >> 1];
+                            const double x0 = (double)((e & 1) ? q4.z : q4.x), x1 = (double)((e & 1) ? q4.w : q4.y);
+                            dmma884(acc[cb][v][0], acc[cb][v][1], f2[e].x, x0);
+                            dmma884(acc[cb][v][0], acc[cb][v][1], f2[e].y, x1);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            } else if (WSTEP && F32) {
+                // stage = 128 rows x 32 columns of floats as [row group of 32][column][32 rows]; lane (g, t) owns rows
+                // 4g..4g+3 of its warp's row group at the columns 8q + 2t + e
+                double2 f[KB][4];
+#pragma unroll
+                for (int cb = 0; cb < KB; ++cb)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        f[cb][q] = lds128(sb + (q >> 1) * F_BOX + ((offF + cb * 1024) ^ ((q & 1) << 6)));
+                float4 a4[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a4[q][0] = lds128f(sb + offA + q * 1024);
+                    a4[q][1] = lds128f(sb + ((offA + 128) ^ 16) + q * 1024);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int cb = 0; cb < KB; ++cb) {
+                        dmma884(acc[cb][0][0], acc[cb][0][1], (double)a4[q][0].x, f[cb][q].x);
+                        dmma884(acc[cb][1][0], acc[cb][1][1], (double)a4[q][0].y, f[cb][q].x);
+                        dmma884(acc[cb][2][0], acc[cb][2][1], (double)a4[q][0].z, f[cb][q].x);
+                        dmma884(acc[cb][3][0], acc[cb][3][1], (double)a4[q][0].w, f[cb][q].x);
+                    }
+#pragma unroll
+                    for (int cb = 0; cb < KB; ++cb) {
+                        dmma884(acc[cb][0][0], acc[cb][0][1], (double)a4[q][1].x, f[cb][q].y);
+                        dmma884(acc[cb][1][0], acc[cb][1][1], (double)a4[q][1].y, f[cb][q].y);
+                        dmma884(acc[cb][2][0], acc[cb][2][1], (double)a4[q][1].z, f[cb][q].y);
+                        dmma884(acc[cb][3][0], acc[cb][3][1], (double)a4[q][1].w, f[cb][q].y);
+                    }
+                }
+            } else if (!WSTEP && KB >= 6) {
                 // large ranks: the 16 KB accumulator tile leaves no room for all factor fragments at once, so they
                 // are fetched rank block by rank block (same accumulation order per accumulator as below)
                 double2 b[4][2];
@@ -898,6 +986,7 @@ struct mfb_als {
     int *counters, *gram_counter;
     int nsolve_h, nsolve_w;       // solve-kernel grids
     bool attr_set = false;
+    bool f32 = false;             // A is resident in single precision
     std::vector<cudaEvent_t> *prof = nullptr;   // mfb_als_profile: one event after every kernel
     AlsCtrl *ctrl;
     double *trace_dev;
@@ -927,17 +1016,18 @@ static int max_slots(long long T, long long SPT, int G) {
     return mx;
 }
 
-static int encode_map(CUtensorMap *tm, double *base, int64_t rows, int64_t cols, int64_t lda, int box_rows, int box_cols) {
+static int encode_map(CUtensorMap *tm, void *base, int64_t rows, int64_t cols, int64_t lda, int box_rows, int box_cols,
+                      bool f32 = false) {
     mfb_encode_tiled_fn enc = mfb_get_encode_tiled();
     if (!enc) {
         mfb_set_error("cuTensorMapEncodeTiled unavailable");
         return MFB_ERR_CUDA;
     }
     cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
-    cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(double)};
+    cuuint64_t strides[1] = {(cuuint64_t)lda * (f32 ? sizeof(float) : sizeof(double))};
     cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr,
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -947,16 +1037,18 @@ static int encode_map(CUtensorMap *tm, double *base, int64_t rows, int64_t cols,
     return MFB_OK;
 }
 
-static int encode_map_rowgroups(CUtensorMap *tm, double *base, int64_t cols, int64_t lda) {
+static int encode_map_rowgroups(CUtensorMap *tm, void *base, int64_t cols, int64_t lda, bool f32 = false) {
     // 3-D view of the column-major matrix: {16 rows, cols, lda/16 row groups}, strides {lda*8, 128} bytes;
-    // box {16, 32, 8} = a 128-row x 32-column tile that lands as [row group][column][16 rows].
+    // box {16, 32, 8} = a 128-row x 32-column tile that lands as [row group][column][16 rows]
+    // (FP32: {32 rows, cols, lda/32 groups}, box {32, 32, 4}: the same 128-byte rows).
     mfb_encode_tiled_fn enc = mfb_get_encode_tiled();
     if (!enc) { mfb_set_error("cuTensorMapEncodeTiled unavailable"); return MFB_ERR_CUDA; }
-    cuuint64_t dims[3] = {16, (cuuint64_t)cols, (cuuint64_t)(lda / 16)};
-    cuuint64_t strides[2] = {(cuuint64_t)lda * sizeof(double), 128};
-    cuuint32_t box[3] = {16, 32, 8};
+    const int per = f32 ? 32 : 16;
+    cuuint64_t dims[3] = {(cuuint64_t)per, (cuuint64_t)cols, (cuuint64_t)(lda / per)};
+    cuuint64_t strides[2] = {(cuuint64_t)lda * (f32 ? sizeof(float) : sizeof(double)), 128};
+    cuuint32_t box[3] = {(cuuint32_t)per, 32, (cuuint32_t)(128 / per)};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr,
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { mfb_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r); return MFB_ERR_CUDA; }
@@ -991,39 +1083,36 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-template <int KB>
-static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
+template <int KB, bool F32>
+static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
     cudaStream_t st = s->ctx->stream;
     const int G = hp.Gstream;
     const int nsolve = wstep ? s->nsolve_w : s->nsolve_h;
     const bool pdl = (s->prof == nullptr) && !getenv("MFB_NO_PDL");   // events between launches serialise anyway
+    if (!s->attr_set) {
+        MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
+        MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
+        MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+        MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+        s->attr_set = true;
+    }
     if (wstep) {
-        if (!s->attr_set) {
-            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
-            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
-            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
-            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
-            s->attr_set = true;
-        }
-        MFB_CUDA(launch_pdl(als_stream_kernel<KB, true>, G, ALS_THREADS, s->smem_w, st, pdl, s->tm_w, tmF, hp, s->nstage_w));
+        MFB_CUDA(launch_pdl(als_stream_kernel<KB, true, F32>, G, ALS_THREADS, s->smem_w, st, pdl, s->tm_w, tmF, hp, s->nstage_w));
         MFB_TRY(prof_mark(s));
         MFB_CUDA(launch_pdl(als_solve_kernel<KB, true>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
-        MFB_TRY(prof_mark(s));
     } else {
-        if (!s->attr_set) {
-            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
-            MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
-            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
-            MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
-            s->attr_set = true;
-        }
-        MFB_CUDA(launch_pdl(als_stream_kernel<KB, false>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
+        MFB_CUDA(launch_pdl(als_stream_kernel<KB, false, F32>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
         MFB_TRY(prof_mark(s));
         MFB_CUDA(launch_pdl(als_solve_kernel<KB, false>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
-        MFB_TRY(prof_mark(s));
     }
+    MFB_TRY(prof_mark(s));
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
+}
+
+template <int KB>
+static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
+    return s->f32 ? launch_half_t<KB, true>(s, wstep, hp, tmF) : launch_half_t<KB, false>(s, wstep, hp, tmF);
 }
 
 template <int KB>
@@ -1129,8 +1218,9 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     s->iters_total = 0;
     s->resid = resid_old0;
     const int G = ctx->sm_count;
+    s->f32 = A->elem_bytes == 4;
     s->T_h = (int)((s->n + 127) / 128);
-    s->SPT_h = (int)((s->m + 15) / 16);
+    s->SPT_h = (int)((s->m + (s->f32 ? 31 : 15)) / (s->f32 ? 32 : 16));
     s->T_w = (int)((s->m + 127) / 128);
     s->SPT_w = (int)((s->n + 31) / 32);
     s->maxslots_h = ALS_NG * max_slots(s->T_h, s->SPT_h, G);   // x NG consumer groups
@@ -1138,9 +1228,9 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     const size_t KP = s->KP;
     const size_t side = (KP * KP + 2) * sizeof(double) + 16;            // Gram side job scratch
     const size_t budget = 227 * 1024 - 1024 /*align*/ - 2 * 16 * sizeof(uint64_t) - side;
-    const size_t stage_h = 16384 + KP * 128, stage_w = 32768 + 2 * KP * 128;
+    const size_t stage_h = 16384 + (s->f32 ? 2 : 1) * KP * 128, stage_w = (s->f32 ? 16384 : 32768) + 2 * KP * 128;
     s->nstage_h = (int)(budget / stage_h); if (s->nstage_h > 12) s->nstage_h = 12;
-    s->nstage_w = (int)(budget / stage_w); if (s->nstage_w > 6) s->nstage_w = 6;
+    s->nstage_w = (int)(budget / stage_w); if (s->nstage_w > (s->f32 ? 12 : 6)) s->nstage_w = s->f32 ? 12 : 6;
     // The ring depth must be a multiple of the number of consumer groups (2): a stage is then always drained by
     // the same group, which therefore waits on EVERY phase of that stage's full-barrier.  With an odd depth a
     // group skips every other phase and the parity wait aliases (returns on a phase two fills old).
@@ -1175,8 +1265,8 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     ALLOC(s->trace_dev, (size_t)s->max_trace * 3)
 #undef ALLOC
     // tensor maps over A: dims {m rows (contiguous), n cols}
-    if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, 16, 128)) != MFB_OK ||
-        (rc = encode_map_rowgroups(&s->tm_w, A->d, A->n, A->lda)) != MFB_OK) {
+    if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, s->f32 ? 32 : 16, 128, s->f32)) != MFB_OK ||
+        (rc = encode_map_rowgroups(&s->tm_w, A->d, A->n, A->lda, s->f32)) != MFB_OK) {
         mfb_als_end(s);
         return rc;
     }

@@ -72,7 +72,8 @@ struct DevBuf {
 
 struct mfb_matrix {
     mfb_context *ctx = nullptr;
-    double *d = nullptr;      // column-major, leading dimension lda
+    double *d = nullptr;      // column-major, leading dimension lda (elements); float data when elem_bytes == 4
+    int elem_bytes = 8;
     int64_t m = 0, n = 0, lda = 0;
     bool owned = false;
     bool stats_valid = false;

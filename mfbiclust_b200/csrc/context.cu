@@ -163,14 +163,15 @@ struct Stat5 {
     double mn, mx, ss, nan, sum;
 };
 
-__global__ void __launch_bounds__(256) stats_partial_kernel(const double *__restrict__ A, int64_t m, int64_t n,
+template <typename T>
+__global__ void __launch_bounds__(256) stats_partial_kernel(const T *__restrict__ A, int64_t m, int64_t n,
                                                             int64_t lda, Stat5 *__restrict__ part) {
     double mn = INFINITY, mx = -INFINITY, ss = 0.0, nn = 0.0, sm = 0.0;
     // one column at a time per block; threads stride over rows (coalesced)
     for (int64_t j = blockIdx.x; j < n; j += gridDim.x) {
-        const double *col = A + j * lda;
+        const T *col = A + j * lda;
         for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
-            double v = col[i];
+            double v = (double)col[i];
             if (v != v) {
                 nn += 1.0;
             } else {
@@ -221,12 +222,24 @@ __global__ void stats_final_kernel(const Stat5 *__restrict__ part, int nb, doubl
     }
 }
 
-__global__ void __launch_bounds__(256) shift_kernel(double *__restrict__ A, int64_t m, int64_t n, int64_t lda,
+template <typename T>
+__global__ void __launch_bounds__(256) shift_kernel(T *__restrict__ A, int64_t m, int64_t n, int64_t lda,
                                                     double shift) {
     for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
-        double *col = A + j * lda;
+        T *col = A + j * lda;
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-            col[i] += shift;
+            col[i] = (T)((double)col[i] + shift);
+    }
+}
+
+// dst (float, ld = ldd, zero padded rows) <- src (double, ld = lds)
+__global__ void __launch_bounds__(256) to_f32_kernel(const double *__restrict__ src, int64_t m, int64_t n, int64_t lds,
+                                                     float *__restrict__ dst, int64_t ldd) {
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+        const double *col = src + j * lds;
+        float *out = dst + j * ldd;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ldd; i += (int64_t)gridDim.x * blockDim.x)
+            out[i] = (i < m) ? (float)col[i] : 0.0f;
     }
 }
 
@@ -250,6 +263,37 @@ int mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t n
     if (A->lda != m) MFB_CUDA(cudaMemsetAsync(A->d, 0, bytes, ctx->stream));
     MFB_CUDA(cudaMemcpy2DAsync(A->d, A->lda * sizeof(double), host, m * sizeof(double), m * sizeof(double), n,
                                cudaMemcpyHostToDevice, ctx->stream));
+    *out = A;
+    return MFB_OK;
+}
+
+int mfb_matrix_upload_f32(mfb_context *ctx, const double *host, int64_t m, int64_t n, mfb_matrix **out) {
+    MFB_ARG(ctx && host && out, "NULL argument");
+    MFB_ARG(m > 0 && n > 0, "matrix dimensions must be positive");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf tmp(ctx);
+    double *stage = nullptr;
+    {
+        int rc = tmp.alloc(&stage, (size_t)m * n);
+        if (rc != MFB_OK) return rc;
+    }
+    MFB_CUDA(cudaMemcpyAsync(stage, host, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    mfb_matrix *A = new mfb_matrix();
+    A->ctx = ctx;
+    A->m = m;
+    A->n = n;
+    A->elem_bytes = 4;
+    A->lda = round_up(m, 32);   // 128-byte aligned columns of floats
+    A->owned = true;
+    if (mfb_pool_alloc(ctx, (void **)&A->d, (size_t)A->lda * n * sizeof(float) + 256) != MFB_OK) {
+        delete A;
+        return MFB_ERR_ALLOC;
+    }
+    int gy = (int)(n < 65535 ? n : 65535), gx = (int)((A->lda + 255) / 256);
+    if (gx > 64) gx = 64;
+    to_f32_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(stage, m, n, m, (float *)A->d, A->lda);
+    MFB_CUDA(cudaGetLastError());
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));     // the staging buffer goes back to the pool
     *out = A;
     return MFB_OK;
 }
@@ -297,7 +341,10 @@ int mfb_matrix_stats(mfb_matrix *A, double stats[5]) {
             part = (Stat5 *)raw;
         }
         dout = (double *)(part + nb);
-        stats_partial_kernel<<<nb, 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, part);
+        if (A->elem_bytes == 4)
+            stats_partial_kernel<float><<<nb, 256, 0, ctx->stream>>>((const float *)A->d, A->m, A->n, A->lda, part);
+        else
+            stats_partial_kernel<double><<<nb, 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, part);
         stats_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, dout);
         MFB_CUDA(cudaGetLastError());
         MFB_CUDA(cudaMemcpyAsync(A->stats, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -315,7 +362,10 @@ int mfb_matrix_shift(mfb_matrix *A, double shift) {
     int gy = (int)(A->n < 65535 ? A->n : 65535);
     int gx = (int)((A->m + 255) / 256);
     if (gx > 64) gx = 64;
-    shift_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, shift);
+    if (A->elem_bytes == 4)
+        shift_kernel<float><<<dim3(gx, gy), 256, 0, ctx->stream>>>((float *)A->d, A->m, A->n, A->lda, shift);
+    else
+        shift_kernel<double><<<dim3(gx, gy), 256, 0, ctx->stream>>>(A->d, A->m, A->n, A->lda, shift);
     MFB_CUDA(cudaGetLastError());
     A->stats_valid = false;
     return MFB_OK;

@@ -410,6 +410,7 @@ extern "C" {
 int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale, int maxiter, double tol,
                int gramschmidt, double *scores, double *loadings, double *eig, int *iters) {
     MFB_ARG(ctx && x && scores && loadings, "NULL argument");
+    if (x->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
     MFB_ARG(ncomp >= 1 && ncomp <= 60, "ncomp must be in 1..60");
     MFB_ARG(ncomp <= x->m && ncomp <= x->n, "ncomp exceeds a matrix dimension");
     MFB_ARG(maxiter >= 2, "maxiter must be at least 2");

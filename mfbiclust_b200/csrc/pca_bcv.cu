@@ -204,6 +204,7 @@ extern "C" {
 
 int mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, int *kout) {
     MFB_ARG(ctx && A && W && H, "NULL argument");
+    if (A->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
     MFB_ARG(k >= 1, "k must be positive");
     MFB_CUDA(cudaSetDevice(ctx->device));
     double stats[5];
@@ -243,6 +244,7 @@ int mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, in
 int mfb_bcv_cells(mfb_context *ctx, mfb_matrix *Y, const int32_t *row_fold, const int32_t *col_fold, int holdouts,
                   const int32_t *ks, int nks, int cell_begin, int cell_end, double *err) {
     MFB_ARG(ctx && Y && row_fold && col_fold && ks && err, "NULL argument");
+    if (Y->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
     MFB_ARG(holdouts >= 2, "holdouts must be at least 2");
     MFB_ARG(nks >= 1, "ks is empty");
     MFB_ARG(cell_begin >= 0 && cell_end <= holdouts * holdouts && cell_begin <= cell_end, "cell range out of bounds");

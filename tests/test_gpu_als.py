@@ -203,3 +203,27 @@ def test_als_full_size_properties():
     scale = np.abs(R).max()
     assert np.abs(grad[W > 0]).max() <= 1e-9 * scale                  # stationarity on the passive set
     assert grad[W == 0].max() <= 1e-9 * scale                         # no positive gradient left on the active set
+
+
+@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1037, 333, 10), (70, 45, 3), (640, 1030, 24), (600, 400, 64)])
+def test_als_fp32_storage(m, n, k):
+    """FP32 path of BASELINE.json configs[3]: A resident in single precision, FP64 accumulation.  Against the
+    oracle on the float32-rounded matrix it is the same computation (1e-8); against the oracle on the original
+    matrix it must stay within the north-star FP32 tolerance of 1e-4 relative Frobenius error."""
+    import mfbiclust_b200 as mfb
+    A = pseudovalues(gen_sim_data(n=4, cluster_height=min(m, n) // 5, cluster_width=min(m, n) // 5, dimx=m, dimy=n,
+                                  bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=m + n))
+    W0, H0 = make_init(m, n, k, 44)
+    ctx = mfb.default_context()
+    Ad = mfb.Matrix(ctx, host=A, precision="f32")
+    try:
+        st = Ad.stats()
+        A32 = A.astype(np.float32).astype(np.float64)
+        assert st["max"] == A32.max() and st["min"] == A32.min()
+        got = mfb.als_replicate(Ad, k, W0, H0, maxIter=8, fixed_iters=True)
+    finally:
+        Ad.free()
+    ref32 = oracle_replicate(A32, W0, H0, max_iter=8, fixed_iters=True)
+    ref64 = oracle_replicate(A, W0, H0, max_iter=8, fixed_iters=True)
+    assert rel_fro(got["W"], ref32["W"]) < 1e-8 and rel_fro(got["H"], ref32["H"]) < 1e-8
+    assert rel_fro(got["W"], ref64["W"]) < 1e-4 and rel_fro(got["H"], ref64["H"]) < 1e-4
