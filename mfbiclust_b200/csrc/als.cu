@@ -1167,9 +1167,11 @@ extern "C" {
 
 void mfb_als_end(mfb_als *s) {
     if (!s) return;
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    for (void *p : s->allocs) mfb_pool_free(s->ctx, p);
+    if (mfb_context_alive(s->ctx)) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+        for (void *p : s->allocs) mfb_pool_free(s->ctx, p);
+    }
     delete s;
 }
 

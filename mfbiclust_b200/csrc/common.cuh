@@ -52,6 +52,8 @@ struct mfb_context {
     size_t pool_cached_bytes = 0;
 };
 
+bool mfb_context_alive(mfb_context *ctx);      // false once mfb_context_destroy has run
+
 // pooled device allocations (context.cu).  mfb_pool_alloc returns MFB_OK / MFB_ERR_ALLOC.
 int mfb_pool_alloc(mfb_context *ctx, void **p, size_t bytes);
 void mfb_pool_free(mfb_context *ctx, void *p);

@@ -24,6 +24,15 @@ mfb_encode_tiled_fn mfb_get_encode_tiled() {
     return fn;
 }
 
+// contexts that have not been destroyed: handles that outlive their context (e.g. finalisers run in arbitrary
+// order by a garbage collector) must not touch it -- mfb_context_destroy has already released their device memory
+static std::vector<mfb_context *> g_live_contexts;
+bool mfb_context_alive(mfb_context *ctx) {
+    for (mfb_context *c : g_live_contexts)
+        if (c == ctx) return true;
+    return false;
+}
+
 static size_t pool_round(size_t bytes) {
     if (bytes <= 512) return 512;
     if (bytes <= ((size_t)1 << 20)) {
@@ -122,12 +131,15 @@ int mfb_context_create(int device, mfb_context **out) {
     MFB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->pinned_bytes = 1 << 20;
     MFB_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+    g_live_contexts.push_back(c);
     *out = c;
     return MFB_OK;
 }
 
 void mfb_context_destroy(mfb_context *ctx) {
-    if (!ctx) return;
+    if (!ctx || !mfb_context_alive(ctx)) return;
+    for (size_t i = 0; i < g_live_contexts.size(); ++i)
+        if (g_live_contexts[i] == ctx) { g_live_contexts.erase(g_live_contexts.begin() + i); break; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     mfb_pool_release(ctx);
@@ -316,7 +328,7 @@ int mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb
 
 void mfb_matrix_free(mfb_matrix *A) {
     if (!A) return;
-    if (A->owned && A->d) {
+    if (A->owned && A->d && mfb_context_alive(A->ctx)) {
         cudaSetDevice(A->ctx->device);
         mfb_pool_free(A->ctx, A->d);
     }

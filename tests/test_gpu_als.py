@@ -227,3 +227,17 @@ def test_als_fp32_storage(m, n, k):
     ref64 = oracle_replicate(A, W0, H0, max_iter=8, fixed_iters=True)
     assert rel_fro(got["W"], ref32["W"]) < 1e-8 and rel_fro(got["H"], ref32["H"]) < 1e-8
     assert rel_fro(got["W"], ref64["W"]) < 1e-4 and rel_fro(got["H"], ref64["H"]) < 1e-4
+
+
+def test_handles_may_outlive_their_context():
+    # finalisers run in arbitrary order under a garbage collector (R's too): destroying the context first must be safe
+    import mfbiclust_b200 as mfb
+    ctx = mfb.Context(0)
+    A = np.asfortranarray(np.random.default_rng(0).random((64, 40)) + 0.1)
+    Ad = mfb.Matrix(ctx, host=A)
+    W0, H0 = make_init(64, 40, 3, 1)
+    sess = mfb.AlsSession(Ad, 3, W0, H0, 1.0)
+    sess.iterate(2, fixed_iters=True)
+    ctx.close()
+    sess.close()
+    Ad.free()
