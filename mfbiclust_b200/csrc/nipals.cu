@@ -425,7 +425,7 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, nipals_kernel, NIP_THREADS,
                                                            2 * NIP_WARPS * 256 * sizeof(double)));
     int nb = nb_max * ctx->sm_count;
-    if (nb > ctx->sm_count) nb = ctx->sm_count;               // one block per SM is plenty; keeps grid.sync cheap
+    if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;       // two blocks per SM: twice the loads in flight
     const int64_t want = (m + NIP_THREADS - 1) / NIP_THREADS > n ? (m + NIP_THREADS - 1) / NIP_THREADS : n;
     if (want < nb) nb = (int)(want < 1 ? 1 : want);
     const size_t PW = ncomp + 4;
