@@ -1,8 +1,10 @@
 #!/bin/bash
-# GPU round trip used during development (under gpurun): parity tests, smoke, short bench
+# GPU round trip used during development (under gpurun): parity tests, smoke, default bench line
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 timeout 900 python -m pytest tests -q -m gpu -x --timeout 300 ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?"; tail -40 gpurun_out/pytest_gpu.log
+echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-echo "smoke rc=$?"; tail -5 gpurun_out/smoke.log
+echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench rc=$?"; tail -1 gpurun_out/bench.json | cut -c1-400
