@@ -67,6 +67,10 @@ int  mfb_matrix_upload(mfb_context *ctx, const double *host, int64_t m, int64_t 
 int  mfb_matrix_upload_f32(mfb_context *ctx, const double *host, int64_t m, int64_t n, mfb_matrix **out);
 /* Wrap an existing device buffer (column-major, ld = m); not owned. */
 int  mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb_matrix **out);
+/* Non-owning alias of a resident matrix for ANOTHER context on the same device (one host thread per context: this is
+ * how several threads, each with its own context and stream, work on one resident matrix, e.g. the independent cells
+ * of a bcv call).  The owner must outlive the view and must have finished writing (mfb_context_sync). */
+int  mfb_matrix_view(mfb_context *ctx, mfb_matrix *A, mfb_matrix **out);
 void mfb_matrix_free(mfb_matrix *A);
 /* stats[0..4] = min, max, sum of squares, #NaN/NA, sum  (max(A): R/bicluster.R:81; any(A<0): :76; pseudovalues: R/helperFunctions.R:270-278) */
 int  mfb_matrix_stats(mfb_matrix *A, double stats[5]);

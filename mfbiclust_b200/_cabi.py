@@ -36,6 +36,7 @@ PROTOTYPES = {
     "mfb_matrix_upload": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_upload_f32": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_wrap_dev": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_vp)]),
+    "mfb_matrix_view": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "mfb_matrix_free": (None, [_vp]),
     "mfb_matrix_stats": (C.c_int, [_vp, _dp]),
     "mfb_matrix_shift": (C.c_int, [_vp, C.c_double]),
@@ -169,6 +170,14 @@ class Matrix:
     @property
     def handle(self):
         return self._h
+
+    def view(self, ctx: "Context") -> "Matrix":
+        """Non-owning alias for another context on the same device (``mfb_matrix_view``)."""
+        v = Matrix.__new__(Matrix)
+        v.ctx, v.shape, v.precision, v._h = ctx, self.shape, self.precision, _vp()
+        v._owner = self                       # keep the owner alive
+        check(lib().mfb_matrix_view(ctx.handle, self._h, C.byref(v._h)))
+        return v
 
     def stats(self):
         out = np.zeros(5)

@@ -394,33 +394,20 @@ def shard_cells(ncell, nks, compute, ctx_device=0, group=None):
     return err
 
 
-def bcvGivenKs(Y, ks, holdouts=10, folds=None, rng=None, ctx=None, group=None, cell_errors=False):
+def bcvGivenKs(Y, ks, holdouts=10, folds=None, rng=None, ctx=None, group=None, cell_errors=False, streams=None):
     """``bcvGivenKs(Y, ks, holdouts)`` (``R/bcv.R:164-239``) on a resident matrix.
 
     The ``holdouts^2`` cells are independent given the fold vectors: under ``torch.distributed`` every rank
     computes a contiguous block of cells on its own GPU and only the per-cell error vectors are exchanged
-    (:func:`shard_cells`)."""
+    (:func:`shard_cells`); within a rank the cells are spread over ``streams`` concurrent CUDA streams."""
     ctx = ctx or _cabi.default_context()
-    rank, world, dist = _dist_info(group)
     own = not isinstance(Y, _cabi.Matrix)
     Yd = _cabi.Matrix(ctx, host=Y) if own else Y
     try:
         n, p = Yd.shape
-        ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
         if folds is None:
-            rf, cf = draw_folds(rng or HostRng(), n, p, holdouts)
-        else:
-            rf, cf = (np.ascontiguousarray(np.asarray(f, dtype=np.int32)) for f in folds)
-        if dist is not None and world > 1:
-            rf, cf = _bcast_folds(rf, cf, ctx.device, dist, group)
-
-        def compute(c0, c1):
-            loc = np.zeros((c1 - c0, len(ks)))
-            check(lib().mfb_bcv_cells(ctx.handle, Yd.handle, rf.ctypes.data_as(C.POINTER(C.c_int32)),
-                                      cf.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
-                                      ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), c0, c1, dptr(loc)))
-            return loc
-        err = shard_cells(holdouts * holdouts, len(ks), compute, ctx.device, group)
+            folds = draw_folds(rng or HostRng(), n, p, holdouts)
+        err = _bcv_cells_all(Yd, ks, holdouts, [folds], ctx, group, streams)[0]
     finally:
         if own:
             Yd.free()
@@ -450,10 +437,31 @@ def bcv(Y, ks=None, holdouts=10, interactive=True, rng=None, folds=None, ctx=Non
     return {int(k): float(v) for k, v in zip(ks, res)}
 
 
-def bcv_batch(Yd, ks, holdouts, folds_list, ctx=None, group=None):
-    """``bcvGivenKs`` for several fold draws at once: the ``len(folds_list) * holdouts^2`` cells are one flat work
-    list sharded over the ranks (:func:`shard_cells`).  Returns ``(len(folds_list), len(ks))`` BCV values."""
+_worker_ctx = {}
+
+
+def _worker_contexts(device, count):
+    """Extra contexts (own stream, own workspace pool) on ``device`` for concurrent host threads."""
+    lst = _worker_ctx.setdefault(device, [])
+    while len(lst) < count:
+        lst.append(_cabi.Context(device))
+    return lst[:count]
+
+
+def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=None):
+    """Per-cell errors ``(len(folds_list), holdouts^2, len(ks))`` for several fold draws at once: the ``len(folds_list) * holdouts^2`` cells are one flat work
+    list sharded over the ranks (:func:`shard_cells`).
+
+    A cell of a small matrix is latency-bound (a grid barrier per Householder column), so the cells of a rank are
+    additionally spread over ``streams`` host threads (default 3; ``MFBICLUST_BCV_STREAMS``), each with its own
+    context / CUDA stream working on a view of the resident matrix.  Every cell is still computed by one kernel
+    sequence on one stream: the values do not depend on ``streams``."""
     ctx = ctx or _cabi.default_context()
+    if streams is None:
+        import os as _os
+        streams = int(_os.environ.get("MFBICLUST_BCV_STREAMS", "3"))
+        if Yd.shape[0] * Yd.shape[1] * 8 > (2 << 30):   # large cells are bandwidth-bound and need their memory: one at a time
+            streams = 1
     rank, world, dist = _dist_info(group)
     ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
     h2 = holdouts * holdouts
@@ -465,22 +473,54 @@ def bcv_batch(Yd, ks, holdouts, folds_list, ctx=None, group=None):
         flat = [(np.ascontiguousarray(rf, dtype=np.int32), np.ascontiguousarray(cf, dtype=np.int32))
                 for rf, cf in folds_list]
 
-    def compute(c0, c1):
-        out = np.zeros((c1 - c0, len(ks)))
+    def run_range(wctx, Yw, c0, c1, out, off):
         c = c0
         while c < c1:
             it, lo = divmod(c, h2)
             hi = min(h2, lo + (c1 - c))
             rf, cf = flat[it]
             loc = np.zeros((hi - lo, len(ks)))
-            check(lib().mfb_bcv_cells(ctx.handle, Yd.handle, rf.ctypes.data_as(C.POINTER(C.c_int32)),
+            check(lib().mfb_bcv_cells(wctx.handle, Yw.handle, rf.ctypes.data_as(C.POINTER(C.c_int32)),
                                       cf.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
                                       ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), lo, hi, dptr(loc)))
-            out[c - c0:c - c0 + (hi - lo)] = loc
+            out[off + c - c0:off + c - c0 + (hi - lo)] = loc
             c += hi - lo
+
+    def compute(c0, c1):
+        out = np.zeros((c1 - c0, len(ks)))
+        nthr = max(1, min(int(streams), c1 - c0))
+        if nthr == 1:
+            run_range(ctx, Yd, c0, c1, out, 0)
+            return out
+        import threading
+        ctx.sync()                                    # the resident matrix is complete before other streams read it
+        workers = _worker_contexts(ctx.device, nthr)
+        views = [Yd.view(w) for w in workers]
+        bounds = [c0 + (c1 - c0) * t // nthr for t in range(nthr + 1)]
+        errors = []
+
+        def job(t):
+            try:
+                run_range(workers[t], views[t], bounds[t], bounds[t + 1], out, bounds[t] - c0)
+            except Exception as e:                     # re-raised on the calling thread
+                errors.append(e)
+        threads = [threading.Thread(target=job, args=(t,)) for t in range(nthr)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        for v in views:
+            v.free()
+        if errors:
+            raise errors[0]
         return out
     err = shard_cells(len(flat) * h2, len(ks), compute, ctx.device, group)
-    return err.reshape(len(flat), h2, len(ks)).sum(axis=1)
+    return err.reshape(len(flat), h2, len(ks))
+
+
+def bcv_batch(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=None):
+    """BCV values ``(len(folds_list), len(ks))`` of several fold draws (see :func:`_bcv_cells_all`)."""
+    return _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx, group, streams).sum(axis=1)
 
 
 def _iters_until_stable(distr, distrOld, tol, winner, keys, limit):

@@ -326,6 +326,17 @@ int mfb_matrix_wrap_dev(mfb_context *ctx, double *dev, int64_t m, int64_t n, mfb
     return MFB_OK;
 }
 
+int mfb_matrix_view(mfb_context *ctx, mfb_matrix *A, mfb_matrix **out) {
+    MFB_ARG(ctx && A && out, "NULL argument");
+    MFB_ARG(ctx->device == A->ctx->device, "a view must live on the device of the matrix");
+    mfb_matrix *V = new mfb_matrix();
+    *V = *A;
+    V->ctx = ctx;
+    V->owned = false;
+    *out = V;
+    return MFB_OK;
+}
+
 void mfb_matrix_free(mfb_matrix *A) {
     if (!A) return;
     if (A->owned && A->d && mfb_context_alive(A->ctx)) {

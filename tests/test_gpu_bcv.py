@@ -89,3 +89,15 @@ def test_auto_bcv_speculation_is_invisible(yeast):
     a = mfb.auto_bcv(Y, rng=mfb.HostRng(7), speculate=1)
     b = mfb.auto_bcv(Y, rng=mfb.HostRng(7), speculate=5)
     assert a == b
+
+
+def test_bcv_streams_do_not_change_values(yeast):
+    # cells spread over concurrent streams (worker contexts on views of the resident matrix): same values bit for bit
+    import mfbiclust_b200 as mfb
+    Y = yeast[1]
+    rs = np.random.default_rng(77)
+    ks = B.k_limiter(3, min(Y.shape), np.arange(1, min(Y.shape)))
+    rf, cf = _folds(rs, *Y.shape, 3)
+    a, ca = mfb.bcvGivenKs(Y, ks, 3, folds=(rf, cf), cell_errors=True, streams=1)
+    b, cb = mfb.bcvGivenKs(Y, ks, 3, folds=(rf, cf), cell_errors=True, streams=4)
+    assert np.array_equal(ca, cb) and np.array_equal(a, b)
