@@ -106,6 +106,24 @@ int  mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_i
                      int *iters_total, int *converged);
 int  mfb_als_restart(mfb_als *s, const double *Wnew);
 /*
+ * Row-sharded replicate: one very large A split by rows over several devices / processes (north star: "very
+ * large single matrices are row-sharded, with the k x k and k x n partial products all-reduced by NCCL").  Each
+ * rank opens a session on ITS row block A_rows (m_local x n) with its rows of W0 and the full (replicated) Hold0;
+ * every rank then calls mfb_als_iterate / mfb_als_restart (with its rows of the new W) / mfb_als_result (its rows of
+ * W, the full H) in lockstep.  Per iteration the library asks the host for two sum-all-reduces, IN PLACE on a device
+ * buffer and ordered on the context's stream: [W_r'A_r | W_r'W_r] (k n + k^2 doubles, before the H-step NNLS, which
+ * every rank then solves identically) and the three iteration scalars (||A - WH||^2 terms, ||dW||^2).  The library
+ * has no link-time dependency on NCCL / MPI: the host supplies the collective (ncclAllReduce on `stream`, or
+ * torch.distributed in the Python harness).  The callback returns 0 on success.  All status codes, the restart
+ * protocol, traces and convergence decisions are identical on every rank (they derive from all-reduced values).
+ * resid_old0 = max(A) over the WHOLE matrix.  mfb_als_begin_sharded itself performs one 4-double all-reduce
+ * (||A||^2; negative / NA verdict), so all ranks must call it together.
+ */
+typedef int (*mfb_allreduce_fn)(void *user, double *dev_buf, int64_t count, void *stream);
+int  mfb_als_begin_sharded(mfb_context *ctx, mfb_matrix *A_rows, int64_t m_global, int k,
+                           const double *W0_rows, const double *Hold0, double resid_old0,
+                           mfb_allreduce_fn allreduce, void *user, mfb_als **out);
+/*
  * Measurement aid for bench.py: runs `iters` further fixed iterations with a CUDA event recorded (on the
  * context's stream) after every kernel, and returns the mean duration in ms of the four launches of an
  * iteration: ms[0] H-step stream, ms[1] H-step solve, ms[2] W-step stream, ms[3] W-step solve.

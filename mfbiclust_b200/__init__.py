@@ -7,7 +7,8 @@ CPU fallback: importing works anywhere the shared library is built, calling need
 """
 from . import _cabi  # noqa: F401
 from ._cabi import Context, Matrix, MfbError, default_context  # noqa: F401
-from .backends import (AlsSession, BiclusterExperiment, BiclusterStrategy, HostRng, addStrat,  # noqa: F401
+from .backends import (AlsSession, HostAllReduce, ShardedAlsSession, als_nmf_sharded, als_replicate_sharded,
+                       gather_rows, row_range, BiclusterExperiment, BiclusterStrategy, HostRng, addStrat,  # noqa: F401
                        als_nmf, als_replicate, auto_bcv, bcv, bcv_batch, bcvGivenKs, cell_range, clean, draw_folds,
                        genericFactorization, genericFit, kLimiter, nipals, nipals_pca, nipals_pca_nocatch, nnls,
                        otsuHelper, pseudovalues, shard_cells, svd_pca, threshold, thresholdHelper, validateKM)

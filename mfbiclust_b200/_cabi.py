@@ -42,6 +42,7 @@ PROTOTYPES = {
     "mfb_matrix_shift": (C.c_int, [_vp, C.c_double]),
     "mfb_matrix_dev_ptr": (_vp, [_vp]),
     "mfb_als_begin": (C.c_int, [_vp, _vp, C.c_int, _dp, _dp, C.c_double, C.POINTER(_vp)]),
+    "mfb_als_begin_sharded": (C.c_int, [_vp, _vp, _i64, C.c_int, _dp, _dp, C.c_double, _vp, _vp, C.POINTER(_vp)]),
     "mfb_als_iterate": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip]),
     "mfb_als_restart": (C.c_int, [_vp, _dp]),
     "mfb_als_profile": (C.c_int, [_vp, C.c_int, _dp]),
@@ -59,6 +60,10 @@ PROTOTYPES = {
                              _dp, _dp, _dp, _ip]),
     "mfb_bcv_cells": (C.c_int, [_vp, _vp, _i32p, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _dp]),
 }
+
+
+# int (*mfb_allreduce_fn)(void *user, double *dev_buf, int64_t count, void *stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _i64, _vp)
 
 
 class MfbError(RuntimeError):

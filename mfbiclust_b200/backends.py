@@ -200,6 +200,219 @@ def als_nmf(A, k, reps=4, maxIter=100, eps_conv=1e-4, verbose=False, rng=None, i
     return res
 
 
+# ---------------------------------------------------------------------------
+# als_nmf on one very large matrix: rows of A and W sharded over the ranks
+# ---------------------------------------------------------------------------
+def row_range(m, rank, world):
+    """Contiguous block of rows of A (and of W) owned by ``rank``."""
+    return (m * rank) // world, (m * (rank + 1)) // world
+
+
+class _DeviceDoubles:
+    """``__cuda_array_interface__`` view of ``count`` doubles at a raw device pointer (no copy, not owned)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = dict(shape=(int(count),), typestr="<f8", data=(int(ptr), False),
+                                             strides=None, version=3)
+
+
+class HostAllReduce:
+    """The sum-all-reduce the library asks its host for (``mfb_allreduce_fn``): in place on a device buffer of the
+    library, ordered on the library's stream.  NCCL process groups reduce the buffer where it lies (the library's
+    stream is made torch's current stream, so the collective is stream-ordered and the host does not block); any
+    other back-end (gloo in the tests) stages through host memory.  World size 1 / no process group: nothing to do."""
+
+    def __init__(self, ctx, group=None):
+        self.rank, self.world, self.dist = _dist_info(group)
+        self.group = group
+        self.device = ctx.device
+        self.calls = 0
+        self.bytes = 0
+        self.error = None
+        self._views = {}
+        self._stream = None
+        self._ctx = ctx
+        self.c_callback = _cabi.ALLREDUCE_FN(self._call)       # keep the thunk alive as long as the session
+
+    def _view(self, ptr, count):
+        import torch
+        key = (ptr, count)
+        if key not in self._views:
+            self._views[key] = torch.as_tensor(_DeviceDoubles(ptr, count), device=torch.device("cuda", self.device))
+        return self._views[key]
+
+    def _call(self, user, ptr, count, stream):
+        try:
+            self.calls += 1
+            self.bytes += 8 * int(count)
+            if self.dist is None or self.world == 1:
+                return 0
+            import torch
+            if self._stream is None:
+                self._stream = torch.cuda.ExternalStream(int(stream or 0), device=torch.device("cuda", self.device))
+            t = self._view(int(ptr), int(count))
+            with torch.cuda.stream(self._stream):
+                if self.dist.get_backend(self.group) == "nccl":
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+                else:
+                    h = t.cpu()                                     # stream-ordered copy, then the host waits
+                    self.dist.all_reduce(h, op=self.dist.ReduceOp.SUM, group=self.group)
+                    t.copy_(h)
+                    self._stream.synchronize()
+            return 0
+        except BaseException as e:          # never unwind through the C frames
+            self.error = e
+            return 1
+
+
+class ShardedAlsSession(AlsSession):
+    """One ``als_nmf`` replicate on a matrix whose rows are split over the ranks of ``group``
+    (``mfb_als_begin_sharded``): this rank holds ``A_rows`` and the matching rows of W; H is replicated."""
+
+    def __init__(self, A_rows: _cabi.Matrix, m_global: int, k: int, W0_rows, Hold0, resid_old0: float, group=None):
+        self.A = A_rows
+        self.k = int(k)
+        self.m, self.n = A_rows.shape
+        self.m_global = int(m_global)
+        W0_rows = as_f(W0_rows)
+        Hold0 = as_f(Hold0)
+        if W0_rows.shape != (self.m, self.k) or Hold0.shape != (self.k, self.n):
+            raise ValueError("W0_rows must be m_local x k and Hold0 k x n")
+        self.reduce = HostAllReduce(A_rows.ctx, group)
+        self._h = C.c_void_p()
+        self._check(lib().mfb_als_begin_sharded(A_rows.ctx.handle, A_rows.handle, self.m_global, self.k, dptr(W0_rows),
+                                                dptr(Hold0), float(resid_old0),
+                                                C.cast(self.reduce.c_callback, C.c_void_p), None, C.byref(self._h)))
+        self.iters = 0
+
+    def _check(self, status):
+        if self.reduce.error is not None:
+            e, self.reduce.error = self.reduce.error, None
+            raise e
+        return check(status)
+
+    def iterate(self, max_new_iters, eps_conv=1e-4, fixed_iters=False):
+        it, conv = C.c_int(0), C.c_int(0)
+        st = self._check(lib().mfb_als_iterate(self._h, int(max_new_iters), float(eps_conv), int(bool(fixed_iters)),
+                                               C.byref(it), C.byref(conv)))
+        self.iters = it.value
+        return st, it.value, bool(conv.value)
+
+
+def _allreduce_host(values, op, ctx_device, group):
+    """Tiny host-side all-reduce (global max / min of A) over the process group."""
+    rank, world, dist = _dist_info(group)
+    v = np.asarray(values, dtype=np.float64)
+    if dist is None or world == 1:
+        return v
+    import torch
+    dev = torch.device("cuda", ctx_device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(v.copy()).to(dev)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op), group=group)
+    return t.cpu().numpy()
+
+
+def gather_rows(W_rows, m_global, ctx_device=0, group=None):
+    """All ranks' row blocks of W, in rank order, as one ``m_global x k`` matrix on every rank (one all-reduce of the
+    zero-padded matrix: every entry has exactly one non-zero contributor, so the result is exact)."""
+    rank, world, dist = _dist_info(group)
+    if dist is None or world == 1:
+        return np.asfortranarray(W_rows)
+    import torch
+    r0, r1 = row_range(m_global, rank, world)
+    full = np.zeros((m_global, W_rows.shape[1]))
+    full[r0:r1] = W_rows
+    dev = torch.device("cuda", ctx_device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(full).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return np.asfortranarray(t.cpu().numpy())
+
+
+def als_replicate_sharded(A_rows, m_global, k, W0, Hold0, maxIter=100, eps_conv=1e-4, fixed_iters=False, rng=None,
+                          ctx=None, group=None, gather=True):
+    """:func:`als_replicate` with the rows of A split over the ranks of ``group``.
+
+    ``A_rows`` is THIS rank's block ``A[row_range(m_global, rank, world), :]`` (host array or resident
+    :class:`Matrix`); ``W0`` (``m_global x k``), ``Hold0`` and ``rng`` are REPLICATED: every rank holds the same
+    start and draws the same restart matrices (same seed), and keeps its own rows -- exactly what one R process
+    would draw.  Status codes, restarts, traces and the convergence decision are identical on every rank.  Returns
+    the full W when ``gather`` (default), else this rank's rows."""
+    ctx = ctx or _cabi.default_context()
+    rank, world, _ = _dist_info(group)
+    r0, r1 = row_range(m_global, rank, world)
+    own = not isinstance(A_rows, _cabi.Matrix)
+    Ad = _cabi.Matrix(ctx, host=A_rows) if own else A_rows
+    try:
+        if Ad.shape[0] != r1 - r0:
+            raise ValueError(f"rank {rank} of {world} owns rows [{r0}, {r1}) but A_rows has {Ad.shape[0]} rows")
+        st = Ad.stats()
+        amin, = _allreduce_host([st["min"]], "MIN", ctx.device, group)
+        amax, = _allreduce_host([st["max"]], "MAX", ctx.device, group)
+        if amin < 0:
+            raise ValueError("Negative values are not allowed")                     # :76
+        if eps_conv <= 0:
+            raise ValueError("ALS-NMF: Invalid argument 'eps_conv' - value should be positive")   # :86
+        W0 = np.asarray(W0)
+        if W0.shape != (m_global, k):
+            raise ValueError("W0 must be the full m_global x k start")
+        sess = ShardedAlsSession(Ad, m_global, k, W0[r0:r1], Hold0, float(amax), group)
+        try:
+            nrestart = 0
+            total = 0
+            converged = False
+            while total < maxIter:
+                status, total, converged = sess.iterate(maxIter - total, eps_conv, fixed_iters)
+                if status == MFB_OK:
+                    break
+                nrestart += 1
+                if nrestart >= 10:
+                    warnings.warn("als_nmf: Factorization failed too many times "
+                                  "[Computation stopped after the 9th restart]")
+                    break
+                if rng is None:
+                    raise _cabi.MfbError(status, "ALS iteration failed (singular Gram / zero row of H) and no "
+                                                 "rng was supplied for restart()")
+                sess.restart(_normalised_random_W(rng, m_global, k)[r0:r1])          # same draw on every rank
+            W, H, resid, trace = sess.result()
+            stats = dict(allreduce_calls=sess.reduce.calls, allreduce_bytes=sess.reduce.bytes)
+        finally:
+            sess.close()
+    finally:
+        if own:
+            Ad.free()
+    if gather:
+        W = gather_rows(W, m_global, ctx.device, group)
+    return dict(obj=resid, W=W, H=H, iters=total, converged=converged, trace=trace, rows=(r0, r1), **stats)
+
+
+def als_nmf_sharded(A_rows, m_global, k, reps=4, maxIter=100, eps_conv=1e-4, rng=None, inits=None, ctx=None,
+                    group=None, **_):
+    """``als_nmf`` for a matrix too large for (or simply spread over) one device: same replicates, same winner
+    (``which.min`` of the residuals, which are identical on every rank) -> :class:`genericFit` with the full W, H."""
+    ctx = ctx or _cabi.default_context()
+    A_rows = as_f(A_rows)
+    rng = rng or HostRng(0)
+    n = A_rows.shape[1]
+    Ad = _cabi.Matrix(ctx, host=A_rows)
+    try:
+        sols = []
+        for rep in range(int(reps)):
+            if inits is not None:
+                W0, Hold0 = inits[rep]
+            else:
+                W0 = _normalised_random_W(rng, m_global, k)
+                Hold0 = np.asarray(rng.runif(k * n), dtype=np.float64).reshape((k, n), order="F")
+            sols.append(als_replicate_sharded(Ad, m_global, k, W0, Hold0, maxIter, eps_conv, rng=rng, ctx=ctx,
+                                              group=group))
+        best = int(np.argmin([s["obj"] for s in sols]))
+    finally:
+        Ad.free()
+    res = genericFit(genericFactorization(W=sols[best]["W"], H=sols[best]["H"]), "als-nmf")
+    res.solutions = sols
+    res.best = best
+    return res
+
+
 def nnls(Cmat, B, ctx=None):
     """``NMF::.fcnnls(x = C, y = B)[[1]]``: exact column-wise NNLS (unit-test entry point)."""
     ctx = ctx or _cabi.default_context()

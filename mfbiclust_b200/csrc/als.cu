@@ -68,6 +68,8 @@ struct HalfParams {
     long long U;                          // T * SPT
     long long nvalid;                     // number of real units (n for H-step, m for W-step)
     int Gstream;                          // grid size of the stream kernel (stream-K partition)
+    int shard;                            // != 0: A is one row block of a matrix sharded over several devices
+    double *xscal;                        // shard mode: [4] iteration scalars of the W-step, summed over the ranks
 };
 
 // ---------------------------------------------------------------------------
@@ -188,6 +190,30 @@ struct SolveCfg {
     static constexpr size_t SMEM = (size_t)(2 * KP * KP + KP * XS + SOLVE_WARPS * NnlsCfg<KP>::SCR + 8) * sizeof(double);
 };
 
+// end of an iteration (R/bicluster.R:173-187): residNorm, rms(dW), rms(dH), trace row, convergence test
+__device__ __forceinline__ void finish_iteration(AlsCtrl *c, double *trace, double sd2, double st1, double st2) {
+    double r2 = (c->normA2 - 2.0 * st1 + st2) / c->mn;
+    const double resid = sqrt(r2 > 0.0 ? r2 : 0.0);
+    const double dW = sqrt(sd2 / c->mk);
+    const double dH = sqrt(c->dH2 / c->kn);
+    const int it = c->iters_done;
+    if (it < c->max_trace) {
+        trace[it * 3 + 0] = resid;
+        trace[it * 3 + 1] = dW;
+        trace[it * 3 + 2] = dH;
+    }
+    c->resid = resid;
+    c->dW = dW;
+    c->dH = dH;
+    c->iters_done = it + 1;
+    if (!c->fixed && (fabs(c->resid_old - resid) <= c->eps || (dW <= c->eps && dH <= c->eps))) {
+        c->stop = 1;
+        c->reason = 1;
+    } else {
+        c->resid_old = resid;
+    }
+}
+
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : 1) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
@@ -217,6 +243,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
             expected = ALS_NG * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
         else
             expected = ALS_NG * p.SPT;
+        if (p.shard && !WSTEP) expected = 1;                 // P = the all-reduced W'A, one slot per tile
     }
     // (a) right-hand sides: sum the partials in slot order
     for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
@@ -341,27 +368,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
             const unsigned long long m = c->nzmask;
             c->nzmask = 0ull;
             if ((m & fullm) != fullm) { c->stop = 1; c->reason = 2; }
+        } else if (p.shard) {
+            // this rank's share of the sums; the host all-reduces them and als_shard_finish_kernel closes the iteration
+            p.xscal[0] = sd2; p.xscal[1] = st1; p.xscal[2] = st2; p.xscal[3] = 0.0;
         } else {
-            double r2 = (c->normA2 - 2.0 * st1 + st2) / c->mn;
-            const double resid = sqrt(r2 > 0.0 ? r2 : 0.0);
-            const double dW = sqrt(sd2 / c->mk);
-            const double dH = sqrt(c->dH2 / c->kn);
-            const int it = c->iters_done;
-            if (it < c->max_trace) {
-                p.trace[it * 3 + 0] = resid;
-                p.trace[it * 3 + 1] = dW;
-                p.trace[it * 3 + 2] = dH;
-            }
-            c->resid = resid;
-            c->dW = dW;
-            c->dH = dH;
-            c->iters_done = it + 1;
-            if (!c->fixed && (fabs(c->resid_old - resid) <= c->eps || (dW <= c->eps && dH <= c->eps))) {
-                c->stop = 1;
-                c->reason = 1;
-            } else {
-                c->resid_old = resid;
-            }
+            finish_iteration(c, p.trace, sd2, st1, st2);
         }
         __threadfence();
     }
@@ -480,6 +491,9 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
         p.G[e] = s;
     }
     gram_bar();
+    // row-sharded H-step: this is only this rank's W_r'W_r; it is summed over the ranks with W_r'A_r and inverted
+    // by als_shard_invert_kernel
+    if (p.shard && !WSTEP) return;
     int sing;
     if constexpr (KP <= 16) {
         if (w == 0) {
@@ -911,6 +925,66 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const double *__rest
     if (threadIdx.x == 0) *singular = sing;
 }
 
+// ---------------------------------------------------------------------------
+// row-sharded ALS: A and W are split by rows over the ranks, H is replicated
+// ---------------------------------------------------------------------------
+// The H-step needs  W'A = sum_r W_r'A_r  and  W'W = sum_r W_r'W_r : after the local stream kernel this kernel sums the
+// stream-K partials of every tile in slot order (the order the one-device solve kernel uses) into the exchange
+// buffer  [tile][KP][128] | G (KP x KP) , which the host all-reduces over the ranks (one collective per iteration,
+// 8 (k n + k^2) bytes).  The buffer has the layout of a partial array with ONE slot per tile, so the H-step solve
+// kernel reads it unchanged.  The W-step is local to a rank (its rows of W); only its three iteration scalars are
+// summed over the ranks (second, 32-byte collective).
+__global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg) {
+    if (*(volatile int *)&p.ctrl->stop) return;
+    const int tile = (int)blockIdx.x / KP, c = (int)blockIdx.x % KP, u = threadIdx.x;
+    const long long tb = (long long)tile * p.SPT;
+    int expected;
+    if (p.U >= p.Gstream)
+        expected = ALS_NG * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
+    else
+        expected = ALS_NG * p.SPT;
+    double r = 0.0;
+    if (c < p.k && (long long)tile * TILE_UNITS + u < p.nvalid) {
+        const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + u;
+        for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
+    }
+    xchg[((size_t)tile * KP + c) * TILE_UNITS + u] = r;
+    if (blockIdx.x == 0)
+        for (int e = u; e < KP * KP; e += TILE_UNITS) xchg[(size_t)p.T * KP * TILE_UNITS + e] = ldcg(&p.G[e]);
+}
+
+// after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve() failure: reason 3)
+__global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams p, int KP, const double *__restrict__ Gsum) {
+    extern __shared__ double sh[];   // KP*KP + 2
+    if (*(volatile int *)&p.ctrl->stop) return;
+    double *sG = sh, *scr = sh + KP * KP;
+    const int k = p.k;
+    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        const double v = (c1 < k && c2 < k) ? Gsum[e] : 0.0;
+        sG[e] = v;
+        p.G[e] = v;
+    }
+    __syncthreads();
+    const int sing = gauss_jordan_inverse(sG, k, KP, threadIdx.x, 256, scr, [] { __syncthreads(); });
+    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        p.Minv[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
+    }
+    if (threadIdx.x == 0 && sing) {
+        p.ctrl->reason = 3;
+        __threadfence();
+        p.ctrl->stop = 1;
+    }
+}
+
+// after the all-reduce of the W-step scalars: close the iteration on every rank (identical inputs, identical result)
+__global__ void als_shard_finish_kernel(const HalfParams p) {
+    AlsCtrl *c = p.ctrl;
+    if (c->stop) return;
+    finish_iteration(c, p.trace, p.xscal[0], p.xscal[1], p.xscal[2]);
+}
+
 // r = F a  style helper for mfb_nnls: R[c][j] = sum_i C[i][c] B[i][j]  (small, test entry point)
 __global__ void __launch_bounds__(256) small_crossprod_kernel(const double *__restrict__ C, const double *__restrict__ B,
                                                               int64_t r, int k, int64_t pcols, double *__restrict__ R) {
@@ -1002,6 +1076,12 @@ struct mfb_als {
     std::vector<double> trace;   // host copy: iters_total x 3
     double resid;
     std::vector<void *> allocs;
+    // row-sharded mode (mfb_als_begin_sharded): this session holds one row block of the matrix
+    bool shard = false;
+    mfb_allreduce_fn allreduce = nullptr;
+    void *allreduce_user = nullptr;
+    int64_t m_global = 0;
+    double *xchg = nullptr, *xscal = nullptr;   // [T_h][KP][128] + KP*KP exchange buffer; [4] scalars
 };
 
 static int max_slots(long long T, long long SPT, int G) {
@@ -1084,11 +1164,13 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 }
 
 template <int KB, bool F32>
-static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
+static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which) {
+    // which: 0 = stream + solve, 1 = stream kernel only, 2 = solve kernel only (row-sharded H-step)
     cudaStream_t st = s->ctx->stream;
     const int G = hp.Gstream;
     const int nsolve = wstep ? s->nsolve_w : s->nsolve_h;
-    const bool pdl = (s->prof == nullptr) && !getenv("MFB_NO_PDL");   // events between launches serialise anyway
+    // events between launches serialise anyway; in sharded mode collectives sit between the kernels
+    const bool pdl = (s->prof == nullptr) && !s->shard && !getenv("MFB_NO_PDL");
     if (!s->attr_set) {
         MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
         MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
@@ -1100,19 +1182,24 @@ static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUt
         MFB_CUDA(launch_pdl(als_stream_kernel<KB, true, F32>, G, ALS_THREADS, s->smem_w, st, pdl, s->tm_w, tmF, hp, s->nstage_w));
         MFB_TRY(prof_mark(s));
         MFB_CUDA(launch_pdl(als_solve_kernel<KB, true>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
-    } else {
-        MFB_CUDA(launch_pdl(als_stream_kernel<KB, false, F32>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
         MFB_TRY(prof_mark(s));
-        MFB_CUDA(launch_pdl(als_solve_kernel<KB, false>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
+    } else {
+        if (which != 2) {
+            MFB_CUDA(launch_pdl(als_stream_kernel<KB, false, F32>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
+            MFB_TRY(prof_mark(s));
+        }
+        if (which != 1) {
+            MFB_CUDA(launch_pdl(als_solve_kernel<KB, false>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
+            MFB_TRY(prof_mark(s));
+        }
     }
-    MFB_TRY(prof_mark(s));
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
 
 template <int KB>
-static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
-    return s->f32 ? launch_half_t<KB, true>(s, wstep, hp, tmF) : launch_half_t<KB, false>(s, wstep, hp, tmF);
+static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which) {
+    return s->f32 ? launch_half_t<KB, true>(s, wstep, hp, tmF, which) : launch_half_t<KB, false>(s, wstep, hp, tmF, which);
 }
 
 template <int KB>
@@ -1142,14 +1229,14 @@ static int check_mbar_abort(const char *where) {
     return MFB_ERR_CUDA;
 }
 
-static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF) {
+static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which = 0) {
     switch (s->KB) {
-        case 1: return launch_half<1>(s, wstep, hp, tmF);
-        case 2: return launch_half<2>(s, wstep, hp, tmF);
-        case 3: return launch_half<3>(s, wstep, hp, tmF);
-        case 4: return launch_half<4>(s, wstep, hp, tmF);
-        case 6: return launch_half<6>(s, wstep, hp, tmF);
-        case 8: return launch_half<8>(s, wstep, hp, tmF);
+        case 1: return launch_half<1>(s, wstep, hp, tmF, which);
+        case 2: return launch_half<2>(s, wstep, hp, tmF, which);
+        case 3: return launch_half<3>(s, wstep, hp, tmF, which);
+        case 4: return launch_half<4>(s, wstep, hp, tmF, which);
+        case 6: return launch_half<6>(s, wstep, hp, tmF, which);
+        case 8: return launch_half<8>(s, wstep, hp, tmF, which);
     }
     mfb_set_error("unsupported rank block %d", s->KB);
     return MFB_ERR_UNSUPPORTED;
@@ -1186,23 +1273,31 @@ static int als_upload_H(mfb_als *s, const double *H_host, double *dst) {
     return MFB_OK;
 }
 
-int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, const double *Hold0, double resid_old0,
-                  mfb_als **out) {
+static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int k, const double *W0, const double *Hold0,
+                         double resid_old0, mfb_allreduce_fn allreduce, void *user, mfb_als **out) {
     MFB_ARG(ctx && A && W0 && Hold0 && out, "NULL argument");
     MFB_ARG(k >= 1 && k <= 64, "k must be in 1..64");
-    MFB_ARG(k <= A->m && k <= A->n, "k exceeds a matrix dimension");
+    const bool shard = allreduce != nullptr;
+    MFB_ARG(k <= (shard ? m_global : A->m) && k <= A->n, "k exceeds a matrix dimension");
+    MFB_ARG(!shard || (A->m >= 1 && A->m <= m_global), "row block larger than the matrix");
     MFB_CUDA(cudaSetDevice(ctx->device));
     double stats[5];
     MFB_TRY(mfb_matrix_stats(A, stats));
-    if (stats[3] > 0) {
-        mfb_set_error("als_nmf: matrix has NA/NaN entries");
-        return MFB_ERR_ARG;
-    }
-    if (stats[0] < 0) {
-        mfb_set_error("Negative values are not allowed");
-        return MFB_ERR_NEGATIVE;
+    if (!shard) {      // (sharded: the ranks agree on these through the first collective, below)
+        if (stats[3] > 0) {
+            mfb_set_error("als_nmf: matrix has NA/NaN entries");
+            return MFB_ERR_ARG;
+        }
+        if (stats[0] < 0) {
+            mfb_set_error("Negative values are not allowed");
+            return MFB_ERR_NEGATIVE;
+        }
     }
     mfb_als *s = new mfb_als();
+    s->shard = shard;
+    s->allreduce = allreduce;
+    s->allreduce_user = user;
+    s->m_global = shard ? m_global : A->m;
     s->ctx = ctx;
     s->A = A;
     s->k = k;
@@ -1265,6 +1360,24 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     ALLOC(s->ctrl, 1)
     s->max_trace = 4096;
     ALLOC(s->trace_dev, (size_t)s->max_trace * 3)
+    if (shard) {
+        ALLOC(s->xchg, (size_t)s->T_h * KP * TILE_UNITS + KP * KP)
+        ALLOC(s->xscal, 4)
+        // first collective: ||A||^2 of the whole matrix, and one verdict on negative / NA entries for all ranks
+        double *hs = (double *)ctx->pinned;
+        hs[0] = stats[2]; hs[1] = stats[0] < 0 ? 1.0 : 0.0; hs[2] = stats[3] > 0 ? 1.0 : 0.0; hs[3] = 0.0;
+        MFB_CUDA(cudaMemcpyAsync(s->xscal, hs, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (allreduce(user, s->xscal, 4, (void *)ctx->stream) != 0) {
+            mfb_als_end(s);
+            mfb_set_error("mfb_als_begin_sharded: the all-reduce callback failed");
+            return MFB_ERR_CUDA;
+        }
+        MFB_CUDA(cudaMemcpyAsync(hs, s->xscal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        stats[2] = hs[0];
+        if (hs[2] > 0) { mfb_als_end(s); mfb_set_error("als_nmf: matrix has NA/NaN entries"); return MFB_ERR_ARG; }
+        if (hs[1] > 0) { mfb_als_end(s); mfb_set_error("Negative values are not allowed"); return MFB_ERR_NEGATIVE; }
+    }
 #undef ALLOC
     // tensor maps over A: dims {m rows (contiguous), n cols}
     if ((rc = encode_map(&s->tm_h, A->d, A->m, A->n, A->lda, s->f32 ? 32 : 16, 128, s->f32)) != MFB_OK ||
@@ -1289,14 +1402,25 @@ int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, cons
     memset(&c, 0, sizeof(c));
     c.resid_old = resid_old0;
     c.normA2 = stats[2];
-    c.mn = (double)s->m * (double)s->n;
-    c.mk = (double)s->m * k;
+    c.mn = (double)s->m_global * (double)s->n;
+    c.mk = (double)s->m_global * k;
     c.kn = (double)k * s->n;
     c.max_trace = s->max_trace;
     MFB_CUDA(cudaMemcpyAsync(s->ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
     MFB_CUDA(cudaStreamSynchronize(st));
     *out = s;
     return MFB_OK;
+}
+
+int mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, const double *Hold0, double resid_old0,
+                  mfb_als **out) {
+    return als_begin_impl(ctx, A, A ? A->m : 0, k, W0, Hold0, resid_old0, nullptr, nullptr, out);
+}
+
+int mfb_als_begin_sharded(mfb_context *ctx, mfb_matrix *A_rows, int64_t m_global, int k, const double *W0_rows,
+                          const double *Hold0, double resid_old0, mfb_allreduce_fn allreduce, void *user, mfb_als **out) {
+    MFB_ARG(allreduce != nullptr, "NULL all-reduce callback");
+    return als_begin_impl(ctx, A_rows, m_global, k, W0_rows, Hold0, resid_old0, allreduce, user, out);
 }
 
 int mfb_als_restart(mfb_als *s, const double *Wnew) {
@@ -1323,7 +1447,28 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.ctrl = s->ctrl; h.trace = s->trace_dev;
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
     h.Gstream = s->ctx->sm_count;
-    MFB_TRY(launch_half_dispatch(s, false, h, use_restart_w ? s->tm_W[2] : s->tm_W[cur]));
+    h.shard = s->shard ? 1 : 0; h.xscal = s->xscal;
+    const CUtensorMap &tmW = use_restart_w ? s->tm_W[2] : s->tm_W[cur];
+    if (!s->shard) {
+        MFB_TRY(launch_half_dispatch(s, false, h, tmW));
+    } else {
+        // local W_r'A_r and W_r'W_r -> one buffer -> sum over the ranks -> invert -> NNLS (replicated, identical H)
+        cudaStream_t st = s->ctx->stream;
+        const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
+        MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1));
+        als_shard_fold_kernel<<<(unsigned)(s->T_h * s->KP), TILE_UNITS, 0, st>>>(h, s->KP, s->xchg);
+        MFB_CUDA(cudaGetLastError());
+        if (s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
+            mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
+            return MFB_ERR_CUDA;
+        }
+        als_shard_invert_kernel<<<1, 256, (size_t)(s->KP * s->KP + 2) * sizeof(double), st>>>(
+            h, s->KP, s->xchg + (size_t)s->T_h * s->KP * TILE_UNITS);
+        MFB_CUDA(cudaGetLastError());
+        HalfParams hs = h;
+        hs.P = s->xchg; hs.maxslots = 1;
+        MFB_TRY(launch_half_dispatch(s, false, hs, tmW, 2));
+    }
     HalfParams w = h;
     w.Fin = s->Hb[nxt]; w.ldin = s->ldh; w.nfix = s->n;
     w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
@@ -1331,6 +1476,15 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     w.P = s->P_w; w.maxslots = s->maxslots_w;
     w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
     MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt]));
+    if (s->shard) {
+        cudaStream_t st = s->ctx->stream;
+        if (s->allreduce(s->allreduce_user, s->xscal, 4, (void *)st) != 0) {
+            mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
+            return MFB_ERR_CUDA;
+        }
+        als_shard_finish_kernel<<<1, 1, 0, st>>>(w);
+        MFB_CUDA(cudaGetLastError());
+    }
     return MFB_OK;
 }
 
@@ -1393,6 +1547,7 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
 
 int mfb_als_profile(mfb_als *s, int iters, double ms[4]) {
     MFB_ARG(s && ms && iters >= 1, "bad argument");
+    if (s->shard) { mfb_set_error("mfb_als_profile: not available for a row-sharded session"); return MFB_ERR_UNSUPPORTED; }
     MFB_CUDA(cudaSetDevice(s->ctx->device));
     std::vector<cudaEvent_t> ev;
     cudaEvent_t e0;

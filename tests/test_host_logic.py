@@ -117,6 +117,55 @@ def test_bcv_cell_sharding_gloo_world2(tmp_path):
         assert f"rank {r} ok" in o
 
 
+SHARD_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np
+    import torch.distributed as dist
+    rank = int(sys.argv[1])
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+    import mfbiclust_b200 as mfb
+    from mfbiclust_b200.backends import _allreduce_host
+    m, k = 101, 3
+    W = np.random.default_rng(1).random((m, k))
+    r0, r1 = mfb.row_range(m, rank, 2)
+    assert (r0, r1) == ((0, 50) if rank == 0 else (50, 101))
+    full = mfb.gather_rows(np.asfortranarray(W[r0:r1]), m)
+    assert np.array_equal(full, W)                      # exact: one non-zero contributor per entry
+    lo, = _allreduce_host([W[r0:r1].min()], "MIN", 0, None)
+    hi, = _allreduce_host([W[r0:r1].max()], "MAX", 0, None)
+    assert lo == W.min() and hi == W.max()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_als_row_sharding_host_side_gloo_world2(tmp_path):
+    """Host logic of the row-sharded als_nmf (mfb_als_begin_sharded): row blocks, exact gather of W, global max/min."""
+    import socket
+    import mfbiclust_b200 as mfb
+    for m in (1, 7, 128, 20000):
+        for world in (1, 2, 3, 8):
+            blocks = [mfb.row_range(m, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == m
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
+
+
 def test_auto_bcv_batch_sizing_matches_the_stopping_rule():
     # R/bcv.R:56-87: with one k winning every time the rule fires at iteration 22 on an 11-candidate grid
     # (vignettes/my-vignette.html:408-413: counts = 22); the batch sizing must predict exactly that
