@@ -253,6 +253,63 @@ def run_auto_bcv(mfb, ctx, rank, world, with_cpu):
     return info
 
 
+def run_sharded(mfb, ctx, Ad_full, A, W0, H0, rank, world, local_rank, k=RANK, iters=40):
+    """Row-sharded als_nmf (mfb_als_begin_sharded) over the ranks, NCCL all-reduce of
+    [W_r'A_r | W_r'W_r] (k n + k^2 doubles) + 4 scalars per iteration through torch.distributed:
+    (strong) D4 itself split by rows; (weak) every rank holds a full D4 as its row block, i.e. one
+    (20000 N) x 5000 matrix.  Device-timed (CUDA events on the library's stream), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    m, n = A.shape
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    amax = Ad_full.stats()["max"]
+    out = {"n_gpus": world, "exchange_doubles_per_iteration": ((n + 127) // 128) * 128 * 16 + 256 + 4,
+           "modes": "peer_memory = cudaIpc-mapped exchange blocks, one-shot all-reduce over NVLink fused into the "
+                    "invert / H-solve / finish kernels; nccl_callback = NCCL all-reduce (torch.distributed) on the "
+                    "library's exchange buffer between the kernels, stream-ordered"}
+
+    def timed(sess):
+        st, _, _ = sess.iterate(5, fixed_iters=True)
+        assert st == 0, st
+        ctx.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st, _, _ = sess.iterate(iters, fixed_iters=True)
+        e1.record(stream)
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, _ = peaks()
+    r0, r1 = mfb.row_range(m, rank, world)
+    Ar = mfb.Matrix(ctx, host=np.asfortranarray(A[r0:r1]))
+    Wst = np.asfortranarray(W0 / np.sqrt(world))
+    for exchange in ("peer", "callback"):
+        # strong: D4 split by rows
+        sess = mfb.ShardedAlsSession(Ar, m, k, W0[r0:r1], H0, amax, exchange=exchange)
+        ms = timed(sess)
+        _, _, resid, _ = sess.result()
+        sess.close()
+        res = {"strong": {"workload": "D4 20000x5000 k=16 FP64 row-sharded over %d GPUs" % world,
+                          "iters_per_s": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "final_resid": resid,
+                          "aggregate_GBps": 2.0 * m * n * 8 * iters / (ms * 1e-3) / 1e9}}
+        # weak: every rank's row block is a whole D4 -> one (m * world) x n matrix
+        sess = mfb.ShardedAlsSession(Ad_full, m * world, k, Wst, H0, amax, exchange=exchange)
+        ms = timed(sess)
+        _, _, resid, _ = sess.result()
+        sess.close()
+        gbs = 2.0 * m * world * n * 8 * iters / (ms * 1e-3) / 1e9
+        res["weak"] = {"workload": "%dx5000 k=16 FP64 (one D4 per GPU as its row block) over %d GPUs" % (m * world, world),
+                       "iters_per_s": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "final_resid": resid,
+                       "aggregate_GBps": gbs, "frac_of_aggregate_hbm": gbs / (peak * world)}
+        out["peer_memory" if exchange == "peer" else "nccl_callback"] = res
+    Ar.free()
+    return out
+
+
 def run_reference(args, rank, world):
     """Reference arm: the CPU oracle port (literal R loop) on all host cores, rank 0 only."""
     if rank != 0:
@@ -293,6 +350,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bcv", action="store_true", help="skip the auto_bcv wall-time leg (second half of the metric)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the NIPALS / svd_pca / Otsu timings on D4")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the row-sharded ALS leg (N > 1 only)")
     ap.add_argument("--k", type=int, default=RANK, help="rank (default 16 = the headline; 64 = BASELINE configs[3]'s "
                                                         "compute-bound variant, reported against the FP64 pipe)")
     args = ap.parse_args()
@@ -393,6 +451,9 @@ def main():
                "note": f"mfb_als_run_host: upload A from pinned host memory + {K} iterations + download W,H; "
                        f"one call = {K} steps"}
         assert np.allclose(Wout, Wout) and itc.value == K
+    sharded = None
+    if world > 1 and not args.no_sharded and RANK_ == RANK:
+        sharded = run_sharded(mfb, ctx, Ad, A, W0, H0, rank, world, local_rank)
     secondary = None
     if not args.no_secondary and rank == 0:
         secondary = run_secondary(mfb, ctx, Ad, m, n)
@@ -452,7 +513,7 @@ def main():
                         "step_note": "whole iteration (all 4 launches + gaps): 2*m*n*8*K / timed seconds; this is "
                                      "the north-star '% of HBM roofline' figure"},
            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "auto_bcv": bcv_info,
-           "secondary": secondary,
+           "secondary": secondary, "als_row_sharded": sharded,
            "final_resid": resid}
     print(json.dumps(out), flush=True)
     if world > 1:

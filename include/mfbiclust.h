@@ -124,6 +124,22 @@ int  mfb_als_begin_sharded(mfb_context *ctx, mfb_matrix *A_rows, int64_t m_globa
                            const double *W0_rows, const double *Hold0, double resid_old0,
                            mfb_allreduce_fn allreduce, void *user, mfb_als **out);
 /*
+ * Optional, when all ranks are on ONE node: exchange over peer memory instead of the callback.  Every rank exports
+ * the cudaIpc handle (64 bytes) of its exchange block, the host gathers the handles of all ranks (rank order) and
+ * every rank connects BEFORE the first iteration.  From then on the two per-iteration exchanges are a one-shot
+ * all-reduce fused into the kernels that consume the sums: each rank publishes its folded [W_r'A_r | W_r'W_r] and
+ * its scalars with a system-scope release flag in every peer's block, and the invert / H-step solve / finish kernels
+ * read all ranks' buffers over NVLink and add them in rank order (bit-identical on every rank; no collective launch,
+ * no host involvement).  At most 16 ranks.  mfb_als_shard_connect returns MFB_ERR_UNSUPPORTED when a peer block
+ * cannot be mapped (the session then keeps using the callback; the ranks must agree on the outcome).  No rank may
+ * call mfb_als_end before every rank has its result (the blocks are read remotely until then).  A peer that never
+ * arrives makes the waiting kernels time out (20 s) and the call fail with MFB_ERR_CUDA.
+ */
+int  mfb_als_shard_export(mfb_als *s, void *handle64);
+int  mfb_als_shard_connect(mfb_als *s, int rank, int world, const void *handles /* world x 64 bytes */);
+/* Undo a successful connect before the first iteration (another rank could not connect): back to the callback. */
+int  mfb_als_shard_disconnect(mfb_als *s);
+/*
  * Measurement aid for bench.py: runs `iters` further fixed iterations with a CUDA event recorded (on the
  * context's stream) after every kernel, and returns the mean duration in ms of the four launches of an
  * iteration: ms[0] H-step stream, ms[1] H-step solve, ms[2] W-step stream, ms[3] W-step solve.

@@ -43,6 +43,9 @@ PROTOTYPES = {
     "mfb_matrix_dev_ptr": (_vp, [_vp]),
     "mfb_als_begin": (C.c_int, [_vp, _vp, C.c_int, _dp, _dp, C.c_double, C.POINTER(_vp)]),
     "mfb_als_begin_sharded": (C.c_int, [_vp, _vp, _i64, C.c_int, _dp, _dp, C.c_double, _vp, _vp, C.POINTER(_vp)]),
+    "mfb_als_shard_export": (C.c_int, [_vp, _vp]),
+    "mfb_als_shard_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "mfb_als_shard_disconnect": (C.c_int, [_vp]),
     "mfb_als_iterate": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip]),
     "mfb_als_restart": (C.c_int, [_vp, _dp]),
     "mfb_als_profile": (C.c_int, [_vp, C.c_int, _dp]),

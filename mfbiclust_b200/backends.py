@@ -269,7 +269,11 @@ class ShardedAlsSession(AlsSession):
     """One ``als_nmf`` replicate on a matrix whose rows are split over the ranks of ``group``
     (``mfb_als_begin_sharded``): this rank holds ``A_rows`` and the matching rows of W; H is replicated."""
 
-    def __init__(self, A_rows: _cabi.Matrix, m_global: int, k: int, W0_rows, Hold0, resid_old0: float, group=None):
+    def __init__(self, A_rows: _cabi.Matrix, m_global: int, k: int, W0_rows, Hold0, resid_old0: float, group=None,
+                 exchange="auto"):
+        """``exchange``: ``"peer"`` = one-shot all-reduce over cudaIpc peer memory fused into the consuming kernels
+        (all ranks on one node), ``"callback"`` = the host's collective (NCCL / gloo through torch.distributed),
+        ``"auto"`` = peer memory if every rank can map every other rank's block, else the callback."""
         self.A = A_rows
         self.k = int(k)
         self.m, self.n = A_rows.shape
@@ -284,6 +288,38 @@ class ShardedAlsSession(AlsSession):
                                                 dptr(Hold0), float(resid_old0),
                                                 C.cast(self.reduce.c_callback, C.c_void_p), None, C.byref(self._h)))
         self.iters = 0
+        self.group = group
+        self.exchange = "callback"
+        if exchange in ("auto", "peer"):
+            self._connect_peers(required=(exchange == "peer"))
+
+    def _connect_peers(self, required):
+        rank, world, dist = self.reduce.rank, self.reduce.world, self.reduce.dist
+        mine = np.zeros(64, dtype=np.uint8)
+        ok = lib().mfb_als_shard_export(self._h, mine.ctypes.data_as(C.c_void_p)) == MFB_OK
+        table = np.zeros((world, 65))
+        table[rank, :64] = mine
+        table[rank, 64] = 0.0 if ok else 1.0
+        table = _allreduce_host(table, "SUM", self.A.ctx.device, self.group)       # exact: one contributor per row
+        ok = table[:, 64].sum() == 0
+        if ok:
+            handles = np.ascontiguousarray(table[:, :64].astype(np.uint8))
+            ok = lib().mfb_als_shard_connect(self._h, rank, world, handles.ctypes.data_as(C.c_void_p)) == MFB_OK
+        # the ranks must agree: if one of them could not map a peer, all of them keep the callback
+        bad, = _allreduce_host([0.0 if ok else 1.0], "SUM", self.A.ctx.device, self.group)
+        if bad == 0:
+            self.exchange = "peer"
+        else:
+            if ok:
+                check(lib().mfb_als_shard_disconnect(self._h))      # back to the callback, like the ranks that failed
+            if required:
+                raise _cabi.MfbError(_cabi.MFB_ERR_UNSUPPORTED, "peer-memory exchange is not available on every "
+                                     "rank: " + lib().mfb_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self._h and self.exchange == "peer" and self.reduce.dist is not None and self.reduce.world > 1:
+            self.reduce.dist.barrier(group=self.group)      # peers may still be reading this rank's exchange block
+        super().close()
 
     def _check(self, status):
         if self.reduce.error is not None:
@@ -329,7 +365,7 @@ def gather_rows(W_rows, m_global, ctx_device=0, group=None):
 
 
 def als_replicate_sharded(A_rows, m_global, k, W0, Hold0, maxIter=100, eps_conv=1e-4, fixed_iters=False, rng=None,
-                          ctx=None, group=None, gather=True):
+                          ctx=None, group=None, gather=True, exchange="auto"):
     """:func:`als_replicate` with the rows of A split over the ranks of ``group``.
 
     ``A_rows`` is THIS rank's block ``A[row_range(m_global, rank, world), :]`` (host array or resident
@@ -355,7 +391,7 @@ def als_replicate_sharded(A_rows, m_global, k, W0, Hold0, maxIter=100, eps_conv=
         W0 = np.asarray(W0)
         if W0.shape != (m_global, k):
             raise ValueError("W0 must be the full m_global x k start")
-        sess = ShardedAlsSession(Ad, m_global, k, W0[r0:r1], Hold0, float(amax), group)
+        sess = ShardedAlsSession(Ad, m_global, k, W0[r0:r1], Hold0, float(amax), group, exchange=exchange)
         try:
             nrestart = 0
             total = 0
@@ -374,7 +410,7 @@ def als_replicate_sharded(A_rows, m_global, k, W0, Hold0, maxIter=100, eps_conv=
                                                  "rng was supplied for restart()")
                 sess.restart(_normalised_random_W(rng, m_global, k)[r0:r1])          # same draw on every rank
             W, H, resid, trace = sess.result()
-            stats = dict(allreduce_calls=sess.reduce.calls, allreduce_bytes=sess.reduce.bytes)
+            stats = dict(allreduce_calls=sess.reduce.calls, allreduce_bytes=sess.reduce.bytes, exchange=sess.exchange)
         finally:
             sess.close()
     finally:
@@ -386,7 +422,7 @@ def als_replicate_sharded(A_rows, m_global, k, W0, Hold0, maxIter=100, eps_conv=
 
 
 def als_nmf_sharded(A_rows, m_global, k, reps=4, maxIter=100, eps_conv=1e-4, rng=None, inits=None, ctx=None,
-                    group=None, **_):
+                    group=None, exchange="auto", **_):
     """``als_nmf`` for a matrix too large for (or simply spread over) one device: same replicates, same winner
     (``which.min`` of the residuals, which are identical on every rank) -> :class:`genericFit` with the full W, H."""
     ctx = ctx or _cabi.default_context()
@@ -403,7 +439,7 @@ def als_nmf_sharded(A_rows, m_global, k, reps=4, maxIter=100, eps_conv=1e-4, rng
                 W0 = _normalised_random_W(rng, m_global, k)
                 Hold0 = np.asarray(rng.runif(k * n), dtype=np.float64).reshape((k, n), order="F")
             sols.append(als_replicate_sharded(Ad, m_global, k, W0, Hold0, maxIter, eps_conv, rng=rng, ctx=ctx,
-                                              group=group))
+                                              group=group, exchange=exchange))
         best = int(np.argmin([s["obj"] for s in sols]))
     finally:
         Ad.free()

@@ -70,7 +70,46 @@ struct HalfParams {
     int Gstream;                          // grid size of the stream kernel (stream-K partition)
     int shard;                            // != 0: A is one row block of a matrix sharded over several devices
     double *xscal;                        // shard mode: [4] iteration scalars of the W-step, summed over the ranks
+    const struct ShardPeers *peers;       // shard mode over peer memory (NULL: the host's all-reduce callback is used)
+    int epoch;                            // shard mode: number of this iteration since the session began (1-based)
 };
+
+// Row-sharded mode over peer memory (NVLink / NVSwitch, cudaIpc mappings): every rank owns one SHARED BLOCK
+//   int flagsA[16] | int flagsB[16] | int fold_counter | .. | double xscal[2][4] @256 | double xchg[2][cnt] @512
+// mapped into every peer.  Epoch e uses the buffers of parity e & 1.  flagsA[q] = e: rank q's exchange buffer
+// [W_q'A_q | W_q'W_q] of epoch e is complete; flagsB[q] = e: rank q's W-step scalars of epoch e are complete (both
+// written by rank q into EVERY rank's block with a system-scope release store).  The consumers (invert / H-step
+// solve / finish kernels) read all ranks' buffers straight over NVLink and add them in rank order, so every rank
+// forms bit-identical sums: a one-shot all-reduce fused into the kernels that need the result, no collective launch.
+#define SHARD_MAXP 16
+#define SHARD_OFF_FLAGSB 64
+#define SHARD_OFF_COUNTER 128
+#define SHARD_OFF_XSCAL 256
+#define SHARD_OFF_XCHG 512
+struct ShardPeers {
+    int world, rank;
+    long long cnt;                        // doubles per exchange buffer: T * KP * 128 + KP * KP
+    unsigned char *base[SHARD_MAXP];      // base[q] = rank q's shared block as mapped here (base[rank] = local)
+};
+__device__ __forceinline__ double *shard_xchg(const ShardPeers *sp, int q, int parity) {
+    return (double *)(sp->base[q] + SHARD_OFF_XCHG) + (size_t)parity * sp->cnt;
+}
+__device__ __forceinline__ double *shard_xscal(const ShardPeers *sp, int q, int parity) {
+    return (double *)(sp->base[q] + SHARD_OFF_XSCAL) + parity * 4;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA
@@ -152,6 +191,23 @@ __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 // cta index that owns unit u under the balanced partition u0(c) = floor(c * U / G)
 __device__ __forceinline__ int cta_of_unit(long long u, long long U, int G) {
     return (int)(((u + 1) * (long long)G + U - 1) / U) - 1;
+}
+
+// wait until rank q has published epoch `e` in this rank's flag array (bounded: a dead peer must not hang the GPU;
+// on a time-out the launch chain drains with ctrl->stop and the host reports MFB_ERR_CUDA, kind 5)
+__device__ __noinline__ void shard_wait_flag(const int *flag, int e, int q, AlsCtrl *ctrl) {
+    if (ld_acquire_sys(flag) >= e) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < e) {
+        if (*(volatile int *)&g_mbar_abort) return;
+        if (globaltimer_ns() - t0 > 20000000000ull) {        // 20 s
+            mbar_timeout(5, e, q, *(volatile const int *)flag);
+            ctrl->stop = 1;
+            ctrl->reason = 5;
+            return;
+        }
+        __nanosleep(200);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -246,10 +302,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         if (p.shard && !WSTEP) expected = 1;                 // P = the all-reduced W'A, one slot per tile
     }
     // (a) right-hand sides: sum the partials in slot order
+    const bool peer_sum = !WSTEP && p.shard && p.peers != nullptr;
     for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
         const int u = e % SU, c = e / SU;
         double r = 0.0;
-        if (c < k && u < nvalid_local) {
+        if (peer_sum) {
+            // W'A = sum over the ranks of their folded W_q'A_q, read over NVLink in rank order (all loads in flight)
+            if (c < k && u < nvalid_local) {
+                const ShardPeers *sp = p.peers;
+                const size_t off = ((size_t)tile * KP + c) * (size_t)TILE_UNITS + uoff + u;
+                const int world = sp->world, par = p.epoch & 1;
+                double v[SHARD_MAXP];
+#pragma unroll
+                for (int q = 0; q < SHARD_MAXP; ++q) v[q] = (q < world) ? ldcg(shard_xchg(sp, q, par) + off) : 0.0;
+#pragma unroll
+                for (int q = 0; q < SHARD_MAXP; ++q) r += v[q];
+            }
+        } else if (c < k && u < nvalid_local) {
             const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + uoff + u;
             if (expected <= 12) {                            // all slots in flight at once, summed in slot order
                 double v[12];
@@ -370,7 +439,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
             if ((m & fullm) != fullm) { c->stop = 1; c->reason = 2; }
         } else if (p.shard) {
             // this rank's share of the sums; the host all-reduces them and als_shard_finish_kernel closes the iteration
-            p.xscal[0] = sd2; p.xscal[1] = st1; p.xscal[2] = st2; p.xscal[3] = 0.0;
+            if (p.peers) {
+                const ShardPeers *sp = p.peers;
+                double *xs2 = shard_xscal(sp, sp->rank, p.epoch & 1);
+                xs2[0] = sd2; xs2[1] = st1; xs2[2] = st2; xs2[3] = 0.0;
+                __threadfence_system();
+                for (int q = 0; q < sp->world; ++q)
+                    st_release_sys((int *)(sp->base[q] + SHARD_OFF_FLAGSB) + sp->rank, p.epoch);
+            } else {
+                p.xscal[0] = sd2; p.xscal[1] = st1; p.xscal[2] = st2; p.xscal[3] = 0.0;
+            }
         } else {
             finish_iteration(c, p.trace, sd2, st1, st2);
         }
@@ -951,6 +1029,20 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
     xchg[((size_t)tile * KP + c) * TILE_UNITS + u] = r;
     if (blockIdx.x == 0)
         for (int e = u; e < KP * KP; e += TILE_UNITS) xchg[(size_t)p.T * KP * TILE_UNITS + e] = ldcg(&p.G[e]);
+    if (p.peers) {
+        // publish: the last block to finish tells every rank (itself included) that this buffer is complete
+        const ShardPeers *sp = p.peers;
+        __threadfence_system();
+        __syncthreads();
+        if (u == 0) {
+            int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
+            if (atomicAdd(counter, 1) == (int)gridDim.x - 1) {
+                *counter = 0;
+                __threadfence_system();
+                for (int q = 0; q < sp->world; ++q) st_release_sys((int *)sp->base[q] + sp->rank, p.epoch);
+            }
+        }
+    }
 }
 
 // after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve() failure: reason 3)
@@ -959,9 +1051,24 @@ __global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams 
     if (*(volatile int *)&p.ctrl->stop) return;
     double *sG = sh, *scr = sh + KP * KP;
     const int k = p.k;
+    const ShardPeers *sp = p.peers;
+    if (sp) {
+        if ((int)threadIdx.x < sp->world)
+            shard_wait_flag((const int *)sp->base[sp->rank] + threadIdx.x, p.epoch, (int)threadIdx.x, p.ctrl);
+        __syncthreads();
+        if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
+    }
     for (int e = threadIdx.x; e < KP * KP; e += 256) {
         const int c1 = e / KP, c2 = e - c1 * KP;
-        const double v = (c1 < k && c2 < k) ? Gsum[e] : 0.0;
+        double v = 0.0;
+        if (c1 < k && c2 < k) {
+            if (sp) {
+                for (int q = 0; q < sp->world; ++q)          // rank order: the same sum on every rank
+                    v += ldcg(shard_xchg(sp, q, p.epoch & 1) + (size_t)p.T * KP * TILE_UNITS + e);
+            } else {
+                v = Gsum[e];
+            }
+        }
         sG[e] = v;
         p.G[e] = v;
     }
@@ -979,10 +1086,26 @@ __global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams 
 }
 
 // after the all-reduce of the W-step scalars: close the iteration on every rank (identical inputs, identical result)
-__global__ void als_shard_finish_kernel(const HalfParams p) {
+__global__ void __launch_bounds__(32) als_shard_finish_kernel(const HalfParams p) {
     AlsCtrl *c = p.ctrl;
-    if (c->stop) return;
-    finish_iteration(c, p.trace, p.xscal[0], p.xscal[1], p.xscal[2]);
+    if (*(volatile int *)&c->stop) return;
+    const ShardPeers *sp = p.peers;
+    if (!sp) {
+        if (threadIdx.x == 0) finish_iteration(c, p.trace, p.xscal[0], p.xscal[1], p.xscal[2]);
+        return;
+    }
+    const int lane = threadIdx.x;
+    if (lane < sp->world)
+        shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, p.epoch, lane, c);
+    __syncwarp();
+    if (lane == 0 && !*(volatile int *)&c->stop) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int q = 0; q < sp->world; ++q) {
+            const double *xq = shard_xscal(sp, q, p.epoch & 1);
+            a0 += ldcg(xq + 0); a1 += ldcg(xq + 1); a2 += ldcg(xq + 2);
+        }
+        finish_iteration(c, p.trace, a0, a1, a2);
+    }
 }
 
 // r = F a  style helper for mfb_nnls: R[c][j] = sum_i C[i][c] B[i][j]  (small, test entry point)
@@ -1082,6 +1205,13 @@ struct mfb_als {
     void *allreduce_user = nullptr;
     int64_t m_global = 0;
     double *xchg = nullptr, *xscal = nullptr;   // [T_h][KP][128] + KP*KP exchange buffer; [4] scalars
+    // ... over peer memory (mfb_als_shard_export / mfb_als_shard_connect)
+    unsigned char *shared = nullptr;            // this rank's shared block (cudaMalloc, cudaIpc-exported)
+    size_t xchg_cnt = 0;
+    ShardPeers peers_host;
+    ShardPeers *peers_dev = nullptr;
+    std::vector<void *> peer_maps;              // cudaIpcOpenMemHandle mappings to close
+    int epoch = 0;
 };
 
 static int max_slots(long long T, long long SPT, int G) {
@@ -1258,6 +1388,8 @@ void mfb_als_end(mfb_als *s) {
         cudaSetDevice(s->ctx->device);
         cudaStreamSynchronize(s->ctx->stream);
         for (void *p : s->allocs) mfb_pool_free(s->ctx, p);
+        for (void *p : s->peer_maps) cudaIpcCloseMemHandle(p);
+        if (s->shared) cudaFree(s->shared);
     }
     delete s;
 }
@@ -1361,8 +1493,16 @@ static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int
     s->max_trace = 4096;
     ALLOC(s->trace_dev, (size_t)s->max_trace * 3)
     if (shard) {
-        ALLOC(s->xchg, (size_t)s->T_h * KP * TILE_UNITS + KP * KP)
+        s->xchg_cnt = (size_t)s->T_h * KP * TILE_UNITS + KP * KP;
+        ALLOC(s->xchg, s->xchg_cnt)
         ALLOC(s->xscal, 4)
+        ALLOC(s->peers_dev, 1)
+        {
+            // the shared block is a cudaMalloc of its own (not pooled): it is exported through cudaIpc
+            const size_t bytes = SHARD_OFF_XCHG + 2 * s->xchg_cnt * sizeof(double);
+            if (cudaMalloc((void **)&s->shared, bytes) != cudaSuccess) { cudaGetLastError(); s->shared = nullptr; mfb_als_end(s); mfb_set_error("cudaMalloc of the shared exchange block failed"); return MFB_ERR_ALLOC; }
+            MFB_CUDA(cudaMemsetAsync(s->shared, 0, bytes, ctx->stream));
+        }
         // first collective: ||A||^2 of the whole matrix, and one verdict on negative / NA entries for all ranks
         double *hs = (double *)ctx->pinned;
         hs[0] = stats[2]; hs[1] = stats[0] < 0 ? 1.0 : 0.0; hs[2] = stats[3] > 0 ? 1.0 : 0.0; hs[3] = 0.0;
@@ -1423,6 +1563,58 @@ int mfb_als_begin_sharded(mfb_context *ctx, mfb_matrix *A_rows, int64_t m_global
     return als_begin_impl(ctx, A_rows, m_global, k, W0_rows, Hold0, resid_old0, allreduce, user, out);
 }
 
+int mfb_als_shard_export(mfb_als *s, void *handle64) {
+    MFB_ARG(s && handle64 && s->shard && s->shared, "not a row-sharded session");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));          // the block is zeroed before anybody can signal into it
+    cudaIpcMemHandle_t h;
+    MFB_CUDA(cudaIpcGetMemHandle(&h, s->shared));
+    memcpy(handle64, &h, 64);
+    return MFB_OK;
+}
+
+int mfb_als_shard_connect(mfb_als *s, int rank, int world, const void *handles) {
+    MFB_ARG(s && s->shard && s->shared && handles, "not a row-sharded session");
+    MFB_ARG(world >= 1 && world <= SHARD_MAXP && rank >= 0 && rank < world, "rank / world out of range (at most 16 ranks)");
+    MFB_ARG(s->peer_maps.empty() && s->epoch == 0, "connect once, before the first iteration");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    ShardPeers &sp = s->peers_host;
+    memset(&sp, 0, sizeof(sp));
+    sp.world = world; sp.rank = rank; sp.cnt = (long long)s->xchg_cnt;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) { sp.base[q] = s->shared; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)q * 64, 64);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (void *m : s->peer_maps) cudaIpcCloseMemHandle(m);
+            s->peer_maps.clear();
+            sp.world = 0;
+            mfb_set_error("cudaIpcOpenMemHandle for rank %d failed: %s (the all-reduce callback stays in use)", q,
+                          cudaGetErrorString(e));
+            return MFB_ERR_UNSUPPORTED;
+        }
+        s->peer_maps.push_back(ptr);
+        sp.base[q] = (unsigned char *)ptr;
+    }
+    MFB_CUDA(cudaMemcpyAsync(s->peers_dev, &sp, sizeof(sp), cudaMemcpyHostToDevice, s->ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return MFB_OK;
+}
+
+int mfb_als_shard_disconnect(mfb_als *s) {
+    MFB_ARG(s && s->shard, "not a row-sharded session");
+    MFB_ARG(s->epoch == 0, "disconnect before the first iteration");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    for (void *m : s->peer_maps) cudaIpcCloseMemHandle(m);
+    s->peer_maps.clear();
+    s->peers_host.world = 0;
+    return MFB_OK;
+}
+
 int mfb_als_restart(mfb_als *s, const double *Wnew) {
     MFB_ARG(s && Wnew, "NULL argument");
     MFB_CUDA(cudaSetDevice(s->ctx->device));
@@ -1448,6 +1640,9 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
     h.Gstream = s->ctx->sm_count;
     h.shard = s->shard ? 1 : 0; h.xscal = s->xscal;
+    const bool peer = s->shard && s->peer_maps.size() + 1 == (size_t)s->peers_host.world && s->peers_host.world > 0;
+    if (s->shard) h.epoch = ++s->epoch;
+    h.peers = peer ? s->peers_dev : nullptr;
     const CUtensorMap &tmW = use_restart_w ? s->tm_W[2] : s->tm_W[cur];
     if (!s->shard) {
         MFB_TRY(launch_half_dispatch(s, false, h, tmW));
@@ -1456,9 +1651,10 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         cudaStream_t st = s->ctx->stream;
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1));
-        als_shard_fold_kernel<<<(unsigned)(s->T_h * s->KP), TILE_UNITS, 0, st>>>(h, s->KP, s->xchg);
+        double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
+        als_shard_fold_kernel<<<(unsigned)(s->T_h * s->KP), TILE_UNITS, 0, st>>>(h, s->KP, xbuf);
         MFB_CUDA(cudaGetLastError());
-        if (s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
+        if (!peer && s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
             mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
             return MFB_ERR_CUDA;
         }
@@ -1478,11 +1674,11 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt]));
     if (s->shard) {
         cudaStream_t st = s->ctx->stream;
-        if (s->allreduce(s->allreduce_user, s->xscal, 4, (void *)st) != 0) {
+        if (!peer && s->allreduce(s->allreduce_user, s->xscal, 4, (void *)st) != 0) {
             mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
             return MFB_ERR_CUDA;
         }
-        als_shard_finish_kernel<<<1, 1, 0, st>>>(w);
+        als_shard_finish_kernel<<<1, 32, 0, st>>>(w);
         MFB_CUDA(cudaGetLastError());
     }
     return MFB_OK;
