@@ -300,11 +300,15 @@ def run_sharded(mfb, ctx, Ad_full, A, W0, H0, rank, world, local_rank, k=RANK, i
         sess = mfb.ShardedAlsSession(Ad_full, m * world, k, Wst, H0, amax, exchange=exchange)
         ms = timed(sess)
         _, _, resid, _ = sess.result()
+        kern = [float(v) for v in sess.profile(10)] if exchange == "peer" else None
         sess.close()
         gbs = 2.0 * m * world * n * 8 * iters / (ms * 1e-3) / 1e9
         res["weak"] = {"workload": "%dx5000 k=16 FP64 (one D4 per GPU as its row block) over %d GPUs" % (m * world, world),
                        "iters_per_s": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "final_resid": resid,
                        "aggregate_GBps": gbs, "frac_of_aggregate_hbm": gbs / (peak * world)}
+        if kern:
+            res["weak"]["kernel_ms"] = dict(zip(("h_stream", "fold_wait_invert", "h_solve", "w_stream",
+                                                 "w_solve_wait_finish"), kern))
         out["peer_memory" if exchange == "peer" else "nccl_callback"] = res
     Ar.free()
     return out

@@ -142,9 +142,12 @@ int  mfb_als_shard_disconnect(mfb_als *s);
 /*
  * Measurement aid for bench.py: runs `iters` further fixed iterations with a CUDA event recorded (on the
  * context's stream) after every kernel, and returns the mean duration in ms of the four launches of an
- * iteration: ms[0] H-step stream, ms[1] H-step solve, ms[2] W-step stream, ms[3] W-step solve.
+ * iteration: ms[0] H-step stream, ms[1] H-step solve, ms[2] W-step stream, ms[3] W-step solve.  A row-sharded
+ * session has seven launches with the callback exchange (H stream, fold, invert, H solve, W stream, W solve, finish)
+ * and five over peer memory (H stream, fold + wait for the peers + invert, H solve, W stream, W solve + wait for
+ * the peers' scalars + finish).  ms must hold 8 doubles.
  */
-int  mfb_als_profile(mfb_als *s, int iters, double ms[4]);
+int  mfb_als_profile(mfb_als *s, int iters, double *ms /* [8] */);
 /* trace: iters_total x 3 row-major (residNorm, rms dW, rms dH) per completed iteration (NaN rows for failed ones). */
 int  mfb_als_result(mfb_als *s, double *W, double *H, double *resid, double *trace);
 void mfb_als_end(mfb_als *s);

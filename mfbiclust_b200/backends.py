@@ -82,11 +82,15 @@ class AlsSession:
 
     def profile(self, iters):
         """Mean duration (ms) of the four kernel launches of an iteration over ``iters`` further fixed
-        iterations: ``[H stream, H solve, W stream, W solve]`` (``mfb_als_profile``)."""
-        ms = np.zeros(4)
+        iterations: ``[H stream, H solve, W stream, W solve]`` (``mfb_als_profile``); for a row-sharded session
+        ``[H stream, fold, invert, H solve, W stream, W solve, finish]`` (callback exchange) or
+        ``[H stream, fold + wait + invert, H solve, W stream, W solve + wait + finish]`` (peer memory)."""
+        ms = np.zeros(8)
         check(lib().mfb_als_profile(self._h, int(iters), dptr(ms)))
         self.iters += int(iters)
-        return ms
+        if isinstance(self, ShardedAlsSession):
+            return ms[:5] if self.exchange == "peer" else ms[:7]
+        return ms[:4]
 
     def restart(self, Wnew):
         Wnew = as_f(Wnew)

@@ -454,6 +454,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         }
         __threadfence();
     }
+    if (WSTEP && p.shard && p.peers) {
+        // peer mode: this warp also closes the iteration: wait for every rank's scalars, add them in rank order
+        const ShardPeers *sp = p.peers;
+        __syncwarp();
+        if (lane < sp->world)
+            shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, p.epoch, lane, p.ctrl);
+        __syncwarp();
+        if (lane == 0 && !*(volatile int *)&p.ctrl->stop) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int q = 0; q < sp->world; ++q) {
+                const double *xq = shard_xscal(sp, q, p.epoch & 1);
+                a0 += ldcg(xq + 0); a1 += ldcg(xq + 1); a2 += ldcg(xq + 2);
+            }
+            finish_iteration(p.ctrl, p.trace, a0, a1, a2);
+            __threadfence();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1013,6 +1030,8 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const double *__rest
 // kernel reads it unchanged.  The W-step is local to a rank (its rows of W); only its three iteration scalars are
 // summed over the ranks (second, 32-byte collective).
 __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg) {
+    extern __shared__ double fold_sh[];   // KP*KP + 2 (peer mode: Gram sum + inverse by the last block)
+    pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     const int tile = (int)blockIdx.x / KP, c = (int)blockIdx.x % KP, u = threadIdx.x;
     const long long tb = (long long)tile * p.SPT;
@@ -1024,30 +1043,75 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
     double r = 0.0;
     if (c < p.k && (long long)tile * TILE_UNITS + u < p.nvalid) {
         const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + u;
-        for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
+        if (expected <= 12) {                                // all slots in flight at once, summed in slot order
+            double v[12];
+#pragma unroll
+            for (int s = 0; s < 12; ++s) v[s] = (s < expected) ? ldcg(Pt + (size_t)s * (KP * TILE_UNITS)) : 0.0;
+#pragma unroll
+            for (int s = 0; s < 12; ++s) r += v[s];
+        } else {
+#pragma unroll 4
+            for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
+        }
     }
     xchg[((size_t)tile * KP + c) * TILE_UNITS + u] = r;
     if (blockIdx.x == 0)
         for (int e = u; e < KP * KP; e += TILE_UNITS) xchg[(size_t)p.T * KP * TILE_UNITS + e] = ldcg(&p.G[e]);
-    if (p.peers) {
-        // publish: the last block to finish tells every rank (itself included) that this buffer is complete
-        const ShardPeers *sp = p.peers;
-        __threadfence_system();
-        __syncthreads();
-        if (u == 0) {
-            int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
-            if (atomicAdd(counter, 1) == (int)gridDim.x - 1) {
-                *counter = 0;
-                __threadfence_system();
-                for (int q = 0; q < sp->world; ++q) st_release_sys((int *)sp->base[q] + sp->rank, p.epoch);
-            }
+    const ShardPeers *sp = p.peers;
+    if (!sp) return;
+    // peer mode.  The last block to finish publishes the buffer to every rank (itself included), waits until all
+    // ranks have published theirs, adds the W_q'W_q in rank order and inverts: the H-step solve kernel follows directly.
+    __shared__ int is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (u == 0) {
+        int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
+        const int last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+        if (last) {
+            *counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < sp->world; ++q) st_release_sys((int *)sp->base[q] + sp->rank, p.epoch);
         }
+        is_last = last;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    if (u < sp->world) shard_wait_flag((const int *)sp->base[sp->rank] + u, p.epoch, u, p.ctrl);
+    __syncthreads();
+    if (*(volatile int *)&p.ctrl->stop) return;              // a peer never arrived
+    double *sG = fold_sh, *scr = fold_sh + KP * KP;
+    const int k = p.k, par = p.epoch & 1;
+    for (int e = u; e < KP * KP; e += TILE_UNITS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        double v = 0.0;
+        if (c1 < k && c2 < k) {
+            double g[SHARD_MAXP];
+#pragma unroll
+            for (int q = 0; q < SHARD_MAXP; ++q)
+                g[q] = (q < sp->world) ? ldcg(shard_xchg(sp, q, par) + (size_t)p.T * KP * TILE_UNITS + e) : 0.0;
+#pragma unroll
+            for (int q = 0; q < SHARD_MAXP; ++q) v += g[q];  // rank order: the same sum on every rank
+        }
+        sG[e] = v;
+        p.G[e] = v;
+    }
+    __syncthreads();
+    const int sing = gauss_jordan_inverse(sG, k, KP, u, TILE_UNITS, scr, [] { __syncthreads(); });
+    for (int e = u; e < KP * KP; e += TILE_UNITS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        p.Minv[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
+    }
+    if (u == 0 && sing) {                                    // R's solve() failure inside .fcnnls: reason 3
+        p.ctrl->reason = 3;
+        __threadfence();
+        p.ctrl->stop = 1;
     }
 }
 
 // after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve() failure: reason 3)
 __global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams p, int KP, const double *__restrict__ Gsum) {
     extern __shared__ double sh[];   // KP*KP + 2
+    pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     double *sG = sh, *scr = sh + KP * KP;
     const int k = p.k;
@@ -1087,6 +1151,7 @@ __global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams 
 
 // after the all-reduce of the W-step scalars: close the iteration on every rank (identical inputs, identical result)
 __global__ void __launch_bounds__(32) als_shard_finish_kernel(const HalfParams p) {
+    pdl_prologue();
     AlsCtrl *c = p.ctrl;
     if (*(volatile int *)&c->stop) return;
     const ShardPeers *sp = p.peers;
@@ -1293,14 +1358,21 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+static bool als_peer_mode(const mfb_als *s) {
+    return s->shard && s->peers_host.world > 0 && s->peer_maps.size() + 1 == (size_t)s->peers_host.world;
+}
+static bool als_use_pdl(const mfb_als *s) {
+    // events between launches serialise anyway; with the callback exchange collectives sit between the kernels
+    return (s->prof == nullptr) && (!s->shard || als_peer_mode(s)) && !getenv("MFB_NO_PDL");
+}
+
 template <int KB, bool F32>
 static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which) {
     // which: 0 = stream + solve, 1 = stream kernel only, 2 = solve kernel only (row-sharded H-step)
     cudaStream_t st = s->ctx->stream;
     const int G = hp.Gstream;
     const int nsolve = wstep ? s->nsolve_w : s->nsolve_h;
-    // events between launches serialise anyway; in sharded mode collectives sit between the kernels
-    const bool pdl = (s->prof == nullptr) && !s->shard && !getenv("MFB_NO_PDL");
+    const bool pdl = als_use_pdl(s);
     if (!s->attr_set) {
         MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
         MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
@@ -1640,7 +1712,8 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
     h.Gstream = s->ctx->sm_count;
     h.shard = s->shard ? 1 : 0; h.xscal = s->xscal;
-    const bool peer = s->shard && s->peer_maps.size() + 1 == (size_t)s->peers_host.world && s->peers_host.world > 0;
+    const bool peer = als_peer_mode(s);
+    const bool pdl = als_use_pdl(s);
     if (s->shard) h.epoch = ++s->epoch;
     h.peers = peer ? s->peers_dev : nullptr;
     const CUtensorMap &tmW = use_restart_w ? s->tm_W[2] : s->tm_W[cur];
@@ -1652,15 +1725,18 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1));
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
-        als_shard_fold_kernel<<<(unsigned)(s->T_h * s->KP), TILE_UNITS, 0, st>>>(h, s->KP, xbuf);
-        MFB_CUDA(cudaGetLastError());
-        if (!peer && s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
-            mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
-            return MFB_ERR_CUDA;
+        const size_t gsm = (size_t)(s->KP * s->KP + 2) * sizeof(double);
+        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, gsm, st, pdl, h, s->KP, xbuf));
+        MFB_TRY(prof_mark(s));
+        if (!peer) {
+            if (s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
+                mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
+                return MFB_ERR_CUDA;
+            }
+            MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 256, gsm, st, pdl, h, s->KP,
+                                (const double *)(s->xchg + (size_t)s->T_h * s->KP * TILE_UNITS)));
+            MFB_TRY(prof_mark(s));
         }
-        als_shard_invert_kernel<<<1, 256, (size_t)(s->KP * s->KP + 2) * sizeof(double), st>>>(
-            h, s->KP, s->xchg + (size_t)s->T_h * s->KP * TILE_UNITS);
-        MFB_CUDA(cudaGetLastError());
         HalfParams hs = h;
         hs.P = s->xchg; hs.maxslots = 1;
         MFB_TRY(launch_half_dispatch(s, false, hs, tmW, 2));
@@ -1672,14 +1748,14 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     w.P = s->P_w; w.maxslots = s->maxslots_w;
     w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
     MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt]));
-    if (s->shard) {
+    if (s->shard && !peer) {
         cudaStream_t st = s->ctx->stream;
-        if (!peer && s->allreduce(s->allreduce_user, s->xscal, 4, (void *)st) != 0) {
+        if (s->allreduce(s->allreduce_user, s->xscal, 4, (void *)st) != 0) {
             mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
             return MFB_ERR_CUDA;
         }
-        als_shard_finish_kernel<<<1, 32, 0, st>>>(w);
-        MFB_CUDA(cudaGetLastError());
+        MFB_CUDA(launch_pdl(als_shard_finish_kernel, 1, 32, 0, st, pdl, w));
+        MFB_TRY(prof_mark(s));
     }
     return MFB_OK;
 }
@@ -1741,9 +1817,8 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
     return status;
 }
 
-int mfb_als_profile(mfb_als *s, int iters, double ms[4]) {
+int mfb_als_profile(mfb_als *s, int iters, double *ms) {
     MFB_ARG(s && ms && iters >= 1, "bad argument");
-    if (s->shard) { mfb_set_error("mfb_als_profile: not available for a row-sharded session"); return MFB_ERR_UNSUPPORTED; }
     MFB_CUDA(cudaSetDevice(s->ctx->device));
     std::vector<cudaEvent_t> ev;
     cudaEvent_t e0;
@@ -1756,17 +1831,20 @@ int mfb_als_profile(mfb_als *s, int iters, double ms[4]) {
     const int rc = mfb_als_iterate(s, iters, 1e-4, 1, &it, &conv);
     s->prof = nullptr;
     MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
-    double acc[4] = {0, 0, 0, 0};
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const size_t nk = ev.size() - 1;
+    // sharded, callback exchange: H stream, fold, invert, H solve, W stream, W solve, finish (collectives in between);
+    // sharded, peer memory: H stream, fold (+ wait for the peers, invert), H solve, W stream, W solve (+ wait, finish)
+    const size_t per = s->shard ? (als_peer_mode(s) ? 5 : 7) : 4;
     for (size_t i = 0; i < nk; ++i) {
         float t = 0.f;
         MFB_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
-        acc[i & 3] += t;
+        acc[i % per] += t;
     }
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (rc != MFB_OK) return rc;
-    if (nk != (size_t)4 * iters) { mfb_set_error("mfb_als_profile: expected %d kernel launches, saw %zu", 4 * iters, nk); return MFB_ERR_CUDA; }
-    for (int q = 0; q < 4; ++q) ms[q] = acc[q] / iters;
+    if (nk != per * iters) { mfb_set_error("mfb_als_profile: expected %d kernel launches, saw %zu", (int)per * iters, nk); return MFB_ERR_CUDA; }
+    for (size_t q = 0; q < per; ++q) ms[q] = acc[q] / iters;
     return MFB_OK;
 }
 
