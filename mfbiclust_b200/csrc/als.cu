@@ -75,17 +75,24 @@ struct HalfParams {
 };
 
 // Row-sharded mode over peer memory (NVLink / NVSwitch, cudaIpc mappings): every rank owns one SHARED BLOCK
-//   int flagsA[16] | int flagsB[16] | int fold_counter | .. | double xscal[2][4] @256 | double xchg[2][cnt] @512
-// mapped into every peer.  Epoch e uses the buffers of parity e & 1.  flagsA[q] = e: rank q's exchange buffer
-// [W_q'A_q | W_q'W_q] of epoch e is complete; flagsB[q] = e: rank q's W-step scalars of epoch e are complete (both
-// written by rank q into EVERY rank's block with a system-scope release store).  The consumers (invert / H-step
-// solve / finish kernels) read all ranks' buffers straight over NVLink and add them in rank order, so every rank
-// forms bit-identical sums: a one-shot all-reduce fused into the kernels that need the result, no collective launch.
+//   int flagsA[16] | int flagsB[16] | int fold_counter | stamps @192 | double xscal[2][4] @256 | int flagsG[16] @320
+//   | double xchg[2][cnt] @512 | double gram[2][64*64]
+// mapped into every peer.  Epoch e uses the buffers of parity e & 1.  flagsG[q] = e: rank q's W_q'W_q is in its
+// gram buffer; flagsA[q] = e: rank q's folded W_q'A_q is in its exchange buffer; flagsB[q] = e: rank q's W-step
+// scalars are complete (all written by rank q into EVERY rank's block with a system-scope release store).  The
+// consumers read all ranks' buffers straight over NVLink and add them in rank order, so every rank forms
+// bit-identical sums -- a one-shot all-reduce fused into the kernels that need the result, no collective launch:
+//   * W'W: the Gram side job of the H-step stream kernel publishes, waits, sums and inverts while A is streaming;
+//   * W'A: the fold kernel publishes and waits; the H-step solve kernel sums while it loads its right-hand sides;
+//   * scalars: the last warp of the W-step solve kernel publishes, waits, sums and closes the iteration.
 #define SHARD_MAXP 16
 #define SHARD_OFF_FLAGSB 64
 #define SHARD_OFF_COUNTER 128
+#define SHARD_OFF_STAMPS 192              // 8 x u64 debug time stamps (globaltimer) of the last fold launch
 #define SHARD_OFF_XSCAL 256
+#define SHARD_OFF_FLAGSG 320
 #define SHARD_OFF_XCHG 512
+#define SHARD_GRAM_DOUBLES 4096           // 64 x 64
 struct ShardPeers {
     int world, rank;
     long long cnt;                        // doubles per exchange buffer: T * KP * 128 + KP * KP
@@ -93,6 +100,9 @@ struct ShardPeers {
 };
 __device__ __forceinline__ double *shard_xchg(const ShardPeers *sp, int q, int parity) {
     return (double *)(sp->base[q] + SHARD_OFF_XCHG) + (size_t)parity * sp->cnt;
+}
+__device__ __forceinline__ double *shard_gram(const ShardPeers *sp, int q, int parity) {
+    return (double *)(sp->base[q] + SHARD_OFF_XCHG) + 2 * (size_t)sp->cnt + (size_t)parity * SHARD_GRAM_DOUBLES;
 }
 __device__ __forceinline__ double *shard_xscal(const ShardPeers *sp, int q, int parity) {
     return (double *)(sp->base[q] + SHARD_OFF_XSCAL) + parity * 4;
@@ -586,9 +596,33 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
         p.G[e] = s;
     }
     gram_bar();
-    // row-sharded H-step: this is only this rank's W_r'W_r; it is summed over the ranks with W_r'A_r and inverted
-    // by als_shard_invert_kernel
-    if (p.shard && !WSTEP) return;
+    // row-sharded H-step: this is only this rank's W_r'W_r
+    if (p.shard && !WSTEP) {
+        if (!p.peers) return;            // callback exchange: summed with W_r'A_r by the host, inverted by als_shard_invert_kernel
+        // peer memory: publish, wait for the other ranks' Gram matrices, add them in rank order -- all of it (and the
+        // inversion below) while the consumer warps are still streaming A
+        const ShardPeers *sp = p.peers;
+        const int par = p.epoch & 1;
+        double *mine = shard_gram(sp, sp->rank, par);
+        for (int e = t; e < KP * KP; e += GRAM_THREADS) mine[e] = sGm[e];
+        gram_bar();
+        if (t == 0) {
+            __threadfence_system();
+            for (int q = 0; q < sp->world; ++q) st_release_sys((int *)(sp->base[q] + SHARD_OFF_FLAGSG) + sp->rank, p.epoch);
+        }
+        if (t < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + t, p.epoch, t, p.ctrl);
+        gram_bar();
+        if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
+        for (int e = t; e < KP * KP; e += GRAM_THREADS) {
+            const int c1 = e / KP, c2 = e - c1 * KP;
+            double v = 0.0;
+            if (c1 < k && c2 < k)
+                for (int q = 0; q < sp->world; ++q) v += ldcg(shard_gram(sp, q, par) + e);
+            sGm[e] = v;
+            p.G[e] = v;
+        }
+        gram_bar();
+    }
     int sing;
     if constexpr (KP <= 16) {
         if (w == 0) {
@@ -1030,7 +1064,6 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const double *__rest
 // kernel reads it unchanged.  The W-step is local to a rank (its rows of W); only its three iteration scalars are
 // summed over the ranks (second, 32-byte collective).
 __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg) {
-    extern __shared__ double fold_sh[];   // KP*KP + 2 (peer mode: Gram sum + inverse by the last block)
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     const int tile = (int)blockIdx.x / KP, c = (int)blockIdx.x % KP, u = threadIdx.x;
@@ -1055,17 +1088,20 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
         }
     }
     xchg[((size_t)tile * KP + c) * TILE_UNITS + u] = r;
-    if (blockIdx.x == 0)
-        for (int e = u; e < KP * KP; e += TILE_UNITS) xchg[(size_t)p.T * KP * TILE_UNITS + e] = ldcg(&p.G[e]);
     const ShardPeers *sp = p.peers;
-    if (!sp) return;
-    // peer mode.  The last block to finish publishes the buffer to every rank (itself included), waits until all
-    // ranks have published theirs, adds the W_q'W_q in rank order and inverts: the H-step solve kernel follows directly.
+    if (!sp) {                                               // callback exchange: W_r'W_r rides in the same buffer
+        if (blockIdx.x == 0)
+            for (int e = u; e < KP * KP; e += TILE_UNITS) xchg[(size_t)p.T * KP * TILE_UNITS + e] = ldcg(&p.G[e]);
+        return;
+    }
+    if (u == 0) atomicMin((unsigned long long *)(sp->base[sp->rank] + SHARD_OFF_STAMPS) + 4, globaltimer_ns());
+    // peer mode.  The last block to finish publishes the buffer to every rank (itself included) and waits until all
+    // ranks have published theirs: the H-step solve kernel, next in the stream, reads them over NVLink.
     __shared__ int is_last;
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                                         // the block's stores happen-before thread 0's fence
     if (u == 0) {
         int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
+        __threadfence();
         const int last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
         if (last) {
             *counter = 0;
@@ -1076,36 +1112,11 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
     }
     __syncthreads();
     if (!is_last) return;
+    unsigned long long *stamp = (unsigned long long *)(sp->base[sp->rank] + SHARD_OFF_STAMPS);
+    if (u == 0) stamp[0] = globaltimer_ns();
     if (u < sp->world) shard_wait_flag((const int *)sp->base[sp->rank] + u, p.epoch, u, p.ctrl);
     __syncthreads();
-    if (*(volatile int *)&p.ctrl->stop) return;              // a peer never arrived
-    double *sG = fold_sh, *scr = fold_sh + KP * KP;
-    const int k = p.k, par = p.epoch & 1;
-    for (int e = u; e < KP * KP; e += TILE_UNITS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        double v = 0.0;
-        if (c1 < k && c2 < k) {
-            double g[SHARD_MAXP];
-#pragma unroll
-            for (int q = 0; q < SHARD_MAXP; ++q)
-                g[q] = (q < sp->world) ? ldcg(shard_xchg(sp, q, par) + (size_t)p.T * KP * TILE_UNITS + e) : 0.0;
-#pragma unroll
-            for (int q = 0; q < SHARD_MAXP; ++q) v += g[q];  // rank order: the same sum on every rank
-        }
-        sG[e] = v;
-        p.G[e] = v;
-    }
-    __syncthreads();
-    const int sing = gauss_jordan_inverse(sG, k, KP, u, TILE_UNITS, scr, [] { __syncthreads(); });
-    for (int e = u; e < KP * KP; e += TILE_UNITS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        p.Minv[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
-    }
-    if (u == 0 && sing) {                                    // R's solve() failure inside .fcnnls: reason 3
-        p.ctrl->reason = 3;
-        __threadfence();
-        p.ctrl->stop = 1;
-    }
+    if (u == 0) stamp[1] = globaltimer_ns();
 }
 
 // after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve() failure: reason 3)
@@ -1571,7 +1582,7 @@ static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int
         ALLOC(s->peers_dev, 1)
         {
             // the shared block is a cudaMalloc of its own (not pooled): it is exported through cudaIpc
-            const size_t bytes = SHARD_OFF_XCHG + 2 * s->xchg_cnt * sizeof(double);
+            const size_t bytes = SHARD_OFF_XCHG + (2 * s->xchg_cnt + 2 * SHARD_GRAM_DOUBLES) * sizeof(double);
             if (cudaMalloc((void **)&s->shared, bytes) != cudaSuccess) { cudaGetLastError(); s->shared = nullptr; mfb_als_end(s); mfb_set_error("cudaMalloc of the shared exchange block failed"); return MFB_ERR_ALLOC; }
             MFB_CUDA(cudaMemsetAsync(s->shared, 0, bytes, ctx->stream));
         }
@@ -1677,6 +1688,17 @@ int mfb_als_shard_connect(mfb_als *s, int rank, int world, const void *handles) 
     return MFB_OK;
 }
 
+// development aid: globaltimer stamps (ns) of the last fold launch: [0] last block elected, [1] peers arrived,
+// [4] earliest block past its stores (reset by the caller)
+int mfb_als_shard_stamps(mfb_als *s, unsigned long long out[8], int reset) {
+    MFB_ARG(s && s->shard && s->shared && out, "not a row-sharded session");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    MFB_CUDA(cudaMemcpy(out, s->shared + SHARD_OFF_STAMPS, 64, cudaMemcpyDeviceToHost));
+    if (reset) MFB_CUDA(cudaMemset(s->shared + SHARD_OFF_STAMPS, 0xff, 64));
+    return MFB_OK;
+}
+
 int mfb_als_shard_disconnect(mfb_als *s) {
     MFB_ARG(s && s->shard, "not a row-sharded session");
     MFB_ARG(s->epoch == 0, "disconnect before the first iteration");
@@ -1726,7 +1748,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1));
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
         const size_t gsm = (size_t)(s->KP * s->KP + 2) * sizeof(double);
-        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, gsm, st, pdl, h, s->KP, xbuf));
+        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, 0, st, pdl, h, s->KP, xbuf));
         MFB_TRY(prof_mark(s));
         if (!peer) {
             if (s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {

@@ -15,27 +15,32 @@
 template <typename Bar>
 __device__ int gauss_jordan_inverse(double *a, int k, int ld, int tid, int nthreads, double *scratch /* >= 2 doubles */,
                                     Bar bar) {
-    // R's solve() refuses the system when a pivot vanishes or rcond (1-norm) < .Machine$double.eps
+    // R's solve() refuses the system when a pivot vanishes or rcond (1-norm) < .Machine$double.eps.
+    // 1-norms: thread j sums column j (rows in order), the maximum is formed with an integer atomicMax on the bit
+    // pattern (non-negative doubles order like their bit patterns; NaN patterns order above +inf and fail isfinite)
+    unsigned long long *nrm = (unsigned long long *)scratch;
     if (tid == 0) {
-        double an = 0.0;
-        for (int j = 0; j < k; ++j) {
-            double cs = 0.0;
-            for (int i = 0; i < k; ++i) cs += fabs(a[i * ld + j]);
-            an = fmax(an, cs);
-        }
-        scratch[0] = an;
+        nrm[0] = 0ull;
         scratch[1] = 0.0;  // singular flag
     }
     bar();
+    for (int j = tid; j < k; j += nthreads) {
+        double cs = 0.0;
+        for (int i = 0; i < k; ++i) cs += fabs(a[i * ld + j]);
+        atomicMax(&nrm[0], (unsigned long long)__double_as_longlong(cs));
+    }
+    bar();
+    const double an = __longlong_as_double((long long)nrm[0]);
+    bar();
+    if (tid == 0) nrm[0] = 0ull;
     for (int p = 0; p < k; ++p) {
         double piv = a[p * ld + p];
         if (!(piv > 0.0) || !isfinite(piv)) {
             if (tid == 0) scratch[1] = 1.0;
             piv = 1.0;
         }
-        bar();
         const double ipiv = 1.0 / piv;
-        // eliminate column p from all other rows (uses the unscaled pivot row)
+        // eliminate column p from all other rows (uses the unscaled pivot row; row p and column p are only read)
         for (int e = tid; e < k * k; e += nthreads) {
             int i = e / k, j = e - i * k;
             if (i != p && j != p) a[i * ld + j] -= a[i * ld + p] * ipiv * a[p * ld + j];
@@ -50,14 +55,15 @@ __device__ int gauss_jordan_inverse(double *a, int k, int ld, int tid, int nthre
         if (tid == 0) a[p * ld + p] = ipiv;
         bar();
     }
+    for (int j = tid; j < k; j += nthreads) {
+        double cs = 0.0;
+        for (int i = 0; i < k; ++i) cs += fabs(a[i * ld + j]);
+        atomicMax(&nrm[0], (unsigned long long)__double_as_longlong(cs));
+    }
+    bar();
     if (tid == 0) {
-        double in = 0.0;
-        for (int j = 0; j < k; ++j) {
-            double cs = 0.0;
-            for (int i = 0; i < k; ++i) cs += fabs(a[i * ld + j]);
-            in = fmax(in, cs);
-        }
-        if (!isfinite(in) || scratch[0] * in * 2.220446049250313e-16 > 1.0) scratch[1] = 1.0;
+        const double in = __longlong_as_double((long long)nrm[0]);
+        if (!isfinite(in) || an * in * 2.220446049250313e-16 > 1.0) scratch[1] = 1.0;
     }
     bar();
     return scratch[1] != 0.0;
