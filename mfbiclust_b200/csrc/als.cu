@@ -623,17 +623,9 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
         }
         gram_bar();
     }
-    int sing;
-    if constexpr (KP <= 16) {
-        if (w == 0) {
-            const int sg = warp_gauss_jordan_inverse<KP>(sGm, k, KP, lane);
-            if (lane == 0) *gflag = sg;
-        }
-        gram_bar();
-        sing = *gflag;
-    } else {
-        sing = gauss_jordan_inverse(sGm, k, KP, t, GRAM_THREADS, sGm + KP * KP, [] { gram_bar(); });
-    }
+    // all 96 threads on the shared matrix (two barriers per pivot): a single warp with the rows in registers is
+    // latency-bound (~35 us at k = 16 and worse next to the streaming warps), which small or sharded matrices feel
+    const int sing = gauss_jordan_inverse(sGm, k, KP, t, GRAM_THREADS, sGm + KP * KP, [] { gram_bar(); });
     for (int e = t; e < KP * KP; e += GRAM_THREADS) {
         const int c1 = e / KP, c2 = e - c1 * KP;
         p.Minv[e] = (c1 < k && c2 < k) ? sGm[e] : 0.0;
