@@ -110,6 +110,18 @@ __device__ __forceinline__ double *shard_xscal(const ShardPeers *sp, int q, int 
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(int *p, int v) {
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// publish epoch `e` in flag slot `rank` of the flag array at byte offset `off` of EVERY rank's block: thread q of the
+// calling group signals rank q (one fence, then all remote stores in flight at once).  The caller has synchronised
+// the group after the data stores (bar.sync / __syncwarp), so they happen-before each signalling thread's fence.
+__device__ __forceinline__ void shard_publish(const ShardPeers *sp, int off, int e, int q) {
+    if (q < sp->world) {
+        __threadfence_system();
+        st_relaxed_sys((int *)(sp->base[q] + off) + sp->rank, e);
+    }
+}
 __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -453,9 +465,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
                 const ShardPeers *sp = p.peers;
                 double *xs2 = shard_xscal(sp, sp->rank, p.epoch & 1);
                 xs2[0] = sd2; xs2[1] = st1; xs2[2] = st2; xs2[3] = 0.0;
-                __threadfence_system();
-                for (int q = 0; q < sp->world; ++q)
-                    st_release_sys((int *)(sp->base[q] + SHARD_OFF_FLAGSB) + sp->rank, p.epoch);
             } else {
                 p.xscal[0] = sd2; p.xscal[1] = st1; p.xscal[2] = st2; p.xscal[3] = 0.0;
             }
@@ -468,15 +477,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         // peer mode: this warp also closes the iteration: wait for every rank's scalars, add them in rank order
         const ShardPeers *sp = p.peers;
         __syncwarp();
+        shard_publish(sp, SHARD_OFF_FLAGSB, p.epoch, lane);
         if (lane < sp->world)
             shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, p.epoch, lane, p.ctrl);
         __syncwarp();
+        // lane q fetches rank q's three sums (all remote loads in flight at once); lane 0 adds them in rank order
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+        if (lane < sp->world) {
+            const double *xq = shard_xscal(sp, lane, p.epoch & 1);
+            x0 = ldcg(xq + 0); x1 = ldcg(xq + 1); x2 = ldcg(xq + 2);
+        }
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int q = 0; q < sp->world; ++q) {
+            a0 += __shfl_sync(0xffffffffu, x0, q);
+            a1 += __shfl_sync(0xffffffffu, x1, q);
+            a2 += __shfl_sync(0xffffffffu, x2, q);
+        }
         if (lane == 0 && !*(volatile int *)&p.ctrl->stop) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            for (int q = 0; q < sp->world; ++q) {
-                const double *xq = shard_xscal(sp, q, p.epoch & 1);
-                a0 += ldcg(xq + 0); a1 += ldcg(xq + 1); a2 += ldcg(xq + 2);
-            }
             finish_iteration(p.ctrl, p.trace, a0, a1, a2);
             __threadfence();
         }
@@ -606,18 +623,20 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
         double *mine = shard_gram(sp, sp->rank, par);
         for (int e = t; e < KP * KP; e += GRAM_THREADS) mine[e] = sGm[e];
         gram_bar();
-        if (t == 0) {
-            __threadfence_system();
-            for (int q = 0; q < sp->world; ++q) st_release_sys((int *)(sp->base[q] + SHARD_OFF_FLAGSG) + sp->rank, p.epoch);
-        }
+        shard_publish(sp, SHARD_OFF_FLAGSG, p.epoch, t);
         if (t < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + t, p.epoch, t, p.ctrl);
         gram_bar();
         if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
         for (int e = t; e < KP * KP; e += GRAM_THREADS) {
             const int c1 = e / KP, c2 = e - c1 * KP;
             double v = 0.0;
-            if (c1 < k && c2 < k)
-                for (int q = 0; q < sp->world; ++q) v += ldcg(shard_gram(sp, q, par) + e);
+            if (c1 < k && c2 < k) {
+                double g[SHARD_MAXP];                        // all ranks' loads in flight, then added in rank order
+#pragma unroll
+                for (int q = 0; q < SHARD_MAXP; ++q) g[q] = (q < sp->world) ? ldcg(shard_gram(sp, q, par) + e) : 0.0;
+#pragma unroll
+                for (int q = 0; q < SHARD_MAXP; ++q) v += g[q];
+            }
             sGm[e] = v;
             p.G[e] = v;
         }
@@ -1095,15 +1114,12 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
         int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
         __threadfence();
         const int last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
-        if (last) {
-            *counter = 0;
-            __threadfence_system();
-            for (int q = 0; q < sp->world; ++q) st_release_sys((int *)sp->base[q] + sp->rank, p.epoch);
-        }
+        if (last) *counter = 0;
         is_last = last;
     }
     __syncthreads();
     if (!is_last) return;
+    shard_publish(sp, 0 /* flagsA */, p.epoch, u);
     unsigned long long *stamp = (unsigned long long *)(sp->base[sp->rank] + SHARD_OFF_STAMPS);
     if (u == 0) stamp[0] = globaltimer_ns();
     if (u < sp->world) shard_wait_flag((const int *)sp->base[sp->rank] + u, p.epoch, u, p.ctrl);
