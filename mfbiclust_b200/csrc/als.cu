@@ -1127,31 +1127,17 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
     if (u == 0) stamp[1] = globaltimer_ns();
 }
 
-// after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve() failure: reason 3)
+// callback exchange, after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve()
+// failure: reason 3).  (Peer-memory exchange: the Gram side job of the stream kernel does this, see gram_side_job.)
 __global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams p, int KP, const double *__restrict__ Gsum) {
     extern __shared__ double sh[];   // KP*KP + 2
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     double *sG = sh, *scr = sh + KP * KP;
     const int k = p.k;
-    const ShardPeers *sp = p.peers;
-    if (sp) {
-        if ((int)threadIdx.x < sp->world)
-            shard_wait_flag((const int *)sp->base[sp->rank] + threadIdx.x, p.epoch, (int)threadIdx.x, p.ctrl);
-        __syncthreads();
-        if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
-    }
     for (int e = threadIdx.x; e < KP * KP; e += 256) {
         const int c1 = e / KP, c2 = e - c1 * KP;
-        double v = 0.0;
-        if (c1 < k && c2 < k) {
-            if (sp) {
-                for (int q = 0; q < sp->world; ++q)          // rank order: the same sum on every rank
-                    v += ldcg(shard_xchg(sp, q, p.epoch & 1) + (size_t)p.T * KP * TILE_UNITS + e);
-            } else {
-                v = Gsum[e];
-            }
-        }
+        const double v = (c1 < k && c2 < k) ? Gsum[e] : 0.0;
         sG[e] = v;
         p.G[e] = v;
     }
@@ -1168,28 +1154,13 @@ __global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams 
     }
 }
 
-// after the all-reduce of the W-step scalars: close the iteration on every rank (identical inputs, identical result)
+// callback exchange, after the all-reduce of the W-step scalars: close the iteration on every rank (identical inputs,
+// identical result).  (Peer-memory exchange: the last warp of the W-step solve kernel does this.)
 __global__ void __launch_bounds__(32) als_shard_finish_kernel(const HalfParams p) {
     pdl_prologue();
     AlsCtrl *c = p.ctrl;
     if (*(volatile int *)&c->stop) return;
-    const ShardPeers *sp = p.peers;
-    if (!sp) {
-        if (threadIdx.x == 0) finish_iteration(c, p.trace, p.xscal[0], p.xscal[1], p.xscal[2]);
-        return;
-    }
-    const int lane = threadIdx.x;
-    if (lane < sp->world)
-        shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, p.epoch, lane, c);
-    __syncwarp();
-    if (lane == 0 && !*(volatile int *)&c->stop) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int q = 0; q < sp->world; ++q) {
-            const double *xq = shard_xscal(sp, q, p.epoch & 1);
-            a0 += ldcg(xq + 0); a1 += ldcg(xq + 1); a2 += ldcg(xq + 2);
-        }
-        finish_iteration(c, p.trace, a0, a1, a2);
-    }
+    if (threadIdx.x == 0) finish_iteration(c, p.trace, p.xscal[0], p.xscal[1], p.xscal[2]);
 }
 
 // r = F a  style helper for mfb_nnls: R[c][j] = sum_i C[i][c] B[i][j]  (small, test entry point)

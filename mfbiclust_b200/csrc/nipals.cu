@@ -31,6 +31,8 @@ struct NipalsParams {
     double *colabs;       // n
     double *phn;          // [nblocks][n] block-private normalised loading
     double *part;         // [nblocks][ncomp + 4] per-block partials
+    double *spart;        // [nblocks][m] per-block partial scores (complete-data S3: blocks own COLUMNS)
+    int chunk;            // rows of the shared-memory score accumulator per pass
     int *status;          // 0 ok, 1 maxiter reached on some component, 2 constant column under scale
 };
 
@@ -263,9 +265,90 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
                 pp_den = p2;
                 __syncthreads();
             }
-            // S3: th_new = x ph / (ph'ph) for this block's rows, 256 rows per pass: warp w sums its eighth of the
-            // columns for all eight 32-row groups of the pass (two columns x eight row groups of loads in flight)
-            for (int64_t rb = r0; rb < r1; rb += 256) {
+            // S3, complete data: th_new = x ph / (ph'ph) with the blocks owning COLUMNS, like S1: a block streams whole
+            // column segments (contiguous, DRAM-page friendly; four columns x four rows of loads in flight per thread)
+            // and accumulates its partial scores for `chunk` rows in shared memory (thread t only ever touches the
+            // entries t, t + 256, ...: no barriers), then the blocks' partials are added in block order by the owner of
+            // each row.  (Row-owning blocks -- the missing-value branch below -- read 768-byte pieces 160 KB apart.)
+            if (!p.has_na) {
+                const int nbc = (n < (int64_t)nb) ? (int)n : nb;            // blocks that own columns
+                if (b < nbc) {
+                    const int64_t jlo = n * b / nbc, jhi = n * (b + 1) / nbc;
+                    for (int64_t c0 = 0; c0 < m; c0 += p.chunk) {
+                        const int len = (int)((m - c0 < p.chunk) ? m - c0 : p.chunk);
+                        for (int i = tid; i < len; i += NIP_THREADS) nsm[i] = 0.0;
+                        int64_t j = jlo;
+                        for (; j + 3 < jhi; j += 4) {
+                            const double q0 = phn[j], q1 = phn[j + 1], q2 = phn[j + 2], q3 = phn[j + 3];
+                            const double *ca = p.x + j * ld + c0;
+                            int i = tid;
+                            for (; i + 3 * NIP_THREADS < len; i += 4 * NIP_THREADS) {
+                                double v[4][4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) v[c][u] = __ldcg(&ca[c * ld + i + u * NIP_THREADS]);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    nsm[i + u * NIP_THREADS] += (v[0][u] * q0 + v[1][u] * q1) + (v[2][u] * q2 + v[3][u] * q3);
+                            }
+                            for (; i < len; i += NIP_THREADS)
+                                nsm[i] += (__ldcg(&ca[i]) * q0 + __ldcg(&ca[ld + i]) * q1) +
+                                          (__ldcg(&ca[2 * ld + i]) * q2 + __ldcg(&ca[3 * ld + i]) * q3);
+                        }
+                        for (; j < jhi; ++j) {
+                            const double q0 = phn[j];
+                            const double *ca = p.x + j * ld + c0;
+                            for (int i = tid; i < len; i += NIP_THREADS) nsm[i] += __ldcg(&ca[i]) * q0;
+                        }
+                        double *dst = p.spart + (size_t)b * m + c0;
+                        for (int i = tid; i < len; i += NIP_THREADS) dst[i] = nsm[i];
+                    }
+                }
+                grid.sync();
+                // add the blocks' partials for this block's rows in block order: 256 rows per pass, warp w takes its
+                // eighth of the blocks for all eight 32-row groups (4 blocks x 8 groups of loads in flight), then the
+                // warps' sums are added in warp order
+                for (int64_t rb = r0; rb < r1; rb += 256) {
+                    const int blo = nbc * warp / NIP_WARPS, bhi = nbc * (warp + 1) / NIP_WARPS;
+                    double acc[8];
+                    bool ok[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) { acc[g] = 0.0; ok[g] = rb + 32 * g + lane < r1; }
+                    int bb = blo;
+                    for (; bb + 3 < bhi; bb += 4) {
+                        double v[4][8];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                v[u][g] = ok[g] ? __ldcg(&p.spart[(size_t)(bb + u) * m + rb + 32 * g + lane]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) acc[g] += v[u][g];
+                    }
+                    for (; bb < bhi; ++bb)
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            if (ok[g]) acc[g] += __ldcg(&p.spart[(size_t)bb * m + rb + 32 * g + lane]);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) nsm[warp * 256 + 32 * g + lane] = acc[g];
+                    __syncthreads();
+                    const int64_t i = rb + tid;
+                    if (tid < 256 && i < r1) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int w = 0; w < NIP_WARPS; ++w) sacc += nsm[w * 256 + tid];
+                        p.th_old[i] = p.th[i];
+                        p.th[i] = sacc / pp_den;
+                    }
+                    __syncthreads();
+                }
+            }
+            // S3, missing values: this block's rows, 256 rows per pass: warp w sums its eighth of the columns for all
+            // eight 32-row groups of the pass (two columns x eight row groups of loads in flight)
+            for (int64_t rb = r0; p.has_na && rb < r1; rb += 256) {
                 const int64_t jlo = n * warp / NIP_WARPS, jhi = n * (warp + 1) / NIP_WARPS;
                 double acc[8], dacc[8];
 #pragma unroll
@@ -421,16 +504,22 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     if (rc != MFB_OK) return rc;
     const int has_na = stats[3] > 0;
     const int64_t m = x->m, n = x->n, ld = x->lda;
+    // shared memory: the 256-row pass scratch of the missing-value S3, or the score accumulator of the complete-data
+    // S3 (the rows are cut into equal chunks of at most 12288 = 96 KB, so that two blocks still fit an SM)
+    const int64_t nchunk = (m + 12287) / 12288;
+    const int chunk = (int)(((m + nchunk - 1) / nchunk + NIP_THREADS - 1) / NIP_THREADS * NIP_THREADS);
+    size_t smem = 2 * NIP_WARPS * 256 * sizeof(double);
+    if (!has_na && (size_t)chunk * sizeof(double) > smem) smem = (size_t)chunk * sizeof(double);
+    MFB_CUDA(cudaFuncSetAttribute(nipals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb_max = 0;
-    MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, nipals_kernel, NIP_THREADS,
-                                                           2 * NIP_WARPS * 256 * sizeof(double)));
+    MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, nipals_kernel, NIP_THREADS, smem));
     int nb = nb_max * ctx->sm_count;
     if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;       // two blocks per SM: twice the loads in flight
     const int64_t want = (m + NIP_THREADS - 1) / NIP_THREADS > n ? (m + NIP_THREADS - 1) / NIP_THREADS : n;
     if (want < nb) nb = (int)(want < 1 ? 1 : want);
     const size_t PW = ncomp + 4;
     size_t nd = (size_t)ld * n + (size_t)m * ncomp + (size_t)n * ncomp + ncomp + 2 * (size_t)m + 2 * (size_t)n + (size_t)nb * PW +
-                (size_t)nb * n;
+                (size_t)nb * n + (has_na ? 0 : (size_t)nb * m);
     DevBuf pool(ctx);
     double *buf = nullptr;
     int *ibuf = nullptr;
@@ -439,7 +528,8 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
         if (rc2 == MFB_OK) rc2 = pool.alloc(&ibuf, (size_t)ncomp + 1);
         if (rc2 != MFB_OK) return rc2;
     }
-    MFB_CUDA(cudaMemsetAsync(buf, 0, nd * sizeof(double), st));
+    // (the working copy of x, the first ld * n doubles, is overwritten below: zero only what follows it)
+    MFB_CUDA(cudaMemsetAsync(buf + (size_t)ld * n, 0, (nd - (size_t)ld * n) * sizeof(double), st));
     MFB_CUDA(cudaMemsetAsync(ibuf, 0, (ncomp + 1) * sizeof(int), st));
     NipalsParams p;
     p.x = buf;
@@ -452,6 +542,8 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     p.colabs = p.ph + n;
     p.part = p.colabs + n;
     p.phn = p.part + (size_t)nb * PW;
+    p.spart = p.phn + (size_t)nb * n;
+    p.chunk = chunk;
     p.iters = ibuf;
     p.status = ibuf + ncomp;
     p.m = m; p.n = n; p.ld = ld;
@@ -460,8 +552,7 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     p.has_na = has_na;
     MFB_CUDA(cudaMemcpyAsync(p.x, x->d, (size_t)ld * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     void *args[] = {&p};
-    MFB_CUDA(cudaLaunchCooperativeKernel((void *)nipals_kernel, dim3(nb), dim3(NIP_THREADS), args,
-                                         2 * NIP_WARPS * 256 * sizeof(double), st));
+    MFB_CUDA(cudaLaunchCooperativeKernel((void *)nipals_kernel, dim3(nb), dim3(NIP_THREADS), args, smem, st));
     std::vector<double> hE(ncomp);
     std::vector<int> hI(ncomp + 1);
     MFB_CUDA(cudaMemcpyAsync(scores, p.T, (size_t)m * ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));
