@@ -36,8 +36,8 @@ sys.path.insert(0, ROOT)
 
 M_ROWS, N_COLS, RANK = 20000, 5000, 16
 # dram__bytes_read.sum + dram__bytes_write.sum per stream-kernel launch from the committed ncu --set full capture
-# (profiles/r01_final_als_ncu_full_selected.csv: H-step 811.0 + 17.4 MB, W-step 801.1 + 18.5 MB; mean of both)
-TRAFFIC_BYTES_PER_LAUNCH = 824.0e6
+# (profiles/r01e_als_ncu_full_selected.csv: H-step 809.3 + 18.1 MB, W-step 801.1 + 20.2 MB; mean of both)
+TRAFFIC_BYTES_PER_LAUNCH = 824.4e6
 METRIC = "ALS-NMF iters/s @20kx5k k=16 (FP64)"
 UNIT = "iter/s"
 WORKLOAD = ("ALS-NMF 20000x5000 k=16 FP64, genSimData-shaped (D4, BASELINE configs[3]), fixed iterations, "
