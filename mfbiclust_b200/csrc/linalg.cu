@@ -223,10 +223,25 @@ __device__ __forceinline__ double tri_block_sum(double v, double *sh) {
 }
 
 // Householder reduction to tridiagonal form (LAPACK dsytd2, lower): A = Q T Q', reflector i stored in A[i+2:N, i]
-// (v[i+1] = 1 implicit), tau[i], T = (d, e).  One cooperative launch, two grid-wide barriers per column.  Block b
-// owns the columns c with c % gridDim.x == b of the (symmetric, fully stored) trailing block for both the
-// matrix-vector product p = tau A22 v and the rank-2 update A22 -= v w' + w v'; it works on four columns at a time
-// so that every thread has ~20 independent loads in flight (the sweep is latency-, not bandwidth-bound).
+// (v[i+1] = 1 implicit), tau[i], T = (d, e).  One cooperative launch, ONE pass over the trailing block and ONE
+// grid-wide barrier per column: the rank-2 update of step i,  A22 -= v w' + w v',  is fused with the matrix-vector
+// product of step i + 1,  p = tau A22' v',  on the freshly updated entries.  That is possible because the next
+// reflector only depends on column i + 1 of the updated block, which every block recomputes for itself from the old
+// column and the vectors v, w (an O(N) job) before it starts the pass.  Block b owns the columns c with
+// c % gridDim.x == b of the (symmetric, fully stored) trailing block; it works on four columns and two rows at a
+// time so that every thread has ~16 independent loads in flight.  Arithmetic and summation orders are those of the
+// two-pass formulation (update expression a - (v_r w_c + w_r v_c), row-strided sums, warp -> block folds).
+// vbuf / pbuf hold two vectors each (current / next reflector and product).
+__device__ __forceinline__ void tri_reflector(double alpha, double xnorm, double &beta, double &tq, double &scale) {
+    if (xnorm == 0.0) {
+        beta = alpha; tq = 0.0; scale = 0.0;
+    } else {
+        beta = -copysign(hypot(alpha, xnorm), alpha);
+        tq = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+}
+
 __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t N, double *d, double *e,
                                                               double *tau, double *vbuf, double *pbuf,
                                                               double *part) {
@@ -236,28 +251,20 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
     __shared__ double spv[4];
     const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    for (int64_t i = 0; i + 1 < N; ++i) {
-        // phase 0 (redundant per block): reflector from column i
-        // (column i was last written by its owner block before the grid barrier: read it through L2)
-        const double alpha = __ldcg(&A[(i + 1) + i * N]);
+    double tq;                   // tau of the current reflector (every block computes it for itself)
+    // ---- prologue: reflector 0 from the untouched column 0, p_0 = tau_0 A22 v_0 on the owned columns ----
+    {
+        const double alpha = __ldcg(&A[1]);
         double q = 0.0;
-        for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) { const double v = __ldcg(&A[r + i * N]); q += v * v; }
+        for (int64_t r = 2 + tid; r < N; r += TRI_THREADS) { const double v = __ldcg(&A[r]); q += v * v; }
         const double xnorm = sqrt(tri_block_sum(q, sh));
-        double beta, tq, scale;
-        if (xnorm == 0.0) {
-            beta = alpha; tq = 0.0; scale = 0.0;
-        } else {
-            beta = -copysign(hypot(alpha, xnorm), alpha);
-            tq = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) vbuf[r] = (r == i + 1) ? 1.0 : __ldcg(&A[r + i * N]) * scale;
-        if (b == 0 && tid == 0) { d[i] = __ldcg(&A[i + i * N]); e[i] = beta; tau[i] = tq; }
+        double beta, scale;
+        tri_reflector(alpha, xnorm, beta, tq, scale);
+        for (int64_t r = 1 + tid; r < N; r += TRI_THREADS) vbuf[r] = (r == 1) ? 1.0 : __ldcg(&A[r]) * scale;
+        if (b == 0 && tid == 0) { d[0] = __ldcg(&A[0]); e[0] = beta; tau[0] = tq; }
         __syncthreads();
-        const double *v = vbuf;      // (no __restrict__ / read-only path: these buffers are rewritten inside the kernel)
-        // first owned column >= i + 1
-        const int64_t cfirst = (i + 1) + (((int64_t)b - (i + 1)) % nb + nb) % nb;
-        // phase 1: p = tau * A22 v on the owned columns
+        const double *v = vbuf;
+        const int64_t cfirst = 1 + (((int64_t)b - 1) % nb + nb) % nb;
         double pvs = 0.0;
         for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
             const double *col[4];
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
             }
             double s4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 2
-            for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) {
+            for (int64_t r = 1 + tid; r < N; r += TRI_THREADS) {
                 const double vr = v[r];
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) s4[qq] += col[qq][r] * vr;
@@ -296,12 +303,42 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         __syncthreads();
         if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
         grid.sync();
-        // phase 2: w = p - (tau/2)(p'v) v ;  A22 -= v w' + w v' on the owned columns
+    }
+    for (int64_t i = 0; i + 1 < N; ++i) {
+        const int cur = (int)(i & 1);
+        const double *v = vbuf + (size_t)cur * N, *pb = pbuf + (size_t)cur * N;
+        double *vn = vbuf + (size_t)(cur ^ 1) * N, *pn = pbuf + (size_t)(cur ^ 1) * N;
+        // keep reflector i for the back-transformation (nobody reads column i any more)
+        if (b == 0)
+            for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) A[r + i * N] = v[r];
+        // w = p - (tau/2)(p'v) v
         double pv = 0.0;
         for (int bb = tid; bb < nb; bb += TRI_THREADS) pv += __ldcg(&part[bb]);
         pv = tri_block_sum(pv, sh);
         const double alpha2 = -0.5 * tq * pv;
-        const double *pb = pbuf;
+        // column j = i + 1 of the updated block, recomputed by every block: a'[r] = A[r,j] - (v_r w_j + w_r v_j)
+        const int64_t j = i + 1;
+        const double vj = v[j], wj = __ldcg(&pb[j]) + alpha2 * vj;
+        auto upd = [&](int64_t r) {
+            const double vr = v[r], wr = __ldcg(&pb[r]) + alpha2 * vr;
+            return __ldcg(&A[r + j * N]) - (vr * wj + wr * vj);
+        };
+        if (j == N - 1) {            // only the last diagonal entry is left
+            if (b == 0 && tid == 0) { d[N - 1] = upd(N - 1); e[N - 1] = 0.0; tau[N - 1] = 0.0; }
+            break;
+        }
+        const double alpha = upd(j + 1);
+        double q = 0.0;
+        for (int64_t r = j + 2 + tid; r < N; r += TRI_THREADS) { const double a = upd(r); q += a * a; }
+        const double xnorm = sqrt(tri_block_sum(q, sh));
+        double beta, tqn, scale;
+        tri_reflector(alpha, xnorm, beta, tqn, scale);
+        for (int64_t r = j + 1 + tid; r < N; r += TRI_THREADS) vn[r] = (r == j + 1) ? 1.0 : upd(r) * scale;
+        if (b == 0 && tid == 0) { d[j] = upd(j); e[j] = beta; tau[j] = tqn; }
+        __syncthreads();
+        // fused pass over the owned columns c >= j + 1, rows r >= j + 1:  a' = a - (v_r w_c + w_r v_c);  s_c += a' v'_r
+        const int64_t cfirst = (j + 1) + (((int64_t)b - (j + 1)) % nb + nb) % nb;
+        double pvs = 0.0;
         for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
             double *col[4];
             double vc[4], wc[4];
@@ -310,15 +347,17 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
                 const int64_t cq = c0 + qq * (int64_t)nb;
                 const bool ok = cq < N;
                 col[qq] = ok ? A + cq * N : nullptr;
-                vc[qq] = ok ? __ldcg(&vbuf[cq]) : 0.0;
-                wc[qq] = ok ? __ldcg(&pbuf[cq]) + alpha2 * vc[qq] : 0.0;
+                vc[qq] = ok ? v[cq] : 0.0;
+                wc[qq] = ok ? __ldcg(&pb[cq]) + alpha2 * vc[qq] : 0.0;
             }
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
             // two rows per trip, all loads before the stores (the compiler cannot reorder them itself)
-            for (int64_t r = i + 1 + tid; r < N; r += 2 * TRI_THREADS) {
+            for (int64_t r = j + 1 + tid; r < N; r += 2 * TRI_THREADS) {
                 const int64_t r2 = r + TRI_THREADS;
                 const bool ok2 = r2 < N;
-                const double vr = v[r], wr = __ldcg(&pb[r]) + alpha2 * vr;
+                const double vr = v[r], wr = __ldcg(&pb[r]) + alpha2 * vr, nr = vn[r];
                 const double vr2 = ok2 ? v[r2] : 0.0, wr2 = ok2 ? __ldcg(&pb[r2]) + alpha2 * vr2 : 0.0;
+                const double nr2 = ok2 ? vn[r2] : 0.0;
                 double a1[4], a2[4];
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
@@ -328,19 +367,41 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     if (col[qq]) {
-                        col[qq][r] = a1[qq] - (vr * wc[qq] + wr * vc[qq]);
-                        if (ok2) col[qq][r2] = a2[qq] - (vr2 * wc[qq] + wr2 * vc[qq]);
+                        const double n1 = a1[qq] - (vr * wc[qq] + wr * vc[qq]);
+                        col[qq][r] = n1;
+                        s4[qq] += n1 * nr;
+                        if (ok2) {
+                            const double n2 = a2[qq] - (vr2 * wc[qq] + wr2 * vc[qq]);
+                            col[qq][r2] = n2;
+                            s4[qq] += n2 * nr2;
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const double t = warp_sum(s4[qq]);
+                if (lane == 0) shq[warp][qq] = t;
+            }
+            __syncthreads();
+            if (tid < 4) {
+                const int64_t cq = c0 + tid * (int64_t)nb;
+                if (cq < N) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < TRI_THREADS / 32; ++w) t += shq[w][tid];
+                    const double pc = tqn * t;
+                    pn[cq] = pc;
+                    pvs += pc * vn[cq];
+                }
+            }
+            __syncthreads();
         }
-        if (b == 0)   // keep the reflector for the back-transformation
-            for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) A[r + i * N] = vbuf[r];
+        if (tid < 4) spv[tid] = pvs;
+        __syncthreads();
+        if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
+        tq = tqn;
         grid.sync();
-    }
-    if (b == 0 && tid == 0) {
-        d[N - 1] = A[(N - 1) + (N - 1) * N];
-        if (N >= 1) { e[N - 1] = 0.0; tau[N - 1] = 0.0; }
     }
 }
 
@@ -539,12 +600,12 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
     cudaStream_t st = ctx->stream;
     DevBuf buf(ctx);
     double *wk = nullptr;
-    const size_t nwork = (size_t)5 * N + (size_t)ctx->sm_count + (size_t)k * 5 * N + 16;
+    const size_t nwork = (size_t)7 * N + (size_t)ctx->sm_count + (size_t)k * 5 * N + 16;
     {
         int rc = buf.alloc(&wk, nwork);
         if (rc != MFB_OK) return rc;
     }
-    double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + N, *part = pbuf + N;
+    double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + 2 * N, *part = pbuf + 2 * N;
     double *work = part + ctx->sm_count;
     if (N == 1) {
         MFB_CUDA(cudaMemcpyAsync(evals, G, sizeof(double), cudaMemcpyDeviceToDevice, st));
