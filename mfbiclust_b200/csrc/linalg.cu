@@ -329,10 +329,12 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         }
         const double alpha = upd(j + 1);
         double q = 0.0;
+#pragma unroll 4
         for (int64_t r = j + 2 + tid; r < N; r += TRI_THREADS) { const double a = upd(r); q += a * a; }
         const double xnorm = sqrt(tri_block_sum(q, sh));
         double beta, tqn, scale;
         tri_reflector(alpha, xnorm, beta, tqn, scale);
+#pragma unroll 4
         for (int64_t r = j + 1 + tid; r < N; r += TRI_THREADS) vn[r] = (r == j + 1) ? 1.0 : upd(r) * scale;
         if (b == 0 && tid == 0) { d[j] = upd(j); e[j] = beta; tau[j] = tqn; }
         __syncthreads();
@@ -600,13 +602,13 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
     cudaStream_t st = ctx->stream;
     DevBuf buf(ctx);
     double *wk = nullptr;
-    const size_t nwork = (size_t)7 * N + (size_t)ctx->sm_count + (size_t)k * 5 * N + 16;
+    const size_t nwork = (size_t)7 * N + (size_t)2 * ctx->sm_count + (size_t)k * 5 * N + 16;
     {
         int rc = buf.alloc(&wk, nwork);
         if (rc != MFB_OK) return rc;
     }
     double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + 2 * N, *part = pbuf + 2 * N;
-    double *work = part + ctx->sm_count;
+    double *work = part + 2 * ctx->sm_count;
     if (N == 1) {
         MFB_CUDA(cudaMemcpyAsync(evals, G, sizeof(double), cudaMemcpyDeviceToDevice, st));
         const double one = 1.0;
@@ -615,7 +617,17 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
         return MFB_OK;
     }
     int nb = (int)((N + 7) / 8);          // one warp per column of the trailing block, 8 warps per block
-    if (nb > ctx->sm_count) nb = ctx->sm_count;
+    {
+        // large matrices stream from HBM: two blocks per SM keep twice the loads in flight
+        int per_sm = 1;
+        if (N >= 4096 && !getenv("MFB_TRI_ONE_BLOCK")) {
+            int occ = 0;
+            MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tridiag_kernel, TRI_THREADS, 0));
+            if (occ >= 2) per_sm = 2;
+        }
+        if (nb > per_sm * ctx->sm_count) nb = per_sm * ctx->sm_count;
+    }
+    if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
     if (nb < 1) nb = 1;
     void *args[] = {&G, &N, &d, &e, &tau, &vbuf, &pbuf, &part};
     MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_kernel, dim3(nb), dim3(TRI_THREADS), args, 0, st));
