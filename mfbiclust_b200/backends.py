@@ -791,6 +791,19 @@ def _iters_until_stable(distr, distrOld, tol, winner, keys, limit):
     return limit
 
 
+def _earliest_stop(distr, tol, limit):
+    """Lower bound on the number of further outer iterations before ``auto_bcv``'s stopping rule can fire on ANY
+    sequence of winners.  The rule needs, for the winner w of the deciding iteration,
+    ``((d_w + 1) / (S + 1) - d_w / S)^2 < tol`` (S = sum of the counts before it); the left side decreases with
+    d_w, and after t - 1 further iterations no count exceeds ``max(distr) + t - 1``: the path on which the current
+    leader wins every time fires first.  Iterations up to this bound can be computed as ONE batch without waste."""
+    S, D = sum(distr.values()), max(distr.values())
+    for t in range(1, limit + 1):
+        if ((D + t) / (S + t) - (D + t - 1) / (S + t - 1)) ** 2 < tol:
+            return t
+    return limit
+
+
 def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verbose=False, interactive=True,
              rng=None, ctx=None, group=None, speculate=None):
     """``auto_bcv(Y, ks, holdouts = 3L, maxIter = 100L, tol = 1e-4, bestOnly = FALSE, verbose = FALSE,
@@ -800,7 +813,9 @@ def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verb
     ``speculate = B`` (default: the number of ranks, i.e. 1 on a single GPU) the folds of the next B outer
     iterations are drawn in order, their ``B * holdouts^2`` cells are computed as one sharded batch, and the
     stopping rule is then applied iteration by iteration exactly as in R; iterations computed past the one that
-    converges are discarded.  ``best``, ``counts`` and the iteration count are therefore identical for every B and
+    converges are discarded.  Independently of B, the iterations the rule provably cannot do without
+    (:func:`_earliest_stop`: 22 on an 11-candidate grid, 25 on a 20-candidate grid from a fresh start) are always
+    computed as one batch, so their cells fill all streams and all ranks.  ``best``, ``counts`` and the iteration count are therefore identical for every B and
     every number of GPUs; only the number of uniforms consumed from ``rng`` after convergence differs."""
     ctx = ctx or _cabi.default_context()
     rng = rng or HostRng()
@@ -831,9 +846,12 @@ def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verb
         converged = False
         last_best = None
         while not converged and i < maxIter:                                   # :56
-            # batch size: never more than B, and no more than the stopping rule can use if the current winner
-            # keeps winning (it cannot fire earlier on that path; any other path is simply continued next batch)
-            nb = min(B, maxIter - i, _iters_until_stable(distr, distrOld, tol, last_best, keys, B))
+            # batch size: every iteration the stopping rule provably cannot do without (no waste, any number of
+            # ranks); beyond that, speculation: never more than B, and no more than the rule can use if the current
+            # winner keeps winning (it cannot fire earlier on that path; any other path is continued next batch)
+            nb = max(_earliest_stop(distr, tol, maxIter - i),
+                     min(B, _iters_until_stable(distr, distrOld, tol, last_best, keys, B)))
+            nb = min(nb, maxIter - i)
             folds = [draw_folds(rng, n, p, holdouts) for _ in range(nb)]       # in order: the stream R would consume
             vals = bcv_batch(Yd, keys, holdouts, folds, ctx=ctx, group=group)  # :58, nb calls of bcv()
             for j in range(nb):

@@ -195,3 +195,45 @@ def test_auto_bcv_batch_sizing_matches_the_stopping_rule():
     d[11] += 19
     o[11] += 18
     assert _iters_until_stable(d, o, 1e-4, 11, keys, 8) == 3
+
+
+def test_auto_bcv_earliest_stop_is_a_lower_bound_on_every_path():
+    """The first batch of auto_bcv covers every iteration the stopping rule (R/bcv.R:69-84) cannot do without: on no
+    sequence of winners may the rule fire before ``_earliest_stop`` iterations, and on the leader-wins-all path it
+    fires exactly there (vignette: 22 on 11 candidates)."""
+    from mfbiclust_b200.backends import _earliest_stop
+    rs = np.random.default_rng(0)
+    for nkeys in (2, 5, 11, 20, 50):
+        keys = list(range(1, nkeys + 1))
+        for trial in range(40):
+            distr = {k: 1 for k in keys}
+            old = dict(distr)
+            # a random history first (the bound must hold from any state)
+            for _ in range(int(rs.integers(0, 12))):
+                old = dict(distr)
+                distr[int(rs.choice(keys))] += 1
+            L = _earliest_stop(distr, 1e-4, 200)
+            favourite = int(rs.choice(keys))
+            pfav = rs.random()
+            d, o = dict(distr), dict(distr)
+            for t in range(1, L):
+                w = favourite if rs.random() < pfav else int(rs.choice(keys))
+                d[w] += 1
+                sd, so = sum(d.values()), sum(o.values())
+                assert not all((d[k] / sd - o[k] / so) ** 2 < 1e-4 for k in keys), (nkeys, trial, t, L)
+                o = dict(d)
+        # leader wins all: fires exactly at L
+        distr = {k: 1 for k in keys}
+        L = _earliest_stop(distr, 1e-4, 500)
+        d, o = dict(distr), dict(distr)
+        fired = None
+        for t in range(1, L + 1):
+            d[keys[-1]] += 1
+            sd, so = sum(d.values()), sum(o.values())
+            if all((d[k] / sd - o[k] / so) ** 2 < 1e-4 for k in keys):
+                fired = t
+                break
+            o = dict(d)
+        assert fired == L, (nkeys, fired, L)
+    assert _earliest_stop({k: 1 for k in range(11)}, 1e-4, 100) == 22
+    assert _earliest_stop({k: 1 for k in range(20)}, 1e-4, 100) == 25
