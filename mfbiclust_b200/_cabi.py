@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmfbiclust_cuda.so")
+# (MFBICLUST_LIB: another build of the same library, for A/B runs during development)
+LIB_PATH = os.environ.get("MFBICLUST_LIB") or os.path.join(_HERE, "lib", "libmfbiclust_cuda.so")
 
 MFB_OK, MFB_SINGULAR, MFB_ZERO_ROW, MFB_NOT_CONVERGED = 0, 1, 2, 3
 MFB_ERR_ARG, MFB_ERR_CUDA, MFB_ERR_ALLOC, MFB_ERR_NEGATIVE, MFB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5

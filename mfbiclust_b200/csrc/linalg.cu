@@ -231,7 +231,7 @@ __device__ __forceinline__ double tri_block_sum(double v, double *sh) {
 // c % gridDim.x == b of the (symmetric, fully stored) trailing block; it works on four columns and two rows at a
 // time so that every thread has ~16 independent loads in flight.  Arithmetic and summation orders are those of the
 // two-pass formulation (update expression a - (v_r w_c + w_r v_c), row-strided sums, warp -> block folds).
-// vbuf / pbuf hold two vectors each (current / next reflector and product).
+// vbuf / pbuf / part hold two generations each (current / next reflector, product and partial sums of p'v).
 __device__ __forceinline__ void tri_reflector(double alpha, double xnorm, double &beta, double &tq, double &scale) {
     if (xnorm == 0.0) {
         beta = alpha; tq = 0.0; scale = 0.0;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         }
         if (tid < 4) spv[tid] = pvs;
         __syncthreads();
-        if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
+        if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);      // parity 0: read by iteration 0
         grid.sync();
     }
     for (int64_t i = 0; i + 1 < N; ++i) {
@@ -312,8 +312,10 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         if (b == 0)
             for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) A[r + i * N] = v[r];
         // w = p - (tau/2)(p'v) v
+        // (the partial sums are double-buffered like v and p: a fast block finishes its pass, and writes its next
+        //  partial, while a slow one has not read this iteration's yet -- there is only one barrier per column)
         double pv = 0.0;
-        for (int bb = tid; bb < nb; bb += TRI_THREADS) pv += __ldcg(&part[bb]);
+        for (int bb = tid; bb < nb; bb += TRI_THREADS) pv += __ldcg(&part[(size_t)cur * nb + bb]);
         pv = tri_block_sum(pv, sh);
         const double alpha2 = -0.5 * tq * pv;
         // column j = i + 1 of the updated block, recomputed by every block: a'[r] = A[r,j] - (v_r w_j + w_r v_j)
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         }
         if (tid < 4) spv[tid] = pvs;
         __syncthreads();
-        if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
+        if (tid == 0) part[(size_t)(cur ^ 1) * nb + b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
         tq = tqn;
         grid.sync();
     }
@@ -602,13 +604,13 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
     cudaStream_t st = ctx->stream;
     DevBuf buf(ctx);
     double *wk = nullptr;
-    const size_t nwork = (size_t)7 * N + (size_t)2 * ctx->sm_count + (size_t)k * 5 * N + 16;
+    const size_t nwork = (size_t)7 * N + (size_t)4 * ctx->sm_count + (size_t)k * 5 * N + 16;
     {
         int rc = buf.alloc(&wk, nwork);
         if (rc != MFB_OK) return rc;
     }
     double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + 2 * N, *part = pbuf + 2 * N;
-    double *work = part + 2 * ctx->sm_count;
+    double *work = part + 4 * ctx->sm_count;
     if (N == 1) {
         MFB_CUDA(cudaMemcpyAsync(evals, G, sizeof(double), cudaMemcpyDeviceToDevice, st));
         const double one = 1.0;

@@ -101,3 +101,26 @@ def test_bcv_streams_do_not_change_values(yeast):
     a, ca = mfb.bcvGivenKs(Y, ks, 3, folds=(rf, cf), cell_errors=True, streams=1)
     b, cb = mfb.bcvGivenKs(Y, ks, 3, folds=(rf, cf), cell_errors=True, streams=4)
     assert np.array_equal(ca, cb) and np.array_equal(a, b)
+
+
+def test_bcv_batches_are_bit_identical_for_any_stream_count():
+    """Cells of several fold draws computed as one batch on concurrent streams (auto_bcv's first batch) must equal,
+    bit for bit, the same cells computed one draw at a time on one stream, run after run.  (A grid-barrier-per-column
+    eigen-solver that reuses a buffer one barrier too early passes every single-stream test and fails this one.)"""
+    import mfbiclust_b200 as mfb
+    from mfbiclust_b200.backends import _bcv_cells_all
+    from oracle.gen_sim_data import gen_sim_data
+    Y = np.asfortranarray(gen_sim_data(n=4, cluster_height=300, cluster_width=150, dimx=4000, dimy=900, bg_norm=1.0,
+                                       bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=11))
+    ctx = mfb.default_context()
+    Yd = mfb.Matrix(ctx, host=Y)
+    try:
+        ks = list(range(1, 13))
+        rng = mfb.HostRng(3)
+        folds = [mfb.draw_folds(rng, *Y.shape, 3) for _ in range(8)]
+        one = np.stack([_bcv_cells_all(Yd, ks, 3, [f], ctx, None, 1)[0] for f in folds])
+        for streams in (4, 2, 6, 4):
+            got = _bcv_cells_all(Yd, ks, 3, folds, ctx, None, streams)
+            assert np.array_equal(got, one), (streams, float(np.abs(got - one).max()))
+    finally:
+        Yd.free()
