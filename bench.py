@@ -220,6 +220,10 @@ def run_auto_bcv(mfb, ctx, rank, world, with_cpu):
     rf, cf = mfb.draw_folds(mfb.HostRng(50), *Y.shape, 3)
     Yd = mfb.Matrix(ctx, host=Y)
     mfb.bcvGivenKs(Yd, ks, 3, folds=(rf, cf), ctx=ctx)            # warm-up
+    # ... and of every worker stream of every rank (their contexts and workspace pools are created on first use):
+    # a batch with at least 9 cells per rank
+    wrng = mfb.HostRng(49)
+    mfb.bcv_batch(Yd, ks, 3, [mfb.draw_folds(wrng, *Y.shape, 3) for _ in range(max(1, world))], ctx=ctx)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -849,8 +849,9 @@ def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verb
             # batch size: every iteration the stopping rule provably cannot do without (no waste, any number of
             # ranks); beyond that, speculation: never more than B, and no more than the rule can use if the current
             # winner keeps winning (it cannot fire earlier on that path; any other path is continued next batch)
-            nb = max(_earliest_stop(distr, tol, maxIter - i),
-                     min(B, _iters_until_stable(distr, distrOld, tol, last_best, keys, B)))
+            import os as _os
+            pre = 1 if _os.environ.get("MFBICLUST_BCV_NO_PREBATCH") else _earliest_stop(distr, tol, maxIter - i)
+            nb = max(pre, min(B, _iters_until_stable(distr, distrOld, tol, last_best, keys, B)))
             nb = min(nb, maxIter - i)
             folds = [draw_folds(rng, n, p, holdouts) for _ in range(nb)]       # in order: the stream R would consume
             vals = bcv_batch(Yd, keys, holdouts, folds, ctx=ctx, group=group)  # :58, nb calls of bcv()

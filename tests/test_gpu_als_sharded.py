@@ -160,3 +160,24 @@ def test_sharded_gloo_processes_on_one_gpu(tmp_path, world, exchange):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o[-4000:]
         assert f"rank {r} ok" in o
+
+
+@pytest.mark.parametrize("exchange", ["callback", "peer"])
+def test_sharded_fp32_storage_matches_the_one_device_fp32_path(exchange):
+    """The row-sharded session on a single-precision resident block (mfb_matrix_upload_f32): same kernels, same
+    exchange; compared with the one-device FP32-storage path (1e-11) and the FP64 oracle (north star: 1e-4)."""
+    import mfbiclust_b200 as mfb
+    m, n, k = 1500, 700, 10
+    A = pseudovalues(gen_sim_data(n=4, cluster_height=140, cluster_width=140, dimx=m, dimy=n, bg_norm=1.0,
+                                  bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=m + n))
+    W0, H0 = make_init(m, n, k, 43)
+    ctx = mfb.default_context()
+    Af = mfb.Matrix(ctx, host=A, precision="f32")
+    try:
+        got = mfb.als_replicate_sharded(Af, m, k, W0, H0, maxIter=10, fixed_iters=True, exchange=exchange)
+        one = mfb.als_replicate(Af, k, W0, H0, maxIter=10, fixed_iters=True)
+    finally:
+        Af.free()
+    ref = oracle_replicate(A, W0, H0, max_iter=10, fixed_iters=True)
+    assert rel_fro(got["W"], one["W"]) < 1e-11 and rel_fro(got["H"], one["H"]) < 1e-11
+    assert rel_fro(got["W"], ref["W"]) < 1e-4 and rel_fro(got["H"], ref["H"]) < 1e-4
