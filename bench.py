@@ -293,7 +293,11 @@ def run_sharded(mfb, ctx, Ad_full, A, W0, H0, rank, world, local_rank, k=RANK, i
     Wst = np.asfortranarray(W0 / np.sqrt(world))
     for exchange in ("peer", "callback"):
         # strong: D4 split by rows
-        sess = mfb.ShardedAlsSession(Ar, m, k, W0[r0:r1], H0, amax, exchange=exchange)
+        try:
+            sess = mfb.ShardedAlsSession(Ar, m, k, W0[r0:r1], H0, amax, exchange=exchange)
+        except mfb.MfbError as e:          # peer memory cannot be mapped on this box: all ranks agree (see _connect_peers)
+            out["peer_memory" if exchange == "peer" else "nccl_callback"] = {"unavailable": str(e)}
+            continue
         ms = timed(sess)
         _, _, resid, _ = sess.result()
         sess.close()
