@@ -1,5 +1,6 @@
 // Dense FP64 building blocks for svd_pca and the bcv cells (see linalg.cuh).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "linalg.cuh"
 
@@ -630,6 +631,15 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
         if (nb > per_sm * ctx->sm_count) nb = per_sm * ctx->sm_count;
     }
     if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
+    // small (L2-resident, barrier-bound) matrices: two thirds of the SMs.  Such matrices come from bcv cells, three
+    // of which run concurrently on a device; with full grids every SM hosts a block of each and the three grid
+    // barriers fight for the same issue slots (36 cells of D3: 0.38 s with 148 blocks, 0.32 s with 72-112; a
+    // single stream loses nothing measurable)
+    if (N < 4096 && nb > 2 * ctx->sm_count / 3) nb = 2 * ctx->sm_count / 3;
+    if (const char *cap = getenv("MFB_TRI_BLOCKS")) {      // development aid: cap the grid of the tridiagonalisation
+        const int c = atoi(cap);
+        if (c >= 1 && c < nb) nb = c;
+    }
     if (nb < 1) nb = 1;
     void *args[] = {&G, &N, &d, &e, &tau, &vbuf, &pbuf, &part};
     MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_kernel, dim3(nb), dim3(TRI_THREADS), args, 0, st));
