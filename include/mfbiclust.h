@@ -58,6 +58,10 @@ int  mfb_context_sync(mfb_context *ctx);
 void *mfb_context_stream(mfb_context *ctx);
 /* Device buffers are recycled through a per-context pool; this returns the cached ones to the driver. */
 int  mfb_context_trim(mfb_context *ctx);
+/* Hint: `n` contexts (host threads, each with its own context / stream) work on this device at the same time, e.g.
+ * on the independent cells of a bcv call.  Barrier-bound cooperative kernels then size their grids to 1/n of the
+ * device instead of fighting for every SM.  Results never depend on it.  Default 1. */
+int  mfb_context_set_concurrency(mfb_context *ctx, int n);
 
 /* ---- resident matrix ---------------------------------------------------- */
 /* Upload a column-major host matrix (the `A` / `Y` argument of every back-end). */

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mfb_context_sync": (C.c_int, [_vp]),
     "mfb_context_stream": (_vp, [_vp]),
     "mfb_context_trim": (C.c_int, [_vp]),
+    "mfb_context_set_concurrency": (C.c_int, [_vp, C.c_int]),
     "mfb_matrix_upload": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_upload_f32": (C.c_int, [_vp, _dp, _i64, _i64, C.POINTER(_vp)]),
     "mfb_matrix_wrap_dev": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_vp)]),
@@ -128,6 +129,10 @@ class Context:
 
     def stream(self) -> int:
         return int(lib().mfb_context_stream(self._h) or 0)
+
+    def set_concurrency(self, n: int):
+        """``n`` contexts work on this device at the same time (grid sizing hint; results do not depend on it)."""
+        check(lib().mfb_context_set_concurrency(self._h, int(n)))
 
     def trim(self):
         """Return the cached device buffers of the workspace pool to the driver."""

@@ -706,13 +706,18 @@ def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=N
     list sharded over the ranks (:func:`shard_cells`).
 
     A cell of a small matrix is latency-bound (a grid barrier per Householder column), so the cells of a rank are
-    additionally spread over ``streams`` host threads (default 3; ``MFBICLUST_BCV_STREAMS``), each with its own
+    additionally spread over ``streams`` host threads (default 3, or 6 when the rank has 18 or more cells to do;
+    ``MFBICLUST_BCV_STREAMS``), each with its own
     context / CUDA stream working on a view of the resident matrix.  Every cell is still computed by one kernel
     sequence on one stream: the values do not depend on ``streams``."""
     ctx = ctx or _cabi.default_context()
+    auto_streams = streams is None
     if streams is None:
         import os as _os
-        streams = int(_os.environ.get("MFBICLUST_BCV_STREAMS", "3"))
+        streams = int(_os.environ.get("MFBICLUST_BCV_STREAMS", "0"))
+        auto_streams = streams == 0
+        if auto_streams:
+            streams = 3
         if Yd.shape[0] * Yd.shape[1] * 8 > (2 << 30):   # large cells are bandwidth-bound and need their memory: one at a time
             streams = 1
     rank, world, dist = _dist_info(group)
@@ -741,13 +746,19 @@ def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=N
 
     def compute(c0, c1):
         out = np.zeros((c1 - c0, len(ks)))
-        nthr = max(1, min(int(streams), c1 - c0))
+        want = int(streams)
+        if auto_streams and want > 1 and c1 - c0 >= 18:
+            want = 6                                  # a long work list: more, smaller grids side by side
+        nthr = max(1, min(want, c1 - c0))
         if nthr == 1:
+            ctx.set_concurrency(1)
             run_range(ctx, Yd, c0, c1, out, 0)
             return out
         import threading
         ctx.sync()                                    # the resident matrix is complete before other streams read it
         workers = _worker_contexts(ctx.device, nthr)
+        for w in workers:
+            w.set_concurrency(nthr)
         views = [Yd.view(w) for w in workers]
         bounds = [c0 + (c1 - c0) * t // nthr for t in range(nthr + 1)]
         errors = []

@@ -41,6 +41,7 @@ void mfb_set_error(const char *fmt, ...);
 struct mfb_context {
     int device = 0;
     int sm_count = 0;
+    int concurrency = 1;          // contexts working on this device at the same time (mfb_context_set_concurrency)
     cudaStream_t stream = nullptr;
     // small pinned mailbox for control blocks / scalars
     void *pinned = nullptr;

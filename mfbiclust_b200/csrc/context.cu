@@ -159,6 +159,12 @@ int mfb_context_sync(mfb_context *ctx) {
 
 void *mfb_context_stream(mfb_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+int mfb_context_set_concurrency(mfb_context *ctx, int n) {
+    MFB_ARG(ctx && n >= 1, "bad argument");
+    ctx->concurrency = n;
+    return MFB_OK;
+}
+
 int mfb_context_trim(mfb_context *ctx) {
     MFB_ARG(ctx, "ctx is NULL");
     MFB_CUDA(cudaSetDevice(ctx->device));

@@ -232,7 +232,8 @@ __device__ __forceinline__ double tri_block_sum(double v, double *sh) {
 // c % gridDim.x == b of the (symmetric, fully stored) trailing block; it works on four columns and two rows at a
 // time so that every thread has ~16 independent loads in flight.  Arithmetic and summation orders are those of the
 // two-pass formulation (update expression a - (v_r w_c + w_r v_c), row-strided sums, warp -> block folds).
-// vbuf / pbuf / part hold two generations each (current / next reflector, product and partial sums of p'v).
+// vbuf / pbuf hold two generations each (current / next reflector and product): with one barrier per column a fast
+// block writes the next generation while a slow one still reads the current one.
 __device__ __forceinline__ void tri_reflector(double alpha, double xnorm, double &beta, double &tq, double &scale) {
     if (xnorm == 0.0) {
         beta = alpha; tq = 0.0; scale = 0.0;
@@ -249,7 +250,6 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[TRI_THREADS / 32];
     __shared__ double shq[TRI_THREADS / 32][4];
-    __shared__ double spv[4];
     const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     double tq;                   // tau of the current reflector (every block computes it for itself)
@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         __syncthreads();
         const double *v = vbuf;
         const int64_t cfirst = 1 + (((int64_t)b - 1) % nb + nb) % nb;
-        double pvs = 0.0;
         for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
             const double *col[4];
 #pragma unroll
@@ -295,14 +294,10 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
                     for (int w = 0; w < TRI_THREADS / 32; ++w) t += shq[w][tid];
                     const double pc = tq * t;
                     pbuf[cq] = pc;
-                    pvs += pc * v[cq];
                 }
             }
             __syncthreads();
         }
-        if (tid < 4) spv[tid] = pvs;
-        __syncthreads();
-        if (tid == 0) part[b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);      // parity 0: read by iteration 0
         grid.sync();
     }
     for (int64_t i = 0; i + 1 < N; ++i) {
@@ -313,10 +308,12 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         if (b == 0)
             for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) A[r + i * N] = v[r];
         // w = p - (tau/2)(p'v) v
-        // (the partial sums are double-buffered like v and p: a fast block finishes its pass, and writes its next
-        //  partial, while a slow one has not read this iteration's yet -- there is only one barrier per column)
+        // p'v as a fixed-order sum over the columns, formed by every block for itself: the result does not depend on
+        // the grid size (the grid is sized by how many cells share the device), and no per-block partial sums have to
+        // cross the single barrier of a column
         double pv = 0.0;
-        for (int bb = tid; bb < nb; bb += TRI_THREADS) pv += __ldcg(&part[(size_t)cur * nb + bb]);
+#pragma unroll 4
+        for (int64_t c = i + 1 + tid; c < N; c += TRI_THREADS) pv += __ldcg(&pb[c]) * v[c];
         pv = tri_block_sum(pv, sh);
         const double alpha2 = -0.5 * tq * pv;
         // column j = i + 1 of the updated block, recomputed by every block: a'[r] = A[r,j] - (v_r w_j + w_r v_j)
@@ -343,7 +340,6 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
         __syncthreads();
         // fused pass over the owned columns c >= j + 1, rows r >= j + 1:  a' = a - (v_r w_c + w_r v_c);  s_c += a' v'_r
         const int64_t cfirst = (j + 1) + (((int64_t)b - (j + 1)) % nb + nb) % nb;
-        double pvs = 0.0;
         for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
             double *col[4];
             double vc[4], wc[4];
@@ -397,14 +393,10 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t
                     for (int w = 0; w < TRI_THREADS / 32; ++w) t += shq[w][tid];
                     const double pc = tqn * t;
                     pn[cq] = pc;
-                    pvs += pc * vn[cq];
                 }
             }
             __syncthreads();
         }
-        if (tid < 4) spv[tid] = pvs;
-        __syncthreads();
-        if (tid == 0) part[(size_t)(cur ^ 1) * nb + b] = (spv[0] + spv[1]) + (spv[2] + spv[3]);
         tq = tqn;
         grid.sync();
     }
@@ -631,11 +623,16 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
         if (nb > per_sm * ctx->sm_count) nb = per_sm * ctx->sm_count;
     }
     if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
-    // small (L2-resident, barrier-bound) matrices: two thirds of the SMs.  Such matrices come from bcv cells, three
-    // of which run concurrently on a device; with full grids every SM hosts a block of each and the three grid
-    // barriers fight for the same issue slots (36 cells of D3: 0.38 s with 148 blocks, 0.32 s with 72-112; a
-    // single stream loses nothing measurable)
-    if (N < 4096 && nb > 2 * ctx->sm_count / 3) nb = 2 * ctx->sm_count / 3;
+    // small (L2-resident, barrier-bound) matrices come from bcv cells, several of which run concurrently on a device
+    // (mfb_context_set_concurrency): with full grids every SM hosts a block of each cell and their grid barriers fight
+    // for the same issue slots.  36 cells of D3: 3 streams x 148 blocks 0.38 s, 3 x 98 0.32 s, 6 x 48 0.22 s; a single
+    // stream is fastest with the full grid.  (The results do not depend on the grid size.)
+    if (N < 4096) {
+        const int share = ctx->concurrency < 2 ? 2 : ctx->concurrency;
+        int cap = 2 * ctx->sm_count / share;
+        if (cap < 32) cap = 32;
+        if (nb > cap) nb = cap;
+    }
     if (const char *cap = getenv("MFB_TRI_BLOCKS")) {      // development aid: cap the grid of the tridiagonalisation
         const int c = atoi(cap);
         if (c >= 1 && c < nb) nb = c;
