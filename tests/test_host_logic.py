@@ -25,6 +25,27 @@ def test_library_exports_every_declared_symbol():
     assert L.mfb_version() >= 100
 
 
+def test_ctypes_prototypes_match_the_header_arity():
+    """The Python twin of the R shim must pass exactly the arguments include/mfbiclust.h declares (an arity drift is
+    silent with ctypes): parameter counts of every declaration against _cabi.PROTOTYPES."""
+    import mfbiclust_b200._cabi as cabi
+    hdr = open(os.path.join(ROOT, "include", "mfbiclust.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"^\s*typedef[^;]*;", "", hdr, flags=re.M)
+    seen = 0
+    for m in re.finditer(r"\b(mfb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        depth, n = 0, (0 if params in ("", "void") else 1)
+        for ch in params:
+            depth += ch == "("
+            depth -= ch == ")"
+            n += (ch == "," and depth == 0)
+        assert name in cabi.PROTOTYPES, name
+        assert n == len(cabi.PROTOTYPES[name][1]), (name, n, len(cabi.PROTOTYPES[name][1]))
+        seen += 1
+    assert seen == len(cabi.PROTOTYPES), (seen, len(cabi.PROTOTYPES))
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
