@@ -19,6 +19,12 @@
 // half-step but replaces a tail of ~40 (H) / ~100-200 (W) us during which 8 warps per SM ran the NNLS of a whole
 // 128-unit tile with a ~15 us kernel at full occupancy (profiles/r01_*).
 // Nothing but A's two passes touches HBM in bulk: factors, partials and Grams stay in L2.
+//
+// Row-sharded sessions (mfb_als_begin_sharded): A and W are split by rows over several devices,
+// H is replicated.  The same kernels run on every rank's block; W_r'A_r, W_r'W_r and three scalars are summed over
+// the ranks either by a host-supplied collective between the kernels (callback exchange: als_shard_fold / invert /
+// finish kernels) or over cudaIpc-mapped peer memory inside the kernels that consume the sums (ShardPeers: the Gram
+// side job, the fold kernel's last block + the H-step solve kernel, the last warp of the W-step solve kernel).
 #include <stdlib.h>
 
 #include "common.cuh"
