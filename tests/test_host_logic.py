@@ -258,3 +258,32 @@ def test_auto_bcv_earliest_stop_is_a_lower_bound_on_every_path():
         assert fired == L, (nkeys, fired, L)
     assert _earliest_stop({k: 1 for k in range(11)}, 1e-4, 100) == 22
     assert _earliest_stop({k: 1 for k in range(20)}, 1e-4, 100) == 25
+
+
+def test_auto_bcv_batching_replays_the_sequential_loop(yeast, monkeypatch):
+    """auto_bcv's host loop (provable first batch + speculative batches) against the oracle's plain sequential loop
+    (R/bcv.R:56-87) with the SAME bcv values: the device call is replaced by the oracle's bcv, so only the batching,
+    the fold-draw order and the replay of the stopping rule are under test -- on the CPU."""
+    import mfbiclust_b200 as mfb
+    import mfbiclust_b200.backends as BK
+    from mfbiclust_b200 import _cabi
+    from oracle import bcv as OB
+    Y = yeast[0]
+    ks = list(range(1, 12))
+    batches = []
+
+    def fake_batch(Yd, keys, holdouts, folds_list, ctx=None, group=None, streams=None):
+        batches.append(len(folds_list))
+        return np.stack([OB.bcv_given_ks(Y, np.asarray(keys), rf, cf, holdouts) for rf, cf in folds_list])
+    monkeypatch.setattr(BK, "bcv_batch", fake_batch)
+    Yd = _cabi.Matrix.__new__(_cabi.Matrix)             # a resident-matrix handle that is never dereferenced
+    Yd.shape, Yd._h, Yd.ctx, Yd.precision = Y.shape, None, None, "f64"
+    ref_rng = mfb.HostRng(7)
+    best, counts, iters = OB.auto_bcv(Y, np.asarray(ks), 3, lambda: mfb.draw_folds(ref_rng, *Y.shape, 3))
+    for B in (1, 4):
+        batches.clear()
+        got = mfb.auto_bcv(Yd, ks, holdouts=3, rng=mfb.HostRng(7), ctx=object(), speculate=B)
+        assert got["best"] == best and got["iterations"] == iters
+        assert [got["counts"][k] for k in ks] == [int(c) for c in counts]
+        assert batches[0] == 22                       # 11 candidates: the rule cannot fire before iteration 22
+        assert sum(batches) >= iters and all(b <= max(B, 1) for b in batches[1:])
