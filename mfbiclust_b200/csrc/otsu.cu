@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(512) otsu_kernel(const double *__restrict__ M,
     }
     __syncthreads();
     if (tid == 0) {
-        // EBImage::otsu: inclusive class weights, var = (w1*w2) * d * d, threshold = mean of the
+        // EBImage::otsu: inclusive class weights, var = w1 * w2 * (m2/w2 - m1/w1)^2 = (w1*w2) * (d*d) in R's
+        // evaluation order (`^` binds tighter than `*`, x^2 is x*x), threshold = mean of the
         // first and last maximising mid-points.
         double wtot = 0.0, mtot = 0.0;
         for (int i = 0; i < OTSU_LEVELS; ++i) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(512) otsu_kernel(const double *__restrict__ M,
             const double m2 = mtot + cm - m1;
             if (w1 == 0.0 || w2 == 0.0) continue;                    // 0/0 -> NaN in R, dropped by na.rm
             const double d = __dsub_rn(__ddiv_rn(m2, w2), __ddiv_rn(m1, w1));
-            const double var = __dmul_rn(__dmul_rn(__dmul_rn(w1, w2), d), d);
+            const double var = __dmul_rn(__dmul_rn(w1, w2), __dmul_rn(d, d));
             if (var > best) { best = var; first = i; last = i; }
             else if (var == best) last = i;
         }

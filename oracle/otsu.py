@@ -48,7 +48,7 @@ def otsu_from_counts(counts: np.ndarray) -> float:
     m2 = m1[-1] + cm - m1
     with np.errstate(divide="ignore", invalid="ignore"):
         d = m2 / w2 - m1 / w1
-        var = (w1 * w2) * d * d
+        var = (w1 * w2) * (d * d)          # R: w1 * w2 * (...)^2 -- `^` first, then left-to-right `*`
     finite = ~np.isnan(var)
     mx = var[finite].max()
     maxi = np.flatnonzero(finite & (var == mx))
