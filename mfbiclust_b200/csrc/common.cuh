@@ -42,6 +42,7 @@ struct mfb_context {
     int device = 0;
     int sm_count = 0;
     int concurrency = 1;          // contexts working on this device at the same time (mfb_context_set_concurrency)
+    int last_lanczos_steps = 0;   // steps the last sym_eig_topk call needed (diagnostics)
     cudaStream_t stream = nullptr;
     // small pinned mailbox for control blocks / scalars
     void *pinned = nullptr;

@@ -2,7 +2,11 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "linalg.cuh"
+
+#define MFB_TRY_RC(expr) do { int _r = (expr); if (_r != MFB_OK) return _r; } while (0)
 
 namespace cg = cooperative_groups;
 
@@ -14,7 +18,10 @@ namespace cg = cooperative_groups;
 __global__ void __launch_bounds__(128) gemm_tn_kernel(const double *__restrict__ A, int64_t lda,
                                                       const double *__restrict__ B, int64_t ldb,
                                                       double *__restrict__ C, int64_t ldc, int64_t M, int64_t N,
-                                                      int64_t K, int64_t kz, int vec_ok) {
+                                                      int64_t K, int64_t kz, int vec_ok, int sym) {
+    // sym: C = A'A -- only the block tiles on and below the diagonal are computed; dot(a_i, a_j) and dot(a_j, a_i)
+    // are the same products in the same order, so the mirrored entry is the same number
+    if (sym && blockIdx.y > blockIdx.x) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int64_t m0 = ((int64_t)blockIdx.x * 2 + (warp & 1)) * 32;
@@ -73,19 +80,25 @@ __global__ void __launch_bounds__(128) gemm_tn_kernel(const double *__restrict__
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int64_t nc = n0 + 8 * j + 2 * t + e;
-                if (mr < M && nc < N) Cz[mr + nc * ldc] = acc[i][j][e];
+                if (mr < M && nc < N) {
+                    Cz[mr + nc * ldc] = acc[i][j][e];
+                    if (sym == 2 && blockIdx.y < blockIdx.x) Cz[nc + mr * ldc] = acc[i][j][e];   // direct write: mirror
+                }
             }
         }
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const double *__restrict__ part, int Z, int64_t M,
                                                             int64_t N, int64_t ldp, double *__restrict__ C,
-                                                            int64_t ldc) {
+                                                            int64_t ldc, int sym) {
     const int64_t total = M * N;
     for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
         const int64_t n = e / M, m = e - n * M;
+        // symmetric product: the partials of a block tile above the diagonal live in its mirror image
+        const bool flip = sym && (m / 64 < n / 64);
+        const int64_t pm = flip ? n : m, pn = flip ? m : n;
         double s = 0.0;
-        for (int z = 0; z < Z; ++z) s += part[(size_t)z * ldp * N + m + n * ldp];
+        for (int z = 0; z < Z; ++z) s += part[(size_t)z * ldp * N + pm + pn * ldp];
         C[m + n * ldc] = s;
     }
 }
@@ -114,22 +127,23 @@ int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int
     int64_t kz = (K + Z - 1) / Z;
     kz = (kz + 15) / 16 * 16;
     const int vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A) % 32 == 0) && (((uintptr_t)B) % 32 == 0);
+    const int sym = (A == B && lda == ldb && M == N) ? 1 : 0;       // Gram matrix: half the tiles
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)Z);
     if (Z == 1) {
-        gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, kz, vec_ok);
+        gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, kz, vec_ok, sym ? 2 : 0);
     } else {
         MFB_ARG(work != nullptr, "gemm_tn: split-K needs a workspace");
-        gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, work, M, M, N, K, kz, vec_ok);
+        gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, work, M, M, N, K, kz, vec_ok, sym);
         int nb = (int)((M * N + 255) / 256);
         if (nb > 4 * ctx->sm_count) nb = 4 * ctx->sm_count;
-        splitk_reduce_kernel<<<nb, 256, 0, ctx->stream>>>(work, Z, M, N, M, C, ldc);
+        splitk_reduce_kernel<<<nb, 256, 0, ctx->stream>>>(work, Z, M, N, M, C, ldc, sym);
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
 
 // ---------------------------------------------------------------------------
-// C = A V  for a tall A and a thin V (kk <= 64)
+// C = A V  for a tall A and a thin V (64 columns of V per launch)
 // ---------------------------------------------------------------------------
 // Block = 32 rows x 8 column slices: warp w walks the columns c = w, w + 8, ... of A (a warp reads 256 contiguous
 // bytes per column, four columns of loads in flight), V is staged through shared memory 32 columns at a time, and
@@ -199,7 +213,16 @@ static int launch_tall_times_small(mfb_context *ctx, const double *A, int64_t ld
 
 int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv, double *C,
                      int64_t ldc, int64_t rows, int64_t inner, int kk, const double *colscale) {
-    MFB_ARG(kk >= 1 && kk <= 64, "tall_times_small: kk must be in 1..64");
+    MFB_ARG(kk >= 1, "tall_times_small: kk must be positive");
+    if (kk > 64) {                                  // 64 output columns per launch
+        for (int j0 = 0; j0 < kk; j0 += 64) {
+            const int kc = (kk - j0 < 64) ? kk - j0 : 64;
+            const int rc = tall_times_small(ctx, A, lda, V + (int64_t)j0 * ldv, ldv, C + (int64_t)j0 * ldc, ldc, rows,
+                                            inner, kc, colscale ? colscale + j0 : nullptr);
+            if (rc != MFB_OK) return rc;
+        }
+        return MFB_OK;
+    }
     if (kk <= 8) return launch_tall_times_small<8>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
     if (kk <= 16) return launch_tall_times_small<16>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
     if (kk <= 32) return launch_tall_times_small<32>(ctx, A, lda, V, ldv, C, ldc, rows, inner, kk, colscale);
@@ -207,11 +230,70 @@ int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const doubl
 }
 
 // ---------------------------------------------------------------------------
-// symmetric eigen-solver, top-k
+// symmetric eigen-solver, top-k: Lanczos tridiagonalisation with full re-orthogonalisation
 // ---------------------------------------------------------------------------
-#define TRI_THREADS 256
+// svd_pca and the bcv cells need the kk LARGEST eigenpairs of a Gram matrix G (N x N), kk << N in the configurations
+// that cost time (kk = 20 of N = 1333 per D3 cell, 50 of 13 333 per D5 cell).  A Householder reduction touches the
+// whole trailing block once per column (N passes, 16 N^3 / 3 bytes); the Lanczos recurrence
+//     G Q_J = Q_J T_J + beta_J q_{J+1} e_J',      Q_J orthonormal (classical Gram-Schmidt applied twice per step)
+// reads G once per STEP and the leading Ritz pairs of the tridiagonal T_J converge to machine precision after
+// J ~ 10 kk steps on these spectra (planted components + the edge of a noise bulk) -- 208 steps instead of 1333
+// columns on a D3 cell, ~550 instead of 13 333 on D5, and nothing is written back to G.  Carried to J = N the
+// recurrence IS a complete orthogonal tridiagonalisation, so small problems and kk close to N need no second code
+// path.  T_J is handed to the bisection / inverse-iteration kernel below; a Ritz pair (theta, s) is accepted when
+// its residual  |beta_J s_J|  (= ||G x - theta x||, x = Q_J s) is below 2e-13 theta_1.
+//
+// One persistent cooperative launch runs a chunk of steps; per step five grid barriers:
+//   matvec (a warp per column of G: a dot product of two contiguous vectors) | dots h = Q'w (a warp per basis
+//   vector) | update w -= Q h (a 32-row slab per block, the basis vectors split over its warps) | dots | update + norm.
+// Every sum has a fixed order that does not depend on the grid size, so results are bit-identical for any number of
+// concurrent cells (the grid is sized by mfb_context_set_concurrency).  Exact breakdown (an invariant subspace: G of
+// low rank, repeated blocks) continues with a deterministic pseudo-random vector orthogonalised against the basis.
+#define LZ_THREADS 512
+#define LZ_WARPS (LZ_THREADS / 32)
 
-__device__ __forceinline__ double tri_block_sum(double v, double *sh) {
+struct LanczosArgs {
+    const double *G;
+    int64_t ldg, N;
+    double *Q;            // N x (Jcap + 1), ld = ldq
+    int64_t ldq;
+    double *alpha, *beta; // Jcap each: T = tridiag(beta, alpha, beta); beta[J-1] = residual norm of the J-step recurrence
+    double *wa, *wb;      // N each: candidate for the next basis vector / product being orthogonalised
+    double *h;            // 2 x hstride: coefficients of the two Gram-Schmidt passes
+    int64_t hstride;
+    double *nrm;          // per 32-row slab: sum of squares of the candidate
+    double *state;        // [0] anorm, [1] which of wa / wb holds the candidate, [2] steps done, [3] error flag
+    unsigned *bar;        // grid barrier counter (zeroed before every launch)
+    int j_begin, j_end;
+    int w_in_smem;
+};
+
+__device__ __forceinline__ bool lz_barrier(unsigned *bar, unsigned &target, unsigned nb, int *abort_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nb;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((int)(v - target) >= 0) break;
+            if ((++spins & 0x3ffu) == 0) {          // bounded wait: a lost block must not hang the device
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) { *abort_flag = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    return *abort_flag != 0;
+}
+
+// fixed-order block sum (thread-strided partials -> warp shuffles -> warps in order); every thread gets the result
+__device__ __forceinline__ double lz_block_sum(double v, double *sh) {
     v = warp_sum(v);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     __syncthreads();
@@ -219,187 +301,204 @@ __device__ __forceinline__ double tri_block_sum(double v, double *sh) {
     __syncthreads();
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < TRI_THREADS / 32; ++i) s += sh[i];
+    for (int i = 0; i < LZ_WARPS; ++i) s += sh[i];
     return s;
 }
 
-// Householder reduction to tridiagonal form (LAPACK dsytd2, lower): A = Q T Q', reflector i stored in A[i+2:N, i]
-// (v[i+1] = 1 implicit), tau[i], T = (d, e).  One cooperative launch, ONE pass over the trailing block and ONE
-// grid-wide barrier per column: the rank-2 update of step i,  A22 -= v w' + w v',  is fused with the matrix-vector
-// product of step i + 1,  p = tau A22' v',  on the freshly updated entries.  That is possible because the next
-// reflector only depends on column i + 1 of the updated block, which every block recomputes for itself from the old
-// column and the vectors v, w (an O(N) job) before it starts the pass.  Block b owns the columns c with
-// c % gridDim.x == b of the (symmetric, fully stored) trailing block; it works on four columns and two rows at a
-// time so that every thread has ~16 independent loads in flight.  Arithmetic and summation orders are those of the
-// two-pass formulation (update expression a - (v_r w_c + w_r v_c), row-strided sums, warp -> block folds).
-// vbuf / pbuf hold two generations each (current / next reflector and product): with one barrier per column a fast
-// block writes the next generation while a slow one still reads the current one.
-__device__ __forceinline__ void tri_reflector(double alpha, double xnorm, double &beta, double &tq, double &scale) {
-    if (xnorm == 0.0) {
-        beta = alpha; tq = 0.0; scale = 0.0;
-    } else {
-        beta = -copysign(hypot(alpha, xnorm), alpha);
-        tq = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
-    }
+__device__ __forceinline__ double lz_start_entry(int64_t r, int salt) {
+    // deterministic and well spread (a constant vector would lie in the null space of a centred row-side Gram matrix)
+    unsigned x = (unsigned)(r * 2654435761u) ^ (unsigned)(salt * 40503u + 0x9e3779b9u);
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    const double u = (double)(x & 0xffffffu) / 16777216.0;          // [0, 1)
+    return 2.0 * u - 1.0;
 }
 
-__global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(double *A, int64_t N, double *d, double *e,
-                                                              double *tau, double *vbuf, double *pbuf,
-                                                              double *part) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[TRI_THREADS / 32];
-    __shared__ double shq[TRI_THREADS / 32][4];
-    const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    double tq;                   // tau of the current reflector (every block computes it for itself)
-    // ---- prologue: reflector 0 from the untouched column 0, p_0 = tau_0 A22 v_0 on the owned columns ----
-    {
-        const double alpha = __ldcg(&A[1]);
-        double q = 0.0;
-        for (int64_t r = 2 + tid; r < N; r += TRI_THREADS) { const double v = __ldcg(&A[r]); q += v * v; }
-        const double xnorm = sqrt(tri_block_sum(q, sh));
-        double beta, scale;
-        tri_reflector(alpha, xnorm, beta, tq, scale);
-        for (int64_t r = 1 + tid; r < N; r += TRI_THREADS) vbuf[r] = (r == 1) ? 1.0 : __ldcg(&A[r]) * scale;
-        if (b == 0 && tid == 0) { d[0] = __ldcg(&A[0]); e[0] = beta; tau[0] = tq; }
-        __syncthreads();
-        const double *v = vbuf;
-        const int64_t cfirst = 1 + (((int64_t)b - 1) % nb + nb) % nb;
-        for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
-            const double *col[4];
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const int64_t cq = c0 + qq * (int64_t)nb;
-                col[qq] = A + ((cq < N) ? cq : c0) * N;
+__global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
+    extern __shared__ double lsm[];
+    __shared__ double sh[LZ_WARPS];
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = gridDim.x, b = blockIdx.x;
+    const int64_t N = P.N, ldq = P.ldq, ldg = P.ldg;
+    const int64_t nslab = (N + 31) / 32;
+    const int WT = nb * LZ_WARPS, gw = b * LZ_WARPS + warp;
+    double *red = lsm;                                  // LZ_WARPS x 32
+    double *hs = red + LZ_WARPS * 32;                   // j_end + 1 coefficients
+    double *ws = hs + (P.j_end + 1);                    // N entries of the current vector (when it fits)
+    unsigned target = 0;
+    if (tid == 0) s_abort = 0;
+    __syncthreads();
+
+    // || cand ||^2 from the slab partials, in slab order
+    auto cand_norm2 = [&]() {
+        double v = 0.0;
+        for (int64_t s = tid; s < nslab; s += LZ_THREADS) v += __ldcg(&P.nrm[s]);
+        return lz_block_sum(v, sh);
+    };
+    // two passes of classical Gram-Schmidt of `buf` against Q[:, 0 .. cnt-1]; leaves the slab norms of the result
+    auto reorth = [&](double *buf, int cnt) -> bool {
+        for (int pass = 0; pass < 2; ++pass) {
+            double *hp = P.h + (size_t)pass * P.hstride;
+            if (P.w_in_smem) {
+                for (int64_t r = tid; r < N; r += LZ_THREADS) ws[r] = __ldcg(&buf[r]);
+                __syncthreads();
             }
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
-            for (int64_t r = 1 + tid; r < N; r += TRI_THREADS) {
-                const double vr = v[r];
+            const double *wv = P.w_in_smem ? ws : buf;
+            for (int i = gw; i < cnt; i += WT) {
+                const double *col = P.Q + (size_t)i * ldq;
+                double acc = 0.0;
+                int64_t r = lane;
+                for (; r + 224 < N; r += 256) {
+                    double q[8];
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) s4[qq] += col[qq][r] * vr;
-            }
+                    for (int u = 0; u < 8; ++u) q[u] = __ldcg(&col[r + 32 * u]);
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const double t = warp_sum(s4[qq]);
-                if (lane == 0) shq[warp][qq] = t;
+                    for (int u = 0; u < 8; ++u) acc += q[u] * (P.w_in_smem ? wv[r + 32 * u] : __ldcg(&wv[r + 32 * u]));
+                }
+                for (; r < N; r += 32) acc += __ldcg(&col[r]) * (P.w_in_smem ? wv[r] : __ldcg(&wv[r]));
+                acc = warp_sum(acc);
+                if (lane == 0) hp[i] = acc;
             }
+            if (lz_barrier(P.bar, target, nb, &s_abort)) return true;
+            for (int i = tid; i < cnt; i += LZ_THREADS) hs[i] = __ldcg(&hp[i]);
             __syncthreads();
-            if (tid < 4) {
-                const int64_t cq = c0 + tid * (int64_t)nb;
-                if (cq < N) {
+            const int i0 = (int)(((int64_t)cnt * warp) / LZ_WARPS), i1 = (int)(((int64_t)cnt * (warp + 1)) / LZ_WARPS);
+            for (int64_t s = b; s < nslab; s += nb) {
+                const int64_t r = 32 * s + lane;
+                const bool ok = r < N;
+                const double *row = P.Q + (ok ? r : 0);
+                double acc = 0.0;
+                int i = i0;
+                for (; i + 8 <= i1; i += 8) {
+                    double q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) q[u] = __ldcg(&row[(size_t)(i + u) * ldq]);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc += q[u] * hs[i + u];
+                }
+                for (; i < i1; ++i) acc += __ldcg(&row[(size_t)i * ldq]) * hs[i];
+                red[warp * 32 + lane] = acc;
+                __syncthreads();
+                if (warp == 0) {
                     double t = 0.0;
 #pragma unroll
-                    for (int w = 0; w < TRI_THREADS / 32; ++w) t += shq[w][tid];
-                    const double pc = tq * t;
-                    pbuf[cq] = pc;
+                    for (int w = 0; w < LZ_WARPS; ++w) t += red[w * 32 + lane];
+                    double v = 0.0;
+                    if (ok) { v = __ldcg(&buf[r]) - t; buf[r] = v; }
+                    const double sq = warp_sum(v * v);
+                    if (lane == 0) P.nrm[s] = sq;
                 }
+                __syncthreads();
             }
-            __syncthreads();
+            if (lz_barrier(P.bar, target, nb, &s_abort)) return true;
         }
-        grid.sync();
+        return false;
+    };
+
+    double anorm = __ldcg(&P.state[0]);
+    double *cand = (__ldcg(&P.state[1]) == 0.0) ? P.wa : P.wb;
+    double *out = (cand == P.wa) ? P.wb : P.wa;
+    int j = P.j_begin;
+    if (j == 0) {
+        // start vector (un-normalised) and its slab norms
+        for (int64_t s = b; s < nslab; s += nb) {
+            if (warp == 0) {
+                const int64_t r = 32 * s + lane;
+                double v = 0.0;
+                if (r < N) { v = lz_start_entry(r, 0); cand[r] = v; }
+                const double sq = warp_sum(v * v);
+                if (lane == 0) P.nrm[s] = sq;
+            }
+        }
+        anorm = 0.0;
+        if (lz_barrier(P.bar, target, nb, &s_abort)) goto fail;
     }
-    for (int64_t i = 0; i + 1 < N; ++i) {
-        const int cur = (int)(i & 1);
-        const double *v = vbuf + (size_t)cur * N, *pb = pbuf + (size_t)cur * N;
-        double *vn = vbuf + (size_t)(cur ^ 1) * N, *pn = pbuf + (size_t)(cur ^ 1) * N;
-        // keep reflector i for the back-transformation (nobody reads column i any more)
-        if (b == 0)
-            for (int64_t r = i + 2 + tid; r < N; r += TRI_THREADS) A[r + i * N] = v[r];
-        // w = p - (tau/2)(p'v) v
-        // p'v as a fixed-order sum over the columns, formed by every block for itself: the result does not depend on
-        // the grid size (the grid is sized by how many cells share the device), and no per-block partial sums have to
-        // cross the single barrier of a column
-        double pv = 0.0;
-#pragma unroll 4
-        for (int64_t c = i + 1 + tid; c < N; c += TRI_THREADS) pv += __ldcg(&pb[c]) * v[c];
-        pv = tri_block_sum(pv, sh);
-        const double alpha2 = -0.5 * tq * pv;
-        // column j = i + 1 of the updated block, recomputed by every block: a'[r] = A[r,j] - (v_r w_j + w_r v_j)
-        const int64_t j = i + 1;
-        const double vj = v[j], wj = __ldcg(&pb[j]) + alpha2 * vj;
-        auto upd = [&](int64_t r) {
-            const double vr = v[r], wr = __ldcg(&pb[r]) + alpha2 * vr;
-            return __ldcg(&A[r + j * N]) - (vr * wj + wr * vj);
-        };
-        if (j == N - 1) {            // only the last diagonal entry is left
-            if (b == 0 && tid == 0) { d[N - 1] = upd(N - 1); e[N - 1] = 0.0; tau[N - 1] = 0.0; }
-            break;
-        }
-        const double alpha = upd(j + 1);
-        double q = 0.0;
-#pragma unroll 4
-        for (int64_t r = j + 2 + tid; r < N; r += TRI_THREADS) { const double a = upd(r); q += a * a; }
-        const double xnorm = sqrt(tri_block_sum(q, sh));
-        double beta, tqn, scale;
-        tri_reflector(alpha, xnorm, beta, tqn, scale);
-#pragma unroll 4
-        for (int64_t r = j + 1 + tid; r < N; r += TRI_THREADS) vn[r] = (r == j + 1) ? 1.0 : upd(r) * scale;
-        if (b == 0 && tid == 0) { d[j] = upd(j); e[j] = beta; tau[j] = tqn; }
-        __syncthreads();
-        // fused pass over the owned columns c >= j + 1, rows r >= j + 1:  a' = a - (v_r w_c + w_r v_c);  s_c += a' v'_r
-        const int64_t cfirst = (j + 1) + (((int64_t)b - (j + 1)) % nb + nb) % nb;
-        for (int64_t c0 = cfirst; c0 < N; c0 += 4 * (int64_t)nb) {
-            double *col[4];
-            double vc[4], wc[4];
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const int64_t cq = c0 + qq * (int64_t)nb;
-                const bool ok = cq < N;
-                col[qq] = ok ? A + cq * N : nullptr;
-                vc[qq] = ok ? v[cq] : 0.0;
-                wc[qq] = ok ? __ldcg(&pb[cq]) + alpha2 * vc[qq] : 0.0;
-            }
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-            // two rows per trip, all loads before the stores (the compiler cannot reorder them itself)
-            for (int64_t r = j + 1 + tid; r < N; r += 2 * TRI_THREADS) {
-                const int64_t r2 = r + TRI_THREADS;
-                const bool ok2 = r2 < N;
-                const double vr = v[r], wr = __ldcg(&pb[r]) + alpha2 * vr, nr = vn[r];
-                const double vr2 = ok2 ? v[r2] : 0.0, wr2 = ok2 ? __ldcg(&pb[r2]) + alpha2 * vr2 : 0.0;
-                const double nr2 = ok2 ? vn[r2] : 0.0;
-                double a1[4], a2[4];
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    a1[qq] = col[qq] ? col[qq][r] : 0.0;
-                    a2[qq] = (col[qq] && ok2) ? col[qq][r2] : 0.0;
+    {
+        bool injected = false;
+        int inject_tries = 0;
+        for (;;) {
+            const double beta_prev = sqrt(cand_norm2());
+            if (j > 0 && !injected && b == 0 && tid == 0) P.beta[j - 1] = beta_prev;
+            if (j == P.j_end) break;
+            if ((j > 0 && !injected && beta_prev <= 1e-12 * anorm) || (injected && !(beta_prev > 1e-6))) {
+                // invariant subspace: T decouples (beta = 0); continue with a fresh direction orthogonal to the basis
+                if (b == 0 && tid == 0) P.beta[j - 1] = 0.0;
+                if (++inject_tries > 4) {              // nothing left outside span(Q): the basis is complete
+                    if (b == 0 && tid == 0) P.state[3] = 2.0;
+                    break;
                 }
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    if (col[qq]) {
-                        const double n1 = a1[qq] - (vr * wc[qq] + wr * vc[qq]);
-                        col[qq][r] = n1;
-                        s4[qq] += n1 * nr;
-                        if (ok2) {
-                            const double n2 = a2[qq] - (vr2 * wc[qq] + wr2 * vc[qq]);
-                            col[qq][r2] = n2;
-                            s4[qq] += n2 * nr2;
-                        }
+                for (int64_t s = b; s < nslab; s += nb) {
+                    if (warp == 0) {
+                        const int64_t r = 32 * s + lane;
+                        if (r < N) cand[r] = lz_start_entry(r, j * 8 + inject_tries);
                     }
                 }
+                if (lz_barrier(P.bar, target, nb, &s_abort)) goto fail;
+                if (reorth(cand, j)) goto fail;
+                injected = true;
+                continue;
             }
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const double t = warp_sum(s4[qq]);
-                if (lane == 0) shq[warp][qq] = t;
+            injected = false;
+            inject_tries = 0;
+            const double inv = 1.0 / beta_prev;
+            // q_j = cand / beta: every block keeps a copy in shared memory, the slab owners store it into Q[:, j]
+            if (P.w_in_smem) {
+                for (int64_t r = tid; r < N; r += LZ_THREADS) ws[r] = __ldcg(&cand[r]) * inv;
+                __syncthreads();
             }
-            __syncthreads();
-            if (tid < 4) {
-                const int64_t cq = c0 + tid * (int64_t)nb;
-                if (cq < N) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int w = 0; w < TRI_THREADS / 32; ++w) t += shq[w][tid];
-                    const double pc = tqn * t;
-                    pn[cq] = pc;
+            for (int64_t s = b; s < nslab; s += nb) {
+                if (warp == 0) {
+                    const int64_t r = 32 * s + lane;
+                    if (r < N) P.Q[r + (size_t)j * ldq] = __ldcg(&cand[r]) * inv;
                 }
             }
-            __syncthreads();
+            // out = G q_j: a warp per pair of columns (G symmetric: a column is a row)
+            for (int64_t c0 = 2 * (int64_t)gw; c0 < N; c0 += 2 * (int64_t)WT) {
+                const double *g0 = P.G + (size_t)c0 * ldg;
+                const bool two = c0 + 1 < N;
+                const double *g1 = two ? g0 + ldg : g0;
+                double a0 = 0.0, a1 = 0.0;
+                int64_t r = lane;
+                for (; r + 96 < N; r += 128) {
+                    double x0[4], x1[4], qv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { x0[u] = __ldcg(&g0[r + 32 * u]); x1[u] = __ldcg(&g1[r + 32 * u]); }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) qv[u] = P.w_in_smem ? ws[r + 32 * u] : __ldcg(&cand[r + 32 * u]) * inv;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a0 += x0[u] * qv[u]; a1 += x1[u] * qv[u]; }
+                }
+                for (; r < N; r += 32) {
+                    const double qv = P.w_in_smem ? ws[r] : __ldcg(&cand[r]) * inv;
+                    a0 += __ldcg(&g0[r]) * qv;
+                    a1 += __ldcg(&g1[r]) * qv;
+                }
+                a0 = warp_sum(a0);
+                a1 = warp_sum(a1);
+                if (lane == 0) { out[c0] = a0; if (two) out[c0 + 1] = a1; }
+            }
+            if (lz_barrier(P.bar, target, nb, &s_abort)) goto fail;
+            if (reorth(out, j + 1)) goto fail;
+            const double aj = __ldcg(&P.h[j]) + __ldcg(&P.h[P.hstride + j]);
+            if (b == 0 && tid == 0) P.alpha[j] = aj;
+            {
+                double nb2 = 0.0;
+                for (int64_t s = tid; s < nslab; s += LZ_THREADS) nb2 += __ldcg(&P.nrm[s]);
+                nb2 = lz_block_sum(nb2, sh);
+                anorm = fmax(anorm, fabs(aj) + beta_prev * (j > 0 ? 1.0 : 0.0) + sqrt(nb2));
+            }
+            double *t = cand; cand = out; out = t;
+            ++j;
         }
-        tq = tqn;
-        grid.sync();
     }
+    if (b == 0 && tid == 0) {
+        P.state[0] = anorm;
+        P.state[1] = (cand == P.wa) ? 0.0 : 1.0;
+        P.state[2] = (double)j;
+    }
+    return;
+fail:
+    if (tid == 0) P.state[3] = 1.0;
 }
 
 // number of eigenvalues of the symmetric tridiagonal (d, e) that are < x  (Sturm sequence, LAPACK dlaebz style)
@@ -416,26 +515,40 @@ __device__ int sturm_count(const double *d, const double *e, int64_t N, double x
     return cnt;
 }
 
-// Top-k eigenpairs of the tridiagonal matrix, one block per eigenpair (cooperative launch, k blocks):
+#define TRI_THREADS 256
+
+__device__ __forceinline__ double tri_block_sum(double v, double *sh) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < TRI_THREADS / 32; ++i) s += sh[i];
+    return s;
+}
+
+// Top-k eigenpairs of the tridiagonal matrix (cooperative launch; block b owns the eigenpairs b, b + gridDim.x, ...):
 //   * eigenvalue j by 256-way multisection on the Sturm count (7 rounds instead of 55 bisection steps),
 //   * inverse iteration: the block's thread 0 runs the pivoted tridiagonal solve in SHARED memory (or in the global
 //     workspace when 7 N doubles do not fit), then block 0 re-orthogonalises clustered vectors (dstein's rule:
 //     eigenvalues closer than 1e-3 ||T||) by modified Gram-Schmidt in eigenvalue order.
-// work: k * 5 * N doubles (only used by the global fall-back).  Z: N x k.
+// work: gridDim.x * 5 * N doubles (only used by the global fall-back).  Z: N x k (ld = N).  lam: k doubles (scratch).
+// resid (optional): resid[j] = |last component of eigenvector j| -- times beta_J it is the Lanczos residual norm.
 __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double *d, const double *e, int64_t N, int k,
                                                                    double *evals, double *Z, double *work,
-                                                                   int use_smem) {
+                                                                   double *lam, int use_smem, double *resid) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double tsm[];
     __shared__ double sh[TRI_THREADS / 32];
     __shared__ double s_lo, s_hi, s_pivmin, s_norm;
     __shared__ int s_cnt[TRI_THREADS];
-    __shared__ double s_lam[64];
-    const int tid = threadIdx.x, j = blockIdx.x;
+    const int tid = threadIdx.x, nbk = gridDim.x;
     // tridiagonal in shared memory when it fits
     const double *dd0 = d, *ee0 = e;
     if (use_smem) {
-        for (int64_t i = tid; i < N; i += TRI_THREADS) { tsm[i] = d[i]; tsm[N + i] = e[i]; }
+        for (int64_t i = tid; i < N; i += TRI_THREADS) { tsm[i] = d[i]; tsm[N + i] = (i + 1 < N) ? e[i] : 0.0; }
         dd0 = tsm; ee0 = tsm + N;
     }
     // Gershgorin bounds
@@ -462,7 +575,7 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
         __syncthreads();
     }
     // eigenvalue with index N-1-j (0-based ascending): smallest x with count(x) >= N - j
-    {
+    for (int j = blockIdx.x; j < k; j += nbk) {
         const int target = (int)(N - j);
         double lo = s_lo, hi = s_hi;
         for (int round = 0; round < 12; ++round) {
@@ -483,78 +596,90 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
         }
         if (tid == 0) evals[j] = 0.5 * (lo + hi);
     }
+    __threadfence();
     grid.sync();
-    // all blocks apply the same separation of coincident eigenvalues (dstein-style perturbation)
-    if (tid == 0) {
+    // one block applies the separation of coincident eigenvalues (dstein-style perturbation) for everybody
+    if (blockIdx.x == 0 && tid == 0) {
         const double sep = 10.0 * 2.3e-16 * s_norm;
-        for (int q = 0; q < k; ++q) s_lam[q] = __ldcg(&evals[q]);
-        for (int q = 1; q < k; ++q)
-            if (s_lam[q - 1] - s_lam[q] < sep) s_lam[q] = s_lam[q - 1] - sep;
+        double prev = __ldcg(&evals[0]);
+        lam[0] = prev;
+        for (int q = 1; q < k; ++q) {
+            double v = __ldcg(&evals[q]);
+            if (prev - v < sep) v = prev - sep;
+            lam[q] = v;
+            prev = v;
+        }
+        __threadfence();
     }
-    __syncthreads();
+    grid.sync();
     double *du, *du2, *dd, *dl, *zl;
     if (use_smem) { du = tsm + 2 * N; du2 = du + N; dd = du2 + N; dl = dd + N; zl = dl + N; }
-    else { du = work + (size_t)j * 5 * N; du2 = du + N; dd = du2 + N; dl = dd + N; zl = Z + (size_t)j * N; }
-    double *zg = Z + (size_t)j * N;
+    else { du = work + (size_t)blockIdx.x * 5 * N; du2 = du + N; dd = du2 + N; dl = dd + N; zl = nullptr; }
     for (int iter = 0; iter < 4; ++iter) {
-        const double lam = s_lam[j];
-        for (int64_t i = tid; i < N; i += TRI_THREADS) {
-            dd[i] = dd0[i] - lam;
-            du[i] = (i + 1 < N) ? ee0[i] : 0.0;
-            dl[i] = (i + 1 < N) ? ee0[i] : 0.0;
-            du2[i] = 0.0;
-            zl[i] = (iter == 0) ? 1.0 / sqrt((double)N) * (1.0 + 0.01 * (double)((i * 2654435761u + j * 40503u) % 97) / 97.0)
-                                : __ldcg(&zg[i]);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // solve (T - lam I) z = b by Gaussian elimination with partial pivoting (tridiagonal)
-            double *z = zl;
-            const double tiny = 2.3e-16 * s_norm + 1e-300;
-            for (int64_t i = 0; i + 1 < N; ++i) {
-                if (fabs(dd[i]) >= fabs(dl[i])) {
-                    if (fabs(dd[i]) < tiny) dd[i] = copysign(tiny, dd[i] == 0.0 ? 1.0 : dd[i]);
-                    const double f = dl[i] / dd[i];
-                    dd[i + 1] -= f * du[i];
-                    z[i + 1] -= f * z[i];
-                    du2[i] = 0.0;
-                } else {
-                    const double f = dd[i] / dl[i];
-                    const double t0 = dd[i + 1];
-                    dd[i] = dl[i];
-                    dd[i + 1] = du[i] - f * t0;
-                    du[i] = t0;
-                    if (i + 2 < N) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
-                    const double zt = z[i];
-                    z[i] = z[i + 1];
-                    z[i + 1] = zt - f * z[i + 1];
-                }
+        for (int j = blockIdx.x; j < k; j += nbk) {
+            double *zg = Z + (size_t)j * N;
+            double *z = use_smem ? zl : zg;
+            const double lamj = __ldcg(&lam[j]);
+            for (int64_t i = tid; i < N; i += TRI_THREADS) {
+                dd[i] = dd0[i] - lamj;
+                du[i] = (i + 1 < N) ? ee0[i] : 0.0;
+                dl[i] = (i + 1 < N) ? ee0[i] : 0.0;
+                du2[i] = 0.0;
+                const double zi = (iter == 0) ? 1.0 / sqrt((double)N) * (1.0 + 0.01 * (double)((i * 2654435761u + j * 40503u) % 97) / 97.0)
+                                              : __ldcg(&zg[i]);
+                z[i] = zi;
             }
-            if (fabs(dd[N - 1]) < tiny) dd[N - 1] = copysign(tiny, dd[N - 1] == 0.0 ? 1.0 : dd[N - 1]);
-            z[N - 1] /= dd[N - 1];
-            if (N >= 2) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) / dd[N - 2];
-            for (int64_t i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) / dd[i];
+            __syncthreads();
+            if (tid == 0) {
+                // solve (T - lam I) z = b by Gaussian elimination with partial pivoting (tridiagonal)
+                const double tiny = 2.3e-16 * s_norm + 1e-300;
+                for (int64_t i = 0; i + 1 < N; ++i) {
+                    if (fabs(dd[i]) >= fabs(dl[i])) {
+                        if (fabs(dd[i]) < tiny) dd[i] = copysign(tiny, dd[i] == 0.0 ? 1.0 : dd[i]);
+                        const double f = dl[i] / dd[i];
+                        dd[i + 1] -= f * du[i];
+                        z[i + 1] -= f * z[i];
+                        du2[i] = 0.0;
+                    } else {
+                        const double f = dd[i] / dl[i];
+                        const double t0 = dd[i + 1];
+                        dd[i] = dl[i];
+                        dd[i + 1] = du[i] - f * t0;
+                        du[i] = t0;
+                        if (i + 2 < N) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+                        const double zt = z[i];
+                        z[i] = z[i + 1];
+                        z[i + 1] = zt - f * z[i + 1];
+                    }
+                }
+                if (fabs(dd[N - 1]) < tiny) dd[N - 1] = copysign(tiny, dd[N - 1] == 0.0 ? 1.0 : dd[N - 1]);
+                z[N - 1] /= dd[N - 1];
+                if (N >= 2) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) / dd[N - 2];
+                for (int64_t i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) / dd[i];
+            }
+            __syncthreads();
+            // crude normalisation against overflow, publish
+            double mx = 0.0;
+            for (int64_t i = tid; i < N; i += TRI_THREADS) mx = fmax(mx, fabs(z[i]));
+            mx = warp_max(mx);
+            __syncthreads();
+            if ((tid & 31) == 0) sh[tid >> 5] = mx;
+            __syncthreads();
+            mx = sh[0];
+            for (int w = 1; w < TRI_THREADS / 32; ++w) mx = fmax(mx, sh[w]);
+            const double inv = 1.0 / mx;
+            for (int64_t i = tid; i < N; i += TRI_THREADS) zg[i] = z[i] * inv;
+            __syncthreads();
         }
-        __syncthreads();
-        // crude normalisation against overflow, publish
-        double mx = 0.0;
-        for (int64_t i = tid; i < N; i += TRI_THREADS) mx = fmax(mx, fabs(zl[i]));
-        mx = warp_max(mx);
-        __syncthreads();
-        if ((tid & 31) == 0) sh[tid >> 5] = mx;
-        __syncthreads();
-        mx = sh[0];
-        for (int w = 1; w < TRI_THREADS / 32; ++w) mx = fmax(mx, sh[w]);
-        const double inv = 1.0 / mx;
-        for (int64_t i = tid; i < N; i += TRI_THREADS) zg[i] = zl[i] * inv;
         __threadfence();
         grid.sync();
         // block 0: modified Gram-Schmidt in eigenvalue order inside clusters, then normalise every vector
-        if (j == 0) {
+        if (blockIdx.x == 0) {
             for (int q = 0; q < k; ++q) {
                 double *zq = Z + (size_t)q * N;
+                const double lq = __ldcg(&lam[q]);
                 for (int l = 0; l < q; ++l) {
-                    if (fabs(s_lam[l] - s_lam[q]) > 1e-3 * s_norm) continue;
+                    if (fabs(__ldcg(&lam[l]) - lq) > 1e-3 * s_norm) continue;
                     const double *zp = Z + (size_t)l * N;       // (other blocks' vectors: read through L2)
                     double s = 0.0;
                     for (int64_t i = tid; i < N; i += TRI_THREADS) s += __ldcg(&zp[i]) * __ldcg(&zq[i]);
@@ -568,6 +693,7 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
                 const double inv2 = 1.0 / sqrt(s);
                 for (int64_t i = tid; i < N; i += TRI_THREADS) zq[i] = __ldcg(&zq[i]) * inv2;
                 __syncthreads();
+                if (resid && iter == 3 && tid == 0) resid[q] = fabs(zq[N - 1]);
             }
             __threadfence();
         }
@@ -575,35 +701,50 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
     }
 }
 
-// z <- H(0) H(1) ... H(N-2) z, one block per eigenvector column
-__global__ void __launch_bounds__(TRI_THREADS) backtransform_kernel(const double *A, int64_t N, const double *tau,
-                                                                    double *Z) {
-    __shared__ double sh[TRI_THREADS / 32];
-    double *z = Z + (size_t)blockIdx.x * N;
-    const int tid = threadIdx.x;
-    for (int64_t i = N - 2; i >= 0; --i) {
-        const double tq = tau[i];
-        if (tq == 0.0) continue;
-        double s = 0.0;
-        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) s += ((r == i + 1) ? 1.0 : A[r + i * N]) * z[r];
-        s = tq * tri_block_sum(s, sh);
-        for (int64_t r = i + 1 + tid; r < N; r += TRI_THREADS) z[r] -= s * ((r == i + 1) ? 1.0 : A[r + i * N]);
-        __syncthreads();
-    }
+// max_j beta * resid[j] against tol * max(|evals[0]|, |evals[k-1]|)  ->  flag[0] = 1 when every pair has converged
+__global__ void lanczos_check_kernel(const double *resid, const double *evals, int k, const double *beta_last,
+                                     double tol, double *flag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double b = fabs(beta_last[0]);
+    double mx = 0.0;
+    for (int j = 0; j < k; ++j) mx = fmax(mx, b * resid[j]);
+    const double scale = fmax(fabs(evals[0]), fabs(evals[k - 1]));
+    flag[0] = (mx <= tol * scale) ? 1.0 : 0.0;
+    flag[1] = mx;
+    flag[2] = scale;
 }
 
-int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, double *evecs) {
-    MFB_ARG(N >= 1 && k >= 1 && k <= 64 && k <= N, "sym_eig_topk: need 1 <= k <= min(N, 64)");
-    cudaStream_t st = ctx->stream;
-    DevBuf buf(ctx);
-    double *wk = nullptr;
-    const size_t nwork = (size_t)7 * N + (size_t)4 * ctx->sm_count + (size_t)k * 5 * N + 16;
-    {
-        int rc = buf.alloc(&wk, nwork);
-        if (rc != MFB_OK) return rc;
+static int lanczos_grid(mfb_context *ctx, int64_t N, size_t smem) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lanczos_kernel, LZ_THREADS, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return 0;
     }
-    double *d = wk, *e = d + N, *tau = e + N, *vbuf = tau + N, *pbuf = vbuf + 2 * N, *part = pbuf + 2 * N;
-    double *work = part + 4 * ctx->sm_count;
+    // enough warps for a column pair each, never more blocks than can be resident
+    int64_t want = (N / 2 + LZ_WARPS - 1) / LZ_WARPS;
+    const int64_t slabs = (N + 31) / 32;
+    if (want < 1) want = 1;
+    int per_sm = occ > 2 ? 2 : occ;
+    int nb = (int)std::min<int64_t>(want, (int64_t)per_sm * ctx->sm_count);
+    // small (L2-resident, barrier-bound) problems come from bcv cells, several of which run concurrently on a
+    // device (mfb_context_set_concurrency): every cell gets its share of the SMs.  Results do not depend on the grid.
+    if (N < 4096) {
+        const int share = ctx->concurrency < 1 ? 1 : ctx->concurrency;
+        int cap = (ctx->sm_count * (share > 1 ? 2 : 1)) / share;
+        if (cap < 16) cap = 16;
+        if (nb > cap) nb = cap;
+    }
+    (void)slabs;
+    if (const char *capenv = getenv("MFB_LZ_BLOCKS")) {      // development aid
+        const int c = atoi(capenv);
+        if (c >= 1 && c < nb) nb = c;
+    }
+    return nb < 1 ? 1 : nb;
+}
+
+int sym_eig_topk(mfb_context *ctx, const double *G, int64_t ldg, int64_t N, int k, double *evals, double *evecs) {
+    MFB_ARG(N >= 1 && k >= 1 && k <= N && ldg >= N, "sym_eig_topk: need 1 <= k <= N <= ldg");
+    cudaStream_t st = ctx->stream;
     if (N == 1) {
         MFB_CUDA(cudaMemcpyAsync(evals, G, sizeof(double), cudaMemcpyDeviceToDevice, st));
         const double one = 1.0;
@@ -611,46 +752,94 @@ int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, d
         MFB_CUDA(cudaStreamSynchronize(st));
         return MFB_OK;
     }
-    int nb = (int)((N + 7) / 8);          // one warp per column of the trailing block, 8 warps per block
-    {
-        // large matrices stream from HBM: two blocks per SM keep twice the loads in flight
-        int per_sm = 1;
-        if (N >= 4096 && !getenv("MFB_TRI_ONE_BLOCK")) {
-            int occ = 0;
-            MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tridiag_kernel, TRI_THREADS, 0));
-            if (occ >= 2) per_sm = 2;
-        }
-        if (nb > per_sm * ctx->sm_count) nb = per_sm * ctx->sm_count;
-    }
-    if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
-    // small (L2-resident, barrier-bound) matrices come from bcv cells, several of which run concurrently on a device
-    // (mfb_context_set_concurrency): with full grids every SM hosts a block of each cell and their grid barriers fight
-    // for the same issue slots.  36 cells of D3: 3 streams x 148 blocks 0.38 s, 3 x 98 0.32 s, 6 x 48 0.22 s; a single
-    // stream is fastest with the full grid.  (The results do not depend on the grid size.)
-    if (N < 4096) {
-        const int share = ctx->concurrency < 2 ? 2 : ctx->concurrency;
-        int cap = 2 * ctx->sm_count / share;
-        if (cap < 32) cap = 32;
-        if (nb > cap) nb = cap;
-    }
-    if (const char *cap = getenv("MFB_TRI_BLOCKS")) {      // development aid: cap the grid of the tridiagonalisation
-        const int c = atoi(cap);
-        if (c >= 1 && c < nb) nb = c;
-    }
-    if (nb < 1) nb = 1;
-    void *args[] = {&G, &N, &d, &e, &tau, &vbuf, &pbuf, &part};
-    MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_kernel, dim3(nb), dim3(TRI_THREADS), args, 0, st));
-    {
-        size_t tsm = (size_t)7 * N * sizeof(double);
-        int use_smem = tsm <= 200 * 1024;
+    // steps: ~10 k on the spectra of the path (see the header); everything when k is a large part of N
+    int64_t J = 10 * (int64_t)k + 32;
+    if (const char *e = getenv("MFB_LZ_FIRST")) J = atoll(e) * k + 32;
+    if (J > N || 3 * (int64_t)k >= N) J = N;
+    int64_t Jcap = std::min<int64_t>(N, J + J / 2 + 64);
+    const int64_t ldq = round_up(N, 16);
+    DevBuf buf(ctx);
+    double *Q = nullptr, *sc = nullptr, *S = nullptr, *twork = nullptr;
+    const int64_t nslab = (N + 31) / 32;
+    auto alloc_q = [&](int64_t cap, double **q) { return buf.alloc(q, (size_t)ldq * (cap + 1)); };
+    { int rc = alloc_q(Jcap, &Q); if (rc != MFB_OK) return rc; }
+    // scalars / small vectors: alpha, beta, wa, wb, h(2), nrm, state, flag, resid, lam, barrier
+    const size_t n_sc = (size_t)2 * N + 2 * N + 2 * (N + 1) + nslab + 8 + 8 + N + N + 8;
+    { int rc = buf.alloc(&sc, n_sc); if (rc != MFB_OK) return rc; }
+    double *alpha = sc, *beta = alpha + N, *wa = beta + N, *wb = wa + N, *h = wb + N, *nrm = h + 2 * (N + 1);
+    double *state = nrm + nslab, *flag = state + 8, *resid = flag + 8, *lam = resid + N;
+    unsigned *bar = (unsigned *)(lam + N);
+    MFB_CUDA(cudaMemsetAsync(state, 0, 16 * sizeof(double), st));
+    LanczosArgs P;
+    P.G = G; P.ldg = ldg; P.N = N; P.Q = Q; P.ldq = ldq; P.alpha = alpha; P.beta = beta; P.wa = wa; P.wb = wb;
+    P.h = h; P.hstride = N + 1; P.nrm = nrm; P.state = state; P.bar = bar;
+    int64_t done = 0;
+    double *hflag = (double *)ctx->pinned;             // (one call at a time per context)
+    const double tol = 2e-13;
+    int topk_blocks = 0, use_smem = 0;
+    size_t tsm = 0;
+    for (int round = 0;; ++round) {
+        // ---- a chunk of Lanczos steps: done -> J ----
+        P.j_begin = (int)done; P.j_end = (int)J;
+        size_t smem = (size_t)(LZ_WARPS * 32 + (J + 1) + N) * sizeof(double);
+        P.w_in_smem = 1;
+        if (smem > 200 * 1024) { P.w_in_smem = 0; smem = (size_t)(LZ_WARPS * 32 + (J + 1)) * sizeof(double); }
+        MFB_ARG(smem <= 200 * 1024, "sym_eig_topk: too many Lanczos steps for the shared-memory coefficient buffer");
+        MFB_CUDA(cudaFuncSetAttribute(lanczos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int nb = lanczos_grid(ctx, N, smem);
+        MFB_ARG(nb >= 1, "sym_eig_topk: the Lanczos kernel does not fit on this device");
+        MFB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+        void *args[] = {&P};
+        MFB_CUDA(cudaLaunchCooperativeKernel((void *)lanczos_kernel, dim3(nb), dim3(LZ_THREADS), args, smem, st));
+        done = J;
+        // ---- Ritz pairs of T_J ----
+        if (!S) { int rc = buf.alloc(&S, (size_t)N * k); if (rc != MFB_OK) return rc; }   // J x k, J <= N
+        tsm = (size_t)7 * J * sizeof(double);
+        use_smem = tsm <= 200 * 1024;
         if (!use_smem) tsm = 0;
         MFB_CUDA(cudaFuncSetAttribute(tridiag_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        {
+            int occ = 0;
+            MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tridiag_topk_kernel, TRI_THREADS, tsm));
+            if (occ < 1) occ = 1;
+            if (occ > 2) occ = 2;
+            topk_blocks = std::min<int64_t>(k, (int64_t)occ * ctx->sm_count);
+            if (N < 4096 && ctx->concurrency > 1) topk_blocks = std::min(topk_blocks, std::max(8, 2 * ctx->sm_count / ctx->concurrency));
+        }
+        if (!use_smem && !twork) { int rc = buf.alloc(&twork, (size_t)2 * ctx->sm_count * 5 * N); if (rc != MFB_OK) return rc; }
         int kk = k;
-        void *targs[] = {&d, &e, &N, &kk, &evals, &evecs, &work, &use_smem};
-        MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_topk_kernel, dim3(k), dim3(TRI_THREADS), targs, tsm, st));
+        int64_t Jn = J;
+        void *targs[] = {&alpha, &beta, &Jn, &kk, &evals, &S, &twork, &lam, &use_smem, &resid};
+        MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_topk_kernel, dim3(topk_blocks), dim3(TRI_THREADS), targs, tsm, st));
+        if (J >= N) break;                           // complete tridiagonalisation: exact
+        const double *beta_last = beta + (J - 1);
+        lanczos_check_kernel<<<1, 32, 0, st>>>(resid, evals, k, beta_last, tol, flag);
+        MFB_CUDA(cudaGetLastError());
+        MFB_CUDA(cudaMemcpyAsync(hflag, flag, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaMemcpyAsync(hflag + 4, state, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        if (hflag[4 + 3] == 1.0) { mfb_set_error("sym_eig_topk: grid barrier timed out in the Lanczos kernel"); return MFB_ERR_CUDA; }
+        if (hflag[0] == 1.0 || hflag[4 + 3] == 2.0) break;
+        // not there yet: 25 % more steps (the basis grows; copy it when the first allocation is too small)
+        int64_t Jnext = std::min<int64_t>(N, J + std::max<int64_t>(J / 4, 16));
+        if (Jnext > Jcap) {
+            double *Q2 = nullptr;
+            const int64_t cap2 = std::min<int64_t>(N, std::max<int64_t>(2 * Jcap, Jnext));
+            { int rc = alloc_q(cap2, &Q2); if (rc != MFB_OK) return rc; }
+            MFB_CUDA(cudaMemcpyAsync(Q2, Q, (size_t)ldq * (Jcap + 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            Q = Q2; P.Q = Q2; Jcap = cap2;
+        }
+        J = Jnext;
     }
-    backtransform_kernel<<<k, TRI_THREADS, 0, st>>>(G, N, tau, evecs);
-    MFB_CUDA(cudaGetLastError());
+    {
+        MFB_CUDA(cudaMemcpyAsync(hflag + 4, state, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        if (hflag[4 + 3] == 1.0) { mfb_set_error("sym_eig_topk: grid barrier timed out in the Lanczos kernel"); return MFB_ERR_CUDA; }
+    }
+    // Ritz vectors: evecs (N x k, ld = N) = Q_J S
+    MFB_TRY_RC(tall_times_small(ctx, Q, ldq, S, done, evecs, N, N, done, k, nullptr));
     MFB_CUDA(cudaStreamSynchronize(st));
+    ctx->last_lanczos_steps = (int)done;
+    if (getenv("MFB_LZ_VERBOSE")) fprintf(stderr, "sym_eig_topk: N=%lld k=%d steps=%lld\n", (long long)N, k, (long long)done);
     return MFB_OK;
 }

@@ -9,12 +9,13 @@ size_t gemm_tn_workspace(int64_t M, int64_t N, int64_t K, int sm_count);
 int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
             int64_t M, int64_t N, int64_t K, double *work);
 
-// C[rows x kk] (ldc) = A[rows x inner] (lda) * V[inner x kk] (ldv), kk <= 64: 32 rows x 8 column slices per block.
-// Optional per-column scale: C[:, j] *= colscale[j].
+// C[rows x kk] (ldc) = A[rows x inner] (lda) * V[inner x kk] (ldv): 32 rows x 8 column slices per block, 64 columns of
+// V per launch.  Optional per-column scale: C[:, j] *= colscale[j].
 int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const double *V, int64_t ldv, double *C,
                      int64_t ldc, int64_t rows, int64_t inner, int kk, const double *colscale);
 
-// Top-`k` eigenpairs (largest first) of the symmetric N x N matrix G (column-major, ld = N, destroyed):
-// Householder tridiagonalisation (cooperative persistent kernel), Sturm bisection, inverse iteration with
-// modified Gram-Schmidt, reflector back-transformation.  evals: k, evecs: N x k (ld = N), device pointers.
-int sym_eig_topk(mfb_context *ctx, double *G, int64_t N, int k, double *evals, double *evecs);
+// Top-`k` eigenpairs (largest first, 1 <= k <= N) of the symmetric N x N matrix G (column-major, ld = ldg, untouched):
+// Lanczos tridiagonalisation with full re-orthogonalisation in a persistent cooperative kernel, run until the k
+// leading Ritz pairs have converged (or to completion, N steps), Sturm multisection + inverse iteration on the
+// tridiagonal matrix, Ritz vectors Q S.  evals: k, evecs: N x k (ld = N), device pointers.
+int sym_eig_topk(mfb_context *ctx, const double *G, int64_t ldg, int64_t N, int k, double *evals, double *evecs);

@@ -92,6 +92,47 @@ def test_als_simdata_degenerate_restarts(simdata):
     assert np.isfinite(got["W"]).all()
 
 
+def test_als_simdata_overlapped_restarts_then_matches(simdata):
+    """The fourth simdata matrix (BASELINE.json configs[0] runs all four): fiveSquareOverlapped has rank 4, so at
+    k = 5 the first iterations die in solve() and als_nmf's restart() redraws W (R/bicluster.R:107-116, :123-161)
+    until a start survives.  Same start and the same redraw stream on both sides: the same number of restarts, then
+    the same factors, zero patterns and traces."""
+    import mfbiclust_b200 as mfb
+    from oracle.als_nmf import als_replicate as orep
+    A = pseudovalues(simdata["fiveSquareOverlapped"])
+    W0, H0 = make_init(80, 80, 5, 41)
+
+    class Stream:                                   # runif() source shared by both sides
+        def __init__(self):
+            self.g = np.random.default_rng(5)
+            self.calls = 0
+
+        def runif(self, n):
+            self.calls += 1
+            return self.g.random(n)
+
+    so, sg = Stream(), Stream()
+
+    def redraw():
+        W = so.runif(80 * 5).reshape((80, 5), order="F")
+        return W / np.sqrt((W ** 2).sum(0))[None, :]
+    tr = []
+    ref = orep(A, W0, H0, max_iter=12, fixed_iters=True, redraw=redraw, trace=tr)
+    assert ref["status"] == "maxiter" and so.calls >= 1
+    got = mfb.als_replicate(A, 5, W0, H0, maxIter=12, fixed_iters=True, rng=sg)
+    assert sg.calls == so.calls                     # same restarts
+    assert got["iters"] == ref["iters"] == 12
+    assert rel_fro(got["W"], ref["W"]) < 1e-8 and rel_fro(got["H"], ref["H"]) < 1e-8
+    assert np.array_equal(got["W"] == 0, ref["W"] == 0) and np.array_equal(got["H"] == 0, ref["H"] == 0)
+    first = tr[0][0]                                # iterations consumed by failed attempts leave no trace row
+    ref_tr = np.array([t[1:] for t in tr])
+    assert np.allclose(got["trace"][first - 1:], ref_tr, rtol=1e-9, atol=1e-12)
+    # thresholds / memberships on the GPU factors
+    ft, st, rn, nc = O.threshold_helper(got["W"], got["H"])
+    assert np.array_equal(mfb.otsuHelper(got["W"]), ft) and np.array_equal(mfb.otsuHelper(got["H"].T), st)
+    assert np.array_equal(mfb.threshold(got["W"], ft, 2), rn) and np.array_equal(mfb.threshold(got["H"], st, 1), nc)
+
+
 def test_als_yeast_k3(yeast):
     A = pseudovalues(yeast[0])
     _check_replicate(A, 3, 10, seed=42)
@@ -174,9 +215,59 @@ def test_als_rejects_negative_and_bad_eps():
         mfb.AlsSession(mfb.Matrix(mfb.default_context(), host=A), 2, W0, H0, 1.0)
 
 
+def _d4(k, seed_init):
+    m, n = 20000, 5000
+    A = np.asfortranarray(pseudovalues(gen_sim_data(n=5, cluster_height=1000, cluster_width=1000, dimx=m, dimy=n,
+                                                    bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0,
+                                                    seed=4)))
+    W0, H0 = make_init(m, n, k, seed_init)
+    return A, W0, H0
+
+
+def test_als_full_size_matches_oracle():
+    """BASELINE.json configs[3] itself (20000 x 5000, k = 16, the bench workload): three literal oracle iterations
+    take a few seconds on the host; the GPU trajectory must equal them -- factors to 1e-8 relative Frobenius error,
+    identical zero patterns, identical traces -- not merely end in a KKT point."""
+    import mfbiclust_b200 as mfb
+    A, W0, H0 = _d4(16, 40)
+    tr = []
+    ref = oracle_replicate(A, W0, H0, max_iter=3, fixed_iters=True, trace=tr)
+    got = mfb.als_replicate(A, 16, W0, H0, maxIter=3, fixed_iters=True)
+    assert rel_fro(got["W"], ref["W"]) < 1e-8, rel_fro(got["W"], ref["W"])
+    assert rel_fro(got["H"], ref["H"]) < 1e-8, rel_fro(got["H"], ref["H"])
+    assert np.array_equal(got["W"] == 0, ref["W"] == 0) and np.array_equal(got["H"] == 0, ref["H"] == 0)
+    assert np.allclose(got["trace"], np.array([t[1:] for t in tr]), rtol=1e-9, atol=1e-12)
+
+
+def test_als_full_size_k64_properties():
+    """BASELINE.json configs[3]'s k = 64 variant at full size.  The literal oracle cannot be the checker here: at
+    k = 64 NMF::.fcnnls hits its cumulative sweep cap (see test_nnls_is_optimal_where_the_reference_hits_its_sweep_cap)
+    and returns non-optimal columns.  Size-independent properties instead: the W-step ends in the KKT point of its
+    NNLS problem, the reported residual equals ||A - WH|| computed independently, reruns are bit-identical."""
+    import mfbiclust_b200 as mfb
+    A, W0, H0 = _d4(64, 41)
+    ctx = mfb.default_context()
+    Ad = mfb.Matrix(ctx, host=A)
+    try:
+        a = mfb.als_replicate(Ad, 64, W0, H0, maxIter=3, fixed_iters=True)
+        b = mfb.als_replicate(Ad, 64, W0, H0, maxIter=3, fixed_iters=True)
+    finally:
+        Ad.free()
+    W, H = a["W"], a["H"]
+    assert np.array_equal(W, b["W"]) and np.array_equal(H, b["H"])
+    assert (W >= 0).all() and (H >= 0).all()
+    resid = np.sqrt(np.mean((A - W @ H) ** 2))
+    assert abs(a["trace"][-1, 0] - resid) <= 1e-10 * resid
+    G, R = H @ H.T, A @ H.T
+    grad = R - W @ G
+    scale = np.abs(R).max()
+    assert np.abs(grad[W > 0]).max() <= 1e-9 * scale
+    assert grad[W == 0].max() <= 1e-9 * scale
+
+
 def test_als_full_size_properties():
-    """BASELINE.json configs[3] at full size (20000 x 5000, k = 16), where the oracle is too slow to run:
-    size-independent properties instead -- the reported residual equals ||A - WH|| computed independently, the
+    """BASELINE.json configs[3] at full size (20000 x 5000, k = 16) beyond the three iterations the oracle is run
+    for in test_als_full_size_matches_oracle: size-independent properties -- the reported residual equals ||A - WH|| computed independently, the
     final W satisfies the KKT conditions of its NNLS problem given the final H, factors are non-negative, the
     residual trace never increases, and two runs are bit-identical."""
     import mfbiclust_b200 as mfb
