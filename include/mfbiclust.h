@@ -201,6 +201,15 @@ int  mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scal
 int  mfb_bcv_cells(mfb_context *ctx, mfb_matrix *Y,
                    const int32_t *row_fold, const int32_t *col_fold, int holdouts,
                    const int32_t *ks, int nks, int cell_begin, int cell_end, double *err);
+/*
+ * The same for `nfolds` fold draws at once -- auto_bcv's outer iterations (R/bcv.R:56-58): their fold draws do not
+ * depend on the data, so the cells of several bcv() calls form ONE work list.  row_folds: nfolds x n, col_folds:
+ * nfolds x p (draw after draw); cells are numbered draw * h^2 + (x-1)*h + (y-1); err: (cell_end - cell_begin) x nks.
+ * The cells of a batch share one launch of the eigen-solver; values do not depend on the batching.
+ */
+int  mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds,
+                         const int32_t *row_folds, const int32_t *col_folds, int holdouts,
+                         const int32_t *ks, int nks, int cell_begin, int cell_end, double *err);
 
 #ifdef __cplusplus
 }

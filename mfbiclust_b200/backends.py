@@ -616,16 +616,16 @@ def cell_range(ncell, rank, world):
     return (ncell * rank) // world, (ncell * (rank + 1)) // world
 
 
-def _bcast_folds(rf, cf, ctx_device, dist, group):
-    """Every rank must hold rank 0's fold vectors."""
+def _bcast_folds_many(folds_list, n, p, ctx_device, dist, group):
+    """Rank 0's fold vectors of several draws in ONE broadcast."""
     import torch
-    n = rf.size
-    t = torch.from_numpy(np.concatenate([rf, cf]).astype(np.int32))
+    arr = np.concatenate([np.concatenate([np.asarray(rf, dtype=np.int32), np.asarray(cf, dtype=np.int32)])
+                          for rf, cf in folds_list]).astype(np.int32)
     dev = torch.device("cuda", ctx_device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    t = t.to(dev)
+    t = torch.from_numpy(arr).to(dev)
     dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    t = t.cpu().numpy()
-    return np.ascontiguousarray(t[:n]), np.ascontiguousarray(t[n:])
+    a = t.cpu().numpy().reshape(len(folds_list), n + p)
+    return [(np.ascontiguousarray(a[i, :n]), np.ascontiguousarray(a[i, n:])) for i in range(len(folds_list))]
 
 
 def shard_cells(ncell, nks, compute, ctx_device=0, group=None):
@@ -690,93 +690,34 @@ def bcv(Y, ks=None, holdouts=10, interactive=True, rng=None, folds=None, ctx=Non
     return {int(k): float(v) for k, v in zip(ks, res)}
 
 
-_worker_ctx = {}
-
-
-def _worker_contexts(device, count):
-    """Extra contexts (own stream, own workspace pool) on ``device`` for concurrent host threads."""
-    lst = _worker_ctx.setdefault(device, [])
-    while len(lst) < count:
-        lst.append(_cabi.Context(device))
-    return lst[:count]
-
-
 def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=None):
-    """Per-cell errors ``(len(folds_list), holdouts^2, len(ks))`` for several fold draws at once: the ``len(folds_list) * holdouts^2`` cells are one flat work
-    list sharded over the ranks (:func:`shard_cells`).
-
-    A cell of a small matrix is latency-bound (a grid barrier per Householder column), so the cells of a rank are
-    additionally spread over ``streams`` host threads (default 3, or 6 when the rank has 18 or more cells to do;
-    ``MFBICLUST_BCV_STREAMS``), each with its own
-    context / CUDA stream working on a view of the resident matrix.  Every cell is still computed by one kernel
-    sequence on one stream: the values do not depend on ``streams``."""
+    """Per-cell errors ``(len(folds_list), holdouts^2, len(ks))`` for several fold draws at once: the
+    ``len(folds_list) * holdouts^2`` cells are one flat work list sharded over the ranks (:func:`shard_cells`); a
+    rank hands its whole share to ONE ``mfb_bcv_cells_multi`` call, which batches the cells on the device (one
+    cooperative launch of the eigen-solver per batch, the thin products of the cells side by side on auxiliary
+    streams).  Every cell is computed by the same arithmetic whatever the batching: the values do not depend on
+    the number of ranks or on the batch size.  ``streams`` is accepted for compatibility and ignored."""
     ctx = ctx or _cabi.default_context()
-    auto_streams = streams is None
-    if streams is None:
-        import os as _os
-        streams = int(_os.environ.get("MFBICLUST_BCV_STREAMS", "0"))
-        auto_streams = streams == 0
-        if auto_streams:
-            streams = 3
-        if Yd.shape[0] * Yd.shape[1] * 8 > (2 << 30):   # large cells are bandwidth-bound and need their memory: one at a time
-            streams = 1
     rank, world, dist = _dist_info(group)
     ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
     h2 = holdouts * holdouts
-    n = Yd.shape[0]
+    n, p = Yd.shape
     if dist is not None and world > 1:
-        flat = [_bcast_folds(np.ascontiguousarray(rf, dtype=np.int32), np.ascontiguousarray(cf, dtype=np.int32),
-                             ctx.device, dist, group) for rf, cf in folds_list]
+        flat = _bcast_folds_many(folds_list, n, p, ctx.device, dist, group)
     else:
         flat = [(np.ascontiguousarray(rf, dtype=np.int32), np.ascontiguousarray(cf, dtype=np.int32))
                 for rf, cf in folds_list]
-
-    def run_range(wctx, Yw, c0, c1, out, off):
-        c = c0
-        while c < c1:
-            it, lo = divmod(c, h2)
-            hi = min(h2, lo + (c1 - c))
-            rf, cf = flat[it]
-            loc = np.zeros((hi - lo, len(ks)))
-            check(lib().mfb_bcv_cells(wctx.handle, Yw.handle, rf.ctypes.data_as(C.POINTER(C.c_int32)),
-                                      cf.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
-                                      ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), lo, hi, dptr(loc)))
-            out[off + c - c0:off + c - c0 + (hi - lo)] = loc
-            c += hi - lo
+    rfs = np.ascontiguousarray(np.stack([f[0] for f in flat]), dtype=np.int32)
+    cfs = np.ascontiguousarray(np.stack([f[1] for f in flat]), dtype=np.int32)
+    if rfs.shape != (len(flat), n) or cfs.shape != (len(flat), p):
+        raise ValueError("fold vectors must have one entry per row / column of Y")
 
     def compute(c0, c1):
         out = np.zeros((c1 - c0, len(ks)))
-        want = int(streams)
-        if auto_streams and want > 1 and c1 - c0 >= 18:
-            want = 6                                  # a long work list: more, smaller grids side by side (see DESIGN 3.3)
-        nthr = max(1, min(want, c1 - c0))
-        if nthr == 1:
-            ctx.set_concurrency(1)
-            run_range(ctx, Yd, c0, c1, out, 0)
-            return out
-        import threading
-        ctx.sync()                                    # the resident matrix is complete before other streams read it
-        workers = _worker_contexts(ctx.device, nthr)
-        for w in workers:
-            w.set_concurrency(nthr)
-        views = [Yd.view(w) for w in workers]
-        bounds = [c0 + (c1 - c0) * t // nthr for t in range(nthr + 1)]
-        errors = []
-
-        def job(t):
-            try:
-                run_range(workers[t], views[t], bounds[t], bounds[t + 1], out, bounds[t] - c0)
-            except Exception as e:                     # re-raised on the calling thread
-                errors.append(e)
-        threads = [threading.Thread(target=job, args=(t,)) for t in range(nthr)]
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        for v in views:
-            v.free()
-        if errors:
-            raise errors[0]
+        ctx.set_concurrency(1)
+        check(lib().mfb_bcv_cells_multi(ctx.handle, Yd.handle, len(flat), rfs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        cfs.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
+                                        ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), int(c0), int(c1), dptr(out)))
         return out
     err = shard_cells(len(flat) * h2, len(ks), compute, ctx.device, group)
     return err.reshape(len(flat), h2, len(ks))

@@ -44,6 +44,10 @@ struct mfb_context {
     int concurrency = 1;          // contexts working on this device at the same time (mfb_context_set_concurrency)
     int last_lanczos_steps = 0;   // steps the last sym_eig_topk call needed (diagnostics)
     cudaStream_t stream = nullptr;
+    // auxiliary streams / events: independent small jobs of one call (the per-cell stages of a bcv batch) run side by
+    // side and join the main stream again through events; created on first use
+    std::vector<cudaStream_t> aux_streams;
+    std::vector<cudaEvent_t> aux_events;
     // small pinned mailbox for control blocks / scalars
     void *pinned = nullptr;
     size_t pinned_bytes = 0;

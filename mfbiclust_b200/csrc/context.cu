@@ -145,6 +145,8 @@ void mfb_context_destroy(mfb_context *ctx) {
     mfb_pool_release(ctx);
     for (auto &kv : ctx->pool_live) cudaFree(kv.first);     // handles the caller forgot to release
     ctx->pool_live.clear();
+    for (cudaStream_t a : ctx->aux_streams) cudaStreamDestroy(a);
+    for (cudaEvent_t e : ctx->aux_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;

@@ -266,6 +266,7 @@ struct LanczosArgs {
     unsigned *bar;        // grid barrier counter (zeroed before every launch)
     int j_begin, j_end;
     int w_in_smem;
+    unsigned long long *dbg;   // development aid: ns spent by block 0 in [matvec, barrier, dots, barrier, update, barrier, top, -]
 };
 
 __device__ __forceinline__ bool lz_barrier(unsigned *bar, unsigned &target, unsigned nb, int *abort_flag) {
@@ -313,7 +314,18 @@ __device__ __forceinline__ double lz_start_entry(int64_t r, int salt) {
     return 2.0 * u - 1.0;
 }
 
-__global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
+__device__ __forceinline__ unsigned long long lz_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define LZ_TICK(slot) do { if (P.dbg && b == 0 && tid == 0) { const unsigned long long n_ = lz_now(); P.dbg[slot] += n_ - tmark; tmark = n_; } } while (0)
+
+__global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(const LanczosArgs *__restrict__ problems) {
+    // blockIdx.y = problem (independent matrices advance side by side, each with its own barrier counter: their
+    // blocks share the SMs and fill each other's barrier and latency gaps); blockIdx.x = block within the problem
+    const LanczosArgs P = problems[blockIdx.y];
+    if (P.j_begin >= P.j_end) return;
     extern __shared__ double lsm[];
     __shared__ double sh[LZ_WARPS];
     __shared__ int s_abort;
@@ -322,10 +334,11 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
     const int64_t N = P.N, ldq = P.ldq, ldg = P.ldg;
     const int64_t nslab = (N + 31) / 32;
     const int WT = nb * LZ_WARPS, gw = b * LZ_WARPS + warp;
-    double *red = lsm;                                  // LZ_WARPS x 32
-    double *hs = red + LZ_WARPS * 32;                   // j_end + 1 coefficients
+    double *red = lsm;                                  // 2 x LZ_WARPS x 32
+    double *hs = red + 2 * LZ_WARPS * 32;                   // j_end + 1 coefficients
     double *ws = hs + (P.j_end + 1);                    // N entries of the current vector (when it fits)
     unsigned target = 0;
+    unsigned long long tmark = (P.dbg && b == 0 && tid == 0) ? lz_now() : 0ull;
     if (tid == 0) s_abort = 0;
     __syncthreads();
 
@@ -335,8 +348,22 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
         for (int64_t s = tid; s < nslab; s += LZ_THREADS) v += __ldcg(&P.nrm[s]);
         return lz_block_sum(v, sh);
     };
-    // two passes of classical Gram-Schmidt of `buf` against Q[:, 0 .. cnt-1]; leaves the slab norms of the result
-    auto reorth = [&](double *buf, int cnt) -> bool {
+    // Orthogonalisation of `buf` against Q[:, 0 .. cnt-1]; leaves the slab norms of the result.
+    //  * jloc >= 0 (a Lanczos step, buf = G q_jloc): the two LARGE components, alpha = q_j'w and q_{j-1}'w ~ beta_{j-1},
+    //    are removed first, one after the other, by every block on its own shared-memory copy of the vector (no
+    //    barrier: the sums have a fixed order, all copies stay identical); `alpha` returns the first.  What is left
+    //    has norm ~ beta_j and only rounding-level components along Q, so ONE classical Gram-Schmidt pass restores
+    //    orthogonality to the eps level.  (Classical Gram-Schmidt on G q_j itself would multiply the existing loss of
+    //    orthogonality by alpha / beta_j > 1 in every step.)
+    //  * a second full pass follows when the first one still removed a large part of the vector
+    //    (||after|| < 0.5 ||before||: Daniel-Gragg-Kaufman-Stewart), always for jloc < 0 (restart vectors) and when
+    //    the vector does not fit in shared memory.
+    // `passes` returns how many full passes ran (every block takes the same decision from the same numbers).
+    auto reorth = [&](double *buf, int cnt, int jloc, double &alpha, int &passes) -> bool {
+        double before2 = 0.0;
+        passes = 0;
+        alpha = 0.0;
+        const bool local = jloc >= 0 && P.w_in_smem;
         for (int pass = 0; pass < 2; ++pass) {
             double *hp = P.h + (size_t)pass * P.hstride;
             if (P.w_in_smem) {
@@ -344,53 +371,104 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
                 __syncthreads();
             }
             const double *wv = P.w_in_smem ? ws : buf;
+            if (pass == 0) {
+                if (local) {
+                    const double *qj = P.Q + (size_t)jloc * ldq;
+                    double v = 0.0;
+                    for (int64_t r = tid; r < N; r += LZ_THREADS) v += __ldcg(&qj[r]) * ws[r];
+                    alpha = lz_block_sum(v, sh);
+                    for (int64_t r = tid; r < N; r += LZ_THREADS) ws[r] -= alpha * __ldcg(&qj[r]);
+                    if (jloc > 0) {
+                        const double *qp = qj - ldq;
+                        v = 0.0;
+                        for (int64_t r = tid; r < N; r += LZ_THREADS) v += __ldcg(&qp[r]) * ws[r];
+                        const double c = lz_block_sum(v, sh);
+                        for (int64_t r = tid; r < N; r += LZ_THREADS) ws[r] -= c * __ldcg(&qp[r]);
+                    }
+                }
+                double v = 0.0;
+                for (int64_t r = tid; r < N; r += LZ_THREADS) { const double x = P.w_in_smem ? wv[r] : __ldcg(&wv[r]); v += x * x; }
+                before2 = lz_block_sum(v, sh);             // (also orders the updates of ws before the reads below)
+            }
             for (int i = gw; i < cnt; i += WT) {
                 const double *col = P.Q + (size_t)i * ldq;
                 double acc = 0.0;
                 int64_t r = lane;
-                for (; r + 224 < N; r += 256) {
-                    double q[8];
+                for (; r + 480 < N; r += 512) {          // 16 independent loads in flight per lane
+                    double q[16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) q[u] = __ldcg(&col[r + 32 * u]);
+                    for (int u = 0; u < 16; ++u) q[u] = __ldcg(&col[r + 32 * u]);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc += q[u] * (P.w_in_smem ? wv[r + 32 * u] : __ldcg(&wv[r + 32 * u]));
+                    for (int u = 0; u < 16; ++u) acc += q[u] * (P.w_in_smem ? wv[r + 32 * u] : __ldcg(&wv[r + 32 * u]));
                 }
-                for (; r < N; r += 32) acc += __ldcg(&col[r]) * (P.w_in_smem ? wv[r] : __ldcg(&wv[r]));
+                {
+                    double q[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) q[u] = (r + 32 * u < N) ? __ldcg(&col[r + 32 * u]) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (r + 32 * u < N) acc += q[u] * (P.w_in_smem ? wv[r + 32 * u] : __ldcg(&wv[r + 32 * u]));
+                }
                 acc = warp_sum(acc);
                 if (lane == 0) hp[i] = acc;
             }
+            LZ_TICK(2);
             if (lz_barrier(P.bar, target, nb, &s_abort)) return true;
+            LZ_TICK(3);
             for (int i = tid; i < cnt; i += LZ_THREADS) hs[i] = __ldcg(&hp[i]);
             __syncthreads();
             const int i0 = (int)(((int64_t)cnt * warp) / LZ_WARPS), i1 = (int)(((int64_t)cnt * (warp + 1)) / LZ_WARPS);
-            for (int64_t s = b; s < nslab; s += nb) {
-                const int64_t r = 32 * s + lane;
-                const bool ok = r < N;
-                const double *row = P.Q + (ok ? r : 0);
-                double acc = 0.0;
-                int i = i0;
-                for (; i + 8 <= i1; i += 8) {
-                    double q[8];
+            // two 32-row slabs per trip: 32 independent loads in flight per lane
+            for (int64_t sA = b; sA < nslab; sA += 2 * (int64_t)nb) {
+                const int64_t sB = sA + nb;
+                const int64_t rA = 32 * sA + lane, rB = 32 * sB + lane;
+                const bool okA = rA < N, okB = sB < nslab && rB < N;
+                const double *rowA = P.Q + (okA ? rA : 0), *rowB = P.Q + (okB ? rB : 0);
+                double accA = 0.0, accB = 0.0;
+                for (int i = i0; i < i1; i += 16) {
+                    double qa[16], qb[16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) q[u] = __ldcg(&row[(size_t)(i + u) * ldq]);
+                    for (int u = 0; u < 16; ++u) {
+                        const bool in = i + u < i1;
+                        qa[u] = (in && okA) ? __ldcg(&rowA[(size_t)(i + u) * ldq]) : 0.0;
+                        qb[u] = (in && okB) ? __ldcg(&rowB[(size_t)(i + u) * ldq]) : 0.0;
+                    }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc += q[u] * hs[i + u];
+                    for (int u = 0; u < 16; ++u) {
+                        if (i + u < i1) {
+                            const double hv = hs[i + u];
+                            accA += qa[u] * hv;
+                            accB += qb[u] * hv;
+                        }
+                    }
                 }
-                for (; i < i1; ++i) acc += __ldcg(&row[(size_t)i * ldq]) * hs[i];
-                red[warp * 32 + lane] = acc;
+                red[warp * 32 + lane] = accA;
+                red[LZ_WARPS * 32 + warp * 32 + lane] = accB;
                 __syncthreads();
-                if (warp == 0) {
-                    double t = 0.0;
+                if (warp < 2) {
+                    const int64_t sx = warp == 0 ? sA : sB, r = warp == 0 ? rA : rB;
+                    const bool ok = warp == 0 ? okA : okB;
+                    if (sx < nslab) {
+                        double t = 0.0;
 #pragma unroll
-                    for (int w = 0; w < LZ_WARPS; ++w) t += red[w * 32 + lane];
-                    double v = 0.0;
-                    if (ok) { v = __ldcg(&buf[r]) - t; buf[r] = v; }
-                    const double sq = warp_sum(v * v);
-                    if (lane == 0) P.nrm[s] = sq;
+                        for (int w = 0; w < LZ_WARPS; ++w) t += red[warp * LZ_WARPS * 32 + w * 32 + lane];
+                        double v = 0.0;
+                        // (pass 0 of a Lanczos step starts from the locally orthogonalised copy in shared memory)
+                        if (ok) { v = ((pass == 0 && local) ? ws[r] : __ldcg(&buf[r])) - t; buf[r] = v; }
+                        const double sq = warp_sum(v * v);
+                        if (lane == 0) P.nrm[sx] = sq;
+                    }
                 }
                 __syncthreads();
             }
+            LZ_TICK(4);
             if (lz_barrier(P.bar, target, nb, &s_abort)) return true;
+            LZ_TICK(5);
+            passes = pass + 1;
+            if (pass == 0 && local) {
+                const double after2 = cand_norm2();
+                if (after2 >= 0.25 * before2) break;
+            }
         }
         return false;
     };
@@ -434,13 +512,16 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
                     }
                 }
                 if (lz_barrier(P.bar, target, nb, &s_abort)) goto fail;
-                if (reorth(cand, j)) goto fail;
+                int np_ = 0;
+                double a_ = 0.0;
+                if (reorth(cand, j, -1, a_, np_)) goto fail;
                 injected = true;
                 continue;
             }
             injected = false;
             inject_tries = 0;
             const double inv = 1.0 / beta_prev;
+            LZ_TICK(6);
             // q_j = cand / beta: every block keeps a copy in shared memory, the slab owners store it into Q[:, j]
             if (P.w_in_smem) {
                 for (int64_t r = tid; r < N; r += LZ_THREADS) ws[r] = __ldcg(&cand[r]) * inv;
@@ -459,27 +540,45 @@ __global__ void __launch_bounds__(LZ_THREADS) lanczos_kernel(LanczosArgs P) {
                 const double *g1 = two ? g0 + ldg : g0;
                 double a0 = 0.0, a1 = 0.0;
                 int64_t r = lane;
-                for (; r + 96 < N; r += 128) {
-                    double x0[4], x1[4], qv[4];
+                for (; r + 224 < N; r += 256) {          // 16 independent loads in flight per lane
+                    double x0[8], x1[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { x0[u] = __ldcg(&g0[r + 32 * u]); x1[u] = __ldcg(&g1[r + 32 * u]); }
+                    for (int u = 0; u < 8; ++u) { x0[u] = __ldcg(&g0[r + 32 * u]); x1[u] = __ldcg(&g1[r + 32 * u]); }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qv[u] = P.w_in_smem ? ws[r + 32 * u] : __ldcg(&cand[r + 32 * u]) * inv;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { a0 += x0[u] * qv[u]; a1 += x1[u] * qv[u]; }
+                    for (int u = 0; u < 8; ++u) {
+                        const double qv = P.w_in_smem ? ws[r + 32 * u] : __ldcg(&cand[r + 32 * u]) * inv;
+                        a0 += x0[u] * qv;
+                        a1 += x1[u] * qv;
+                    }
                 }
-                for (; r < N; r += 32) {
-                    const double qv = P.w_in_smem ? ws[r] : __ldcg(&cand[r]) * inv;
-                    a0 += __ldcg(&g0[r]) * qv;
-                    a1 += __ldcg(&g1[r]) * qv;
+                {
+                    double x0[8], x1[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool in = r + 32 * u < N;
+                        x0[u] = in ? __ldcg(&g0[r + 32 * u]) : 0.0;
+                        x1[u] = in ? __ldcg(&g1[r + 32 * u]) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (r + 32 * u < N) {
+                            const double qv = P.w_in_smem ? ws[r + 32 * u] : __ldcg(&cand[r + 32 * u]) * inv;
+                            a0 += x0[u] * qv;
+                            a1 += x1[u] * qv;
+                        }
+                    }
                 }
                 a0 = warp_sum(a0);
                 a1 = warp_sum(a1);
                 if (lane == 0) { out[c0] = a0; if (two) out[c0 + 1] = a1; }
             }
+            LZ_TICK(0);
             if (lz_barrier(P.bar, target, nb, &s_abort)) goto fail;
-            if (reorth(out, j + 1)) goto fail;
-            const double aj = __ldcg(&P.h[j]) + __ldcg(&P.h[P.hstride + j]);
+            LZ_TICK(1);
+            int npass = 0;
+            double aloc = 0.0;
+            if (reorth(out, j + 1, j, aloc, npass)) goto fail;
+            const double aj = aloc + __ldcg(&P.h[j]) + (npass > 1 ? __ldcg(&P.h[P.hstride + j]) : 0.0);
             if (b == 0 && tid == 0) P.alpha[j] = aj;
             {
                 double nb2 = 0.0;
@@ -529,16 +628,27 @@ __device__ __forceinline__ double tri_block_sum(double v, double *sh) {
     return s;
 }
 
-// Top-k eigenpairs of the tridiagonal matrix (cooperative launch; block b owns the eigenpairs b, b + gridDim.x, ...):
+// Top-k eigenpairs of the tridiagonal matrices of a batch (cooperative launch; blockIdx.y = problem, block x owns the
+// eigenpairs x, x + gridDim.x, ... of its problem):
 //   * eigenvalue j by 256-way multisection on the Sturm count (7 rounds instead of 55 bisection steps),
 //   * inverse iteration: the block's thread 0 runs the pivoted tridiagonal solve in SHARED memory (or in the global
 //     workspace when 7 N doubles do not fit), then block 0 re-orthogonalises clustered vectors (dstein's rule:
 //     eigenvalues closer than 1e-3 ||T||) by modified Gram-Schmidt in eigenvalue order.
 // work: gridDim.x * 5 * N doubles (only used by the global fall-back).  Z: N x k (ld = N).  lam: k doubles (scratch).
-// resid (optional): resid[j] = |last component of eigenvector j| -- times beta_J it is the Lanczos residual norm.
-__global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double *d, const double *e, int64_t N, int k,
-                                                                   double *evals, double *Z, double *work,
-                                                                   double *lam, int use_smem, double *resid) {
+// resid: resid[j] = |last component of eigenvector j| -- times beta_J it is the Lanczos residual norm.
+struct TopkArgs {
+    const double *d, *e;
+    int64_t N;
+    int k, use_smem;
+    double *evals, *Z, *work, *lam, *resid;
+};
+
+__global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const TopkArgs *__restrict__ problems) {
+    const TopkArgs T = problems[blockIdx.y];
+    const double *d = T.d, *e = T.e;
+    const int64_t N = T.N;
+    const int k = T.k, use_smem = T.use_smem;
+    double *evals = T.evals, *Z = T.Z, *work = T.work, *lam = T.lam, *resid = T.resid;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double tsm[];
     __shared__ double sh[TRI_THREADS / 32];
@@ -701,145 +811,245 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_topk_kernel(const double 
     }
 }
 
-// max_j beta * resid[j] against tol * max(|evals[0]|, |evals[k-1]|)  ->  flag[0] = 1 when every pair has converged
-__global__ void lanczos_check_kernel(const double *resid, const double *evals, int k, const double *beta_last,
-                                     double tol, double *flag) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double b = fabs(beta_last[0]);
+// per problem: max_j beta * resid[j] against tol * max(|evals[0]|, |evals[k-1]|)  ->  flag[0] = 1 when every pair has
+// converged; flag[3] = the Lanczos kernel's status word
+struct CheckArgs {
+    const double *resid, *evals, *beta_last, *state;
+    int k;
+};
+__global__ void lanczos_check_kernel(const CheckArgs *__restrict__ problems, int np, double tol, double *flags) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const CheckArgs C = problems[p];
+    const double b = fabs(C.beta_last[0]);
     double mx = 0.0;
-    for (int j = 0; j < k; ++j) mx = fmax(mx, b * resid[j]);
-    const double scale = fmax(fabs(evals[0]), fabs(evals[k - 1]));
-    flag[0] = (mx <= tol * scale) ? 1.0 : 0.0;
-    flag[1] = mx;
-    flag[2] = scale;
+    for (int j = 0; j < C.k; ++j) mx = fmax(mx, b * C.resid[j]);
+    const double scale = fmax(fabs(C.evals[0]), fabs(C.evals[C.k - 1]));
+    flags[4 * p + 0] = (mx <= tol * scale) ? 1.0 : 0.0;
+    flags[4 * p + 1] = mx;
+    flags[4 * p + 2] = scale;
+    flags[4 * p + 3] = C.state[3];
 }
 
-static int lanczos_grid(mfb_context *ctx, int64_t N, size_t smem) {
+namespace {
+struct EigState {              // host-side bookkeeping of one problem of a batch
+    EigProblem pr;
+    int64_t J = 0, Jcap = 0, done = 0, ldq = 0, nslab = 0;
+    double *Q = nullptr, *S = nullptr, *sc = nullptr, *twork = nullptr;
+    double *alpha, *beta, *wa, *wb, *h, *nrm, *state, *resid, *lam;
+    unsigned *bar;
+    bool finished = false;
+};
+}  // namespace
+
+static int sym_eig_group(mfb_context *ctx, int np, const EigProblem *probs, int lz_limit, int topk_limit);
+
+int sym_eig_topk_batch(mfb_context *ctx, int np, const EigProblem *probs) {
+    MFB_ARG(np >= 1 && probs, "sym_eig_topk_batch: empty batch");
+    for (int p = 0; p < np; ++p)
+        MFB_ARG(probs[p].N >= 1 && probs[p].k >= 1 && probs[p].k <= probs[p].N && probs[p].ldg >= probs[p].N,
+                "sym_eig_topk: need 1 <= k <= N <= ldg");
+    MFB_CUDA(cudaFuncSetAttribute(lanczos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MFB_CUDA(cudaFuncSetAttribute(tridiag_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // co-residency: every block of a cooperative launch must fit on the device at once.  Groups of at most
+    // limit / 8 problems (at least 8 blocks each); the pinned mailbox holds the argument blocks of 64 problems.
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lanczos_kernel, LZ_THREADS, smem) != cudaSuccess || occ < 1) {
-        cudaGetLastError();
-        return 0;
+    MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lanczos_kernel, LZ_THREADS, 48 * 1024));
+    if (occ < 1) occ = 1;
+    if (occ > 2) occ = 2;
+    const int lz_limit = occ * ctx->sm_count;
+    int occ2 = 0;
+    MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, tridiag_topk_kernel, TRI_THREADS, 64 * 1024));
+    if (occ2 < 1) occ2 = 1;
+    if (occ2 > 3) occ2 = 3;
+    const int topk_limit = occ2 * ctx->sm_count;
+    int gmax = std::min(64, std::max(1, lz_limit / 8));
+    if (const char *e = getenv("MFB_LZ_GROUP")) { const int g = atoi(e); if (g >= 1 && g < gmax) gmax = g; }
+    for (int p0 = 0; p0 < np; p0 += gmax)
+        MFB_TRY_RC(sym_eig_group(ctx, std::min(gmax, np - p0), probs + p0, lz_limit, topk_limit));
+    return MFB_OK;
+}
+
+static int sym_eig_group(mfb_context *ctx, int np, const EigProblem *probs, int lz_limit, int topk_limit) {
+    cudaStream_t st = ctx->stream;
+    DevBuf buf(ctx);
+    std::vector<EigState> E(np);
+    LanczosArgs *d_largs = nullptr;
+    TopkArgs *d_targs = nullptr;
+    CheckArgs *d_cargs = nullptr;
+    double *d_flags = nullptr;
+    MFB_TRY_RC(buf.alloc(&d_largs, (size_t)np));
+    MFB_TRY_RC(buf.alloc(&d_targs, (size_t)np));
+    MFB_TRY_RC(buf.alloc(&d_cargs, (size_t)np));
+    MFB_TRY_RC(buf.alloc(&d_flags, (size_t)4 * np));
+    unsigned long long *d_dbg = nullptr;
+    if (getenv("MFB_LZ_PHASES")) {
+        MFB_TRY_RC(buf.alloc(&d_dbg, (size_t)8));
+        MFB_CUDA(cudaMemsetAsync(d_dbg, 0, 8 * sizeof(unsigned long long), st));
     }
-    // enough warps for a column pair each, never more blocks than can be resident
-    int64_t want = (N / 2 + LZ_WARPS - 1) / LZ_WARPS;
-    const int64_t slabs = (N + 31) / 32;
-    if (want < 1) want = 1;
-    int per_sm = occ > 2 ? 2 : occ;
-    int nb = (int)std::min<int64_t>(want, (int64_t)per_sm * ctx->sm_count);
-    // small (L2-resident, barrier-bound) problems come from bcv cells, several of which run concurrently on a
-    // device (mfb_context_set_concurrency): every cell gets its share of the SMs.  Results do not depend on the grid.
-    if (N < 4096) {
-        const int share = ctx->concurrency < 1 ? 1 : ctx->concurrency;
-        int cap = (ctx->sm_count * (share > 1 ? 2 : 1)) / share;
-        if (cap < 16) cap = 16;
-        if (nb > cap) nb = cap;
+    // pinned mailbox: flags | Lanczos args | top-k args | check args
+    double *hflags = (double *)ctx->pinned;
+    LanczosArgs *h_largs = (LanczosArgs *)((char *)ctx->pinned + 4096);
+    TopkArgs *h_targs = (TopkArgs *)((char *)h_largs + sizeof(LanczosArgs) * 64);
+    CheckArgs *h_cargs = (CheckArgs *)((char *)h_targs + sizeof(TopkArgs) * 64);
+    const double tol = 2e-13;
+    int unfinished = 0;
+    for (int p = 0; p < np; ++p) {
+        EigState &e = E[p];
+        e.pr = probs[p];
+        const int64_t N = e.pr.N;
+        const int k = e.pr.k;
+        if (N == 1) {
+            MFB_CUDA(cudaMemcpyAsync(e.pr.evals, e.pr.G, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            static const double one = 1.0;
+            MFB_CUDA(cudaMemcpyAsync(e.pr.evecs, &one, sizeof(double), cudaMemcpyHostToDevice, st));
+            e.finished = true;
+            continue;
+        }
+        // steps: ~10 k on the spectra of the path (see the header); everything when k is a large part of N
+        int64_t J = 10 * (int64_t)k + 32;
+        if (const char *env = getenv("MFB_LZ_FIRST")) J = atoll(env) * k + 32;
+        if (J > N || 3 * (int64_t)k >= N) J = N;
+        e.J = J;
+        e.Jcap = std::min<int64_t>(N, J + J / 2 + 64);
+        e.ldq = round_up(N, 16);
+        e.nslab = (N + 31) / 32;
+        MFB_TRY_RC(buf.alloc(&e.Q, (size_t)e.ldq * (e.Jcap + 1)));
+        MFB_TRY_RC(buf.alloc(&e.S, (size_t)N * k));                 // J x k, J <= N
+        // scalars / small vectors: alpha, beta, wa, wb, h (2 passes), nrm, state, resid, lam, barrier counter
+        const size_t n_sc = (size_t)4 * N + 2 * (N + 1) + e.nslab + 8 + 2 * N + 8;
+        MFB_TRY_RC(buf.alloc(&e.sc, n_sc));
+        e.alpha = e.sc; e.beta = e.alpha + N; e.wa = e.beta + N; e.wb = e.wa + N; e.h = e.wb + N;
+        e.nrm = e.h + 2 * (N + 1); e.state = e.nrm + e.nslab; e.resid = e.state + 8; e.lam = e.resid + N;
+        e.bar = (unsigned *)(e.lam + N);
+        MFB_CUDA(cudaMemsetAsync(e.state, 0, 8 * sizeof(double), st));
+        ++unfinished;
     }
-    (void)slabs;
-    if (const char *capenv = getenv("MFB_LZ_BLOCKS")) {      // development aid
-        const int c = atoi(capenv);
-        if (c >= 1 && c < nb) nb = c;
+    while (unfinished > 0) {
+        // ---- a chunk of Lanczos steps for every unfinished problem: done -> J ----
+        int na = 0;
+        size_t smem = 0;
+        int64_t want = 1;
+        std::vector<int> act;
+        for (int p = 0; p < np; ++p) {
+            EigState &e = E[p];
+            if (e.finished) continue;
+            const int64_t N = e.pr.N;
+            LanczosArgs &P = h_largs[na];
+            P.G = e.pr.G; P.ldg = e.pr.ldg; P.N = N; P.Q = e.Q; P.ldq = e.ldq; P.alpha = e.alpha; P.beta = e.beta;
+            P.wa = e.wa; P.wb = e.wb; P.h = e.h; P.hstride = N + 1; P.nrm = e.nrm; P.state = e.state; P.bar = e.bar;
+            P.j_begin = (int)e.done; P.j_end = (int)e.J;
+            P.dbg = (na == 0) ? d_dbg : nullptr;
+            size_t sm = (size_t)(2 * LZ_WARPS * 32 + (e.J + 1) + N) * sizeof(double);
+            P.w_in_smem = 1;
+            if (sm > 200 * 1024) { P.w_in_smem = 0; sm = (size_t)(2 * LZ_WARPS * 32 + (e.J + 1)) * sizeof(double); }
+            MFB_ARG(sm <= 200 * 1024, "sym_eig_topk: too many Lanczos steps for the shared-memory coefficient buffer");
+            smem = std::max(smem, sm);
+            want = std::max<int64_t>(want, (N / 2 + LZ_WARPS - 1) / LZ_WARPS);   // a column pair per warp
+            MFB_CUDA(cudaMemsetAsync(e.bar, 0, sizeof(unsigned), st));
+            act.push_back(p);
+            ++na;
+        }
+        int occ = 0;
+        MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lanczos_kernel, LZ_THREADS, smem));
+        MFB_ARG(occ >= 1, "sym_eig_topk: the Lanczos kernel does not fit on this device");
+        if (occ > 2) occ = 2;
+        int limit = std::min(lz_limit, occ * ctx->sm_count);
+        if (ctx->concurrency > 1) limit = std::max(na, limit / ctx->concurrency);   // other contexts share the device
+        int nbc = (int)std::min<int64_t>(want, limit / na);
+        if (const char *env = getenv("MFB_LZ_BLOCKS")) { const int c = atoi(env); if (c >= 1) nbc = std::min(c, limit / na); }
+        MFB_ARG(nbc >= 1, "sym_eig_topk: batch too large for a cooperative launch");
+        MFB_CUDA(cudaMemcpyAsync(d_largs, h_largs, sizeof(LanczosArgs) * na, cudaMemcpyHostToDevice, st));
+        {
+            const LanczosArgs *argp = d_largs;
+            void *args[] = {(void *)&argp};
+            MFB_CUDA(cudaLaunchCooperativeKernel((void *)lanczos_kernel, dim3(nbc, na), dim3(LZ_THREADS), args, smem, st));
+        }
+        // ---- Ritz pairs of every T_J ----
+        size_t tsm = 0;
+        int kmax = 1;
+        bool all_smem = true;
+        for (int a = 0; a < na; ++a) {
+            EigState &e = E[act[a]];
+            e.done = e.J;
+            const size_t need = (size_t)7 * e.J * sizeof(double);
+            if (need > 200 * 1024) all_smem = false;
+            tsm = std::max(tsm, need);
+            kmax = std::max(kmax, e.pr.k);
+        }
+        if (!all_smem) tsm = 0;
+        int occ2 = 0;
+        MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, tridiag_topk_kernel, TRI_THREADS, tsm));
+        if (occ2 < 1) occ2 = 1;
+        if (occ2 > 3) occ2 = 3;
+        int tlimit = std::min(topk_limit, occ2 * ctx->sm_count);
+        if (ctx->concurrency > 1) tlimit = std::max(na, tlimit / ctx->concurrency);
+        const int kb = std::max(1, std::min(kmax, tlimit / na));
+        for (int a = 0; a < na; ++a) {
+            EigState &e = E[act[a]];
+            if (!all_smem && !e.twork) MFB_TRY_RC(buf.alloc(&e.twork, (size_t)kb * 5 * e.pr.N));
+            TopkArgs &T = h_targs[a];
+            T.d = e.alpha; T.e = e.beta; T.N = e.J; T.k = e.pr.k; T.use_smem = all_smem ? 1 : 0;
+            T.evals = e.pr.evals; T.Z = e.S; T.work = e.twork; T.lam = e.lam; T.resid = e.resid;
+            CheckArgs &C = h_cargs[a];
+            C.resid = e.resid; C.evals = e.pr.evals; C.beta_last = e.beta + (e.J - 1); C.state = e.state; C.k = e.pr.k;
+        }
+        MFB_CUDA(cudaMemcpyAsync(d_targs, h_targs, sizeof(TopkArgs) * na, cudaMemcpyHostToDevice, st));
+        MFB_CUDA(cudaMemcpyAsync(d_cargs, h_cargs, sizeof(CheckArgs) * na, cudaMemcpyHostToDevice, st));
+        {
+            const TopkArgs *argp = d_targs;
+            void *targs[] = {(void *)&argp};
+            MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_topk_kernel, dim3(kb, na), dim3(TRI_THREADS), targs, tsm, st));
+        }
+        lanczos_check_kernel<<<(na + 31) / 32, 32, 0, st>>>(d_cargs, na, tol, d_flags);
+        MFB_CUDA(cudaGetLastError());
+        MFB_CUDA(cudaMemcpyAsync(hflags, d_flags, 4 * na * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        if (d_dbg) {
+            unsigned long long hd[8];
+            cudaMemcpy(hd, d_dbg, sizeof(hd), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "lanczos phases of problem 0, block 0 (us): matvec %.0f | bar %.0f | dots %.0f | bar %.0f | update %.0f | bar %.0f | top %.0f\n",
+                    hd[0] * 1e-3, hd[1] * 1e-3, hd[2] * 1e-3, hd[3] * 1e-3, hd[4] * 1e-3, hd[5] * 1e-3, hd[6] * 1e-3);
+        }
+        if (getenv("MFB_LZ_VERBOSE"))
+            fprintf(stderr, "sym_eig round: %d problems, %d blocks each, top-k %d blocks each, J=%lld, max resid/scale %.2e\n",
+                    na, nbc, kb, (long long)E[act[0]].J, hflags[1] / hflags[2]);
+        for (int a = 0; a < na; ++a) {
+            EigState &e = E[act[a]];
+            const double *f = hflags + 4 * a;
+            if (f[3] == 1.0) { mfb_set_error("sym_eig_topk: grid barrier timed out in the Lanczos kernel"); return MFB_ERR_CUDA; }
+            if (e.J >= e.pr.N || f[0] == 1.0 || f[3] == 2.0) {       // complete tridiagonalisation is exact
+                e.finished = true;
+                --unfinished;
+                continue;
+            }
+            // not there yet: 25 % more steps (the basis grows; copy it when the first allocation is too small)
+            const int64_t Jnext = std::min<int64_t>(e.pr.N, e.J + std::max<int64_t>(e.J / 4, 16));
+            if (Jnext > e.Jcap) {
+                double *Q2 = nullptr;
+                const int64_t cap2 = std::min<int64_t>(e.pr.N, std::max<int64_t>(2 * e.Jcap, Jnext));
+                MFB_TRY_RC(buf.alloc(&Q2, (size_t)e.ldq * (cap2 + 1)));
+                MFB_CUDA(cudaMemcpyAsync(Q2, e.Q, (size_t)e.ldq * (e.Jcap + 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                e.Q = Q2; e.Jcap = cap2;
+            }
+            e.J = Jnext;
+        }
     }
-    return nb < 1 ? 1 : nb;
+    // Ritz vectors: evecs (N x k, ld = N) = Q_J S
+    for (int p = 0; p < np; ++p) {
+        EigState &e = E[p];
+        if (e.pr.N == 1) continue;
+        MFB_TRY_RC(tall_times_small(ctx, e.Q, e.ldq, e.S, e.done, e.pr.evecs, e.pr.N, e.pr.N, e.done, e.pr.k, nullptr));
+        ctx->last_lanczos_steps = (int)e.done;
+        if (getenv("MFB_LZ_VERBOSE"))
+            fprintf(stderr, "sym_eig_topk: N=%lld k=%d steps=%lld\n", (long long)e.pr.N, e.pr.k, (long long)e.done);
+    }
+    MFB_CUDA(cudaStreamSynchronize(st));
+    return MFB_OK;
 }
 
 int sym_eig_topk(mfb_context *ctx, const double *G, int64_t ldg, int64_t N, int k, double *evals, double *evecs) {
-    MFB_ARG(N >= 1 && k >= 1 && k <= N && ldg >= N, "sym_eig_topk: need 1 <= k <= N <= ldg");
-    cudaStream_t st = ctx->stream;
-    if (N == 1) {
-        MFB_CUDA(cudaMemcpyAsync(evals, G, sizeof(double), cudaMemcpyDeviceToDevice, st));
-        const double one = 1.0;
-        MFB_CUDA(cudaMemcpyAsync(evecs, &one, sizeof(double), cudaMemcpyHostToDevice, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
-        return MFB_OK;
-    }
-    // steps: ~10 k on the spectra of the path (see the header); everything when k is a large part of N
-    int64_t J = 10 * (int64_t)k + 32;
-    if (const char *e = getenv("MFB_LZ_FIRST")) J = atoll(e) * k + 32;
-    if (J > N || 3 * (int64_t)k >= N) J = N;
-    int64_t Jcap = std::min<int64_t>(N, J + J / 2 + 64);
-    const int64_t ldq = round_up(N, 16);
-    DevBuf buf(ctx);
-    double *Q = nullptr, *sc = nullptr, *S = nullptr, *twork = nullptr;
-    const int64_t nslab = (N + 31) / 32;
-    auto alloc_q = [&](int64_t cap, double **q) { return buf.alloc(q, (size_t)ldq * (cap + 1)); };
-    { int rc = alloc_q(Jcap, &Q); if (rc != MFB_OK) return rc; }
-    // scalars / small vectors: alpha, beta, wa, wb, h(2), nrm, state, flag, resid, lam, barrier
-    const size_t n_sc = (size_t)2 * N + 2 * N + 2 * (N + 1) + nslab + 8 + 8 + N + N + 8;
-    { int rc = buf.alloc(&sc, n_sc); if (rc != MFB_OK) return rc; }
-    double *alpha = sc, *beta = alpha + N, *wa = beta + N, *wb = wa + N, *h = wb + N, *nrm = h + 2 * (N + 1);
-    double *state = nrm + nslab, *flag = state + 8, *resid = flag + 8, *lam = resid + N;
-    unsigned *bar = (unsigned *)(lam + N);
-    MFB_CUDA(cudaMemsetAsync(state, 0, 16 * sizeof(double), st));
-    LanczosArgs P;
-    P.G = G; P.ldg = ldg; P.N = N; P.Q = Q; P.ldq = ldq; P.alpha = alpha; P.beta = beta; P.wa = wa; P.wb = wb;
-    P.h = h; P.hstride = N + 1; P.nrm = nrm; P.state = state; P.bar = bar;
-    int64_t done = 0;
-    double *hflag = (double *)ctx->pinned;             // (one call at a time per context)
-    const double tol = 2e-13;
-    int topk_blocks = 0, use_smem = 0;
-    size_t tsm = 0;
-    for (int round = 0;; ++round) {
-        // ---- a chunk of Lanczos steps: done -> J ----
-        P.j_begin = (int)done; P.j_end = (int)J;
-        size_t smem = (size_t)(LZ_WARPS * 32 + (J + 1) + N) * sizeof(double);
-        P.w_in_smem = 1;
-        if (smem > 200 * 1024) { P.w_in_smem = 0; smem = (size_t)(LZ_WARPS * 32 + (J + 1)) * sizeof(double); }
-        MFB_ARG(smem <= 200 * 1024, "sym_eig_topk: too many Lanczos steps for the shared-memory coefficient buffer");
-        MFB_CUDA(cudaFuncSetAttribute(lanczos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        const int nb = lanczos_grid(ctx, N, smem);
-        MFB_ARG(nb >= 1, "sym_eig_topk: the Lanczos kernel does not fit on this device");
-        MFB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
-        void *args[] = {&P};
-        MFB_CUDA(cudaLaunchCooperativeKernel((void *)lanczos_kernel, dim3(nb), dim3(LZ_THREADS), args, smem, st));
-        done = J;
-        // ---- Ritz pairs of T_J ----
-        if (!S) { int rc = buf.alloc(&S, (size_t)N * k); if (rc != MFB_OK) return rc; }   // J x k, J <= N
-        tsm = (size_t)7 * J * sizeof(double);
-        use_smem = tsm <= 200 * 1024;
-        if (!use_smem) tsm = 0;
-        MFB_CUDA(cudaFuncSetAttribute(tridiag_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        {
-            int occ = 0;
-            MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tridiag_topk_kernel, TRI_THREADS, tsm));
-            if (occ < 1) occ = 1;
-            if (occ > 2) occ = 2;
-            topk_blocks = std::min<int64_t>(k, (int64_t)occ * ctx->sm_count);
-            if (N < 4096 && ctx->concurrency > 1) topk_blocks = std::min(topk_blocks, std::max(8, 2 * ctx->sm_count / ctx->concurrency));
-        }
-        if (!use_smem && !twork) { int rc = buf.alloc(&twork, (size_t)2 * ctx->sm_count * 5 * N); if (rc != MFB_OK) return rc; }
-        int kk = k;
-        int64_t Jn = J;
-        void *targs[] = {&alpha, &beta, &Jn, &kk, &evals, &S, &twork, &lam, &use_smem, &resid};
-        MFB_CUDA(cudaLaunchCooperativeKernel((void *)tridiag_topk_kernel, dim3(topk_blocks), dim3(TRI_THREADS), targs, tsm, st));
-        if (J >= N) break;                           // complete tridiagonalisation: exact
-        const double *beta_last = beta + (J - 1);
-        lanczos_check_kernel<<<1, 32, 0, st>>>(resid, evals, k, beta_last, tol, flag);
-        MFB_CUDA(cudaGetLastError());
-        MFB_CUDA(cudaMemcpyAsync(hflag, flag, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaMemcpyAsync(hflag + 4, state, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
-        if (hflag[4 + 3] == 1.0) { mfb_set_error("sym_eig_topk: grid barrier timed out in the Lanczos kernel"); return MFB_ERR_CUDA; }
-        if (hflag[0] == 1.0 || hflag[4 + 3] == 2.0) break;
-        // not there yet: 25 % more steps (the basis grows; copy it when the first allocation is too small)
-        int64_t Jnext = std::min<int64_t>(N, J + std::max<int64_t>(J / 4, 16));
-        if (Jnext > Jcap) {
-            double *Q2 = nullptr;
-            const int64_t cap2 = std::min<int64_t>(N, std::max<int64_t>(2 * Jcap, Jnext));
-            { int rc = alloc_q(cap2, &Q2); if (rc != MFB_OK) return rc; }
-            MFB_CUDA(cudaMemcpyAsync(Q2, Q, (size_t)ldq * (Jcap + 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            Q = Q2; P.Q = Q2; Jcap = cap2;
-        }
-        J = Jnext;
-    }
-    {
-        MFB_CUDA(cudaMemcpyAsync(hflag + 4, state, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
-        if (hflag[4 + 3] == 1.0) { mfb_set_error("sym_eig_topk: grid barrier timed out in the Lanczos kernel"); return MFB_ERR_CUDA; }
-    }
-    // Ritz vectors: evecs (N x k, ld = N) = Q_J S
-    MFB_TRY_RC(tall_times_small(ctx, Q, ldq, S, done, evecs, N, N, done, k, nullptr));
-    MFB_CUDA(cudaStreamSynchronize(st));
-    ctx->last_lanczos_steps = (int)done;
-    if (getenv("MFB_LZ_VERBOSE")) fprintf(stderr, "sym_eig_topk: N=%lld k=%d steps=%lld\n", (long long)N, k, (long long)done);
-    return MFB_OK;
+    EigProblem pr;
+    pr.G = G; pr.ldg = ldg; pr.N = N; pr.k = k; pr.evals = evals; pr.evecs = evecs;
+    return sym_eig_topk_batch(ctx, 1, &pr);
 }

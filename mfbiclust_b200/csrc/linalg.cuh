@@ -19,3 +19,13 @@ int tall_times_small(mfb_context *ctx, const double *A, int64_t lda, const doubl
 // leading Ritz pairs have converged (or to completion, N steps), Sturm multisection + inverse iteration on the
 // tridiagonal matrix, Ritz vectors Q S.  evals: k, evecs: N x k (ld = N), device pointers.
 int sym_eig_topk(mfb_context *ctx, const double *G, int64_t ldg, int64_t N, int k, double *evals, double *evecs);
+
+// The same for a batch of independent matrices: ONE cooperative launch advances all of them (blockIdx.y = problem,
+// a barrier counter per problem), so that their barrier and latency gaps overlap -- the bcv cells of a rank.
+struct EigProblem {
+    const double *G;
+    int64_t ldg, N;
+    int k;
+    double *evals, *evecs;
+};
+int sym_eig_topk_batch(mfb_context *ctx, int np, const EigProblem *probs);

@@ -15,6 +15,7 @@
 // so estA_k = sum_{j<=k, kept} B[:,j] C[j,:] with B = Y[r,-s] V S^-1, C = U' Y[-r,s], and the errors of every k
 // are the running squared norms of rank-1 down-dates of Y[r,s], accumulated in one pass.
 #include <algorithm>
+#include <time.h>
 
 #include "linalg.cuh"
 
@@ -286,11 +287,50 @@ int mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, in
 
 int mfb_bcv_cells(mfb_context *ctx, mfb_matrix *Y, const int32_t *row_fold, const int32_t *col_fold, int holdouts,
                   const int32_t *ks, int nks, int cell_begin, int cell_end, double *err) {
-    MFB_ARG(ctx && Y && row_fold && col_fold && ks && err, "NULL argument");
+    MFB_ARG(cell_begin >= 0 && cell_end <= holdouts * holdouts, "cell range out of bounds");
+    return mfb_bcv_cells_multi(ctx, Y, 1, row_fold, col_fold, holdouts, ks, nks, cell_begin, cell_end, err);
+}
+
+namespace {
+
+// RAII: run the helpers of this file (they launch on ctx->stream) on another stream of the same context
+struct StreamScope {
+    mfb_context *ctx;
+    cudaStream_t saved;
+    StreamScope(mfb_context *c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+    ~StreamScope() { ctx->stream = saved; }
+};
+
+int ensure_aux(mfb_context *ctx, size_t nstreams, size_t nevents) {
+    while (ctx->aux_streams.size() < nstreams) {
+        cudaStream_t s;
+        MFB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(s);
+    }
+    while (ctx->aux_events.size() < nevents) {
+        cudaEvent_t e;
+        MFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->aux_events.push_back(e);
+    }
+    return MFB_OK;
+}
+
+// device buffers of one cell of a batch
+struct CellSlot {
+    double *D, *Dt, *R1, *R2, *mu, *G, *evals, *evecs, *sigma, *colscale, *U, *V, *B, *C, *part, *E, *work1, *work2;
+};
+
+}  // namespace
+
+int mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32_t *row_folds,
+                        const int32_t *col_folds, int holdouts, const int32_t *ks, int nks, int cell_begin,
+                        int cell_end, double *err) {
+    MFB_ARG(ctx && Y && row_folds && col_folds && ks && err, "NULL argument");
     if (Y->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
     MFB_ARG(holdouts >= 2, "holdouts must be at least 2");
-    MFB_ARG(nks >= 1, "ks is empty");
-    MFB_ARG(cell_begin >= 0 && cell_end <= holdouts * holdouts && cell_begin <= cell_end, "cell range out of bounds");
+    MFB_ARG(nks >= 1 && nfolds >= 1, "ks / folds empty");
+    const int h2 = holdouts * holdouts;
+    MFB_ARG(cell_begin >= 0 && cell_end <= nfolds * h2 && cell_begin <= cell_end, "cell range out of bounds");
     MFB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t n = Y->m, p = Y->n, ldy = Y->lda;
@@ -299,102 +339,249 @@ int mfb_bcv_cells(mfb_context *ctx, mfb_matrix *Y, const int32_t *row_fold, cons
         MFB_ARG(ks[q] >= 1, "ks must be positive");
         if (ks[q] > kmax) kmax = ks[q];
     }
-    // index lists per fold (host), in increasing order as R's logical subsetting keeps them
-    std::vector<std::vector<int32_t>> rin(holdouts), rout(holdouts), cin(holdouts), cout(holdouts);
-    for (int64_t i = 0; i < n; ++i) {
-        const int f = row_fold[i];
-        MFB_ARG(f >= 1 && f <= holdouts, "row_fold entries must be in 1..holdouts");
-        for (int x = 0; x < holdouts; ++x) (x == f - 1 ? rout[x] : rin[x]).push_back((int32_t)i);
-    }
-    for (int64_t j = 0; j < p; ++j) {
-        const int f = col_fold[j];
-        MFB_ARG(f >= 1 && f <= holdouts, "col_fold entries must be in 1..holdouts");
-        for (int y = 0; y < holdouts; ++y) (y == f - 1 ? cout[y] : cin[y]).push_back((int32_t)j);
-    }
-    int64_t maxr_in = 0, maxr_out = 0, maxc_in = 0, maxc_out = 0;
-    for (int x = 0; x < holdouts; ++x) {
-        maxr_in = std::max<int64_t>(maxr_in, rin[x].size());
-        maxr_out = std::max<int64_t>(maxr_out, rout[x].size());
-        maxc_in = std::max<int64_t>(maxc_in, cin[x].size());
-        maxc_out = std::max<int64_t>(maxc_out, cout[x].size());
-    }
     const int ncell = cell_end - cell_begin;
     if (ncell == 0) return MFB_OK;
+    // ---- index lists of every fold draw the range touches (host), in increasing order as R's logical subsetting
+    //      keeps them; one upload.  Per draw: [rows in | rows out] per row fold, [cols in | cols out] per col fold ----
+    const int f_lo = cell_begin / h2, f_hi = (cell_end - 1) / h2;
+    const int nf = f_hi - f_lo + 1;
+    std::vector<int32_t> idx((size_t)nf * holdouts * (n + p));
+    std::vector<int64_t> n_rin((size_t)nf * holdouts), n_cin((size_t)nf * holdouts);
+    int64_t maxr_in = 0, maxr_out = 0, maxc_in = 0, maxc_out = 0;
+    for (int f = 0; f < nf; ++f) {
+        const int32_t *rf = row_folds + (size_t)(f_lo + f) * n, *cf = col_folds + (size_t)(f_lo + f) * p;
+        int32_t *base = idx.data() + (size_t)f * holdouts * (n + p);
+        for (int x = 0; x < holdouts; ++x) {
+            int32_t *rin = base + (size_t)x * n;
+            int64_t a = 0, b = n;                    // hold-in from the front, hold-out from the back (reversed below)
+            for (int64_t i = 0; i < n; ++i) {
+                const int fo = rf[i];
+                MFB_ARG(fo >= 1 && fo <= holdouts, "row_fold entries must be in 1..holdouts");
+                if (fo - 1 == x) rin[--b] = (int32_t)i; else rin[a++] = (int32_t)i;
+            }
+            std::reverse(rin + a, rin + n);
+            n_rin[(size_t)f * holdouts + x] = a;
+            maxr_in = std::max(maxr_in, a);
+            maxr_out = std::max(maxr_out, n - a);
+        }
+        for (int y = 0; y < holdouts; ++y) {
+            int32_t *cin = base + (size_t)holdouts * n + (size_t)y * p;
+            int64_t a = 0, b = p;
+            for (int64_t j = 0; j < p; ++j) {
+                const int fo = cf[j];
+                MFB_ARG(fo >= 1 && fo <= holdouts, "col_fold entries must be in 1..holdouts");
+                if (fo - 1 == y) cin[--b] = (int32_t)j; else cin[a++] = (int32_t)j;
+            }
+            std::reverse(cin + a, cin + p);
+            n_cin[(size_t)f * holdouts + y] = a;
+            maxc_in = std::max(maxc_in, a);
+            maxc_out = std::max(maxc_out, p - a);
+        }
+    }
     DevBuf buf(ctx);
-    int32_t *d_rin, *d_rout, *d_cin, *d_cout, *d_ks;
-    double *D, *Dt = nullptr, *R1, *R2, *mu, *sigma, *colscale, *U, *V, *B, *C, *part, *d_err, *work = nullptr;
-    double *E = nullptr;                                         // running residual of Y[r, s] when kmax > 64
-    const int64_t ldD = round_up(maxr_in, 4), ldDt = round_up(maxc_in, 4), ldR1 = round_up(maxr_out, 4);
-    MFB_TRY(buf.alloc(&d_rin, (size_t)maxr_in));
-    MFB_TRY(buf.alloc(&d_rout, (size_t)maxr_out));
-    MFB_TRY(buf.alloc(&d_cin, (size_t)maxc_in));
-    MFB_TRY(buf.alloc(&d_cout, (size_t)maxc_out));
+    int32_t *d_idx, *d_ks;
+    double *d_err;
+    MFB_TRY(buf.alloc(&d_idx, idx.size()));
     MFB_TRY(buf.alloc(&d_ks, (size_t)nks));
-    MFB_TRY(buf.alloc(&D, (size_t)ldD * maxc_in));
-    MFB_TRY(buf.alloc(&Dt, (size_t)ldDt * maxr_in));
-    MFB_TRY(buf.alloc(&R1, (size_t)ldR1 * maxc_in));            // Y[r, -s]
-    MFB_TRY(buf.alloc(&R2, (size_t)ldD * maxc_out));            // Y[-r, s]
-    MFB_TRY(buf.alloc(&mu, (size_t)maxc_in));
-    MFB_TRY(buf.alloc(&sigma, (size_t)kmax));
-    MFB_TRY(buf.alloc(&colscale, (size_t)kmax));
-    MFB_TRY(buf.alloc(&U, (size_t)ldD * kmax));
-    MFB_TRY(buf.alloc(&V, (size_t)ldDt * kmax));
-    MFB_TRY(buf.alloc(&B, (size_t)ldR1 * kmax));
-    MFB_TRY(buf.alloc(&C, (size_t)kmax * maxc_out));
+    MFB_TRY(buf.alloc(&d_err, (size_t)ncell * nks));
+    MFB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(d_ks, ks, nks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // ---- batch size: the cells of a batch go through the eigen-solver together (one cooperative launch, see
+    //      linalg.cu) and their thin products run side by side on auxiliary streams; bounded by workspace ----
+    const int64_t ldD = round_up(maxr_in, 4), ldDt = round_up(maxc_in, 4), ldR1 = round_up(maxr_out, 4);
+    const int64_t Nmax = std::min(maxr_in, maxc_in), Kmax = std::max(maxr_in, maxc_in);
+    const int64_t kkmax = std::min<int64_t>(kmax, Nmax);
+    const int64_t ldG = round_up(Nmax, 4);
     const int nb_err = 2 * ctx->sm_count;
     const int pstride = kmax + 1;
-    MFB_TRY(buf.alloc(&part, (size_t)nb_err * pstride));
-    if (kmax > 64) MFB_TRY(buf.alloc(&E, (size_t)maxr_out * maxc_out));
-    MFB_TRY(buf.alloc(&d_err, (size_t)ncell * nks));
-    {
-        size_t nwork = 0;                                        // split-K scratch of the largest C = U'Y[-r, s] product
-        for (int cell = cell_begin; cell < cell_end; ++cell) {
-            const int x = cell / holdouts, y = cell % holdouts;
-            const int64_t nD = (int64_t)rin[x].size(), pD = (int64_t)cin[y].size(), pA = (int64_t)cout[y].size();
-            const int64_t kk = std::min<int64_t>(kmax, std::min(nD, pD));
-            if (kk > 0 && pA > 0 && nD > 0) nwork = std::max(nwork, gemm_tn_workspace(kk, pA, nD, ctx->sm_count));
-        }
-        if (nwork) MFB_TRY(buf.alloc(&work, nwork));
-    }
-    MFB_CUDA(cudaMemcpyAsync(d_ks, ks, nks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    const double sqrt_eps = 1.4901161193847656e-08;              // sqrt(.Machine$double.eps): MASS::ginv's tol
-
+    const bool any_wide = maxr_in < maxc_in;       // (row counts differ by at most one between folds: all cells alike)
+    size_t w1 = 0, w2 = 0;                          // split-K scratch of the Gram and of the C = U'Y[-r, s] products
     for (int cell = cell_begin; cell < cell_end; ++cell) {
-        const int x = cell / holdouts, y = cell % holdouts;
-        const int64_t nD = (int64_t)rin[x].size(), nA = (int64_t)rout[x].size();
-        const int64_t pD = (int64_t)cin[y].size(), pA = (int64_t)cout[y].size();
-        double *e_out = d_err + (size_t)(cell - cell_begin) * nks;
+        const int f = cell / h2 - f_lo, local = cell % h2, x = local / holdouts, y = local % holdouts;
+        const int64_t nD = n_rin[(size_t)f * holdouts + x], pD = n_cin[(size_t)f * holdouts + y], pA = p - pD;
+        const int64_t N = std::min(nD, pD), K = std::max(nD, pD), kk = std::min<int64_t>(kmax, N);
+        if (N == 0) continue;
+        w1 = std::max(w1, gemm_tn_workspace(N, N, K, ctx->sm_count));
+        if (kk > 0 && pA > 0) w2 = std::max(w2, gemm_tn_workspace(kk, pA, nD, ctx->sm_count));
+    }
+    (void)Kmax; (void)kkmax;
+    const size_t slot_doubles = (size_t)ldD * maxc_in + ((any_wide || maxr_in == maxc_in) ? (size_t)ldDt * maxr_in : 0) +
+                                (size_t)ldR1 * maxc_in + (size_t)ldD * maxc_out + maxc_in + (size_t)ldG * Nmax +
+                                (size_t)kmax * 3 + (size_t)Nmax * kmax + (size_t)ldD * kmax + (size_t)ldDt * kmax +
+                                (size_t)ldR1 * kmax + (size_t)kmax * maxc_out + (size_t)nb_err * pstride +
+                                (kmax > 64 ? (size_t)maxr_out * maxc_out : 0) + w1 + w2 + 64;
+    int B = 16;
+    {
+        const double budget = 6.0 * 1024 * 1024 * 1024;          // bytes of cell workspace per call
+        const double per = (double)slot_doubles * sizeof(double);
+        if (per * B > budget) B = (int)(budget / per);
+        if (B < 1) B = 1;
+        if (const char *e = getenv("MFBICLUST_BCV_BATCH")) { const int b = atoi(e); if (b >= 1) B = b; }
+        if (B > ncell) B = ncell;
+        if (B > 64) B = 64;
+    }
+    int S = B < 4 ? B : 4;                                      // auxiliary streams
+    if (const char *e = getenv("MFBICLUST_BCV_AUX_STREAMS")) { const int v = atoi(e); if (v >= 1) S = std::min(v, B); }
+    // two sets of cell buffers: the gather / Gram stage of the next batch runs while the eigen-solver works on this one
+    const int nsets = (ncell > B) ? 2 : 1;
+    MFB_TRY(ensure_aux(ctx, (size_t)S, (size_t)3 * S + 2));
+    std::vector<CellSlot> slot((size_t)nsets * B);
+    for (int i = 0; i < nsets * B; ++i) {
+        CellSlot &c = slot[i];
+        c.Dt = nullptr; c.E = nullptr; c.work1 = nullptr; c.work2 = nullptr;
+        MFB_TRY(buf.alloc(&c.D, (size_t)ldD * maxc_in));
+        if (any_wide || maxr_in == maxc_in) MFB_TRY(buf.alloc(&c.Dt, (size_t)ldDt * maxr_in));
+        MFB_TRY(buf.alloc(&c.R1, (size_t)ldR1 * maxc_in));            // Y[r, -s]
+        MFB_TRY(buf.alloc(&c.R2, (size_t)ldD * maxc_out));            // Y[-r, s]
+        MFB_TRY(buf.alloc(&c.mu, (size_t)maxc_in));
+        MFB_TRY(buf.alloc(&c.G, (size_t)ldG * Nmax));
+        MFB_TRY(buf.alloc(&c.evals, (size_t)kmax));
+        MFB_TRY(buf.alloc(&c.evecs, (size_t)Nmax * kmax));
+        MFB_TRY(buf.alloc(&c.sigma, (size_t)kmax));
+        MFB_TRY(buf.alloc(&c.colscale, (size_t)kmax));
+        MFB_TRY(buf.alloc(&c.U, (size_t)ldD * kmax));
+        MFB_TRY(buf.alloc(&c.V, (size_t)ldDt * kmax));
+        MFB_TRY(buf.alloc(&c.B, (size_t)ldR1 * kmax));
+        MFB_TRY(buf.alloc(&c.C, (size_t)kmax * maxc_out));
+        MFB_TRY(buf.alloc(&c.part, (size_t)nb_err * pstride));
+        if (kmax > 64) MFB_TRY(buf.alloc(&c.E, (size_t)maxr_out * maxc_out));
+        if (w1) MFB_TRY(buf.alloc(&c.work1, w1));
+        if (w2) MFB_TRY(buf.alloc(&c.work2, w2));
+    }
+    const double sqrt_eps = 1.4901161193847656e-08;              // sqrt(.Machine$double.eps): MASS::ginv's tol
+    cudaEvent_t ev_main = ctx->aux_events[3 * S], ev_eig = ctx->aux_events[3 * S + 1];
+    // aux_events[parity * S + s]: stage 1 of a batch finished on stream s; aux_events[2 S + s]: stage 3 finished
+
+    struct Geo { int64_t nD, nA, pD, pA; const int32_t *rin, *rout, *cin, *cout; int kk; bool tall, empty; };
+    auto geometry = [&](int cell) {
+        Geo g;
+        const int f = cell / h2 - f_lo, local = cell % h2, x = local / holdouts, y = local % holdouts;
+        const int32_t *base = d_idx + (size_t)f * holdouts * (n + p);
+        g.nD = n_rin[(size_t)f * holdouts + x]; g.nA = n - g.nD;
+        g.pD = n_cin[(size_t)f * holdouts + y]; g.pA = p - g.pD;
+        g.rin = base + (size_t)x * n; g.rout = g.rin + g.nD;
+        g.cin = base + (size_t)holdouts * n + (size_t)y * p; g.cout = g.cin + g.pD;
         int kk = kmax;                                           // prcomp(D, rank. = max(ks)): k <- min(rank., dim(D))
-        if (kk > nD) kk = (int)nD;
-        if (kk > pD) kk = (int)pD;
-        if (nD == 0 || pD == 0 || nA == 0 || pA == 0 || kk == 0) {
-            MFB_CUDA(cudaMemsetAsync(e_out, 0, nks * sizeof(double), st));
-            continue;
+        if (kk > g.nD) kk = (int)g.nD;
+        if (kk > g.pD) kk = (int)g.pD;
+        g.kk = kk;
+        g.tall = g.nD >= g.pD;
+        g.empty = g.nD == 0 || g.pD == 0 || g.nA == 0 || g.pA == 0 || kk == 0;
+        return g;
+    };
+
+    // stage 1 (per cell, auxiliary streams): centre and gather the blocks, Gram matrix of the short side
+    auto stage1 = [&](int b0, int nb, int parity, std::vector<EigProblem> &probs) -> int {
+        probs.clear();
+        for (int i = 0; i < nb; ++i) {
+            const Geo g = geometry(b0 + i);
+            if (g.empty) continue;
+            CellSlot &c = slot[(size_t)parity * B + i];
+            cudaStream_t as = ctx->aux_streams[i % S];
+            StreamScope scope(ctx, as);
+            // Dc = scale(Y[-r, -s], center = TRUE, scale = FALSE)       (prcomp(center = TRUE), R/bcv.R:184)
+            gathered_colmean_kernel<<<(unsigned)(g.pD < 4 * ctx->sm_count ? g.pD : 4 * ctx->sm_count), 256, 0, as>>>(
+                Y->d, ldy, g.rin, g.nD, g.cin, g.pD, c.mu);
+            MFB_CUDA(cudaGetLastError());
+            MFB_CUDA(cudaMemsetAsync(c.D, 0, (size_t)ldD * g.pD * sizeof(double), as));
+            MFB_TRY(launch_gather(ctx, Y->d, ldy, g.rin, g.nD, g.cin, g.pD, c.mu, c.D, ldD));
+            MFB_TRY(launch_gather(ctx, Y->d, ldy, g.rout, g.nA, g.cin, g.pD, nullptr, c.R1, ldR1));
+            MFB_TRY(launch_gather(ctx, Y->d, ldy, g.rin, g.nD, g.cout, g.pA, nullptr, c.R2, ldD));
+            const double *Sx = c.D;
+            int64_t lds = ldD;
+            const int64_t N = g.tall ? g.pD : g.nD, K = g.tall ? g.nD : g.pD;
+            if (!g.tall) {
+                MFB_TRY(launch_transpose(ctx, c.D, g.nD, g.pD, ldD, c.Dt, ldDt));
+                Sx = c.Dt;
+                lds = ldDt;
+            }
+            MFB_TRY(gemm_tn(ctx, Sx, lds, Sx, lds, c.G, ldG, N, N, K, c.work1));
+            EigProblem pr;
+            pr.G = c.G; pr.ldg = ldG; pr.N = N; pr.k = g.kk; pr.evals = c.evals; pr.evecs = c.evecs;
+            probs.push_back(pr);
         }
-        MFB_CUDA(cudaMemcpyAsync(d_rin, rin[x].data(), nD * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        MFB_CUDA(cudaMemcpyAsync(d_rout, rout[x].data(), nA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        MFB_CUDA(cudaMemcpyAsync(d_cin, cin[y].data(), pD * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        MFB_CUDA(cudaMemcpyAsync(d_cout, cout[y].data(), pA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        // Dc = scale(Y[-r, -s], center = TRUE, scale = FALSE)       (prcomp(center = TRUE), R/bcv.R:184)
-        gathered_colmean_kernel<<<(unsigned)(pD < 4 * ctx->sm_count ? pD : 4 * ctx->sm_count), 256, 0, st>>>(
-            Y->d, ldy, d_rin, nD, d_cin, pD, mu);
-        MFB_CUDA(cudaGetLastError());
-        MFB_CUDA(cudaMemsetAsync(D, 0, (size_t)ldD * pD * sizeof(double), st));
-        MFB_TRY(launch_gather(ctx, Y->d, ldy, d_rin, nD, d_cin, pD, mu, D, ldD));
-        MFB_TRY(launch_gather(ctx, Y->d, ldy, d_rout, nA, d_cin, pD, nullptr, R1, ldR1));
-        MFB_TRY(launch_gather(ctx, Y->d, ldy, d_rin, nD, d_cout, pA, nullptr, R2, ldD));
-        MFB_TRY(topk_svd(ctx, D, nD, pD, ldD, Dt, ldDt, kk, sqrt_eps, sigma, colscale, U, ldD, V, ldDt));
-        // B = Y[r, -s] V S^-1  (|r| x kk);  C = U' Y[-r, s]  (kk x |s|)
-        MFB_TRY(tall_times_small(ctx, R1, ldR1, V, ldDt, B, ldR1, nA, pD, kk, colscale));
-        MFB_TRY(gemm_tn(ctx, U, ldD, R2, ldD, C, kk, kk, pA, nD, work));
-        if (kk <= 16) bcv_error_kernel<16><<<nb_err, 256, 0, st>>>(Y->d, ldy, d_rout, nA, d_cout, pA, B, ldR1, C, kk, 0, kk, nullptr, 0, part, pstride);
-        else if (kk <= 32) bcv_error_kernel<32><<<nb_err, 256, 0, st>>>(Y->d, ldy, d_rout, nA, d_cout, pA, B, ldR1, C, kk, 0, kk, nullptr, 0, part, pstride);
-        else
-            for (int j0 = 0; j0 < kk; j0 += 64)
-                bcv_error_kernel<64><<<nb_err, 256, 0, st>>>(Y->d, ldy, d_rout, nA, d_cout, pA, B, ldR1, C, kk, j0, kk, E,
-                                                             (j0 + 64 < kk) ? 1 : 0, part, pstride);
-        bcv_error_final_kernel<<<(nks + 63) / 64, 64, 0, st>>>(part, nb_err, pstride, kk, d_ks, nks, e_out);
-        MFB_CUDA(cudaGetLastError());
+        for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaEventRecord(ctx->aux_events[parity * S + s2], ctx->aux_streams[s2]));
+        return MFB_OK;
+    };
+    const bool timing = getenv("MFB_BCV_TIMING") != nullptr;     // development aid: host clock after a sync per stage
+    auto now_ms = [&]() {
+        cudaStreamSynchronize(st);
+        for (int s2 = 0; s2 < S; ++s2) cudaStreamSynchronize(ctx->aux_streams[s2]);
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    MFB_CUDA(cudaEventRecord(ev_main, st));                      // index lists uploaded
+    for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaStreamWaitEvent(ctx->aux_streams[s2], ev_main, 0));
+    std::vector<EigProblem> probs_cur, probs_next;
+    MFB_TRY(stage1(cell_begin, std::min(B, cell_end - cell_begin), 0, probs_cur));
+    int parity = 0;
+    for (int b0 = cell_begin; b0 < cell_end; b0 += B, parity ^= 1) {
+        const int nb = std::min(B, cell_end - b0);
+        double t_b = 0, t_c = 0, t_d = 0;
+        for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaStreamWaitEvent(st, ctx->aux_events[parity * S + s2], 0));
+        // the next batch's gathers and Gram products go to the auxiliary streams now: they overlap the eigen-solver
+        if (b0 + B < cell_end && nsets == 2)
+            MFB_TRY(stage1(b0 + B, std::min(B, cell_end - b0 - B), parity ^ 1, probs_next));
+        if (timing) t_b = now_ms();
+        // ---- stage 2 (the whole batch, main stream): leading eigenpairs of every Gram matrix ----
+        if (!probs_cur.empty()) MFB_TRY(sym_eig_topk_batch(ctx, (int)probs_cur.size(), probs_cur.data()));
+        MFB_CUDA(cudaEventRecord(ev_eig, st));
+        if (timing) t_c = now_ms();
+        // ---- stage 3 (per cell, auxiliary streams): singular triplets, B = Y[r,-s] V S^-1, C = U'Y[-r,s], errors ----
+        for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaStreamWaitEvent(ctx->aux_streams[s2], ev_eig, 0));
+        for (int i = 0; i < nb; ++i) {
+            const Geo g = geometry(b0 + i);
+            double *e_out = d_err + (size_t)(b0 + i - cell_begin) * nks;
+            CellSlot &c = slot[(size_t)parity * B + i];
+            cudaStream_t as = ctx->aux_streams[i % S];
+            StreamScope scope(ctx, as);
+            if (g.empty) {
+                MFB_CUDA(cudaMemsetAsync(e_out, 0, nks * sizeof(double), as));
+                continue;
+            }
+            const int kk = g.kk;
+            // long side: Z = X v (its column norms are the singular values); short side: the eigenvectors
+            if (g.tall) {
+                MFB_CUDA(cudaMemcpy2DAsync(c.V, ldDt * sizeof(double), c.evecs, g.pD * sizeof(double),
+                                           g.pD * sizeof(double), kk, cudaMemcpyDeviceToDevice, as));
+                MFB_TRY(tall_times_small(ctx, c.D, ldD, c.evecs, g.pD, c.U, ldD, g.nD, g.pD, kk, nullptr));
+                colnorm_kernel<<<kk, 256, 0, as>>>(c.U, ldD, g.nD, c.sigma);
+                sigma_scale_kernel<<<kk, 256, 0, as>>>(c.U, ldD, g.nD, kk, c.sigma, c.colscale, sqrt_eps);
+            } else {
+                MFB_CUDA(cudaMemcpy2DAsync(c.U, ldD * sizeof(double), c.evecs, g.nD * sizeof(double),
+                                           g.nD * sizeof(double), kk, cudaMemcpyDeviceToDevice, as));
+                MFB_TRY(tall_times_small(ctx, c.Dt, ldDt, c.evecs, g.nD, c.V, ldDt, g.pD, g.nD, kk, nullptr));
+                colnorm_kernel<<<kk, 256, 0, as>>>(c.V, ldDt, g.pD, c.sigma);
+                sigma_scale_kernel<<<kk, 256, 0, as>>>(c.V, ldDt, g.pD, kk, c.sigma, c.colscale, sqrt_eps);
+            }
+            MFB_CUDA(cudaGetLastError());
+            // B = Y[r, -s] V S^-1  (|r| x kk);  C = U' Y[-r, s]  (kk x |s|)
+            MFB_TRY(tall_times_small(ctx, c.R1, ldR1, c.V, ldDt, c.B, ldR1, g.nA, g.pD, kk, c.colscale));
+            MFB_TRY(gemm_tn(ctx, c.U, ldD, c.R2, ldD, c.C, kk, kk, g.pA, g.nD, c.work2));
+            if (kk <= 16)
+                bcv_error_kernel<16><<<nb_err, 256, 0, as>>>(Y->d, ldy, g.rout, g.nA, g.cout, g.pA, c.B, ldR1, c.C, kk, 0, kk,
+                                                             nullptr, 0, c.part, pstride);
+            else if (kk <= 32)
+                bcv_error_kernel<32><<<nb_err, 256, 0, as>>>(Y->d, ldy, g.rout, g.nA, g.cout, g.pA, c.B, ldR1, c.C, kk, 0, kk,
+                                                             nullptr, 0, c.part, pstride);
+            else
+                for (int j0 = 0; j0 < kk; j0 += 64)
+                    bcv_error_kernel<64><<<nb_err, 256, 0, as>>>(Y->d, ldy, g.rout, g.nA, g.cout, g.pA, c.B, ldR1, c.C, kk, j0,
+                                                                 kk, c.E, (j0 + 64 < kk) ? 1 : 0, c.part, pstride);
+            bcv_error_final_kernel<<<(nks + 63) / 64, 64, 0, as>>>(c.part, nb_err, pstride, kk, d_ks, nks, e_out);
+            MFB_CUDA(cudaGetLastError());
+        }
+        for (int s2 = 0; s2 < S; ++s2) {
+            MFB_CUDA(cudaEventRecord(ctx->aux_events[2 * S + s2], ctx->aux_streams[s2]));
+            MFB_CUDA(cudaStreamWaitEvent(st, ctx->aux_events[2 * S + s2], 0));
+        }
+        if (timing) {
+            t_d = now_ms();
+            fprintf(stderr, "bcv batch of %d cells: eigen %.3f ms, products+errors (+ next gather/Gram) %.3f ms\n", nb,
+                    t_c - t_b, t_d - t_c);
+        }
+        probs_cur.swap(probs_next);
     }
     MFB_CUDA(cudaMemcpyAsync(err, d_err, (size_t)ncell * nks * sizeof(double), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));

@@ -54,23 +54,34 @@ print("D3 oracle bcv call", round(time.perf_counter() - t0, 2), "s; curve rel er
       float(np.abs(got / ref - 1).max()), "argmin", int(np.argmin(got)), int(np.argmin(ref)), flush=True)
 rng = mfb.HostRng(50)
 fl = [mfb.draw_folds(rng, *Y.shape, 3) for _ in range(4)]
-for cap in ("", "148", "84", "42", "24"):
-    if cap:
+def timed(label):
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        mfb.bcvGivenKs(Yd, ks, 3, folds=(rf, cf), ctx=ctx)
+        best = min(best, time.perf_counter() - t0)
+    b36 = 1e9
+    for _ in range(2):
+        t0 = time.perf_counter()
+        mfb.bcv_batch(Yd, ks, 3, fl, ctx=ctx)
+        b36 = min(b36, time.perf_counter() - t0)
+    print(label, "bcv call (9 cells)", round(best, 4), "36 cells", round(b36, 4), flush=True)
+
+
+for batch in ("1", "4", "9", "12", "18", "36"):
+    os.environ["MFBICLUST_BCV_BATCH"] = batch
+    for aux in ("1", "4", "8"):
+        os.environ["MFBICLUST_BCV_AUX_STREAMS"] = aux
+        timed("batch %s aux %s" % (batch, aux))
+os.environ["MFBICLUST_BCV_AUX_STREAMS"] = "4"
+for batch in ("9", "18"):
+    os.environ["MFBICLUST_BCV_BATCH"] = batch
+    for cap in ("8", "12", "16", "24", "32"):
         os.environ["MFB_LZ_BLOCKS"] = cap
-    else:
-        os.environ.pop("MFB_LZ_BLOCKS", None)
-    for streams in (1, 3, 6):
-        best = 1e9
-        for _ in range(3):
-            t0 = time.perf_counter()
-            mfb.bcvGivenKs(Yd, ks, 3, folds=(rf, cf), ctx=ctx, streams=streams)
-            best = min(best, time.perf_counter() - t0)
-        b36 = 1e9
-        for _ in range(2):
-            t0 = time.perf_counter()
-            mfb.bcv_batch(Yd, ks, 3, fl, ctx=ctx, streams=streams)
-            b36 = min(b36, time.perf_counter() - t0)
-        print("cap", cap or "default", "streams", streams, "bcv call (9 cells)", round(best, 4), "36 cells", round(b36, 4), flush=True)
+        timed("batch %s lz_blocks %s" % (batch, cap))
+    os.environ.pop("MFB_LZ_BLOCKS", None)
+os.environ.pop("MFBICLUST_BCV_BATCH", None)
+os.environ.pop("MFBICLUST_BCV_AUX_STREAMS", None)
 os.environ.pop("MFB_LZ_BLOCKS", None)
 for _ in range(2):
     t0 = time.perf_counter()
