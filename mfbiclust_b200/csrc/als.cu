@@ -1007,6 +1007,8 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+#include "als_tf32.cuh"
+
 // ---------------------------------------------------------------------------
 // stand-alone Gram + inverse of a factor [KP][ld] over `len` entries (start / restart only)
 // ---------------------------------------------------------------------------
@@ -1245,6 +1247,13 @@ struct mfb_als {
     int nsolve_h, nsolve_w;       // solve-kernel grids
     bool attr_set = false;
     bool f32 = false;             // A is resident in single precision
+    bool tf32 = false;            // ... and the products run on the TF32 tensor cores (als_tf32.cuh)
+    int KPN = 0;                  // rank padded to the MMA N granularity (16)
+    float *Whi[3] = {nullptr, nullptr, nullptr}, *Wlo[3] = {nullptr, nullptr, nullptr};   // hi / lo FP32 copies of Wb[0], Wb[1], Wr
+    float *Hhi[2] = {nullptr, nullptr}, *Hlo[2] = {nullptr, nullptr};
+    CUtensorMap tmf_Whi[3], tmf_Wlo[3], tmf_Hhi[2], tmf_Hlo[2];
+    size_t smem_h32 = 0, smem_w32 = 0;
+    int nstage_h32 = 0, nstage_w32 = 0;
     std::vector<cudaEvent_t> *prof = nullptr;   // mfb_als_profile: one event after every kernel
     AlsCtrl *ctrl;
     double *trace_dev;
@@ -1362,32 +1371,70 @@ static bool als_use_pdl(const mfb_als *s) {
     return (s->prof == nullptr) && (!s->shard || als_peer_mode(s)) && !getenv("MFB_NO_PDL");
 }
 
+// TF32 path (als_tf32.cuh): tensor maps of the fixed factor's hi / lo FP32 copies, and where the factor produced by
+// this half-step is to be split into
+struct Tf32Extra {
+    const CUtensorMap *bhi = nullptr, *blo = nullptr;
+    float *out_hi = nullptr, *out_lo = nullptr;
+};
+
 template <int KB, bool F32>
-static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which) {
+static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which, const Tf32Extra &x) {
     // which: 0 = stream + solve, 1 = stream kernel only, 2 = solve kernel only (row-sharded H-step)
     cudaStream_t st = s->ctx->stream;
     const int G = hp.Gstream;
     const int nsolve = wstep ? s->nsolve_w : s->nsolve_h;
     const bool pdl = als_use_pdl(s);
+    constexpr bool TF32_OK = F32 && (KB <= 2);
+    const bool tf32 = TF32_OK && s->tf32 && x.bhi != nullptr;
     if (!s->attr_set) {
         MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, true, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w));
         MFB_CUDA(cudaFuncSetAttribute(als_stream_kernel<KB, false, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h));
         MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
         MFB_CUDA(cudaFuncSetAttribute(als_solve_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SolveCfg<KB>::SMEM));
+        if constexpr (TF32_OK) {
+            if (s->tf32) {
+                MFB_CUDA(cudaFuncSetAttribute(als_stream_tf32_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_w32));
+                MFB_CUDA(cudaFuncSetAttribute(als_stream_tf32_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_h32));
+            }
+        }
         s->attr_set = true;
     }
+    auto stream_launch = [&](bool w) -> int {
+        if constexpr (TF32_OK) {
+            if (tf32) {
+                if (w) MFB_CUDA(launch_pdl(als_stream_tf32_kernel<KB, true>, G, TF32_THREADS, s->smem_w32, st, pdl, s->tm_w, *x.bhi, *x.blo, hp, s->nstage_w32));
+                else MFB_CUDA(launch_pdl(als_stream_tf32_kernel<KB, false>, G, TF32_THREADS, s->smem_h32, st, pdl, s->tm_h, *x.bhi, *x.blo, hp, s->nstage_h32));
+                return MFB_OK;
+            }
+        }
+        if (w) MFB_CUDA(launch_pdl(als_stream_kernel<KB, true, F32>, G, ALS_THREADS, s->smem_w, st, pdl, s->tm_w, tmF, hp, s->nstage_w));
+        else MFB_CUDA(launch_pdl(als_stream_kernel<KB, false, F32>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
+        return MFB_OK;
+    };
+    auto split_launch = [&]() -> int {      // hi / lo FP32 copies of the factor the solve kernel has just written
+        if (!(s->tf32 && x.out_hi)) return MFB_OK;
+        const int64_t total = (int64_t)s->KP * hp.ldout;
+        int nb = (int)((total + 255) / 256);
+        if (nb > 2 * s->ctx->sm_count) nb = 2 * s->ctx->sm_count;
+        MFB_CUDA(launch_pdl(als_split_factor_kernel, nb, 256, 0, st, pdl, (const double *)hp.Fout, hp.ldout, s->KP, x.out_hi,
+                            x.out_lo, (const AlsCtrl *)hp.ctrl));
+        return MFB_OK;
+    };
     if (wstep) {
-        MFB_CUDA(launch_pdl(als_stream_kernel<KB, true, F32>, G, ALS_THREADS, s->smem_w, st, pdl, s->tm_w, tmF, hp, s->nstage_w));
+        MFB_TRY(stream_launch(true));
         MFB_TRY(prof_mark(s));
         MFB_CUDA(launch_pdl(als_solve_kernel<KB, true>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
+        MFB_TRY(split_launch());
         MFB_TRY(prof_mark(s));
     } else {
         if (which != 2) {
-            MFB_CUDA(launch_pdl(als_stream_kernel<KB, false, F32>, G, ALS_THREADS, s->smem_h, st, pdl, s->tm_h, tmF, hp, s->nstage_h));
+            MFB_TRY(stream_launch(false));
             MFB_TRY(prof_mark(s));
         }
         if (which != 1) {
             MFB_CUDA(launch_pdl(als_solve_kernel<KB, false>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
+            MFB_TRY(split_launch());
             MFB_TRY(prof_mark(s));
         }
     }
@@ -1396,8 +1443,8 @@ static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUt
 }
 
 template <int KB>
-static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which) {
-    return s->f32 ? launch_half_t<KB, true>(s, wstep, hp, tmF, which) : launch_half_t<KB, false>(s, wstep, hp, tmF, which);
+static int launch_half(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which, const Tf32Extra &x) {
+    return s->f32 ? launch_half_t<KB, true>(s, wstep, hp, tmF, which, x) : launch_half_t<KB, false>(s, wstep, hp, tmF, which, x);
 }
 
 template <int KB>
@@ -1427,14 +1474,15 @@ static int check_mbar_abort(const char *where) {
     return MFB_ERR_CUDA;
 }
 
-static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which = 0) {
+static int launch_half_dispatch(mfb_als *s, bool wstep, const HalfParams &hp, const CUtensorMap &tmF, int which = 0,
+                                const Tf32Extra &x = Tf32Extra()) {
     switch (s->KB) {
-        case 1: return launch_half<1>(s, wstep, hp, tmF, which);
-        case 2: return launch_half<2>(s, wstep, hp, tmF, which);
-        case 3: return launch_half<3>(s, wstep, hp, tmF, which);
-        case 4: return launch_half<4>(s, wstep, hp, tmF, which);
-        case 6: return launch_half<6>(s, wstep, hp, tmF, which);
-        case 8: return launch_half<8>(s, wstep, hp, tmF, which);
+        case 1: return launch_half<1>(s, wstep, hp, tmF, which, x);
+        case 2: return launch_half<2>(s, wstep, hp, tmF, which, x);
+        case 3: return launch_half<3>(s, wstep, hp, tmF, which, x);
+        case 4: return launch_half<4>(s, wstep, hp, tmF, which, x);
+        case 6: return launch_half<6>(s, wstep, hp, tmF, which, x);
+        case 8: return launch_half<8>(s, wstep, hp, tmF, which, x);
     }
     mfb_set_error("unsupported rank block %d", s->KB);
     return MFB_ERR_UNSUPPORTED;
@@ -1540,6 +1588,21 @@ static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int
     }
     s->smem_h = 1024 + (size_t)s->nstage_h * stage_h + 2 * s->nstage_h * sizeof(uint64_t) + side;
     s->smem_w = 1024 + (size_t)s->nstage_w * stage_w + 2 * s->nstage_w * sizeof(uint64_t) + side;
+    // FP32 matrix: the products run on the TF32 tensor cores (als_tf32.cuh) for ranks up to 16; MFB_F32_DMMA=1 keeps
+    // the FP32-storage / FP64-tensor-core kernels (development aid for A/B runs)
+    s->KPN = (int)round_up(s->KP, 16);
+    s->tf32 = s->f32 && s->KB <= 2 && !getenv("MFB_F32_DMMA");
+    if (s->tf32) {
+        const int comp = getenv("MFB_TF32_NOCOMP") ? 0 : 1;
+        cudaMemcpyToSymbol(g_tf32_comp, &comp, sizeof(int));
+        const size_t stage32 = 16384 + 2 * (size_t)s->KPN * 128;
+        const size_t bars32 = 16 * sizeof(uint64_t) + 16;
+        int ns = (int)((227 * 1024 - 1024 - 2 * 16 * sizeof(uint64_t) - bars32 - side) / stage32);
+        if (ns > 10) ns = 10;
+        ns -= ns % 2;
+        s->nstage_h32 = s->nstage_w32 = ns;
+        s->smem_h32 = s->smem_w32 = 1024 + (size_t)ns * stage32 + 2 * ns * sizeof(uint64_t) + bars32 + side;
+    }
     const int SU = solve_units_dispatch(s->KB);
     s->nsolve_h = (int)((s->n + SU - 1) / SU);
     s->nsolve_w = (int)((s->m + SU - 1) / SU);
@@ -1548,6 +1611,10 @@ static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int
 #define ALLOC(ptr, cnt) if ((rc = dev_alloc(s, &(ptr), (cnt))) != MFB_OK) { mfb_als_end(s); return rc; }
     ALLOC(s->Wb[0], KP * s->ldw) ALLOC(s->Wb[1], KP * s->ldw) ALLOC(s->Wr, KP * s->ldw)
     ALLOC(s->Hb[0], KP * s->ldh) ALLOC(s->Hb[1], KP * s->ldh)
+    if (s->tf32) {
+        for (int i = 0; i < 3; ++i) { ALLOC(s->Whi[i], (size_t)s->KPN * s->ldw) ALLOC(s->Wlo[i], (size_t)s->KPN * s->ldw) }
+        for (int i = 0; i < 2; ++i) { ALLOC(s->Hhi[i], (size_t)s->KPN * s->ldh) ALLOC(s->Hlo[i], (size_t)s->KPN * s->ldh) }
+    }
     ALLOC(s->G_W, KP * KP) ALLOC(s->Minv_W, KP * KP) ALLOC(s->G_H, KP * KP) ALLOC(s->Minv_H, KP * KP)
     ALLOC(s->P_h, (size_t)s->T_h * s->maxslots_h * KP * TILE_UNITS)
     ALLOC(s->P_w, (size_t)s->T_w * s->maxslots_w * KP * TILE_UNITS)
@@ -1601,10 +1668,23 @@ static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int
         for (int i = 0; i < 2; ++i)
             if ((rc = encode_map(&s->tm_H[i], s->Hb[i], s->ldh, s->KP, s->ldh, 16, s->KP)) != MFB_OK) { mfb_als_end(s); return rc; }
     }
+    if (s->tf32) {
+        // hi / lo FP32 copies of the factors as B operands: dims {ld (contiguous), KPN}, box {32, KPN} = [KPN][128 bytes]
+        for (int i = 0; i < 3; ++i)
+            if ((rc = encode_map(&s->tmf_Whi[i], s->Whi[i], s->ldw, s->KPN, s->ldw, 32, s->KPN, true)) != MFB_OK ||
+                (rc = encode_map(&s->tmf_Wlo[i], s->Wlo[i], s->ldw, s->KPN, s->ldw, 32, s->KPN, true)) != MFB_OK) { mfb_als_end(s); return rc; }
+        for (int i = 0; i < 2; ++i)
+            if ((rc = encode_map(&s->tmf_Hhi[i], s->Hhi[i], s->ldh, s->KPN, s->ldh, 32, s->KPN, true)) != MFB_OK ||
+                (rc = encode_map(&s->tmf_Hlo[i], s->Hlo[i], s->ldh, s->KPN, s->ldh, 32, s->KPN, true)) != MFB_OK) { mfb_als_end(s); return rc; }
+    }
     // initial factors
     cudaStream_t st = ctx->stream;
     MFB_CUDA(cudaMemcpy2DAsync(s->Wb[0], s->ldw * sizeof(double), W0, s->m * sizeof(double), s->m * sizeof(double), k,
                                cudaMemcpyHostToDevice, st));
+    if (s->tf32) {
+        als_split_factor_kernel<<<2 * ctx->sm_count, 256, 0, st>>>(s->Wb[0], s->ldw, s->KP, s->Whi[0], s->Wlo[0], nullptr);
+        MFB_CUDA(cudaGetLastError());
+    }
     if ((rc = als_upload_H(s, Hold0, s->Hb[0])) != MFB_OK) { mfb_als_end(s); return rc; }
     AlsCtrl c;
     memset(&c, 0, sizeof(c));
@@ -1700,6 +1780,10 @@ int mfb_als_restart(mfb_als *s, const double *Wnew) {
     cudaStream_t st = s->ctx->stream;
     MFB_CUDA(cudaMemcpy2DAsync(s->Wr, s->ldw * sizeof(double), Wnew, s->m * sizeof(double), s->m * sizeof(double), s->k,
                                cudaMemcpyHostToDevice, st));
+    if (s->tf32) {
+        als_split_factor_kernel<<<2 * s->ctx->sm_count, 256, 0, st>>>(s->Wr, s->ldw, s->KP, s->Whi[2], s->Wlo[2], nullptr);
+        MFB_CUDA(cudaGetLastError());
+    }
     MFB_CUDA(cudaStreamSynchronize(st));
     s->restart_pending = true;
     return MFB_OK;
@@ -1724,13 +1808,19 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     if (s->shard) h.epoch = ++s->epoch;
     h.peers = peer ? s->peers_dev : nullptr;
     const CUtensorMap &tmW = use_restart_w ? s->tm_W[2] : s->tm_W[cur];
+    Tf32Extra xh, xw;
+    if (s->tf32) {
+        const int wi = use_restart_w ? 2 : cur;
+        xh.bhi = &s->tmf_Whi[wi]; xh.blo = &s->tmf_Wlo[wi]; xh.out_hi = s->Hhi[nxt]; xh.out_lo = s->Hlo[nxt];
+        xw.bhi = &s->tmf_Hhi[nxt]; xw.blo = &s->tmf_Hlo[nxt]; xw.out_hi = s->Whi[nxt]; xw.out_lo = s->Wlo[nxt];
+    }
     if (!s->shard) {
-        MFB_TRY(launch_half_dispatch(s, false, h, tmW));
+        MFB_TRY(launch_half_dispatch(s, false, h, tmW, 0, xh));
     } else {
         // local W_r'A_r and W_r'W_r -> one buffer -> sum over the ranks -> invert -> NNLS (replicated, identical H)
         cudaStream_t st = s->ctx->stream;
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
-        MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1));
+        MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1, xh));
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
         const size_t gsm = (size_t)(s->KP * s->KP + 2) * sizeof(double);
         MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, 0, st, pdl, h, s->KP, xbuf));
@@ -1746,7 +1836,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         }
         HalfParams hs = h;
         hs.P = s->xchg; hs.maxslots = 1;
-        MFB_TRY(launch_half_dispatch(s, false, hs, tmW, 2));
+        MFB_TRY(launch_half_dispatch(s, false, hs, tmW, 2, xh));
     }
     HalfParams w = h;
     w.Fin = s->Hb[nxt]; w.ldin = s->ldh; w.nfix = s->n;
@@ -1754,7 +1844,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     w.G = s->G_H; w.Minv = s->Minv_H;
     w.P = s->P_w; w.maxslots = s->maxslots_w;
     w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
-    MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt]));
+    MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt], 0, xw));
     if (s->shard && !peer) {
         cudaStream_t st = s->ctx->stream;
         if (s->allreduce(s->allreduce_user, s->xscal, 4, (void *)st) != 0) {
@@ -1824,6 +1914,23 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
     return status;
 }
 
+static void tf32_timing_begin() {
+    if (!getenv("MFB_TF32_TIMING")) return;
+    unsigned long long z[16] = {0};
+    int one = 1;
+    cudaMemcpyToSymbol(g_tf32_ticks, z, sizeof(z));
+    cudaMemcpyToSymbol(g_tf32_timing, &one, sizeof(int));
+}
+static void tf32_timing_end(int iters) {
+    if (!getenv("MFB_TF32_TIMING")) return;
+    unsigned long long t[16];
+    int zero = 0;
+    cudaMemcpyFromSymbol(t, g_tf32_ticks, sizeof(t));
+    cudaMemcpyToSymbol(g_tf32_timing, &zero, sizeof(int));
+    fprintf(stderr, "tf32 converter (block 0, thread 0) clocks per iteration: loop %llu | wait full %llu | lds+split %llu | wait ta_empty %llu | sttm %llu | - %llu | wait d_full %llu | ldtm+fp64 %llu\n",
+            t[0] / iters, t[1] / iters, t[2] / iters, t[3] / iters, t[4] / iters, t[5] / iters, t[6] / iters, t[7] / iters);
+}
+
 int mfb_als_profile(mfb_als *s, int iters, double *ms) {
     MFB_ARG(s && ms && iters >= 1, "bad argument");
     MFB_CUDA(cudaSetDevice(s->ctx->device));
@@ -1835,9 +1942,11 @@ int mfb_als_profile(mfb_als *s, int iters, double *ms) {
     ev.push_back(e0);
     s->prof = &ev;
     int it = 0, conv = 0;
+    tf32_timing_begin();
     const int rc = mfb_als_iterate(s, iters, 1e-4, 1, &it, &conv);
     s->prof = nullptr;
     MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    tf32_timing_end(iters);
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const size_t nk = ev.size() - 1;
     // sharded, callback exchange: H stream, fold, invert, H solve, W stream, W solve, finish (collectives in between);

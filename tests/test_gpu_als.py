@@ -303,15 +303,44 @@ def test_als_full_size_properties():
     assert grad[W == 0].max() <= 1e-9 * scale                         # no positive gradient left on the active set
 
 
-@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1037, 333, 10), (70, 45, 3), (640, 1030, 24), (600, 400, 64)])
-def test_als_fp32_storage(m, n, k):
-    """FP32 path of BASELINE.json configs[3]: A resident in single precision, FP64 accumulation.  Against the
-    oracle on the float32-rounded matrix it is the same computation (1e-8); against the oracle on the original
-    matrix it must stay within the north-star FP32 tolerance of 1e-4 relative Frobenius error."""
-    import mfbiclust_b200 as mfb
+def _fp32_case(m, n, k, seed=44):
     A = pseudovalues(gen_sim_data(n=4, cluster_height=min(m, n) // 5, cluster_width=min(m, n) // 5, dimx=m, dimy=n,
                                   bg_norm=1.0, bicluster_shift=3.0, row_shift=1.0, col_shift=1.0, seed=m + n))
-    W0, H0 = make_init(m, n, k, 44)
+    W0, H0 = make_init(m, n, k, seed)
+    return A, W0, H0
+
+
+@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1037, 333, 10), (70, 45, 3), (640, 384, 8), (6, 6, 1), (1500, 3000, 16)])
+def test_als_fp32_tensor_core_path(m, n, k, monkeypatch):
+    """FP32 path of BASELINE.json configs[3] (north star: factors within 1e-4 relative Frobenius error of the FP64
+    reference after a fixed iteration count): A resident in single precision, the two products of an iteration on the
+    TF32 tensor cores (tcgen05.mma, 3-term split, accumulators flushed per 32-deep stage; csrc/als_tf32.cuh), Gram
+    matrices, NNLS and scalars in FP64.  Ranks up to 16 take this path."""
+    import mfbiclust_b200 as mfb
+    monkeypatch.delenv("MFB_F32_DMMA", raising=False)
+    A, W0, H0 = _fp32_case(m, n, k)
+    ctx = mfb.default_context()
+    Ad = mfb.Matrix(ctx, host=A, precision="f32")
+    try:
+        got = mfb.als_replicate(Ad, k, W0, H0, maxIter=8, fixed_iters=True)
+        again = mfb.als_replicate(Ad, k, W0, H0, maxIter=8, fixed_iters=True)
+    finally:
+        Ad.free()
+    ref64 = oracle_replicate(A, W0, H0, max_iter=8, fixed_iters=True)
+    assert rel_fro(got["W"], ref64["W"]) < 1e-4, rel_fro(got["W"], ref64["W"])          # tolerance: north star, FP32 path
+    assert rel_fro(got["H"], ref64["H"]) < 1e-4, rel_fro(got["H"], ref64["H"])
+    assert abs(got["obj"] - ref64["obj"]) < 1e-4 * ref64["obj"]
+    assert np.array_equal(got["W"], again["W"]) and np.array_equal(got["H"], again["H"])  # deterministic
+
+
+@pytest.mark.parametrize("m,n,k", [(2000, 500, 16), (1037, 333, 10), (70, 45, 3), (640, 1030, 24), (600, 400, 64)])
+def test_als_fp32_storage(m, n, k, monkeypatch):
+    """FP32 STORAGE with FP64 tensor-core accumulation (ranks above 16, or MFB_F32_DMMA=1): against the oracle on the
+    float32-rounded matrix it is the same computation (1e-8); against the oracle on the original matrix it stays far
+    inside the north-star FP32 tolerance of 1e-4 relative Frobenius error."""
+    import mfbiclust_b200 as mfb
+    monkeypatch.setenv("MFB_F32_DMMA", "1")
+    A, W0, H0 = _fp32_case(m, n, k)
     ctx = mfb.default_context()
     Ad = mfb.Matrix(ctx, host=A, precision="f32")
     try:
