@@ -211,6 +211,17 @@ int  mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds,
                          const int32_t *row_folds, const int32_t *col_folds, int holdouts,
                          const int32_t *ks, int nks, int cell_begin, int cell_end, double *err);
 
+/*
+ * The same work list for a matrix WITH missing entries (NaN = NA): the reference then factors every hold-in block
+ * with nipals_pca(center = TRUE, scale = FALSE) instead of prcomp (R/bcv.R:177-181) -- scores and loadings without
+ * singular values -- and NA entries of the products are dropped by sum(..., na.rm = TRUE) (:225-227).  At most 60
+ * components.  MFB_ERR_ARG when a hold-in block has a row or column without a non-zero observed entry (clean()
+ * would drop it and the reference's products become non-conformable).
+ */
+int  mfb_bcv_cells_na(mfb_context *ctx, mfb_matrix *Y, int nfolds,
+                      const int32_t *row_folds, const int32_t *col_folds, int holdouts,
+                      const int32_t *ks, int nks, int cell_begin, int cell_end, double *err);
+
 #ifdef __cplusplus
 }
 #endif

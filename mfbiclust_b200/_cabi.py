@@ -65,6 +65,7 @@ PROTOTYPES = {
                              _dp, _dp, _dp, _ip]),
     "mfb_bcv_cells": (C.c_int, [_vp, _vp, _i32p, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _dp]),
     "mfb_bcv_cells_multi": (C.c_int, [_vp, _vp, C.c_int, _i32p, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _dp]),
+    "mfb_bcv_cells_na": (C.c_int, [_vp, _vp, C.c_int, _i32p, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _dp]),
 }
 
 

@@ -674,8 +674,8 @@ def bcv(Y, ks=None, holdouts=10, interactive=True, rng=None, folds=None, ctx=Non
     shape = Y.shape
     if not isinstance(Y, _cabi.Matrix):
         Y = np.asarray(Y, dtype=np.float64)
-        if np.isnan(Y).any():
-            raise NotImplementedError("bcv: matrices with NA entries need the NIPALS branch (not supported yet)")
+        if np.isnan(Y).any() and interactive:                                  # :128-135 (R asks with menu())
+            print("Since some elements of the matrix are NA, BCV will run a much slower iterative algorithm.")
     minDim = min(shape)
     if ks is None:
         ks = np.arange(1, minDim)
@@ -690,7 +690,7 @@ def bcv(Y, ks=None, holdouts=10, interactive=True, rng=None, folds=None, ctx=Non
     return {int(k): float(v) for k, v in zip(ks, res)}
 
 
-def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=None):
+def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=None, na=None):
     """Per-cell errors ``(len(folds_list), holdouts^2, len(ks))`` for several fold draws at once: the
     ``len(folds_list) * holdouts^2`` cells are one flat work list sharded over the ranks (:func:`shard_cells`); a
     rank hands its whole share to ONE ``mfb_bcv_cells_multi`` call, which batches the cells on the device (one
@@ -712,10 +712,14 @@ def _bcv_cells_all(Yd, ks, holdouts, folds_list, ctx=None, group=None, streams=N
     if rfs.shape != (len(flat), n) or cfs.shape != (len(flat), p):
         raise ValueError("fold vectors must have one entry per row / column of Y")
 
+    if na is None:                                     # R/bcv.R:177: if (any(is.na(Y))) the NIPALS-based pca is used
+        na = Yd.stats()["n_nan"] > 0
+    entry = lib().mfb_bcv_cells_na if na else lib().mfb_bcv_cells_multi
+
     def compute(c0, c1):
         out = np.zeros((c1 - c0, len(ks)))
         ctx.set_concurrency(1)
-        check(lib().mfb_bcv_cells_multi(ctx.handle, Yd.handle, len(flat), rfs.ctypes.data_as(C.POINTER(C.c_int32)),
+        check(entry(ctx.handle, Yd.handle, len(flat), rfs.ctypes.data_as(C.POINTER(C.c_int32)),
                                         cfs.ctypes.data_as(C.POINTER(C.c_int32)), int(holdouts),
                                         ks.ctypes.data_as(C.POINTER(C.c_int32)), len(ks), int(c0), int(c1), dptr(out)))
         return out
@@ -776,8 +780,8 @@ def auto_bcv(Y, ks=None, holdouts=3, maxIter=100, tol=1e-4, bestOnly=False, verb
     own = not isinstance(Y, _cabi.Matrix)
     if own:
         Y = np.asarray(Y, dtype=np.float64)
-        if np.isnan(Y).any():
-            raise NotImplementedError("auto_bcv: matrices with NA entries are not supported yet")
+        if np.isnan(Y).any() and interactive:                                  # :39-46 (R asks with menu())
+            print("Since some elements of the matrix are NA, BCV will run a much slower iterative algorithm.")
     Yd = _cabi.Matrix(ctx, host=Y) if own else Y
     try:
         n, p = Yd.shape

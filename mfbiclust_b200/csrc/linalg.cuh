@@ -29,3 +29,8 @@ struct EigProblem {
     double *evals, *evecs;
 };
 int sym_eig_topk_batch(mfb_context *ctx, int np, const EigProblem *probs);
+
+// nipals.cu: NIPALS PCA of a device matrix with the results left on the device (T: m x ncomp unit columns, P: n x ncomp)
+int nipals_on_device(mfb_context *ctx, const double *xd, int64_t m, int64_t n, int64_t ld, int has_na, int ncomp,
+                     int center, int scale, int maxiter, double tol, int gramschmidt, double *T_out, double *P_out,
+                     double *eig_host, int *iters_host);

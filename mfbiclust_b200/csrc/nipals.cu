@@ -488,22 +488,16 @@ __global__ void __launch_bounds__(NIP_THREADS) nipals_kernel(NipalsParams p) {
     }
 }
 
-extern "C" {
-
-int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale, int maxiter, double tol,
-               int gramschmidt, double *scores, double *loadings, double *eig, int *iters) {
-    MFB_ARG(ctx && x && scores && loadings, "NULL argument");
-    if (x->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
+// NIPALS on a device matrix xd (m x n, leading dimension ld; untouched: a working copy is deflated).  Results stay
+// on the device: T (m x ncomp, ld = m, unit columns), P (n x ncomp, ld = n), eig / iters / status through the pinned
+// mailbox of the context (eig_host, iters_host: ncomp entries; may be NULL).  Returns MFB_OK, MFB_NOT_CONVERGED or an error.
+int nipals_on_device(mfb_context *ctx, const double *xd, int64_t m, int64_t n, int64_t ld, int has_na, int ncomp,
+                     int center, int scale, int maxiter, double tol, int gramschmidt, double *T_out, double *P_out,
+                     double *eig_host, int *iters_host) {
     MFB_ARG(ncomp >= 1 && ncomp <= 60, "ncomp must be in 1..60");
-    MFB_ARG(ncomp <= x->m && ncomp <= x->n, "ncomp exceeds a matrix dimension");
+    MFB_ARG(ncomp <= m && ncomp <= n, "ncomp exceeds a matrix dimension");
     MFB_ARG(maxiter >= 2, "maxiter must be at least 2");
-    MFB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    double stats[5];
-    int rc = mfb_matrix_stats(x, stats);
-    if (rc != MFB_OK) return rc;
-    const int has_na = stats[3] > 0;
-    const int64_t m = x->m, n = x->n, ld = x->lda;
     // shared memory: the 256-row pass scratch of the missing-value S3, or the score accumulator of the complete-data
     // S3 (the rows are cut into equal chunks of at most 12288 = 96 KB, so that two blocks still fit an SM)
     const int64_t nchunk = (m + 12287) / 12288;
@@ -550,25 +544,49 @@ int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale
     p.ncomp = ncomp; p.center = center; p.scale = scale; p.maxiter = maxiter; p.gramschmidt = gramschmidt;
     p.tol = tol;
     p.has_na = has_na;
-    MFB_CUDA(cudaMemcpyAsync(p.x, x->d, (size_t)ld * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(p.x, xd, (size_t)ld * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     void *args[] = {&p};
     MFB_CUDA(cudaLaunchCooperativeKernel((void *)nipals_kernel, dim3(nb), dim3(NIP_THREADS), args, smem, st));
     std::vector<double> hE(ncomp);
     std::vector<int> hI(ncomp + 1);
-    MFB_CUDA(cudaMemcpyAsync(scores, p.T, (size_t)m * ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));
-    MFB_CUDA(cudaMemcpyAsync(loadings, p.P, (size_t)n * ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaMemcpyAsync(T_out, p.T, (size_t)m * ncomp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(P_out, p.P, (size_t)n * ncomp * sizeof(double), cudaMemcpyDeviceToDevice, st));
     MFB_CUDA(cudaMemcpyAsync(hE.data(), p.part, ncomp * sizeof(double), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaMemcpyAsync(hI.data(), ibuf, (ncomp + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
     for (int h = 0; h < ncomp; ++h) {
-        if (eig) eig[h] = hE[h];
-        if (iters) iters[h] = hI[h];
+        if (eig_host) eig_host[h] = hE[h];
+        if (iters_host) iters_host[h] = hI[h];
     }
     if (hI[ncomp] == 2) {
         mfb_set_error("mfb_nipals: a column has zero variance and scale = TRUE");
         return MFB_ERR_ARG;
     }
     return hI[ncomp] == 1 ? MFB_NOT_CONVERGED : MFB_OK;
+}
+
+extern "C" {
+
+int mfb_nipals(mfb_context *ctx, mfb_matrix *x, int ncomp, int center, int scale, int maxiter, double tol,
+               int gramschmidt, double *scores, double *loadings, double *eig, int *iters) {
+    MFB_ARG(ctx && x && scores && loadings, "NULL argument");
+    if (x->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
+    MFB_ARG(ncomp >= 1 && ncomp <= 60, "ncomp must be in 1..60");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    double stats[5];
+    int rc = mfb_matrix_stats(x, stats);
+    if (rc != MFB_OK) return rc;
+    const int64_t m = x->m, n = x->n;
+    DevBuf pool(ctx);
+    double *dT = nullptr, *dP = nullptr;
+    if ((rc = pool.alloc(&dT, (size_t)m * ncomp)) != MFB_OK || (rc = pool.alloc(&dP, (size_t)n * ncomp)) != MFB_OK) return rc;
+    const int st_ = nipals_on_device(ctx, x->d, m, n, x->lda, stats[3] > 0, ncomp, center, scale, maxiter, tol, gramschmidt,
+                                     dT, dP, eig, iters);
+    if (st_ < 0) return st_;
+    MFB_CUDA(cudaMemcpyAsync(scores, dT, (size_t)m * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaMemcpyAsync(loadings, dP, (size_t)n * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return st_;
 }
 
 }  // extern "C"

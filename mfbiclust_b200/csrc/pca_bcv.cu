@@ -588,4 +588,254 @@ int mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32
     return MFB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// bcvGivenKs for matrices with missing entries (R/bcv.R:177-181: pca := nipals_pca(., center = TRUE, scale = FALSE))
+// ---------------------------------------------------------------------------
+// Per cell, as the reference does it: NIPALS (missing-value branch) of the hold-in block D gives scores U (unit
+// columns) and loadings V -- WITHOUT singular values (nipals_pca returns np$scores, which nipals normalises) -- so
+// estD_k = U_k V_k' and ginv(estD_k) = V_k (V_k'V_k)^-1 (U_k'U_k)^-1 U_k' (U_k, V_k have full column rank; NIPALS
+// leaves them orthonormal only up to its tolerance, so the small Gram matrices are kept).  Then
+//     estA_k = Y[r,-s] ginv(estD_k) Y[-r,s] = Bt[:, :k] M_k Ct[:k, :],   Bt = Y[r,-s] V,  Ct = U'Y[-r,s],
+//     M_k = (V_k'V_k)^-1 (U_k'U_k)^-1,
+// and sum((A - estA_k)^2, na.rm = TRUE): a missing entry anywhere in a row of Y[r,-s] or a column of Y[-r,s] makes the
+// whole row / column of estA NA (R's %*% propagates NA), which na.rm then drops -- NaN arithmetic does the same here.
+}  // extern "C"
+
+namespace {
+
+// M_q = (Gv_k)^-1 (Gu_k)^-1 for k = ks[q] (clamped to kk), one block per q; Gauss-Jordan with partial pivoting in
+// shared memory.  Gu, Gv: kk x kk (ld = kk).  M: [nks][kk][kk] (row a, column b at a + b * kk).
+__global__ void __launch_bounds__(128) na_minv_kernel(const double *__restrict__ Gu, const double *__restrict__ Gv, int kk,
+                                                      const int32_t *__restrict__ ks, double *__restrict__ M) {
+    extern __shared__ double sm[];               // two k x 2k augmented systems
+    int k = ks[blockIdx.x];
+    if (k > kk) k = kk;
+    double *Au = sm, *Av = sm + (size_t)k * 2 * k;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < k * 2 * k; e += 128) {
+        const int r = e / (2 * k), c = e - r * 2 * k;
+        Au[e] = (c < k) ? Gu[r + (size_t)c * kk] : ((c - k == r) ? 1.0 : 0.0);
+        Av[e] = (c < k) ? Gv[r + (size_t)c * kk] : ((c - k == r) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int which = 0; which < 2; ++which) {
+        double *A = which ? Av : Au;
+        for (int p = 0; p < k; ++p) {
+            __shared__ int piv;
+            if (tid == 0) {
+                int best = p;
+                double bv = fabs(A[p * 2 * k + p]);
+                for (int r = p + 1; r < k; ++r)
+                    if (fabs(A[r * 2 * k + p]) > bv) { bv = fabs(A[r * 2 * k + p]); best = r; }
+                piv = best;
+            }
+            __syncthreads();
+            if (piv != p)
+                for (int c = tid; c < 2 * k; c += 128) { const double t = A[p * 2 * k + c]; A[p * 2 * k + c] = A[piv * 2 * k + c]; A[piv * 2 * k + c] = t; }
+            __syncthreads();
+            const double ip = 1.0 / A[p * 2 * k + p];
+            __syncthreads();
+            for (int c = tid; c < 2 * k; c += 128) A[p * 2 * k + c] *= ip;
+            __syncthreads();
+            for (int e = tid; e < k * 2 * k; e += 128) {
+                const int r = e / (2 * k), c = e - r * 2 * k;
+                if (r != p && c != p) A[e] -= A[r * 2 * k + p] * A[p * 2 * k + c];
+            }
+            __syncthreads();
+            for (int r = tid; r < k; r += 128)
+                if (r != p) A[r * 2 * k + p] = 0.0;
+            __syncthreads();
+        }
+    }
+    // M = Av^-1 Au^-1 (the right halves)
+    double *Mq = M + (size_t)blockIdx.x * kk * kk;
+    for (int e = tid; e < kk * kk; e += 128) {
+        const int a = e % kk, b = e / kk;
+        double v = 0.0;
+        if (a < k && b < k)
+            for (int c = 0; c < k; ++c) v += Av[a * 2 * k + k + c] * Au[c * 2 * k + k + b];
+        Mq[e] = v;
+    }
+}
+
+// Ck[q][a][c] = sum_b M_q[a][b] Ct[b][c]   (a < kk; rows a >= ks[q] are zero because M_q is)
+__global__ void __launch_bounds__(256) na_ck_kernel(const double *__restrict__ M, const double *__restrict__ Ct, int kk,
+                                                    int64_t pA, double *__restrict__ Ck) {
+    const int q = blockIdx.y;
+    const double *Mq = M + (size_t)q * kk * kk;
+    double *Cq = Ck + (size_t)q * kk * pA;
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < (int64_t)kk * pA; e += (int64_t)gridDim.x * 256) {
+        const int64_t c = e / kk;
+        const int a = (int)(e - c * kk);
+        double v = 0.0;
+        for (int b = 0; b < kk; ++b) v += Mq[a + (size_t)b * kk] * Ct[b + c * kk];
+        Cq[a + c * kk] = v;
+    }
+}
+
+// part[block][q] = sum over this block's held-out entries of (Y[r_i, s_c] - Bt[i, :] Ck[q][:, c])^2, NaN results dropped
+__global__ void __launch_bounds__(256) na_error_kernel(const double *__restrict__ Y, int64_t ldy,
+                                                       const int32_t *__restrict__ rows, int64_t nr,
+                                                       const int32_t *__restrict__ cols, int64_t nc,
+                                                       const double *__restrict__ Bt, int64_t ldb,
+                                                       const double *__restrict__ Ck, int kk, int nks,
+                                                       double *__restrict__ part) {
+    __shared__ double sh[8];
+    const int q = blockIdx.y;
+    const double *Cq = Ck + (size_t)q * kk * nc;
+    double acc = 0.0;
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < nr * nc; e += (int64_t)gridDim.x * 256) {
+        const int64_t c = e / nr, i = e - c * nr;
+        double v = Y[rows[i] + (int64_t)cols[c] * ldy];
+        for (int a = 0; a < kk; ++a) v -= Bt[i + (int64_t)a * ldb] * Cq[a + c * kk];
+        if (v == v) acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        part[(size_t)blockIdx.x * nks + q] = t;
+    }
+}
+
+__global__ void na_error_final_kernel(const double *__restrict__ part, int nb, int nks, double *__restrict__ err) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nks) return;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += part[(size_t)b * nks + q];
+    err[q] = s;
+}
+
+// flags[0] != 0 when a row or a column of the gathered block is entirely NA-or-zero (clean() would drop it and the
+// reference's products become non-conformable: R/bicluster.R:271, R/helperFunctions.R:94-101)
+__global__ void __launch_bounds__(256) na_allbad_kernel(const double *__restrict__ D, int64_t ld, int64_t nr, int64_t nc,
+                                                        int *__restrict__ flags) {
+    // columns: one warp each; rows: one thread each
+    const int64_t gw = (blockIdx.x * 256ll + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t c = gw; c < nc; c += (int64_t)gridDim.x * 8) {
+        int good = 0;
+        for (int64_t i = lane; i < nr; i += 32) { const double v = D[i + c * ld]; good |= (v == v && v != 0.0); }
+        good = __any_sync(0xffffffffu, good);
+        if (!good && lane == 0) atomicExch(&flags[0], 1);
+    }
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < nr; i += (int64_t)gridDim.x * 256) {
+        int good = 0, anynan = 0;
+        for (int64_t c = 0; c < nc; ++c) { const double v = D[i + c * ld]; good |= (v == v && v != 0.0); anynan |= (v != v); }
+        if (!good) atomicExch(&flags[0], 1);
+        if (anynan) atomicExch(&flags[1], 1);               // flags[1]: nipals' has.na = any(is.na(x))
+    }
+}
+
+}  // namespace
+extern "C" {
+
+int mfb_bcv_cells_na(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32_t *row_folds, const int32_t *col_folds,
+                     int holdouts, const int32_t *ks, int nks, int cell_begin, int cell_end, double *err) {
+    MFB_ARG(ctx && Y && row_folds && col_folds && ks && err, "NULL argument");
+    if (Y->elem_bytes != 8) { mfb_set_error("this entry point needs an FP64 resident matrix"); return MFB_ERR_UNSUPPORTED; }
+    MFB_ARG(holdouts >= 2 && nks >= 1 && nfolds >= 1, "bad holdouts / ks / folds");
+    const int h2 = holdouts * holdouts;
+    MFB_ARG(cell_begin >= 0 && cell_end <= nfolds * h2 && cell_begin <= cell_end, "cell range out of bounds");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = Y->m, p = Y->n, ldy = Y->lda;
+    int kmax = 0;
+    for (int q = 0; q < nks; ++q) {
+        MFB_ARG(ks[q] >= 1, "ks must be positive");
+        if (ks[q] > kmax) kmax = ks[q];
+    }
+    MFB_ARG(kmax <= 60, "bcv with missing entries: at most 60 components (nipals)");
+    const int ncell = cell_end - cell_begin;
+    if (ncell == 0) return MFB_OK;
+    DevBuf buf(ctx);
+    std::vector<int32_t> rin, rout, cin, cout;
+    int32_t *d_rin, *d_rout, *d_cin, *d_cout, *d_ks;
+    int *d_flag;
+    MFB_TRY(buf.alloc(&d_rin, (size_t)n)); MFB_TRY(buf.alloc(&d_rout, (size_t)n));
+    MFB_TRY(buf.alloc(&d_cin, (size_t)p)); MFB_TRY(buf.alloc(&d_cout, (size_t)p));
+    MFB_TRY(buf.alloc(&d_ks, (size_t)nks)); MFB_TRY(buf.alloc(&d_flag, (size_t)4));
+    MFB_CUDA(cudaMemcpyAsync(d_ks, ks, nks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    double *d_err;
+    MFB_TRY(buf.alloc(&d_err, (size_t)ncell * nks));
+    const int nb_err = 2 * ctx->sm_count;
+    for (int cell = cell_begin; cell < cell_end; ++cell) {
+        const int f = cell / h2, local = cell % h2, x = local / holdouts, y = local % holdouts;
+        const int32_t *rf = row_folds + (size_t)f * n, *cf = col_folds + (size_t)f * p;
+        rin.clear(); rout.clear(); cin.clear(); cout.clear();
+        for (int64_t i = 0; i < n; ++i) {
+            MFB_ARG(rf[i] >= 1 && rf[i] <= holdouts, "row_fold entries must be in 1..holdouts");
+            (rf[i] - 1 == x ? rout : rin).push_back((int32_t)i);
+        }
+        for (int64_t j = 0; j < p; ++j) {
+            MFB_ARG(cf[j] >= 1 && cf[j] <= holdouts, "col_fold entries must be in 1..holdouts");
+            (cf[j] - 1 == y ? cout : cin).push_back((int32_t)j);
+        }
+        const int64_t nD = (int64_t)rin.size(), nA = (int64_t)rout.size(), pD = (int64_t)cin.size(), pA = (int64_t)cout.size();
+        double *e_out = d_err + (size_t)(cell - cell_begin) * nks;
+        int kk = kmax;
+        if (kk > nD) kk = (int)nD;
+        if (kk > pD) kk = (int)pD;
+        if (nD == 0 || pD == 0 || nA == 0 || pA == 0 || kk == 0) {
+            MFB_CUDA(cudaMemsetAsync(e_out, 0, nks * sizeof(double), st));
+            continue;
+        }
+        MFB_CUDA(cudaMemcpyAsync(d_rin, rin.data(), nD * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MFB_CUDA(cudaMemcpyAsync(d_rout, rout.data(), nA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MFB_CUDA(cudaMemcpyAsync(d_cin, cin.data(), pD * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MFB_CUDA(cudaMemcpyAsync(d_cout, cout.data(), pA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MFB_CUDA(cudaStreamSynchronize(st));               // (the host vectors are reused by the next cell)
+        DevBuf cb(ctx);
+        const int64_t ldD = round_up(nD, 16), ldR1 = round_up(nA, 4);
+        double *D, *R1, *R2, *T, *P, *Bt, *Ct, *Gu, *Gv, *M, *Ck, *part, *work = nullptr;
+        MFB_TRY(cb.alloc(&D, (size_t)ldD * pD)); MFB_TRY(cb.alloc(&R1, (size_t)ldR1 * pD)); MFB_TRY(cb.alloc(&R2, (size_t)ldD * pA));
+        MFB_TRY(cb.alloc(&T, (size_t)nD * kk)); MFB_TRY(cb.alloc(&P, (size_t)pD * kk));
+        MFB_TRY(cb.alloc(&Bt, (size_t)ldR1 * kk)); MFB_TRY(cb.alloc(&Ct, (size_t)kk * pA));
+        MFB_TRY(cb.alloc(&Gu, (size_t)kk * kk)); MFB_TRY(cb.alloc(&Gv, (size_t)kk * kk));
+        MFB_TRY(cb.alloc(&M, (size_t)nks * kk * kk)); MFB_TRY(cb.alloc(&Ck, (size_t)nks * kk * pA));
+        MFB_TRY(cb.alloc(&part, (size_t)nb_err * nks));
+        size_t nwork = std::max(gemm_tn_workspace(kk, pA, nD, ctx->sm_count),
+                                std::max(gemm_tn_workspace(kk, kk, nD, ctx->sm_count), gemm_tn_workspace(kk, kk, pD, ctx->sm_count)));
+        if (nwork) MFB_TRY(cb.alloc(&work, nwork));
+        MFB_CUDA(cudaMemsetAsync(D, 0, (size_t)ldD * pD * sizeof(double), st));
+        MFB_TRY(launch_gather(ctx, Y->d, ldy, d_rin, nD, d_cin, pD, nullptr, D, ldD));
+        MFB_TRY(launch_gather(ctx, Y->d, ldy, d_rout, nA, d_cin, pD, nullptr, R1, ldR1));
+        MFB_TRY(launch_gather(ctx, Y->d, ldy, d_rin, nD, d_cout, pA, nullptr, R2, ldD));
+        MFB_CUDA(cudaMemsetAsync(d_flag, 0, 4 * sizeof(int), st));
+        na_allbad_kernel<<<ctx->sm_count, 256, 0, st>>>(D, ldD, nD, pD, d_flag);
+        MFB_CUDA(cudaGetLastError());
+        int hflags[2] = {0, 0};
+        MFB_CUDA(cudaMemcpyAsync(hflags, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        if (hflags[0]) {
+            mfb_set_error("bcv: a hold-in block has a row or column without any non-zero observed entry (clean() would drop it)");
+            return MFB_ERR_ARG;
+        }
+        // nipals(x = D, ncomp = max(ks), center = TRUE, scale = FALSE, tol = 1e-6)   (R/bcv.R:179, R/bicluster.R:226)
+        const int nst = nipals_on_device(ctx, D, nD, pD, ldD, hflags[1], kk, 1, 0, 500, 1e-6, 1, T, P, nullptr, nullptr);
+        if (nst < 0) return nst;
+        MFB_TRY(tall_times_small(ctx, R1, ldR1, P, pD, Bt, ldR1, nA, pD, kk, nullptr));          // Bt = Y[r,-s] V
+        MFB_TRY(gemm_tn(ctx, T, nD, R2, ldD, Ct, kk, kk, pA, nD, work));                          // Ct = U'Y[-r,s]
+        MFB_TRY(gemm_tn(ctx, T, nD, T, nD, Gu, kk, kk, kk, nD, work));
+        MFB_TRY(gemm_tn(ctx, P, pD, P, pD, Gv, kk, kk, kk, pD, work));
+        const size_t msm = (size_t)4 * kk * kk * sizeof(double);
+        MFB_CUDA(cudaFuncSetAttribute(na_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+        na_minv_kernel<<<nks, 128, msm, st>>>(Gu, Gv, kk, d_ks, M);
+        {
+            int gx = (int)(((int64_t)kk * pA + 255) / 256);
+            if (gx > 4 * ctx->sm_count) gx = 4 * ctx->sm_count;
+            na_ck_kernel<<<dim3(gx, nks), 256, 0, st>>>(M, Ct, kk, pA, Ck);
+        }
+        na_error_kernel<<<dim3(nb_err, nks), 256, 0, st>>>(Y->d, ldy, d_rout, nA, d_cout, pA, Bt, ldR1, Ck, kk, nks, part);
+        na_error_final_kernel<<<(nks + 63) / 64, 64, 0, st>>>(part, nb_err, nks, e_out);
+        MFB_CUDA(cudaGetLastError());
+        MFB_CUDA(cudaStreamSynchronize(st));               // per-cell buffers go back to the pool
+    }
+    MFB_CUDA(cudaMemcpyAsync(err, d_err, (size_t)ncell * nks * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    return MFB_OK;
+}
+
 }  // extern "C"

@@ -67,6 +67,41 @@ def bcv_given_ks_literal(Y, ks, row_fold, col_fold, holdouts):
     return out
 
 
+def bcv_given_ks_na_literal(Y, ks, row_fold, col_fold, holdouts):
+    """``bcvGivenKs`` when ``any(is.na(Y))`` (``R/bcv.R:177-181``): ``pca`` is then
+    ``nipals_pca(., k, center = TRUE, scale = FALSE)$genericFit`` -- scores ``W`` (unit columns: nipals normalises
+    them and ``nipals_pca`` keeps no singular values) and loadings ``H`` -- and the rest is unchanged: per k a
+    ``MASS::ginv`` of ``tcv[,1:k] %*% pcv[1:k,]``, ``%*%`` products that propagate NA along whole rows / columns of
+    ``estA`` and ``sum(resid^2, na.rm = TRUE)``.  Parity unpinned (no artefact of the reference exercises this branch)."""
+    from .pca import nipals
+    from .helpers import clean
+    Y = np.asarray(Y, dtype=np.float64)
+    ks = list(ks)
+    kmax = max(ks)
+    out = np.zeros(len(ks))
+    for x in range(1, holdouts + 1):
+        r = row_fold == x
+        for y in range(1, holdouts + 1):
+            s = col_fold == y
+            A = Y[np.ix_(r, s)]
+            D = Y[np.ix_(~r, ~s)]
+            Dc, good_rows, good_cols = clean(D, 0.0)
+            if not (good_rows.all() and good_cols.all()):
+                raise ValueError("clean() would drop rows / columns of a hold-in block: non-conformable in the reference")
+            res = nipals(D, kmax, center=True, scale=False, tol=1e-6)
+            tcv, pcv = res["scores"], res["loadings"].T
+            Y1, Y2 = Y[np.ix_(r, ~s)], Y[np.ix_(~r, s)]
+            bad_rows, bad_cols = np.isnan(Y1).any(axis=1), np.isnan(Y2).any(axis=0)
+            Y1z, Y2z = np.where(np.isnan(Y1), 0.0, Y1), np.where(np.isnan(Y2), 0.0, Y2)
+            for i, k in enumerate(ks):
+                estD = tcv[:, :k] @ pcv[:k, :]
+                estA = Y1z @ ginv(estD) @ Y2z
+                estA[bad_rows, :] = np.nan                 # NA %*% anything is NA for the whole row ...
+                estA[:, bad_cols] = np.nan                 # ... / column
+                out[i] += float(np.nansum((A - estA) ** 2))
+    return out
+
+
 def bcv_cell_errors(Y, ks, r, s):
     """One (row-fold, col-fold) cell, one SVD: algebraically identical to the
     literal per-k ``ginv`` path (verified to ~1e-16 relative

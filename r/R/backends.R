@@ -105,10 +105,15 @@ nipals_pca <- function(A, k, cleanParam = 0, verbose = TRUE, ...) {   # R/biclus
 }
 
 # bcvGivenKs for several fold draws at once (folds are drawn by the caller with sample(), R/bcv.R:170-174)
-.bcv_cells <- function(Yd, rowFolds, colFolds, ks, holdouts) {
+.bcv_cells <- function(Yd, rowFolds, colFolds, ks, holdouts, na = FALSE) {
     nf <- ncol(rowFolds)
-    err <- .Call(C_mfb_bcv_cells_multi, .mfb_ctx(), Yd, rowFolds, colFolds, as.integer(holdouts), as.integer(ks),
-                 0L, as.integer(nf * holdouts ^ 2))                # nks x cells
+    err <- if (na) {                                              # any(is.na(Y)): NIPALS-based pca, R/bcv.R:177-181
+        .Call(C_mfb_bcv_cells_na, .mfb_ctx(), Yd, rowFolds, colFolds, as.integer(holdouts), as.integer(ks),
+              0L, as.integer(nf * holdouts ^ 2))
+    } else {
+        .Call(C_mfb_bcv_cells_multi, .mfb_ctx(), Yd, rowFolds, colFolds, as.integer(holdouts), as.integer(ks),
+              0L, as.integer(nf * holdouts ^ 2))                   # nks x cells
+    }
     vapply(seq_len(nf), FUN.VALUE = numeric(length(ks)), FUN = function(f) {
         rowSums(err[, (f - 1L) * holdouts ^ 2 + seq_len(holdouts ^ 2), drop = FALSE])            # :231-233
     })
@@ -119,15 +124,18 @@ nipals_pca <- function(A, k, cleanParam = 0, verbose = TRUE, ...) {   # R/biclus
 }
 
 bcvGivenKs <- function(Y, ks, holdouts = 10L, Yd = .Call(C_mfb_upload, .mfb_ctx(), Y)) {
-    if (any(is.na(Y))) stop("bcv: matrices with NA entries need the NIPALS branch (not available on the GPU path)")
     f <- .draw_folds(nrow(Y), ncol(Y), holdouts)
-    rcvs <- .bcv_cells(Yd, matrix(f$rows, ncol = 1L), matrix(f$cols, ncol = 1L), ks, holdouts)[, 1L]
+    rcvs <- .bcv_cells(Yd, matrix(f$rows, ncol = 1L), matrix(f$cols, ncol = 1L), ks, holdouts, na = anyNA(Y))[, 1L]
     names(rcvs) <- as.character(ks)
     rcvs
 }
 
 bcv <- function(Y, ks = seq_len(min(nrow(Y), ncol(Y)) - 1), holdouts = 10L, interactive = TRUE) {   # R/bcv.R:124-159
     if (!inherits(Y, "matrix")) Y <- as.matrix(Y)
+    if (any(is.na(Y)) && interactive) {
+        message(paste("Since some elements of the matrix are NA, BCV will run", "a much slower iterative algorithm. Continue?"))
+        if (menu(c("Yes", "No")) != 1) stop("User choice")
+    }
     minDim <- min(ncol(Y), nrow(Y))
     ks <- kLimiter(holdouts, minDim, ks)
     if (length(ks) > 1 || is.numeric(ks)) {
@@ -147,7 +155,11 @@ bcv <- function(Y, ks = seq_len(min(nrow(Y), ncol(Y)) - 1), holdouts = 10L, inte
 auto_bcv <- function(Y, ks = seq_len(min(nrow(Y), ncol(Y)) - 1), holdouts = 3L, maxIter = 100L, tol = (10 ^ -4),
                      bestOnly = FALSE, verbose = FALSE, interactive = TRUE) {                      # R/bcv.R:31-98
     if (!inherits(Y, "matrix")) Y <- as.matrix(Y)
-    if (any(is.na(Y))) stop("auto_bcv: matrices with NA entries need the NIPALS branch (not available on the GPU path)")
+    na <- anyNA(Y)
+    if (na && interactive) {
+        message(paste("Since some elements of the matrix are NA, BCV will run", "a much slower iterative algorithm. Continue?"))
+        if (menu(c("Yes", "No")) != 1) stop("User choice")
+    }
     ks <- kLimiter(holdouts, min(ncol(Y), nrow(Y)), ks)
     Yd <- .Call(C_mfb_upload, .mfb_ctx(), Y)                       # resident for every bcv() call
     distr <- rep(1L, each = length(ks)); names(distr) <- as.character(ks)
@@ -167,7 +179,7 @@ auto_bcv <- function(Y, ks = seq_len(min(nrow(Y), ncol(Y)) - 1), holdouts = 3L, 
         nb <- max(1L, earliest())
         folds <- lapply(seq_len(nb), function(b) .draw_folds(n, p, holdouts))
         vals <- .bcv_cells(Yd, vapply(folds, function(f) f$rows, integer(n)), vapply(folds, function(f) f$cols, integer(p)),
-                           ks, holdouts)                           # length(ks) x nb
+                           ks, holdouts, na = na)                  # length(ks) x nb
         for (b in seq_len(nb)) {
             res <- vals[, b]; names(res) <- as.character(ks)
             bcvRes <- names(which.min(res))

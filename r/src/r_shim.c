@@ -162,6 +162,18 @@ SEXP C_mfb_bcv_cells_multi(SEXP ctx, SEXP Y, SEXP rowFolds, SEXP colFolds, SEXP 
     return err;
 }
 
+/* the same work list for a matrix with NA entries: NIPALS-based pca per hold-in block (R/bcv.R:177-181) */
+SEXP C_mfb_bcv_cells_na(SEXP ctx, SEXP Y, SEXP rowFolds, SEXP colFolds, SEXP holdouts, SEXP ks, SEXP cellBegin,
+                        SEXP cellEnd) {
+    int nks = LENGTH(ks), c0 = Rf_asInteger(cellBegin), c1 = Rf_asInteger(cellEnd);
+    int nfolds = INTEGER(Rf_getAttrib(rowFolds, R_DimSymbol))[1];
+    SEXP err = PROTECT(Rf_allocMatrix(REALSXP, nks, c1 - c0));
+    CHECK(mfb_bcv_cells_na(ctx_of(ctx), (mfb_matrix *) R_ExternalPtrAddr(Y), nfolds, INTEGER(rowFolds),
+                           INTEGER(colFolds), Rf_asInteger(holdouts), INTEGER(ks), nks, c0, c1, REAL(err)));
+    UNPROTECT(1);
+    return err;
+}
+
 SEXP C_mfb_trim(SEXP ctx) { CHECK(mfb_context_trim(ctx_of(ctx))); return R_NilValue; }
 
 static const R_CallMethodDef calls[] = {
@@ -173,5 +185,6 @@ static const R_CallMethodDef calls[] = {
     {"C_mfb_otsu", (DL_FUNC) &C_mfb_otsu, 2}, {"C_mfb_threshold", (DL_FUNC) &C_mfb_threshold, 4},
     {"C_mfb_upload_f32", (DL_FUNC) &C_mfb_upload_f32, 2}, {"C_mfb_shift", (DL_FUNC) &C_mfb_shift, 2},
     {"C_mfb_bcv_cells_multi", (DL_FUNC) &C_mfb_bcv_cells_multi, 8}, {"C_mfb_trim", (DL_FUNC) &C_mfb_trim, 1},
+    {"C_mfb_bcv_cells_na", (DL_FUNC) &C_mfb_bcv_cells_na, 8},
     {NULL, NULL, 0}};
 void R_init_mfBiclust(DllInfo *dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

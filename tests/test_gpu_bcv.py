@@ -239,3 +239,27 @@ def test_svd_pca_more_than_64_components():
     sgn = np.sign((fit.fit.W * Wr).sum(axis=0))
     assert np.abs(fit.fit.W * sgn[None, :] - Wr).max() < 1e-8
     assert np.abs(fit.fit.H * sgn[:, None] - Hr).max() < 1e-8 * np.abs(Hr).max()
+
+
+def test_bcv_with_missing_entries_uses_the_nipals_branch():
+    """Y with NA entries (R/bcv.R:177-181): every hold-in block is factored by nipals_pca(center = TRUE, scale = FALSE)
+    -- scores and loadings without singular values -- and NA entries of the products are dropped by na.rm.  Against
+    the literal restatement (per-k MASS::ginv, explicit NA propagation); parity unpinned, tolerance 1e-6 relative on
+    the curve (NIPALS stops at tol = 1e-6 on both sides; the iteration counts agree)."""
+    import mfbiclust_b200 as mfb
+    rs = np.random.default_rng(31)
+    Y = rs.standard_normal((240, 4)) @ rs.standard_normal((4, 90)) + 0.4 * rs.standard_normal((240, 90))
+    miss = rs.random(Y.shape) < 0.01
+    Y[miss] = np.nan
+    Y = np.asfortranarray(Y)
+    ks = np.arange(1, 7)
+    rf, cf = _folds(rs, *Y.shape, 3)
+    got = mfb.bcvGivenKs(Y, ks, 3, folds=(rf, cf))
+    ref = B.bcv_given_ks_na_literal(Y, ks, rf, cf, 3)
+    assert np.isfinite(got).all()
+    assert np.abs(got / ref - 1.0).max() < 1e-6, (got, ref)
+    assert int(np.argmin(got)) == int(np.argmin(ref))
+    res = mfb.bcv(Y, ks, holdouts=3, interactive=False, folds=(rf, cf))
+    assert list(res) == [int(k) for k in ks] and np.allclose([res[int(k)] for k in ks], got)
+    out = mfb.auto_bcv(Y, ks, holdouts=3, rng=mfb.HostRng(3), interactive=False, maxIter=30)
+    assert out["best"] in [int(k) for k in ks]
