@@ -108,6 +108,17 @@ int  mfb_als_begin(mfb_context *ctx, mfb_matrix *A, int k,
  */
 int  mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters,
                      int *iters_total, int *converged);
+/*
+ * The same, and *maxcol_draws = the number of uniforms NMF::.fcnnls would have consumed from R's RNG during these
+ * iterations through max.col(ties.method = "random") (call sites R/bicluster.R:123,150): one
+ * max.col row per Lawson-Hanson step back and one per variable entering a passive set, each costing one draw per
+ * (near-)tie met while scanning it -- including the structural ties among leading -Inf / zero entries.  The count
+ * depends on the values only, so the R wrapper can advance .Random.seed by it (runif(draws)) before it draws the
+ * next replicate's start or a restart W: set.seed(); als_nmf() then follows the reference's stream without explicit
+ * starts.  -1 when unknown (ranks above 32 use block pivoting; row-sharded sessions).
+ */
+int  mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters,
+                           int *iters_total, int *converged, long long *maxcol_draws);
 int  mfb_als_restart(mfb_als *s, const double *Wnew);
 /*
  * Row-sharded replicate: one very large A split by rows over several devices / processes (north star: "very
@@ -172,6 +183,9 @@ int  mfb_als_run_host(mfb_context *ctx, const double *A_host, int64_t m, int64_t
 /* Exact NNLS  min ||C K - B||_F, K >= 0  for every column of B: the unit-testable
  * equivalent of NMF::.fcnnls(x = C, y = B)[[1]].  C is r x k, B is r x p, K is k x p. */
 int  mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t p, double *K);
+/* ... and the number of max.col draws of that .fcnnls call (see mfb_als_iterate_draws); -1 for k > 32 */
+int  mfb_nnls_draws(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t pcols,
+                    double *K, long long *maxcol_draws);
 
 /* ---- otsuHelper / threshold (R/BiclusterStrategy.R:442-456, 508-528; EBImage::otsu call site :448) */
 /* One Otsu threshold per COLUMN of the rows x cols matrix M. */

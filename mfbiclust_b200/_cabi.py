@@ -49,6 +49,7 @@ PROTOTYPES = {
     "mfb_als_shard_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "mfb_als_shard_disconnect": (C.c_int, [_vp]),
     "mfb_als_iterate": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip]),
+    "mfb_als_iterate_draws": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip, C.POINTER(C.c_longlong)]),
     "mfb_als_restart": (C.c_int, [_vp, _dp]),
     "mfb_als_profile": (C.c_int, [_vp, C.c_int, _dp]),
     "mfb_als_result": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
@@ -58,6 +59,7 @@ PROTOTYPES = {
     "mfb_als_run_host": (C.c_int, [_vp, _dp, _i64, _i64, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_int,
                                    _dp, _dp, _dp, _ip, _ip, _dp]),
     "mfb_nnls": (C.c_int, [_vp, _dp, _dp, _i64, C.c_int, _i64, _dp]),
+    "mfb_nnls_draws": (C.c_int, [_vp, _dp, _dp, _i64, C.c_int, _i64, _dp, C.POINTER(C.c_longlong)]),
     "mfb_otsu": (C.c_int, [_vp, _dp, _i64, _i64, _dp]),
     "mfb_threshold": (C.c_int, [_vp, _dp, _i64, _i64, _dp, C.c_int, _i32p]),
     "mfb_svd_pca": (C.c_int, [_vp, _vp, C.c_int, _dp, _dp, _ip]),

@@ -80,6 +80,15 @@ class AlsSession:
         self.iters = it.value
         return st, it.value, bool(conv.value)
 
+    def iterate_draws(self, max_new_iters, eps_conv=1e-4, fixed_iters=False):
+        """:meth:`iterate` plus the number of uniforms ``NMF::.fcnnls`` would have drawn through ``max.col`` during
+        these iterations (``mfb_als_iterate_draws``; -1 when unknown)."""
+        it, conv, draws = C.c_int(0), C.c_int(0), C.c_longlong(0)
+        st = check(lib().mfb_als_iterate_draws(self._h, int(max_new_iters), float(eps_conv), int(bool(fixed_iters)),
+                                               C.byref(it), C.byref(conv), C.byref(draws)))
+        self.iters = it.value
+        return st, it.value, bool(conv.value), int(draws.value)
+
     def profile(self, iters):
         """Mean duration (ms) of the four kernel launches of an iteration over ``iters`` further fixed
         iterations: ``[H stream, H solve, W stream, W solve]`` (``mfb_als_profile``); for a row-sharded session
@@ -117,10 +126,15 @@ class AlsSession:
 
 
 def als_replicate(A, k, W0, Hold0, maxIter=100, eps_conv=1e-4, fixed_iters=False, rng=None, ctx=None,
-                  verbose=False):
+                  verbose=False, follow_rng=False):
     """One replicate from a given start (``R/bicluster.R:118-203``), including R's ``restart()``
     protocol: on a failed ``.fcnnls`` or a zero row of H the host redraws W with ``rng`` and
-    re-enters; after the 10th failure it stops with R's warning."""
+    re-enters; after the 10th failure it stops with R's warning.
+
+    ``follow_rng``: also consume from ``rng`` the uniforms ``NMF::.fcnnls`` would have consumed through
+    ``max.col(ties.method = "random")`` (their number is reported by the device), so that a
+    restart W -- and whatever the caller draws next -- comes from the stream position the reference would be at.
+    The result carries ``maxcol_draws``."""
     ctx = ctx or _cabi.default_context()
     own = not isinstance(A, _cabi.Matrix)
     Ad = _cabi.Matrix(ctx, host=A) if own else A
@@ -136,8 +150,17 @@ def als_replicate(A, k, W0, Hold0, maxIter=100, eps_conv=1e-4, fixed_iters=False
             nrestart = 0
             total = 0
             converged = False
+            draws_total = 0
             while total < maxIter:
-                status, total, converged = sess.iterate(maxIter - total, eps_conv, fixed_iters)
+                if follow_rng:
+                    status, total, converged, draws = sess.iterate_draws(maxIter - total, eps_conv, fixed_iters)
+                    if draws < 0:
+                        raise _cabi.MfbError(_cabi.MFB_ERR_UNSUPPORTED, "max.col draw counts are not available for this rank")
+                    draws_total += draws
+                    if draws and rng is not None:
+                        rng.runif(draws)                                             # the uniforms max.col consumed
+                else:
+                    status, total, converged = sess.iterate(maxIter - total, eps_conv, fixed_iters)
                 if status == MFB_OK:
                     break
                 nrestart += 1                                                        # :124,138,153
@@ -163,16 +186,18 @@ def als_replicate(A, k, W0, Hold0, maxIter=100, eps_conv=1e-4, fixed_iters=False
                 print("\t%d\t%f\t%f\t%f" % (i, r, dw, dh))
         if converged:
             print("Converged!")
-    return dict(obj=resid, W=W, H=H, iters=total, converged=converged, trace=trace)
+    return dict(obj=resid, W=W, H=H, iters=total, converged=converged, trace=trace, maxcol_draws=draws_total)
 
 
 def als_nmf(A, k, reps=4, maxIter=100, eps_conv=1e-4, verbose=False, rng=None, inits=None, ctx=None,
-            precision="f64", **_):
+            precision="f64", follow_rng=False, **_):
     """``als_nmf(A, k, reps = 4L, maxIter = 100L, eps_conv = 1e-4, verbose = FALSE, ...)``
     (``R/bicluster.R:70-216``) -> :class:`genericFit`.
 
     ``rng`` supplies ``runif`` (default: a fresh NumPy generator); ``inits`` optionally gives
-    ``[(W0, Hold0), ...]`` per replicate ("identical inputs and initialisation").  ``precision = "f32"`` keeps
+    ``[(W0, Hold0), ...]`` per replicate ("identical inputs and initialisation").  ``follow_rng = True`` (ranks up
+    to 32) additionally consumes the uniforms the reference's ``.fcnnls`` calls would have consumed, so that with an
+    R-compatible ``rng`` (``set.seed``) replicates 2.. and restarts start where they start in R.  ``precision = "f32"`` keeps
     the resident copy of A in single precision (the R side would read ``options(mfBiclust.precision=)``): half
     the HBM traffic per iteration, factors within ~1e-7 of the FP64 path (everything but A's storage stays FP64)."""
     ctx = ctx or _cabi.default_context()
@@ -194,7 +219,8 @@ def als_nmf(A, k, reps=4, maxIter=100, eps_conv=1e-4, verbose=False, rng=None, i
             else:
                 W0 = _normalised_random_W(rng, m, k)                                               # :95-101
                 Hold0 = np.asarray(rng.runif(k * n), dtype=np.float64).reshape((k, n), order="F")  # :104
-            sols.append(als_replicate(Ad, k, W0, Hold0, maxIter, eps_conv, rng=rng, ctx=ctx, verbose=verbose))
+            sols.append(als_replicate(Ad, k, W0, Hold0, maxIter, eps_conv, rng=rng, ctx=ctx, verbose=verbose,
+                                      follow_rng=follow_rng))
         best = int(np.argmin([s["obj"] for s in sols]))                                            # :207
     finally:
         Ad.free()
@@ -453,17 +479,19 @@ def als_nmf_sharded(A_rows, m_global, k, reps=4, maxIter=100, eps_conv=1e-4, rng
     return res
 
 
-def nnls(Cmat, B, ctx=None):
-    """``NMF::.fcnnls(x = C, y = B)[[1]]``: exact column-wise NNLS (unit-test entry point)."""
+def nnls(Cmat, B, ctx=None, return_draws=False):
+    """``NMF::.fcnnls(x = C, y = B)[[1]]``: exact column-wise NNLS (unit-test entry point).  ``return_draws``: also
+    the number of uniforms the call would consume through ``max.col`` in R (-1 for k > 32)."""
     ctx = ctx or _cabi.default_context()
     Cmat, B = as_f(Cmat), as_f(B)
     r, k = Cmat.shape
     p = B.shape[1]
     K = np.zeros((k, p), order="F")
-    st = check(lib().mfb_nnls(ctx.handle, dptr(Cmat), dptr(B), r, k, p, dptr(K)))
+    draws = C.c_longlong(0)
+    st = check(lib().mfb_nnls_draws(ctx.handle, dptr(Cmat), dptr(B), r, k, p, dptr(K), C.byref(draws)))
     if st == MFB_SINGULAR:
         raise np.linalg.LinAlgError("system is computationally singular")
-    return K
+    return (K, int(draws.value)) if return_draws else K
 
 
 # ---------------------------------------------------------------------------

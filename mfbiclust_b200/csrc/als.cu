@@ -49,7 +49,7 @@ struct AlsCtrl {
     int fixed;                 // 1: no convergence break
     int groups_done[2];        // per half-step completion counters of the solve kernel's CTA groups
     int max_trace;
-    int pad0;
+    int count_draws;           // != 0: the solve kernels count the uniforms .fcnnls' max.col calls would consume
     unsigned long long nzmask; // bit c set when row c of H has a non-zero entry
     double eps;
     double resid_old;
@@ -57,6 +57,7 @@ struct AlsCtrl {
     double mn, mk, kn;         // element counts for the RMS values
     double dH2;
     double resid, dW, dH;
+    unsigned long long draws;  // running total of those draws (ranks up to 32)
 };
 
 struct HalfParams {
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     unsigned long long nz = 0ull;
     double t1;
     if constexpr (KP <= 32)      // tableau in registers, one lane per row
-        t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane);
+        t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane, p.ctrl->count_draws ? &p.ctrl->draws : nullptr);
     else                         // compressed active-set solves, two variables per lane
         t1 = nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * UPW, UPW, nvalid_local, lane);
     __syncwarp();
@@ -1195,7 +1196,7 @@ __global__ void __launch_bounds__(256) small_crossprod_kernel(const double *__re
 template <int KB>
 __global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restrict__ G, const double *__restrict__ Minv,
                                                            const double *__restrict__ R, int k, int64_t pcols,
-                                                           double *__restrict__ K) {
+                                                           double *__restrict__ K, unsigned long long *draws) {
     constexpr int KP = KB * 8, SU = 8, XS = SU + 1;
     extern __shared__ double nn_sh[];
     double *sG = nn_sh, *sM = sG + KP * KP, *xs = sM + KP * KP, *scr = xs + KP * XS;
@@ -1212,7 +1213,7 @@ __global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restr
         xs[c * XS + u] = (c < k && u < nvalid) ? R[(j0 + u) * k + c] : 0.0;
     }
     __syncthreads();
-    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sM, k, xs, warp * 2, 2, nvalid, lane);
+    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sM, k, xs, warp * 2, 2, nvalid, lane, draws);
     else nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * 2, 2, nvalid, lane);
     __syncthreads();
     for (int e = tid; e < SU * KP; e += 128) {
@@ -1223,11 +1224,11 @@ __global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restr
 
 template <int KB>
 static int launch_nnls_columns(const double *G, const double *Minv, const double *R, int k, int64_t pcols, double *K,
-                               cudaStream_t st) {
+                               cudaStream_t st, unsigned long long *draws) {
     constexpr int KP = KB * 8;
     const size_t smem = (size_t)(2 * KP * KP + KP * 9 + 4 * NnlsCfg<KP>::SCR) * sizeof(double);
     MFB_CUDA(cudaFuncSetAttribute(nnls_columns_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nnls_columns_kernel<KB><<<(unsigned)((pcols + 7) / 8), 128, smem, st>>>(G, Minv, R, k, pcols, K);
+    nnls_columns_kernel<KB><<<(unsigned)((pcols + 7) / 8), 128, smem, st>>>(G, Minv, R, k, pcols, K, draws);
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
@@ -1858,7 +1859,16 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
 }
 
 int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters, int *iters_total, int *converged) {
+    return mfb_als_iterate_draws(s, max_new_iters, eps_conv, fixed_iters, iters_total, converged, nullptr);
+}
+
+int mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fixed_iters, int *iters_total, int *converged,
+                          long long *maxcol_draws) {
     MFB_ARG(s, "NULL session");
+    const bool count = maxcol_draws != nullptr && s->KP <= 32 && !s->shard;
+    if (maxcol_draws) *maxcol_draws = count ? 0 : -1;
+    unsigned long long draws0 = 0, draws1 = 0;
+    bool first_batch = true;
     MFB_ARG(eps_conv > 0, "ALS-NMF: Invalid argument 'eps_conv' - value should be positive");
     MFB_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
@@ -1873,6 +1883,8 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
         MFB_CUDA(cudaStreamSynchronize(st));
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = fixed_iters ? 1 : 0; hc->eps = eps_conv;
         hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
+        hc->count_draws = count ? 1 : 0;
+        if (first_batch) { draws0 = hc->draws; first_batch = false; }
         if (batch > s->max_trace) { mfb_set_error("too many iterations in one batch"); return MFB_ERR_ARG; }
         MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
         int cur = s->cur;
@@ -1883,6 +1895,7 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
         MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
         MFB_CUDA(cudaStreamSynchronize(st));
         MFB_TRY(check_mbar_abort("mfb_als_iterate"));
+        draws1 = hc->draws;
         const int done = hc->iters_done;
         if (done > 0) {
             const size_t old = s->trace.size();
@@ -1911,6 +1924,7 @@ int mfb_als_iterate(mfb_als *s, int max_new_iters, double eps_conv, int fixed_it
         if (done == 0) break;   // defensive: nothing ran
     }
     if (iters_total) *iters_total = s->iters_total;
+    if (count) *maxcol_draws = (long long)(draws1 - draws0);
     return status;
 }
 
@@ -2017,6 +2031,11 @@ int mfb_als_run_host(mfb_context *ctx, const double *A_host, int64_t m, int64_t 
 }
 
 int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t pcols, double *K) {
+    return mfb_nnls_draws(ctx, C, B, r, k, pcols, K, nullptr);
+}
+
+int mfb_nnls_draws(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t pcols, double *K,
+                   long long *maxcol_draws) {
     MFB_ARG(ctx && C && B && K, "NULL argument");
     MFB_ARG(k >= 1 && k <= 64 && r >= 1 && pcols >= 1, "bad sizes");
     MFB_CUDA(cudaSetDevice(ctx->device));
@@ -2027,7 +2046,16 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     const int KP = KB * 8;
     double *dC, *dB, *dR, *dG, *dM, *dK, *part;
     int *dsing;
+    unsigned long long *ddraws = nullptr;
     DevBuf buf(ctx);
+    if (maxcol_draws) {
+        *maxcol_draws = -1;                                  // unknown (ranks above 32 use block pivoting: no per-variable events)
+        if (k <= 32) {
+            int rc = buf.alloc(&ddraws, (size_t)1);
+            if (rc != MFB_OK) return rc;
+            MFB_CUDA(cudaMemsetAsync(ddraws, 0, sizeof(unsigned long long), st));
+        }
+    }
     {
         int rc = buf.alloc(&dC, (size_t)r * k);
         if (rc == MFB_OK) rc = buf.alloc(&dB, (size_t)r * pcols);
@@ -2049,12 +2077,12 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     {
         int rc = MFB_ERR_UNSUPPORTED;
         switch (KB) {
-            case 1: rc = launch_nnls_columns<1>(dG, dM, dR, k, pcols, dK, st); break;
-            case 2: rc = launch_nnls_columns<2>(dG, dM, dR, k, pcols, dK, st); break;
-            case 3: rc = launch_nnls_columns<3>(dG, dM, dR, k, pcols, dK, st); break;
-            case 4: rc = launch_nnls_columns<4>(dG, dM, dR, k, pcols, dK, st); break;
-            case 6: rc = launch_nnls_columns<6>(dG, dM, dR, k, pcols, dK, st); break;
-            case 8: rc = launch_nnls_columns<8>(dG, dM, dR, k, pcols, dK, st); break;
+            case 1: rc = launch_nnls_columns<1>(dG, dM, dR, k, pcols, dK, st, ddraws); break;
+            case 2: rc = launch_nnls_columns<2>(dG, dM, dR, k, pcols, dK, st, ddraws); break;
+            case 3: rc = launch_nnls_columns<3>(dG, dM, dR, k, pcols, dK, st, ddraws); break;
+            case 4: rc = launch_nnls_columns<4>(dG, dM, dR, k, pcols, dK, st, ddraws); break;
+            case 6: rc = launch_nnls_columns<6>(dG, dM, dR, k, pcols, dK, st, ddraws); break;
+            case 8: rc = launch_nnls_columns<8>(dG, dM, dR, k, pcols, dK, st, ddraws); break;
         }
         if (rc != MFB_OK) return rc;
     }
@@ -2062,7 +2090,10 @@ int mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int 
     int sing = 0;
     MFB_CUDA(cudaMemcpyAsync(K, dK, sizeof(double) * k * pcols, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaMemcpyAsync(&sing, dsing, sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned long long hd = 0;
+    if (ddraws) MFB_CUDA(cudaMemcpyAsync(&hd, ddraws, sizeof(hd), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
+    if (ddraws) *maxcol_draws = sing ? 0 : (long long)hd;    // solve(CtC) fails before .fcnnls reaches a max.col call
     return sing ? MFB_SINGULAR : MFB_OK;
 }
 

@@ -130,9 +130,38 @@ __device__ int warp_gauss_jordan_inverse(double *a, int k, int ld, int lane) {
 // the problems [first, first + count) of xs, 32 / LP at a time; problems >= nvalid are skipped (x = 0).
 // sM: shared G^-1 (ld KP, symmetric).  Returns this lane's partial of sum_i x_i r_i.
 // ---------------------------------------------------------------------------
+// Number of unif_rand() draws base::max.col(ties.method = "random") makes on the row (v_0 .. v_{k-1}) held one entry
+// per lane by an LP-lane group (R_max_col: `large` = max |finite entry|, tol = 1e-5 large, running maximum `a`; every
+// entry with b <= a + tol and b >= a - tol costs one draw -- including the structural ties among leading -Inf / zero
+// entries).  The count depends on the values only, never on the uniforms drawn.
+template <int LP>
+__device__ __forceinline__ int r_max_col_draws(double v, int k, unsigned gmask, int base) {
+    double large = 0.0;
+#pragma unroll
+    for (int j = 0; j < LP; ++j) {
+        const double vj = __shfl_sync(gmask, v, base + j);
+        if (j < k && isfinite(vj)) large = fmax(large, fabs(vj));
+    }
+    const double tol = 1e-5 * large;
+    double a = __shfl_sync(gmask, v, base);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 1; j < LP; ++j) {
+        const double b = __shfl_sync(gmask, v, base + j);
+        if (j < k) {
+            if (b > a + tol) a = b;
+            else if (b >= a - tol) ++cnt;
+        }
+    }
+    return cnt;
+}
+
+// `draws` (optional): the lane with i == 0 of every group adds the number of uniforms NMF::.fcnnls would have drawn
+// for its problems through max.col -- one call per Lawson-Hanson step back (row = -alpha, -Inf off the candidates) and
+// one per variable entering the passive set (row = (!Pset) * W).
 template <int KP, int XS>
 __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, int first, int count, int nvalid,
-                             int lane) {   // (each lane leaves x_i of its problem in xs; see the callers)
+                             int lane, unsigned long long *draws = nullptr) {   // (each lane leaves x_i of its problem in xs)
     constexpr int LP = (KP <= 16) ? 16 : 32;
     constexpr int PPW = 32 / LP;
     const unsigned FULL = 0xffffffffu;
@@ -140,6 +169,7 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
     const bool rowvalid = i < k;
     const unsigned gmask = (LP == 32) ? 0xffffffffu : (0xffffu << base);
     double t1 = 0.0;
+    int ndraw = 0;
     for (int rd = 0; rd < count; rd += PPW) {
         const int unit = first + rd + sub;
         const bool uvalid = (rd + sub < count) && (unit < nvalid);
@@ -176,6 +206,7 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
                     if (__ballot_sync(gmask, isneg) != 0u) {
                         // Lawson-Hanson step length: min over passive entries that went negative
                         double al = isneg ? dv / (dv - x) : INFINITY;
+                        if (draws) ndraw += r_max_col_draws<LP>(-al, k, gmask, base);
                         int ai = i;
 #pragma unroll
                         for (int o = LP / 2; o > 0; o >>= 1) {
@@ -189,6 +220,7 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
                     } else {
                         const bool ispos = (!inS && rowvalid) && qv > 0.0;
                         if (__ballot_sync(gmask, ispos) != 0u) {
+                            if (draws) ndraw += r_max_col_draws<LP>((!inS && rowvalid) ? qv : 0.0, k, gmask, base);
                             double w = ispos ? qv : -1.0;
                             int wi = i;
 #pragma unroll
@@ -236,6 +268,7 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
         t1 += x * ri;
         if (rowvalid && rd + sub < count) xs[i * XS + unit] = x;
     }
+    if (draws && i == 0 && ndraw) atomicAdd(draws, (unsigned long long)ndraw);
     return t1;
 }
 

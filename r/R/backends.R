@@ -57,6 +57,9 @@ als_nmf <- function(A, k, reps = 4L, maxIter = 100L, eps_conv = 1e-4, verbose = 
         repeat {
             r <- .Call(C_mfb_als_iterate, s, as.integer(maxIter - i), eps_conv, FALSE)
             i <- r[2]; converged <- r[3] == 1L
+            # NMF::.fcnnls consumed r[4] uniforms through max.col(ties.method = "random") in the reference: skip them,
+            # so that restart() and the next replicate draw from the stream position they have in the reference
+            if (r[4] > 0L) invisible(runif(r[4]))
             if (r[1] == 0L || i >= maxIter) break                # status 0: converged or maxIter reached
             nrestart <- nrestart + 1L                                                            # :124, :138, :153
             if (nrestart >= 10L) {

@@ -60,13 +60,14 @@ SEXP C_mfb_als_begin(SEXP ctx, SEXP A, SEXP k, SEXP W0, SEXP Hold0, SEXP residOl
     return p;
 }
 
-SEXP C_mfb_als_iterate(SEXP s, SEXP maxNew, SEXP eps, SEXP fixed) {   /* list(status, i, converged) */
+SEXP C_mfb_als_iterate(SEXP s, SEXP maxNew, SEXP eps, SEXP fixed) {   /* c(status, i, converged, maxcol_draws) */
     int it = 0, conv = 0;
-    int st = mfb_als_iterate((mfb_als *) R_ExternalPtrAddr(s), Rf_asInteger(maxNew), Rf_asReal(eps),
-                             Rf_asLogical(fixed), &it, &conv);
+    long long draws = 0;                                   /* uniforms NMF::.fcnnls would have consumed (-1: unknown) */
+    int st = mfb_als_iterate_draws((mfb_als *) R_ExternalPtrAddr(s), Rf_asInteger(maxNew), Rf_asReal(eps),
+                                   Rf_asLogical(fixed), &it, &conv, &draws);
     if (st < 0) Rf_error("%s", mfb_last_error());
-    SEXP out = PROTECT(Rf_allocVector(INTSXP, 3));
-    INTEGER(out)[0] = st; INTEGER(out)[1] = it; INTEGER(out)[2] = conv;
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, 4));
+    INTEGER(out)[0] = st; INTEGER(out)[1] = it; INTEGER(out)[2] = conv; INTEGER(out)[3] = (int) draws;
     UNPROTECT(1);
     return out;
 }

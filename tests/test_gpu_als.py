@@ -368,3 +368,47 @@ def test_handles_may_outlive_their_context():
     ctx.close()
     sess.close()
     Ad.free()
+
+
+@pytest.mark.parametrize("k,r,p", [(1, 40, 9), (3, 200, 33), (8, 300, 500), (16, 257, 129), (20, 100, 40), (32, 150, 90)])
+def test_nnls_reports_the_max_col_draws_of_fcnnls(k, r, p):
+    """NMF::.fcnnls consumes R's RNG through max.col(ties.method = "random") (SURVEY.md App. A.1): the number of
+    uniforms is a deterministic function of the values and is reported by the device, so that an R wrapper can
+    advance .Random.seed exactly as the reference would have."""
+    import mfbiclust_b200 as mfb
+    from oracle.r_rng import RRng
+    rs = np.random.default_rng(k * 100 + p)
+    Cm = rs.random((r, k))
+    Bm = rs.standard_normal((r, p)) + 0.25
+    rng = RRng(1)
+    Kref, _ = fcnnls(Cm, Bm, rng)
+    K, draws = mfb.nnls(Cm, Bm, return_draws=True)
+    assert rel_fro(K, Kref) < 1e-11
+    assert draws == rng.draws, (draws, rng.draws)
+    if k == 1:
+        assert draws == 0                                   # no ties with a single variable
+
+
+def test_als_nmf_follows_the_r_session_of_the_vignette(yeast, vignette):
+    """set.seed(12345); als_nmf(yeast_benchmark[[1]] + 2.71, k = 3) as rendered in vignettes/my-vignette.html:224-399,
+    WITHOUT passing initial factors: the device reports the uniforms the reference's .fcnnls calls consume, the host
+    skips them, and replicates 2..4 therefore start from the stream position they start from in R -- same four
+    objectives, same winner, same factors as the oracle's run of the whole R function under the R generator."""
+    import mfbiclust_b200 as mfb
+    from oracle.als_nmf import als_nmf as oracle_als_nmf
+    from oracle.r_rng import RRng
+    A = pseudovalues(yeast[0])
+    r_ref = RRng(12345)
+    ref = oracle_als_nmf(A, 3, reps=4, max_iter=100, eps_conv=1e-4, rng=r_ref)
+    r_gpu = RRng(12345)
+    got = mfb.als_nmf(A, 3, reps=4, maxIter=100, eps_conv=1e-4, rng=r_gpu, follow_rng=True)
+    assert r_gpu.draws == r_ref.draws                        # the session ends at the same stream position
+    m, n = A.shape
+    per_rep = [s["maxcol_draws"] for s in got.solutions]
+    assert sum(per_rep) == r_ref.draws - 4 * (m * 3 + 3 * n)
+    assert per_rep == [143, 218, 130, 178]                  # SURVEY.md App. A.1: the draws that make the vignette reproducible
+    assert got.best == ref["best"]
+    for gs, rsol in zip(got.solutions, ref["solutions"]):
+        assert abs(gs["obj"] - rsol["obj"]) < 1e-9
+        assert gs["iters"] == rsol["iters"]
+    assert rel_fro(got.fit.W, ref["W"]) < 1e-8 and rel_fro(got.fit.H, ref["H"]) < 1e-8
