@@ -103,11 +103,14 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const double *__rest
     }
 }
 
-static int splitk_factor(int64_t M, int64_t N, int64_t K, int sm_count) {
-    const int64_t tiles = ((M + 63) / 64) * ((N + 63) / 64);
+static int splitk_factor(int64_t M, int64_t N, int64_t K, int sm_count, bool sym) {
+    // a block = four warps with a 32 x 32 tile each, fed by direct global loads: it takes ~4 blocks per SM to hide
+    // the load latency.  A symmetric product only runs the block tiles on and below the diagonal.
+    const int64_t tm = (M + 63) / 64, tn = (N + 63) / 64;
+    const int64_t tiles = sym ? tm * (tm + 1) / 2 : tm * tn;
     int Z = 1;
-    if (tiles < 2 * sm_count) {
-        Z = (int)((2 * sm_count + tiles - 1) / tiles);
+    if (tiles < 4 * sm_count) {
+        Z = (int)((4 * sm_count + tiles - 1) / tiles);
         const int64_t maxz = (K + 255) / 256;
         if (Z > maxz) Z = (int)maxz;
         if (Z < 1) Z = 1;
@@ -117,17 +120,18 @@ static int splitk_factor(int64_t M, int64_t N, int64_t K, int sm_count) {
 }
 
 size_t gemm_tn_workspace(int64_t M, int64_t N, int64_t K, int sm_count) {
-    const int Z = splitk_factor(M, N, K, sm_count);
+    int Z = splitk_factor(M, N, K, sm_count, false);
+    if (M == N) Z = std::max(Z, splitk_factor(M, N, K, sm_count, true));    // (the caller may pass A == B)
     return Z > 1 ? (size_t)Z * M * N : 0;
 }
 
 int gemm_tn(mfb_context *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
             int64_t M, int64_t N, int64_t K, double *work) {
-    const int Z = splitk_factor(M, N, K, ctx->sm_count);
+    const int sym = (A == B && lda == ldb && M == N) ? 1 : 0;       // Gram matrix: half the tiles
+    const int Z = splitk_factor(M, N, K, ctx->sm_count, sym != 0);
     int64_t kz = (K + Z - 1) / Z;
     kz = (kz + 15) / 16 * 16;
     const int vec_ok = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A) % 32 == 0) && (((uintptr_t)B) % 32 == 0);
-    const int sym = (A == B && lda == ldb && M == N) ? 1 : 0;       // Gram matrix: half the tiles
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)Z);
     if (Z == 1) {
         gemm_tn_kernel<<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, kz, vec_ok, sym ? 2 : 0);

@@ -424,7 +424,7 @@ int mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32
     if (const char *e = getenv("MFBICLUST_BCV_AUX_STREAMS")) { const int v = atoi(e); if (v >= 1) S = std::min(v, B); }
     // two sets of cell buffers: the gather / Gram stage of the next batch runs while the eigen-solver works on this one
     const int nsets = (ncell > B) ? 2 : 1;
-    MFB_TRY(ensure_aux(ctx, (size_t)S, (size_t)3 * S + 2));
+    MFB_TRY(ensure_aux(ctx, (size_t)S, (size_t)4 * S + 2));
     std::vector<CellSlot> slot((size_t)nsets * B);
     for (int i = 0; i < nsets * B; ++i) {
         CellSlot &c = slot[i];
@@ -449,8 +449,8 @@ int mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32
         if (w2) MFB_TRY(buf.alloc(&c.work2, w2));
     }
     const double sqrt_eps = 1.4901161193847656e-08;              // sqrt(.Machine$double.eps): MASS::ginv's tol
-    cudaEvent_t ev_main = ctx->aux_events[3 * S], ev_eig = ctx->aux_events[3 * S + 1];
-    // aux_events[parity * S + s]: stage 1 of a batch finished on stream s; aux_events[2 S + s]: stage 3 finished
+    cudaEvent_t ev_main = ctx->aux_events[4 * S], ev_eig = ctx->aux_events[4 * S + 1];
+    // aux_events[parity * S + s]: stage 1 of a batch finished on stream s; aux_events[(2 + parity) S + s]: stage 3 finished
 
     struct Geo { int64_t nD, nA, pD, pA; const int32_t *rin, *rout, *cin, *cout; int kk; bool tall, empty; };
     auto geometry = [&](int cell) {
@@ -520,6 +520,10 @@ int mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32
         const int nb = std::min(B, cell_end - b0);
         double t_b = 0, t_c = 0, t_d = 0;
         for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaStreamWaitEvent(st, ctx->aux_events[parity * S + s2], 0));
+        // stage 3 of the batch before the previous one read the eigenvectors this batch is about to overwrite (the
+        // previous batch's stage 3 keeps running on the auxiliary streams, beside this batch's eigen-solver)
+        if (b0 - 2 * B >= cell_begin)
+            for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaStreamWaitEvent(st, ctx->aux_events[(2 + parity) * S + s2], 0));
         // the next batch's gathers and Gram products go to the auxiliary streams now: they overlap the eigen-solver
         if (b0 + B < cell_end && nsets == 2)
             MFB_TRY(stage1(b0 + B, std::min(B, cell_end - b0 - B), parity ^ 1, probs_next));
@@ -572,16 +576,17 @@ int mfb_bcv_cells_multi(mfb_context *ctx, mfb_matrix *Y, int nfolds, const int32
             bcv_error_final_kernel<<<(nks + 63) / 64, 64, 0, as>>>(c.part, nb_err, pstride, kk, d_ks, nks, e_out);
             MFB_CUDA(cudaGetLastError());
         }
-        for (int s2 = 0; s2 < S; ++s2) {
-            MFB_CUDA(cudaEventRecord(ctx->aux_events[2 * S + s2], ctx->aux_streams[s2]));
-            MFB_CUDA(cudaStreamWaitEvent(st, ctx->aux_events[2 * S + s2], 0));
-        }
+        for (int s2 = 0; s2 < S; ++s2) MFB_CUDA(cudaEventRecord(ctx->aux_events[(2 + parity) * S + s2], ctx->aux_streams[s2]));
         if (timing) {
             t_d = now_ms();
             fprintf(stderr, "bcv batch of %d cells: eigen %.3f ms, products+errors (+ next gather/Gram) %.3f ms\n", nb,
                     t_c - t_b, t_d - t_c);
         }
         probs_cur.swap(probs_next);
+    }
+    for (int s2 = 0; s2 < S; ++s2) {                         // every stage 3 has finished
+        MFB_CUDA(cudaEventRecord(ev_main, ctx->aux_streams[s2]));
+        MFB_CUDA(cudaStreamWaitEvent(st, ev_main, 0));
     }
     MFB_CUDA(cudaMemcpyAsync(err, d_err, (size_t)ncell * nks * sizeof(double), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));

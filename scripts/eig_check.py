@@ -68,13 +68,13 @@ def timed(label):
     print(label, "bcv call (9 cells)", round(best, 4), "36 cells", round(b36, 4), flush=True)
 
 
-for batch in ("1", "4", "9", "12", "18", "36"):
+for batch in ("16",):
     os.environ["MFBICLUST_BCV_BATCH"] = batch
-    for aux in ("1", "4", "8"):
+    for aux in ("4",):
         os.environ["MFBICLUST_BCV_AUX_STREAMS"] = aux
         timed("batch %s aux %s" % (batch, aux))
 os.environ["MFBICLUST_BCV_AUX_STREAMS"] = "4"
-for batch in ("9", "18"):
+for batch in ():
     os.environ["MFBICLUST_BCV_BATCH"] = batch
     for cap in ("8", "12", "16", "24", "32"):
         os.environ["MFB_LZ_BLOCKS"] = cap
