@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     const int k = p.k;
 
     for (int e = tid; e < KP * KP; e += SOLVE_THREADS) {
-        if (WSTEP || KP > 32) sG[e] = p.G[e];               // the H-step tableau solver only needs G^-1
+        sG[e] = p.G[e];
         sM[e] = p.Minv[e];
     }
     const long long unit0 = (long long)blockIdx.x * SU;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     unsigned long long nz = 0ull;
     double t1;
     if constexpr (KP <= 32)      // tableau in registers, one lane per row
-        t1 = nnls_lanes<KP, XS>(sM, k, xs, warp * UPW, UPW, nvalid_local, lane, p.ctrl->count_draws ? &p.ctrl->draws : nullptr);
+        t1 = nnls_lanes<KP, XS>(sG, sM, k, xs, warp * UPW, UPW, nvalid_local, lane, p.ctrl->count_draws ? &p.ctrl->draws : nullptr);
     else                         // compressed active-set solves, two variables per lane
         t1 = nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * UPW, UPW, nvalid_local, lane);
     __syncwarp();
@@ -1213,7 +1213,7 @@ __global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restr
         xs[c * XS + u] = (c < k && u < nvalid) ? R[(j0 + u) * k + c] : 0.0;
     }
     __syncthreads();
-    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sM, k, xs, warp * 2, 2, nvalid, lane, draws);
+    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sG, sM, k, xs, warp * 2, 2, nvalid, lane, draws);
     else nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * 2, 2, nvalid, lane);
     __syncthreads();
     for (int e = tid; e < SU * KP; e += 128) {

@@ -128,7 +128,8 @@ __device__ int warp_gauss_jordan_inverse(double *a, int k, int ld, int lane) {
 //
 // xs: shared [KP][XS] -- right-hand sides r on entry, solutions x on exit (column = problem).  The warp solves
 // the problems [first, first + count) of xs, 32 / LP at a time; problems >= nvalid are skipped (x = 0).
-// sM: shared G^-1 (ld KP, symmetric).  Returns this lane's partial of sum_i x_i r_i.
+// sM: shared G^-1 (ld KP, symmetric); sG: shared G (same layout; nullptr: always start from S = all).
+// Returns this lane's partial of sum_i x_i r_i.
 // ---------------------------------------------------------------------------
 // Number of unif_rand() draws base::max.col(ties.method = "random") makes on the row (v_0 .. v_{k-1}) held one entry
 // per lane by an LP-lane group (R_max_col: `large` = max |finite entry|, tol = 1e-5 large, running maximum `a`; every
@@ -160,8 +161,8 @@ __device__ __forceinline__ int r_max_col_draws(double v, int k, unsigned gmask, 
 // for its problems through max.col -- one call per Lawson-Hanson step back (row = -alpha, -Inf off the candidates) and
 // one per variable entering the passive set (row = (!Pset) * W).
 template <int KP, int XS>
-__device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, int first, int count, int nvalid,
-                             int lane, unsigned long long *draws = nullptr) {   // (each lane leaves x_i of its problem in xs)
+__device__ double nnls_lanes(const double *__restrict__ sG, const double *__restrict__ sM, int k, double *xs, int first,
+                             int count, int nvalid, int lane, unsigned long long *draws = nullptr) {   // (each lane leaves x_i of its problem in xs)
     constexpr int LP = (KP <= 16) ? 16 : 32;
     constexpr int PPW = 32 / LP;
     const unsigned FULL = 0xffffffffu;
@@ -178,19 +179,28 @@ __device__ double nnls_lanes(const double *__restrict__ sM, int k, double *xs, i
             continue;
         }
         const double ri = (rowvalid && uvalid) ? xs[i * XS + unit] : 0.0;
-        double T[KP];
-        double qv = 0.0;
+        // unconstrained solution xu = G^-1 r: .fcnnls' first passive set is P = {xu > 0}
+        double xu = 0.0;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             const double rj = __shfl_sync(FULL, ri, base + (j % LP));
             const double mij = (rowvalid && j < k) ? sM[j * KP + i] : 0.0;
-            T[j] = -mij;
-            qv += mij * rj;
+            xu += mij * rj;
         }
-        bool inS = rowvalid;
-        double dv = qv > 0.0 ? qv : 0.0;
-        const unsigned negs = __ballot_sync(FULL, rowvalid && !(qv > 0.0));
-        unsigned pend = uvalid ? ((negs & gmask) >> base) : 0u;
+        const unsigned negs = (__ballot_sync(FULL, rowvalid && !(xu > 0.0)) & gmask) >> base;
+        const unsigned poss = (__ballot_sync(FULL, rowvalid && xu > 0.0) & gmask) >> base;
+        // The tableau of the basis P is reached from whichever end is closer: from S = all (q = xu, T = -G^-1) by
+        // exchanging the variables of ~P out, or from S = {} (q = r, T = -G) by exchanging those of P in -- the same
+        // principal pivots either way, min(|P|, k - |P|) of them (sparse factors: a handful instead of almost k).
+        const bool fromG = sG != nullptr && __popc(poss) < __popc(negs);
+        const double *__restrict__ src0 = fromG ? sG : sM;
+        double T[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) T[j] = (rowvalid && j < k) ? -src0[j * KP + i] : 0.0;
+        double qv = fromG ? ri : xu;
+        bool inS = rowvalid && !fromG;
+        double dv = xu > 0.0 ? xu : 0.0;
+        unsigned pend = uvalid ? (fromG ? poss : negs) : 0u;
         bool done = !uvalid;
         int iters = 0;
         const int cap = 6 * k + 16;
