@@ -79,6 +79,7 @@ struct HalfParams {
     double *xscal;                        // shard mode: [4] iteration scalars of the W-step, summed over the ranks
     const struct ShardPeers *peers;       // shard mode over peer memory (NULL: the host's all-reduce callback is used)
     int epoch;                            // shard mode: number of this iteration since the session began (1-based)
+    int invert_later;                     // != 0: the stream kernel's side job stops at G; als_shard_invert_kernel inverts it
 };
 
 // Row-sharded mode over peer memory (NVLink / NVSwitch, cudaIpc mappings): every rank owns one SHARED BLOCK
@@ -516,64 +517,108 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
 // same half-step reads G and G^-1; nothing on the critical path waits for them.  R's solve() failure ("system is
 // computationally singular") is raised here: reason 3 = W'W (H-step), 4 = HH' (W-step).
 #define GRAM_THREADS 96
+// development aid (MFB_GRAM_TIMING): globaltimer stamps of the side job of the CTA that ends up inverting, and of its consumers
+__device__ unsigned long long g_gram_stamps[16];
+#define GRAM_STAMP(i) do { if (t == 0) g_gram_stamps[(i)] = globaltimer_ns(); } while (0)
 #define GRAM_GROUP 16            // stream CTAs per fold group
 __device__ __forceinline__ void gram_bar() { asm volatile("bar.sync 2, 96;" ::: "memory"); }
+
+// Partial Gram of the units [lo, hi) of the fixed factor on the FP64 tensor cores.  The KB (KB + 1) / 2 blocks of 8 x 8 on
+// and above the diagonal are dealt round-robin to the three warps (W = this warp's share, all indices compile-time);
+// every warp walks ALL the units once, 4 per DMMA, with the fragments of two k-steps in flight -- fragment b of a
+// k-step, F[8b + g][u + tt], is the A operand of the blocks in block row b and the B operand of those in block column b.
+// The block below the diagonal is the transpose: the same products in the same order, copied.
+template <int KB, int W>
+__device__ __forceinline__ void gram_partial_blocks(const HalfParams &p, long long lo, long long hi, int lane, double *sGm) {
+    constexpr int KP = KB * 8, NB = KB * (KB + 1) / 2;
+    constexpr int MY = (NB > W) ? (NB - W + 2) / 3 : 0;
+    if (MY == 0) return;
+    const int g = lane >> 2, tt = lane & 3;
+    double acc[MY > 0 ? MY : 1][2];
+#pragma unroll
+    for (int q = 0; q < MY; ++q) acc[q][0] = acc[q][1] = 0.0;
+    const double *fp = p.Fin + (size_t)g * p.ldin + tt;
+    for (long long u = lo; u < hi; u += 8) {
+        double fr[2][KB];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            const long long uu = u + 4 * s2;
+            const bool ok = uu + tt < hi;
+#pragma unroll
+            for (int bq = 0; bq < KB; ++bq) fr[s2][bq] = ok ? fp[(size_t)(8 * bq) * p.ldin + uu] : 0.0;
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            int idx = 0, q = 0;
+#pragma unroll
+            for (int i = 0; i < KB; ++i)
+#pragma unroll
+                for (int j = i; j < KB; ++j) {
+                    if (idx % 3 == W) {
+                        dmma884(acc[q][0], acc[q][1], fr[s2][i], fr[s2][j]);
+                        ++q;
+                    }
+                    ++idx;
+                }
+        }
+    }
+    {
+        int idx = 0, q = 0;
+#pragma unroll
+        for (int i = 0; i < KB; ++i)
+#pragma unroll
+            for (int j = i; j < KB; ++j) {
+                if (idx % 3 == W) {
+                    const int row = 8 * i + g, col = 8 * j + 2 * tt;
+                    sGm[row * KP + col] = acc[q][0];
+                    sGm[row * KP + col + 1] = acc[q][1];
+                    sGm[col * KP + row] = acc[q][0];
+                    sGm[(col + 1) * KP + row] = acc[q][1];
+                    ++q;
+                }
+                ++idx;
+            }
+    }
+}
+
+// Fixed-order sum of `nsrc` symmetric KP x KP matrices (src + q * KP * KP, q = 0 .. nsrc - 1) by the 96 side-job threads:
+// only the 8 x 8 blocks on and above the diagonal are read (pairs of entries, 16-byte loads, eight sources in flight);
+// f(row, col, v0, v1) receives the sums of the entries (row, col) and (row, col + 1) and mirrors them itself.
+template <int KB, typename F>
+__device__ __forceinline__ void gram_fold_upper(const double *src, int nsrc, int t, F f) {
+    constexpr int KP = KB * 8, NB = KB * (KB + 1) / 2;
+    for (int q = t; q < NB * 32; q += GRAM_THREADS) {
+        int bidx = q >> 5, i = 0;
+        while (bidx >= KB - i) { bidx -= KB - i; ++i; }
+        const int j = i + bidx, rem = q & 31;
+        const int row = 8 * i + (rem >> 2), col = 8 * j + 2 * (rem & 3);
+        const double *sp = src + row * KP + col;
+        double s0 = 0.0, s1 = 0.0;
+        for (int q0 = 0; q0 < nsrc; q0 += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = (q0 + u < nsrc) ? __ldcg((const double2 *)(sp + (size_t)(q0 + u) * (KP * KP))) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s0 += v[u].x; s1 += v[u].y; }
+        }
+        f(row, col, s0, s1);
+    }
+}
 
 template <int KB, bool WSTEP>
 __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, double *sGm, int *gflag) {
     constexpr int KP = KB * 8;
-    constexpr int NBLK = KB * KB, NGRP = (NBLK + 3) / 4;
     const int k = p.k, G = (int)gridDim.x, b = (int)blockIdx.x;
-    const int w = t >> 5, lane = t & 31, g = lane >> 2, tt = lane & 3;
-    // --- partial Gram of this CTA's slice of units; each warp takes a third of the slice, FP64 tensor cores:
-    //     D(8x8 block i,j) += F[8i+g][u + tt] * F[8j+g][u + tt], 4 units per DMMA, loads of 2 k-steps in flight ---
+    const int w = t >> 5, lane = t & 31;
+    // --- partial Gram of this CTA's slice of units ---
+    const unsigned long long t_begin = globaltimer_ns();
     const long long lo = (long long)b * p.nfix / G, hi = (long long)(b + 1) * p.nfix / G;
-    const long long wlo = lo + (hi - lo) * w / 3, whi = lo + (hi - lo) * (w + 1) / 3;
-    for (int e = t; e < KP * KP; e += GRAM_THREADS) sGm[e] = 0.0;
+    if (w == 0) gram_partial_blocks<KB, 0>(p, lo, hi, lane, sGm);
+    else if (w == 1) gram_partial_blocks<KB, 1>(p, lo, hi, lane, sGm);
+    else gram_partial_blocks<KB, 2>(p, lo, hi, lane, sGm);
     gram_bar();
-    for (int q = 0; q < NGRP; ++q) {
-        double acc[4][2];
-        const double *ra[4], *rb[4];
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-            const int bidx = (4 * q + blk < NBLK) ? 4 * q + blk : NBLK - 1;
-            acc[blk][0] = acc[blk][1] = 0.0;
-            ra[blk] = p.Fin + (size_t)(8 * (bidx / KB) + g) * p.ldin + tt;
-            rb[blk] = p.Fin + (size_t)(8 * (bidx % KB) + g) * p.ldin + tt;
-        }
-        for (long long u = wlo; u < whi; u += 8) {
-            double av[4][2], bv[4][2];
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const long long uu = u + 4 * s2;
-                const bool ok = uu + tt < whi;
-#pragma unroll
-                for (int blk = 0; blk < 4; ++blk) {
-                    av[blk][s2] = ok ? ra[blk][uu] : 0.0;
-                    bv[blk][s2] = ok ? rb[blk][uu] : 0.0;
-                }
-            }
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-                for (int blk = 0; blk < 4; ++blk) dmma884(acc[blk][0], acc[blk][1], av[blk][s2], bv[blk][s2]);
-        }
-        // the three warps add their thirds into the shared matrix one after the other (fixed order)
-        for (int turn = 0; turn < 3; ++turn) {
-            if (turn == w) {
-#pragma unroll
-                for (int blk = 0; blk < 4; ++blk) {
-                    const int bidx = 4 * q + blk;
-                    if (bidx < NBLK) {
-                        const int row = 8 * (bidx / KB) + g, col = 8 * (bidx % KB) + 2 * tt;
-                        sGm[row * KP + col] += acc[blk][0];
-                        sGm[row * KP + col + 1] += acc[blk][1];
-                    }
-                }
-            }
-            gram_bar();
-        }
-    }
+    const unsigned long long t_part = globaltimer_ns();
     for (int e = t; e < KP * KP; e += GRAM_THREADS) p.gram_part[(size_t)b * (KP * KP) + e] = sGm[e];
     __threadfence();
     gram_bar();
@@ -589,13 +634,16 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
     }
     gram_bar();
     if (!*gflag) return;
+    const unsigned long long t_l1 = globaltimer_ns();
     __threadfence();
-    for (int e = t; e < KP * KP; e += GRAM_THREADS) {
-        double s = 0.0;
-#pragma unroll
-        for (int bb = 0; bb < GRAM_GROUP; ++bb)
-            if (bb < gsize) s += ldcg(&p.gram_part[(size_t)(gfirst + bb) * (KP * KP) + e]);
-        p.gram_part2[(size_t)grp * (KP * KP) + e] = s;
+    {
+        double *dst = p.gram_part2 + (size_t)grp * (KP * KP);
+        gram_fold_upper<KB>(p.gram_part + (size_t)gfirst * (KP * KP), gsize, t, [&](int row, int col, double v0, double v1) {
+            dst[row * KP + col] = v0;
+            dst[row * KP + col + 1] = v1;
+            dst[col * KP + row] = v0;
+            dst[(col + 1) * KP + row] = v1;
+        });
     }
     __threadfence();
     gram_bar();
@@ -609,17 +657,20 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
     if (!*gflag) return;
     __threadfence();
     // --- level 2 (one CTA per launch): fold the groups, publish G, invert ---
-    for (int e = t; e < KP * KP; e += GRAM_THREADS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        double s = 0.0;
-        if (c1 < k && c2 < k) {
-#pragma unroll 10
-            for (int gg = 0; gg < ngroups; ++gg) s += ldcg(&p.gram_part2[(size_t)gg * (KP * KP) + e]);
-        }
-        sGm[e] = s;
-        p.G[e] = s;
-    }
+    if (t == 0) { g_gram_stamps[0] = t_begin; g_gram_stamps[1] = t_part; g_gram_stamps[2] = t_l1; }
+    GRAM_STAMP(3);
+    gram_fold_upper<KB>(p.gram_part2, ngroups, t, [&](int row, int col, double v0, double v1) {
+        if (!(row < k && col < k)) v0 = 0.0;
+        if (!(row < k && col + 1 < k)) v1 = 0.0;
+        sGm[row * KP + col] = v0;      p.G[row * KP + col] = v0;
+        sGm[row * KP + col + 1] = v1;  p.G[row * KP + col + 1] = v1;
+        sGm[col * KP + row] = v0;      p.G[col * KP + row] = v0;
+        sGm[(col + 1) * KP + row] = v1; p.G[(col + 1) * KP + row] = v1;
+    });
     gram_bar();
+    // large ranks: the inversion is a long serial chain that competes with this CTA's own DMMA warps for issue slots
+    // (k = 64: ~350 us on the side-job warps, the tail of the whole launch); a one-block kernel does it in ~15 us
+    if (p.invert_later) return;
     // row-sharded H-step: this is only this rank's W_r'W_r
     if (p.shard && !WSTEP) {
         if (!p.peers) return;            // callback exchange: summed with W_r'A_r by the host, inverted by als_shard_invert_kernel
@@ -651,7 +702,9 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
     }
     // all 96 threads on the shared matrix (two barriers per pivot): a single warp with the rows in registers is
     // latency-bound (~35 us at k = 16 and worse next to the streaming warps), which small or sharded matrices feel
+    GRAM_STAMP(4);
     const int sing = gauss_jordan_inverse(sGm, k, KP, t, GRAM_THREADS, sGm + KP * KP, [] { gram_bar(); });
+    GRAM_STAMP(5);
     for (int e = t; e < KP * KP; e += GRAM_THREADS) {
         const int c1 = e / KP, c2 = e - c1 * KP;
         p.Minv[e] = (c1 < k && c2 < k) ? sGm[e] : 0.0;
@@ -892,25 +945,29 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
             } else if (!WSTEP && KB >= 6) {
-                // large ranks: the 16 KB accumulator tile leaves no room for all factor fragments at once, so they
-                // are fetched rank block by rank block (same accumulation order per accumulator as below)
-                double2 b[4][2];
+                // large ranks: the accumulator tile alone is 2 * KB * 8 registers, so the A fragments are taken two column
+                // blocks at a time and the factor fragments rank block by rank block (same accumulation order per
+                // accumulator as below; nothing spills)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    b[v][0] = lds128(sb + offA + v * 1024);
-                    b[v][1] = lds128(sb + (offA ^ 16) + v * 1024);
-                }
+                for (int vh = 0; vh < 2; ++vh) {
+                    double2 b[2][2];
 #pragma unroll
-                for (int cb = 0; cb < KB; ++cb) {
-                    const double2 f0 = lds128(sb + offF + cb * 1024), f1 = lds128(sb + (offF ^ 16) + cb * 1024);
+                    for (int v = 0; v < 2; ++v) {
+                        b[v][0] = lds128(sb + offA + (2 * vh + v) * 1024);
+                        b[v][1] = lds128(sb + (offA ^ 16) + (2 * vh + v) * 1024);
+                    }
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f0.x, b[v][0].x);
+                    for (int cb = 0; cb < KB; ++cb) {
+                        const double2 f0 = lds128(sb + offF + cb * 1024), f1 = lds128(sb + (offF ^ 16) + cb * 1024);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f0.y, b[v][0].y);
+                        for (int v = 0; v < 2; ++v) dmma884(acc[cb][2 * vh + v][0], acc[cb][2 * vh + v][1], f0.x, b[v][0].x);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f1.x, b[v][1].x);
+                        for (int v = 0; v < 2; ++v) dmma884(acc[cb][2 * vh + v][0], acc[cb][2 * vh + v][1], f0.y, b[v][0].y);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) dmma884(acc[cb][v][0], acc[cb][v][1], f1.y, b[v][1].y);
+                        for (int v = 0; v < 2; ++v) dmma884(acc[cb][2 * vh + v][0], acc[cb][2 * vh + v][1], f1.x, b[v][1].x);
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) dmma884(acc[cb][2 * vh + v][0], acc[cb][2 * vh + v][1], f1.y, b[v][1].y);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -1138,26 +1195,26 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
 
 // callback exchange, after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve()
 // failure: reason 3).  (Peer-memory exchange: the Gram side job of the stream kernel does this, see gram_side_job.)
-__global__ void __launch_bounds__(256) als_shard_invert_kernel(const HalfParams p, int KP, const double *__restrict__ Gsum) {
+__global__ void __launch_bounds__(1024) als_shard_invert_kernel(const HalfParams p, int KP, const double *Gsum, int reason) {
     extern __shared__ double sh[];   // KP*KP + 2
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
     double *sG = sh, *scr = sh + KP * KP;
     const int k = p.k;
-    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
         const int c1 = e / KP, c2 = e - c1 * KP;
         const double v = (c1 < k && c2 < k) ? Gsum[e] : 0.0;
         sG[e] = v;
         p.G[e] = v;
     }
     __syncthreads();
-    const int sing = gauss_jordan_inverse(sG, k, KP, threadIdx.x, 256, scr, [] { __syncthreads(); });
-    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+    const int sing = gauss_jordan_inverse(sG, k, KP, threadIdx.x, (int)blockDim.x, scr, [] { __syncthreads(); });
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
         const int c1 = e / KP, c2 = e - c1 * KP;
         p.Minv[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
     }
     if (threadIdx.x == 0 && sing) {
-        p.ctrl->reason = 3;
+        p.ctrl->reason = reason;
         __threadfence();
         p.ctrl->stop = 1;
     }
@@ -1422,9 +1479,16 @@ static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUt
                             x.out_lo, (const AlsCtrl *)hp.ctrl));
         return MFB_OK;
     };
+    auto invert_launch = [&](int reason) -> int {   // (timed with the solve kernel that follows)
+        if (!hp.invert_later) return MFB_OK;
+        MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 1024, (size_t)(s->KP * s->KP + 2) * sizeof(double), st, pdl, hp, s->KP,
+                            (const double *)hp.G, reason));
+        return MFB_OK;
+    };
     if (wstep) {
         MFB_TRY(stream_launch(true));
         MFB_TRY(prof_mark(s));
+        MFB_TRY(invert_launch(4));
         MFB_CUDA(launch_pdl(als_solve_kernel<KB, true>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
         MFB_TRY(split_launch());
         MFB_TRY(prof_mark(s));
@@ -1432,6 +1496,7 @@ static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUt
         if (which != 2) {
             MFB_TRY(stream_launch(false));
             MFB_TRY(prof_mark(s));
+            MFB_TRY(invert_launch(3));
         }
         if (which != 1) {
             MFB_CUDA(launch_pdl(als_solve_kernel<KB, false>, nsolve, SOLVE_THREADS, SolveCfg<KB>::SMEM, st, pdl, hp));
@@ -1804,6 +1869,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.k = s->k; h.T = s->T_h; h.SPT = s->SPT_h; h.U = (long long)s->T_h * s->SPT_h; h.nvalid = s->n;
     h.Gstream = s->ctx->sm_count;
     h.shard = s->shard ? 1 : 0; h.xscal = s->xscal;
+    h.invert_later = (!s->shard && s->KB >= 7 && !getenv("MFB_INVERT_IN_STREAM")) ? 1 : 0;
     const bool peer = als_peer_mode(s);
     const bool pdl = als_use_pdl(s);
     if (s->shard) h.epoch = ++s->epoch;
@@ -1832,7 +1898,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
                 return MFB_ERR_CUDA;
             }
             MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 256, gsm, st, pdl, h, s->KP,
-                                (const double *)(s->xchg + (size_t)s->T_h * s->KP * TILE_UNITS)));
+                                (const double *)(s->xchg + (size_t)s->T_h * s->KP * TILE_UNITS), 3));
             MFB_TRY(prof_mark(s));
         }
         HalfParams hs = h;
@@ -1961,6 +2027,12 @@ int mfb_als_profile(mfb_als *s, int iters, double *ms) {
     s->prof = nullptr;
     MFB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     tf32_timing_end(iters);
+    if (getenv("MFB_GRAM_TIMING")) {
+        unsigned long long st[16];
+        MFB_CUDA(cudaMemcpyFromSymbol(st, g_gram_stamps, sizeof(st)));
+        fprintf(stderr, "gram side job of the inverting CTA (last launch, us): partial %.1f | wait+l1 start %.1f | l1 fold -> l2 start %.1f | l2 fold %.1f | inverse %.1f\n",
+                (st[1] - st[0]) * 1e-3, (st[2] - st[1]) * 1e-3, (st[3] - st[2]) * 1e-3, (st[4] - st[3]) * 1e-3, (st[5] - st[4]) * 1e-3);
+    }
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const size_t nk = ev.size() - 1;
     // sharded, callback exchange: H stream, fold, invert, H solve, W stream, W solve, finish (collectives in between);

@@ -40,10 +40,47 @@ __device__ int gauss_jordan_inverse(double *a, int k, int ld, int tid, int nthre
             piv = 1.0;
         }
         const double ipiv = 1.0 / piv;
-        // eliminate column p from all other rows (uses the unscaled pivot row; row p and column p are only read)
-        for (int e = tid; e < k * k; e += nthreads) {
-            int i = e / k, j = e - i * k;
-            if (i != p && j != p) a[i * ld + j] -= a[i * ld + p] * ipiv * a[p * ld + j];
+        // eliminate column p from all other rows (uses the unscaled pivot row; row p and column p are only read).
+        // Warp w takes every nw-th row, a lane the columns lane, lane + 32, ...: a[i][p] is a broadcast read, the row
+        // segments are conflict-free, and there is no index arithmetic beyond adds (a flat loop over the k * k entries
+        // with a division per entry made this the tail of the stream kernel at k = 64: ~600 000 cycles on the side-job
+        // warps).  Per entry the arithmetic is unchanged: a_ij - ((a_ip * ipiv) * a_pj).
+        {
+            const int w = tid >> 5, l = tid & 31, nw = nthreads >> 5;
+            if (nw > 0) {
+                if (w < nw) {
+                    for (int j0 = 0; j0 < k; j0 += 64) {
+                        const int ja = j0 + l, jb = j0 + l + 32;
+                        const bool oka = ja < k && ja != p, okb = jb < k && jb != p;
+                        const double pa = oka ? a[p * ld + ja] : 0.0, pb = okb ? a[p * ld + jb] : 0.0;
+                        // four rows at a time: all their loads before the first store (a store to a[i][ja] could alias
+                        // the next row's a[i'][p] as far as the compiler knows, which would serialise the rows)
+                        for (int i0 = w; i0 < k; i0 += 4 * nw) {
+                            double f[4], va[4], vb[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = i0 + u * nw;
+                                const bool rok = i < k && i != p;
+                                f[u] = rok ? a[i * ld + p] * ipiv : 0.0;
+                                va[u] = (rok && oka) ? a[i * ld + ja] : 0.0;
+                                vb[u] = (rok && okb) ? a[i * ld + jb] : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = i0 + u * nw;
+                                const bool rok = i < k && i != p;
+                                if (rok && oka) a[i * ld + ja] = va[u] - f[u] * pa;
+                                if (rok && okb) a[i * ld + jb] = vb[u] - f[u] * pb;
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int e = tid; e < k * k; e += nthreads) {
+                    int i = e / k, j = e - i * k;
+                    if (i != p && j != p) a[i * ld + j] -= a[i * ld + p] * ipiv * a[p * ld + j];
+                }
+            }
         }
         bar();
         for (int e = tid; e < k; e += nthreads) {
@@ -180,11 +217,13 @@ __device__ double nnls_lanes(const double *__restrict__ sG, const double *__rest
         }
         const double ri = (rowvalid && uvalid) ? xs[i * XS + unit] : 0.0;
         // unconstrained solution xu = G^-1 r: .fcnnls' first passive set is P = {xu > 0}
+        double T[KP];
         double xu = 0.0;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             const double rj = __shfl_sync(FULL, ri, base + (j % LP));
             const double mij = (rowvalid && j < k) ? sM[j * KP + i] : 0.0;
+            T[j] = -mij;
             xu += mij * rj;
         }
         const unsigned negs = (__ballot_sync(FULL, rowvalid && !(xu > 0.0)) & gmask) >> base;
@@ -193,10 +232,11 @@ __device__ double nnls_lanes(const double *__restrict__ sG, const double *__rest
         // exchanging the variables of ~P out, or from S = {} (q = r, T = -G) by exchanging those of P in -- the same
         // principal pivots either way, min(|P|, k - |P|) of them (sparse factors: a handful instead of almost k).
         const bool fromG = sG != nullptr && __popc(poss) < __popc(negs);
-        const double *__restrict__ src0 = fromG ? sG : sM;
-        double T[KP];
+        if (__any_sync(FULL, fromG)) {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) T[j] = (rowvalid && j < k) ? -src0[j * KP + i] : 0.0;
+            for (int j = 0; j < KP; ++j)
+                if (fromG) T[j] = (rowvalid && j < k) ? -sG[j * KP + i] : 0.0;
+        }
         double qv = fromG ? ri : xu;
         bool inS = rowvalid && !fromG;
         double dv = xu > 0.0 ? xu : 0.0;
@@ -324,6 +364,80 @@ struct NnlsCfg {
     static constexpr int SCR = PPW * (KP + NS + (NS + 1) / 2);   // doubles: xu[KP], y[NS], idx[NS] (ints) per problem
 };
 
+// One exact solve of the current partition on its smaller side S (see nnls_warp below), ns <= ns_max <= NSB: gathers the
+// ns x ns system into registers (lane l = compressed row l), eliminates, back-substitutes so that every lane holds all
+// of y, and forms the primal values on P and the gradient on N.
+template <int KP, int XS, int NSB>
+__device__ __forceinline__ void nnls_partition_solve(const double *Msrc, const double *xu_s, const double *xs, int ucol, const int *idx_s,
+                                                     double *y_s, int i, int base, int ns, int ns_max, bool useN, bool done,
+                                                     unsigned long long smask, const int (&pos_)[NnlsCfg<KP>::R],
+                                                     const bool (&val_)[NnlsCfg<KP>::R], const double (&xu_)[NnlsCfg<KP>::R],
+                                                     const double (&r_)[NnlsCfg<KP>::R], double (&x_)[NnlsCfg<KP>::R],
+                                                     double (&w_)[NnlsCfg<KP>::R]) {
+    constexpr int LP = NnlsCfg<KP>::LP, R = NnlsCfg<KP>::R;
+    const unsigned FULL = 0xffffffffu;
+    // ---- gather the compressed system: lane i < ns owns row i ----
+    double A[NSB], yv[NSB];
+    const bool rowok = i < ns;
+    const int my = rowok ? idx_s[i] : 0;
+#pragma unroll
+    for (int b = 0; b < NSB; ++b) {
+        A[b] = (b == i) ? 1.0 : 0.0;                 // identity padding outside the ns x ns block
+        yv[b] = 0.0;
+        if (b < ns_max) {
+            const int ib = (b < ns) ? idx_s[b] : 0;
+            if (rowok && b < ns) A[b] = Msrc[ib * KP + my];
+        }
+    }
+    double rhs = rowok ? (useN ? xu_s[my] : xs[my * XS + ucol]) : 0.0;
+    // ---- forward elimination (no pivoting: principal sub-matrix of an SPD matrix) ----
+#pragma unroll
+    for (int a = 0; a < NSB; ++a) {
+        if (a < ns_max) {
+            const double pa = __shfl_sync(FULL, A[a], base + a);
+            const double ip = fast_rcp(pa);
+            yv[a] = ip;
+            const double f = (i > a) ? A[a] * ip : 0.0;
+#pragma unroll
+            for (int b = a + 1; b < NSB; ++b)
+                if (b < ns_max) A[b] -= f * __shfl_sync(FULL, A[b], base + a);
+            rhs -= f * __shfl_sync(FULL, rhs, base + a);
+        }
+    }
+    // ---- back substitution: every lane learns every y_a ----
+#pragma unroll
+    for (int a = NSB - 1; a >= 0; --a) {
+        if (a < ns_max) {
+            const double ya = __shfl_sync(FULL, rhs, base + a) * yv[a];
+            yv[a] = ya;
+            if (i < a) rhs -= A[a] * ya;
+            if (i == 0 && a < ns) y_s[a] = ya;
+        }
+    }
+    __syncwarp();
+    // ---- primal values on P, gradient on N ----
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const int v = i + LP * q;
+        if (val_[q] && !done) {
+            const bool inS = (smask >> v) & 1ull;
+            if (inS) {
+                const double ys = y_s[pos_[q]];
+                x_[q] = useN ? 0.0 : ys;
+                w_[q] = useN ? ys : 0.0;
+            } else {
+                double acc = useN ? xu_[q] : r_[q];
+#pragma unroll
+                for (int b = 0; b < NSB; ++b)
+                    if (b < ns) acc -= Msrc[idx_s[b] * KP + v] * yv[b];
+                x_[q] = useN ? acc : 0.0;
+                w_[q] = useN ? 0.0 : acc;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <int KP, int XS>
 __device__ double nnls_warp(const double *__restrict__ sG, const double *__restrict__ sM, int k, double *xs,
                             double *scr, int first, int count, int nvalid, int lane) {
@@ -393,66 +507,17 @@ __device__ double nnls_warp(const double *__restrict__ sG, const double *__restr
                 if (!done && ((smask >> v) & 1ull)) idx_s[pos_[q]] = v;
             }
             __syncwarp();
-            // ---- gather the compressed system: lane i < ns owns row i ----
-            double A[NS], yv[NS];
-            const bool rowok = i < ns;
-            const int my = rowok ? idx_s[i] : 0;
-#pragma unroll
-            for (int b = 0; b < NS; ++b) {
-                A[b] = (b == i) ? 1.0 : 0.0;                 // identity padding outside the ns x ns block
-                yv[b] = 0.0;
-                if (b < ns_max) {
-                    const int ib = (b < ns) ? idx_s[b] : 0;
-                    if (rowok && b < ns) A[b] = Msrc[ib * KP + my];
-                }
-            }
-            double rhs = rowok ? (useN ? xu_s[my] : xs[my * XS + ucol]) : 0.0;
-            // ---- forward elimination (no pivoting: principal sub-matrix of an SPD matrix) ----
-#pragma unroll
-            for (int a = 0; a < NS; ++a) {
-                if (a < ns_max) {
-                    const double pa = __shfl_sync(FULL, A[a], base + a);
-                    const double ip = fast_rcp(pa);
-                    yv[a] = ip;
-                    const double f = (i > a) ? A[a] * ip : 0.0;
-#pragma unroll
-                    for (int b = a + 1; b < NS; ++b)
-                        if (b < ns_max) A[b] -= f * __shfl_sync(FULL, A[b], base + a);
-                    rhs -= f * __shfl_sync(FULL, rhs, base + a);
-                }
-            }
-            // ---- back substitution: every lane learns every y_a ----
-#pragma unroll
-            for (int a = NS - 1; a >= 0; --a) {
-                if (a < ns_max) {
-                    const double ya = __shfl_sync(FULL, rhs, base + a) * yv[a];
-                    yv[a] = ya;
-                    if (i < a) rhs -= A[a] * ya;
-                    if (i == 0 && a < ns) y_s[a] = ya;
-                }
-            }
-            __syncwarp();
-            // ---- primal values on P, gradient on N ----
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int v = i + LP * q;
-                if (val_[q] && !done) {
-                    const bool inS = (smask >> v) & 1ull;
-                    if (inS) {
-                        const double ys = y_s[pos_[q]];
-                        x_[q] = useN ? 0.0 : ys;
-                        w_[q] = useN ? ys : 0.0;
-                    } else {
-                        double acc = useN ? xu_[q] : r_[q];
-#pragma unroll
-                        for (int b = 0; b < NS; ++b)
-                            if (b < ns) acc -= Msrc[idx_s[b] * KP + v] * yv[b];
-                        x_[q] = useN ? acc : 0.0;
-                        w_[q] = useN ? 0.0 : acc;
-                    }
-                }
-            }
-            __syncwarp();
+            // ---- solve the partition on its smaller side with loops unrolled to the smallest bucket that holds it ----
+            // (the systems of one launch are mostly far smaller than KP / 2: unrolled to NS, every elimination step
+            // would issue NS predicated-off updates whatever ns is)
+            if (ns_max <= 4)
+                nnls_partition_solve<KP, XS, (NS < 4 ? NS : 4)>(Msrc, xu_s, xs, ucol, idx_s, y_s, i, base, ns, ns_max, useN, done, smask, pos_, val_, xu_, r_, x_, w_);
+            else if (ns_max <= 8)
+                nnls_partition_solve<KP, XS, (NS < 8 ? NS : 8)>(Msrc, xu_s, xs, ucol, idx_s, y_s, i, base, ns, ns_max, useN, done, smask, pos_, val_, xu_, r_, x_, w_);
+            else if (ns_max <= 16)
+                nnls_partition_solve<KP, XS, (NS < 16 ? NS : 16)>(Msrc, xu_s, xs, ucol, idx_s, y_s, i, base, ns, ns_max, useN, done, smask, pos_, val_, xu_, r_, x_, w_);
+            else
+                nnls_partition_solve<KP, XS, NS>(Msrc, xu_s, xs, ucol, idx_s, y_s, i, base, ns, ns_max, useN, done, smask, pos_, val_, xu_, r_, x_, w_);
             // ---- block principal pivoting ----
             if (!done) {
                 const unsigned gm = (LP == 32) ? FULL : (0xffffu << base);
