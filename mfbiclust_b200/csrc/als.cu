@@ -263,6 +263,9 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 #define SOLVE_THREADS 128
 #endif
 #define SOLVE_WARPS (SOLVE_THREADS / 32)
+#ifndef SOLVE_MINB_LARGE
+#define SOLVE_MINB_LARGE 3        // resident solve CTAs per SM asked for at ranks 33..56 (register cap 168; k = 64 runs better uncapped)
+#endif
 #define SOLVE_GROUP 128          // warps per fold group
 
 template <int KB>
@@ -301,7 +304,7 @@ __device__ __forceinline__ void finish_iteration(AlsCtrl *c, double *trace, doub
 }
 
 template <int KB, bool WSTEP>
-__global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : 1) als_solve_kernel(const HalfParams p) {
+__global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : ((KB >= 5 && KB <= 7) ? SOLVE_MINB_LARGE : 1)) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
     constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW, LP = Cfg::LP, R = Cfg::R;
     pdl_prologue();
