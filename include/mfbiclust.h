@@ -194,6 +194,18 @@ int  mfb_otsu(mfb_context *ctx, const double *M, int64_t rows, int64_t cols, dou
 int  mfb_threshold(mfb_context *ctx, const double *M, int64_t rows, int64_t cols,
                    const double *th, int margin, int32_t *out);
 
+/* ---- bicluster post-processing (R/helperFunctions.R:150-206 filter.biclust, :226-247 overlap, :303-308 sizes,
+ *      :336-345 union.biclust) on the membership matrices threshold() produces */
+/* rowxBicluster: m x k, biclusterxCol: k x n, R logicals (int32, column-major; NA is not TRUE).
+ * sizes[i] = |rows_i| * |cols_i|;  overlaps: k x k column-major, entry (i, j) at i + k * j =
+ * |rows_i & rows_j| * |cols_i & cols_j| / sizes[i]  -- overlap(BiclusterRows, BiclusterCols, matrix = TRUE). */
+int  mfb_bicluster_overlap(mfb_context *ctx, const int32_t *rowxBicluster, int64_t m, const int32_t *biclusterxCol,
+                           int64_t n, int k, double *sizes, double *overlaps);
+/* biclustered: m x n column-major, 1 where any bicluster b with choose[b] TRUE (choose == NULL: all) contains the
+ * element, else 0 -- union.biclust(RowxBiclust, BiclustxCol, choose). */
+int  mfb_bicluster_union(mfb_context *ctx, const int32_t *rowxBicluster, int64_t m, const int32_t *biclusterxCol,
+                         int64_t n, int k, const int32_t *choose, double *biclustered);
+
 /* ---- svd_pca (R/bicluster.R:528-539 -> stats::prcomp(t(A), rank. = k, center = FALSE)) */
 /* W: m x k (left singular vectors of A), H: k x n (= t(W) %*% A), sdev-free.  kout = min(k, m, n). */
 int  mfb_svd_pca(mfb_context *ctx, mfb_matrix *A, int k, double *W, double *H, int *kout);

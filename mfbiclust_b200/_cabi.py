@@ -62,6 +62,8 @@ PROTOTYPES = {
     "mfb_nnls_draws": (C.c_int, [_vp, _dp, _dp, _i64, C.c_int, _i64, _dp, C.POINTER(C.c_longlong)]),
     "mfb_otsu": (C.c_int, [_vp, _dp, _i64, _i64, _dp]),
     "mfb_threshold": (C.c_int, [_vp, _dp, _i64, _i64, _dp, C.c_int, _i32p]),
+    "mfb_bicluster_overlap": (C.c_int, [_vp, _i32p, _i64, _i32p, _i64, C.c_int, _dp, _dp]),
+    "mfb_bicluster_union": (C.c_int, [_vp, _i32p, _i64, _i32p, _i64, C.c_int, _i32p, _dp]),
     "mfb_svd_pca": (C.c_int, [_vp, _vp, C.c_int, _dp, _dp, _ip]),
     "mfb_nipals": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                              _dp, _dp, _dp, _ip]),

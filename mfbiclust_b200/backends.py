@@ -526,6 +526,99 @@ def threshold(m, th, MARGIN=2, ctx=None):
 
 
 # ---------------------------------------------------------------------------
+# post-processing of memberships: sizes / overlap / union.biclust / filter.biclust
+# ---------------------------------------------------------------------------
+def _memberships(rowxBicluster, biclusterxCol):
+    R = np.asfortranarray(np.asarray(rowxBicluster).astype(np.int32))
+    Cm = np.asfortranarray(np.asarray(biclusterxCol).astype(np.int32))
+    if R.ndim != 2 or Cm.ndim != 2 or R.shape[1] != Cm.shape[0]:
+        raise ValueError("RowxBicluster must have the same number of columns asBiclusterxCol")   # R/helperFunctions.R:157-160
+    return R, Cm
+
+
+def biclusterMatrix2List(rowxBicluster, biclusterxCol):
+    """``biclusterMatrix2List`` (``R/helperFunctions.R:25-31``): 1-based row / column indices of every bicluster."""
+    R, Cm = _memberships(rowxBicluster, biclusterxCol)
+    return ([np.flatnonzero(R[:, b]) + 1 for b in range(R.shape[1])],
+            [np.flatnonzero(Cm[b, :]) + 1 for b in range(Cm.shape[0])])
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def overlap_sizes(rowxBicluster, biclusterxCol, ctx=None):
+    """``sizes()`` and ``overlap(..., matrix = TRUE)`` (``R/helperFunctions.R:303-308, 226-247``) of all biclusters in
+    one device call (``mfb_bicluster_overlap``): returns ``(sizes[k], overlaps[k, k])``, ``overlaps[i, j]`` = elements
+    shared by biclusters i and j / size of bicluster i (NaN for an empty bicluster i, as ``0 / 0`` in R)."""
+    ctx = ctx or _cabi.default_context()
+    R, Cm = _memberships(rowxBicluster, biclusterxCol)
+    k = R.shape[1]
+    if k == 0:
+        return np.zeros(0), np.zeros((0, 0))
+    sz = np.zeros(k)
+    ov = np.zeros((k, k), order="F")
+    check(lib().mfb_bicluster_overlap(ctx.handle, _i32p(R), R.shape[0], _i32p(Cm), Cm.shape[1], k, dptr(sz), dptr(ov)))
+    return sz, ov
+
+
+def sizes(rowxBicluster, biclusterxCol, ctx=None):
+    return overlap_sizes(rowxBicluster, biclusterxCol, ctx)[0]
+
+
+def overlap(rowxBicluster, biclusterxCol, matrix=False, ctx=None):
+    ov = overlap_sizes(rowxBicluster, biclusterxCol, ctx)[1]
+    return ov if matrix else [ov[i, :].copy() for i in range(ov.shape[0])]
+
+
+def union_biclust(RowxBiclust, BiclustxCol, choose=None, ctx=None):
+    """``union.biclust(RowxBiclust, BiclustxCol, choose)`` (``R/helperFunctions.R:336-345``): m x n matrix of 0 / 1."""
+    ctx = ctx or _cabi.default_context()
+    R, Cm = _memberships(RowxBiclust, BiclustxCol)
+    k = R.shape[1]
+    out = np.zeros((R.shape[0], Cm.shape[1]), order="F")
+    if k == 0 or out.size == 0:
+        return out
+    ch = None
+    if choose is not None:
+        ch = np.ascontiguousarray(np.asarray(choose).astype(np.int32))
+        if ch.size != k:
+            raise ValueError("choose must have one element per bicluster")
+    check(lib().mfb_bicluster_union(ctx.handle, _i32p(R), R.shape[0], _i32p(Cm), Cm.shape[1], k,
+                                    _i32p(ch) if ch is not None else None, dptr(out)))
+    return out
+
+
+def filter_biclust(rowxBicluster, biclusterxCol, max=None, overlap=0.25, ctx=None):
+    """``filter.biclust(rowxBicluster, biclusterxCol, max = NULL, overlap = 0.25)`` (``R/helperFunctions.R:150-206``):
+    biclusters are taken largest first; one that shares more than ``overlap`` of ITS elements with a chosen one, an
+    empty one and one that covers the whole matrix are never taken.  The pairwise intersections and the union come
+    from the device; the greedy loop over k numbers runs here, statement for statement as in R."""
+    R, Cm = _memberships(rowxBicluster, biclusterxCol)
+    k = R.shape[1]
+    if k == 0:
+        chosen = np.zeros(0, dtype=bool)
+    elif k == 1:
+        chosen = np.ones(1, dtype=bool)                       # no filtering needed (:166-168)
+    else:
+        sz, ov = overlap_sizes(R, Cm, ctx)
+        chosen = np.zeros(k, dtype=bool)
+        pool = np.ones(k, dtype=bool)
+        pool[(sz == 0) | (sz == R.shape[0] * Cm.shape[1])] = False          # :181
+        # `while(all(sum(chosen) < max) && sum(pool) > 0)`: with max = NULL the comparison is logical(0), all() of it TRUE
+        while (max is None or chosen.sum() < max) and pool.sum() > 0:
+            idx = np.flatnonzero(pool)
+            choose_me = idx[np.argmax(sz[idx])]                             # which.max: first maximum in index order
+            chosen[choose_me] = True
+            with np.errstate(invalid="ignore"):
+                pool[ov[:, choose_me] > overlap] = False                    # NaN > x is NA in R: `pool[NA] <- FALSE` only
+            pool[choose_me] = False                                         # touches nothing for NA subscripts of an empty one
+    biclustered = union_biclust(R, Cm, chosen, ctx) if k > 0 else np.zeros((R.shape[0], Cm.shape[1]))
+    return {"RowxBicluster": np.asarray(rowxBicluster)[:, chosen], "BiclusterxCol": np.asarray(biclusterxCol)[chosen, :],
+            "biclustered": biclustered, "chosen": chosen}
+
+
+# ---------------------------------------------------------------------------
 # svd_pca / nipals_pca
 # ---------------------------------------------------------------------------
 def svd_pca(A, k, ctx=None, **_):

@@ -219,3 +219,43 @@ threshold <- function(m, th, MARGIN = 2) {                                # R/Bi
     dimnames(mat) <- dimnames(m)
     mat
 }
+
+# ---- post-processing (R/helperFunctions.R:150-346): the pairwise intersections and the union come from the device,
+# ---- the greedy loop of filter.biclust is the reference's own
+sizes <- function(biclusterRows, biclusterCols)                            # R/helperFunctions.R:303-308 (index lists: host)
+    vapply(seq_along(biclusterRows), FUN.VALUE = numeric(1),
+           FUN = function(b) length(biclusterRows[[b]]) * length(biclusterCols[[b]]))
+
+union.biclust <- function(RowxBiclust, BiclustxCol, choose = rep(TRUE, ncol(RowxBiclust))) {   # :336-345
+    if (ncol(RowxBiclust) == 0) return(matrix(0, nrow = nrow(RowxBiclust), ncol = ncol(BiclustxCol)))
+    storage.mode(RowxBiclust) <- "logical"; storage.mode(BiclustxCol) <- "logical"
+    .Call(C_mfb_bicluster_union, .mfb_ctx(), RowxBiclust, BiclustxCol, as.logical(choose))
+}
+
+filter.biclust <- function(rowxBicluster, biclusterxCol, max = NULL, overlap = 0.25) {         # :150-206
+    if (ncol(rowxBicluster) != nrow(biclusterxCol))
+        stop(paste0("RowxBicluster must have the same number of columns as", "BiclusterxCol"))
+    k <- ncol(rowxBicluster)
+    if (k == 0) {
+        chosen <- rep(FALSE, ncol(rowxBicluster))
+    } else if (k == 1) {
+        chosen <- rep(TRUE, ncol(rowxBicluster))
+    } else {
+        storage.mode(rowxBicluster) <- "logical"; storage.mode(biclusterxCol) <- "logical"
+        so <- .Call(C_mfb_bicluster_overlap, .mfb_ctx(), rowxBicluster, biclusterxCol)
+        sizes <- so[[1]]; names(sizes) <- seq_len(k)
+        overlaps <- so[[2]]
+        chosen <- rep(FALSE, each = k)
+        pool <- rep(TRUE, each = k)
+        pool[sizes == 0 | sizes == nrow(rowxBicluster) * ncol(biclusterxCol)] <- FALSE
+        while (all(sum(chosen) < max) && sum(pool) > 0) {
+            chooseMe <- as.numeric(names(which.max(sizes[which(pool)])))
+            chosen[chooseMe] <- TRUE
+            pool[overlaps[, chooseMe] > overlap] <- FALSE
+            pool[chooseMe] <- FALSE
+        }
+    }
+    biclustered <- union.biclust(rowxBicluster, biclusterxCol, chosen)
+    list(RowxBicluster = rowxBicluster[, chosen, drop = FALSE], BiclusterxCol = biclusterxCol[chosen, , drop = FALSE],
+         biclustered = biclustered, chosen = chosen)
+}

@@ -177,6 +177,31 @@ SEXP C_mfb_bcv_cells_na(SEXP ctx, SEXP Y, SEXP rowFolds, SEXP colFolds, SEXP hol
 
 SEXP C_mfb_trim(SEXP ctx) { CHECK(mfb_context_trim(ctx_of(ctx))); return R_NilValue; }
 
+/* sizes() + overlap(matrix = TRUE) of all biclusters: list(sizes, overlaps)  (R/helperFunctions.R:226-247, 303-308) */
+SEXP C_mfb_bicluster_overlap(SEXP ctx, SEXP rowx, SEXP bicx) {
+    SEXP dr = Rf_getAttrib(rowx, R_DimSymbol), dc = Rf_getAttrib(bicx, R_DimSymbol);
+    const int k = INTEGER(dr)[1];
+    SEXP sz = PROTECT(Rf_allocVector(REALSXP, k));
+    SEXP ov = PROTECT(Rf_allocMatrix(REALSXP, k, k));
+    CHECK(mfb_bicluster_overlap(ctx_of(ctx), (const int32_t *) LOGICAL(rowx), INTEGER(dr)[0], (const int32_t *) LOGICAL(bicx),
+                                INTEGER(dc)[1], k, REAL(sz), REAL(ov)));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, sz);
+    SET_VECTOR_ELT(out, 1, ov);
+    UNPROTECT(3);
+    return out;
+}
+
+/* union.biclust(RowxBiclust, BiclustxCol, choose)  (R/helperFunctions.R:336-345) */
+SEXP C_mfb_bicluster_union(SEXP ctx, SEXP rowx, SEXP bicx, SEXP choose) {
+    SEXP dr = Rf_getAttrib(rowx, R_DimSymbol), dc = Rf_getAttrib(bicx, R_DimSymbol);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, INTEGER(dr)[0], INTEGER(dc)[1]));
+    CHECK(mfb_bicluster_union(ctx_of(ctx), (const int32_t *) LOGICAL(rowx), INTEGER(dr)[0], (const int32_t *) LOGICAL(bicx),
+                              INTEGER(dc)[1], INTEGER(dr)[1], (const int32_t *) LOGICAL(choose), REAL(out)));
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
     {"C_mfb_context", (DL_FUNC) &C_mfb_context, 1}, {"C_mfb_upload", (DL_FUNC) &C_mfb_upload, 2},
     {"C_mfb_stats", (DL_FUNC) &C_mfb_stats, 1}, {"C_mfb_als_begin", (DL_FUNC) &C_mfb_als_begin, 6},
@@ -187,5 +212,6 @@ static const R_CallMethodDef calls[] = {
     {"C_mfb_upload_f32", (DL_FUNC) &C_mfb_upload_f32, 2}, {"C_mfb_shift", (DL_FUNC) &C_mfb_shift, 2},
     {"C_mfb_bcv_cells_multi", (DL_FUNC) &C_mfb_bcv_cells_multi, 8}, {"C_mfb_trim", (DL_FUNC) &C_mfb_trim, 1},
     {"C_mfb_bcv_cells_na", (DL_FUNC) &C_mfb_bcv_cells_na, 8},
+    {"C_mfb_bicluster_overlap", (DL_FUNC) &C_mfb_bicluster_overlap, 3}, {"C_mfb_bicluster_union", (DL_FUNC) &C_mfb_bicluster_union, 4},
     {NULL, NULL, 0}};
 void R_init_mfBiclust(DllInfo *dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

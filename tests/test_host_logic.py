@@ -287,3 +287,32 @@ def test_auto_bcv_batching_replays_the_sequential_loop(yeast, monkeypatch):
         assert [got["counts"][k] for k in ks] == [int(c) for c in counts]
         assert batches[0] == 22                       # 11 candidates: the rule cannot fire before iteration 22
         assert sum(batches) >= iters and all(b <= max(B, 1) for b in batches[1:])
+
+
+def test_filter_biclust_host_loop_replays_the_oracle(monkeypatch):
+    """filter.biclust above the C ABI (R/helperFunctions.R:150-206): with the two device calls stubbed by the oracle's
+    set arithmetic the greedy loop must make the oracle's choices -- ties in size go to the first bicluster, an empty
+    bicluster (overlap NaN) and a whole-matrix one are never chosen, `max` stops the loop."""
+    import mfbiclust_b200.backends as B
+    from oracle import helpers as H
+
+    def fake_overlap_sizes(rowx, bicx, ctx=None):
+        rows, cols = H.bicluster_matrix2list(rowx, bicx)
+        return H.sizes(rows, cols), H.overlap(rows, cols)
+
+    monkeypatch.setattr(B, "overlap_sizes", fake_overlap_sizes)
+    monkeypatch.setattr(B, "union_biclust", lambda r, c, choose=None, ctx=None: H.union_biclust(r, c, choose))
+    rs = np.random.default_rng(11)
+    for trial in range(40):
+        m, n, k = int(rs.integers(4, 60)), int(rs.integers(4, 40)), int(rs.integers(0, 9))
+        rowx, bicx = rs.random((m, k)) < 0.4, rs.random((k, n)) < 0.4
+        if k >= 3 and trial % 3 == 0:
+            rowx[:, 0] = False
+            rowx[:, 1] = rowx[:, 2]
+            bicx[1, :] = bicx[2, :]
+        mx = None if trial % 4 else 2
+        lim = [0.25, 0.0, 0.5, 1.0][trial % 4]
+        got = B.filter_biclust(rowx, bicx, max=mx, overlap=lim)
+        ref = H.filter_biclust(rowx, bicx, max=mx, overlap_limit=lim)
+        assert np.array_equal(got["chosen"], ref["chosen"]), trial
+        assert np.array_equal(got["biclustered"], ref["biclustered"]), trial
