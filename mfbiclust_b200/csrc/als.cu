@@ -1198,33 +1198,83 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
 
 // callback exchange, after the all-reduce: G = W'W of the whole matrix -> p.G, its inverse -> p.Minv (R's solve()
 // failure: reason 3).  (Peer-memory exchange: the Gram side job of the stream kernel does this, see gram_side_job.)
+// One block of 1024 threads, the whole matrix in registers: thread t owns the entries (i = t / 16, j = 4 (t % 16) .. + 3).
+// Per pivot the owners publish row p and column p to a double-buffered shared strip, ONE barrier, and every thread
+// updates its four entries -- the same Gauss-Jordan arithmetic and acceptance rule as gauss_jordan_inverse (nnls.cuh):
+//   a_ij - ((a_ip * ipiv) * a_pj) off the pivot cross, -a_ip * ipiv down column p, a_pj * ipiv along row p, ipiv at (p, p).
+// ~0.2 us per pivot instead of ~1 us with the matrix in shared memory and two barriers per pivot.
 __global__ void __launch_bounds__(1024) als_shard_invert_kernel(const HalfParams p, int KP, const double *Gsum, int reason) {
-    extern __shared__ double sh[];   // KP*KP + 2
+    __shared__ double rowb[2][64], colb[2][64];
+    __shared__ unsigned long long nrm[2];
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
-    double *sG = sh, *scr = sh + KP * KP;
-    const int k = p.k;
-    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        const double v = (c1 < k && c2 < k) ? Gsum[e] : 0.0;
-        sG[e] = v;
-        p.G[e] = v;
+    const int k = p.k, t = threadIdx.x;
+    const int i = t >> 4, jq = t & 15, j0 = jq * 4;
+    double v[4];
+    double rs = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        const bool in = i < k && j < k;
+        v[u] = in ? Gsum[i * KP + j] : 0.0;
+        if (i < KP && j < KP) p.G[i * KP + j] = v[u];
+        rs += fabs(v[u]);
     }
+    if (t < 2) nrm[t] = 0ull;
     __syncthreads();
-    const int sing = gauss_jordan_inverse(sG, k, KP, threadIdx.x, (int)blockDim.x, scr, [] { __syncthreads(); });
-    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        p.Minv[e] = (c1 < k && c2 < k) ? sG[e] : 0.0;
+    // 1-norm of the symmetric matrix = largest absolute row sum (the 16 owners of a row are half a warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (jq == 0 && i < k) atomicMax(&nrm[0], (unsigned long long)__double_as_longlong(rs));
+    int sing = 0;
+    for (int pv = 0; pv < k; ++pv) {
+        const int b = pv & 1;
+        if (i == pv) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rowb[b][j0 + u] = v[u];
+        }
+        if (jq == (pv >> 2)) {
+            const int u = pv & 3;
+            colb[b][i] = (u == 0) ? v[0] : (u == 1) ? v[1] : (u == 2) ? v[2] : v[3];
+        }
+        __syncthreads();
+        double piv = rowb[b][pv];
+        if (!(piv > 0.0) || !isfinite(piv)) { sing = 1; piv = 1.0; }
+        const double ipiv = 1.0 / piv;
+        const double f = colb[b][i] * ipiv;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            const double rj = rowb[b][j];
+            if (i != pv) v[u] = (j != pv) ? v[u] - f * rj : -f;
+            else v[u] = (j != pv) ? rj * ipiv : ipiv;
+        }
     }
-    if (threadIdx.x == 0 && sing) {
-        p.ctrl->reason = reason;
-        __threadfence();
-        p.ctrl->stop = 1;
+    rs = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        const bool in = i < k && j < k;
+        if (i < KP && j < KP) p.Minv[i * KP + j] = in ? v[u] : 0.0;
+        if (in) rs += fabs(v[u]);
+    }
+    // 1-norm of the inverse from its absolute ROW sums (the computed inverse is symmetric up to rounding, and the norm only
+    // feeds the rcond threshold an * in * eps > 1)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (jq == 0 && i < k) atomicMax(&nrm[1], (unsigned long long)__double_as_longlong(rs));
+    __syncthreads();
+    if (t == 0) {
+        const double an = __longlong_as_double((long long)nrm[0]), in = __longlong_as_double((long long)nrm[1]);
+        if (!isfinite(in) || an * in * 2.220446049250313e-16 > 1.0) sing = 1;
+        if (sing) {
+            p.ctrl->reason = reason;
+            __threadfence();
+            p.ctrl->stop = 1;
+        }
     }
 }
 
-// callback exchange, after the all-reduce of the W-step scalars: close the iteration on every rank (identical inputs,
-// identical result).  (Peer-memory exchange: the last warp of the W-step solve kernel does this.)
 __global__ void __launch_bounds__(32) als_shard_finish_kernel(const HalfParams p) {
     pdl_prologue();
     AlsCtrl *c = p.ctrl;
@@ -1484,7 +1534,7 @@ static int launch_half_t(mfb_als *s, bool wstep, const HalfParams &hp, const CUt
     };
     auto invert_launch = [&](int reason) -> int {   // (timed with the solve kernel that follows)
         if (!hp.invert_later) return MFB_OK;
-        MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 1024, (size_t)(s->KP * s->KP + 2) * sizeof(double), st, pdl, hp, s->KP,
+        MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 1024, 0, st, pdl, hp, s->KP,
                             (const double *)hp.G, reason));
         return MFB_OK;
     };
@@ -1892,7 +1942,6 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1, xh));
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
-        const size_t gsm = (size_t)(s->KP * s->KP + 2) * sizeof(double);
         MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, 0, st, pdl, h, s->KP, xbuf));
         MFB_TRY(prof_mark(s));
         if (!peer) {
@@ -1900,7 +1949,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
                 mfb_set_error("mfb_als_iterate: the all-reduce callback failed");
                 return MFB_ERR_CUDA;
             }
-            MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 256, gsm, st, pdl, h, s->KP,
+            MFB_CUDA(launch_pdl(als_shard_invert_kernel, 1, 1024, 0, st, pdl, h, s->KP,
                                 (const double *)(s->xchg + (size_t)s->T_h * s->KP * TILE_UNITS), 3));
             MFB_TRY(prof_mark(s));
         }
