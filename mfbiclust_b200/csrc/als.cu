@@ -58,6 +58,7 @@ struct AlsCtrl {
     double dH2;
     double resid, dW, dH;
     unsigned long long draws;  // running total of those draws (ranks up to 32)
+    int pending_epoch;         // peer-memory sessions: epoch whose W-step scalars are published but not yet summed (0: none)
 };
 
 struct HalfParams {
@@ -92,7 +93,8 @@ struct HalfParams {
 // bit-identical sums -- a one-shot all-reduce fused into the kernels that need the result, no collective launch:
 //   * W'W: the Gram side job of the H-step stream kernel publishes, waits, sums and inverts while A is streaming;
 //   * W'A: the fold kernel publishes and waits; the H-step solve kernel sums while it loads its right-hand sides;
-//   * scalars: the last warp of the W-step solve kernel publishes, waits, sums and closes the iteration.
+//   * scalars: the last warp of the W-step solve kernel publishes; als_shard_close_kernel, placed after the next H-step's
+//     stream kernel (and at the end of a batch), waits, sums and closes the iteration.
 #define SHARD_MAXP 16
 #define SHARD_OFF_FLAGSB 64
 #define SHARD_OFF_COUNTER 128
@@ -485,29 +487,50 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         __threadfence();
     }
     if (WSTEP && p.shard && p.peers) {
-        // peer mode: this warp also closes the iteration: wait for every rank's scalars, add them in rank order
+        // peer mode: publish this rank's scalars and leave.  The iteration is closed by als_shard_close_kernel, which the
+        // host places after the NEXT H-step's stream kernel (or at the end of the batch): by then every rank's flag has
+        // long arrived, so the skew between the ranks' last warps is absorbed by 140 us of streaming instead of sitting
+        // on the critical path (+23 us per iteration at eight GPUs).
         const ShardPeers *sp = p.peers;
         __syncwarp();
         shard_publish(sp, SHARD_OFF_FLAGSB, p.epoch, lane);
-        if (lane < sp->world)
-            shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, p.epoch, lane, p.ctrl);
-        __syncwarp();
-        // lane q fetches rank q's three sums (all remote loads in flight at once); lane 0 adds them in rank order
-        double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-        if (lane < sp->world) {
-            const double *xq = shard_xscal(sp, lane, p.epoch & 1);
-            x0 = ldcg(xq + 0); x1 = ldcg(xq + 1); x2 = ldcg(xq + 2);
-        }
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int q = 0; q < sp->world; ++q) {
-            a0 += __shfl_sync(0xffffffffu, x0, q);
-            a1 += __shfl_sync(0xffffffffu, x1, q);
-            a2 += __shfl_sync(0xffffffffu, x2, q);
-        }
-        if (lane == 0 && !*(volatile int *)&p.ctrl->stop) {
-            finish_iteration(p.ctrl, p.trace, a0, a1, a2);
+        if (lane == 0) {
+            p.ctrl->pending_epoch = p.epoch;
             __threadfence();
         }
+    }
+}
+
+// Closes the iteration whose W-step scalars were published last (peer-memory sessions): waits for every rank's flag,
+// adds the ranks' sums in rank order (bit-identical on every rank) and runs the end of R's loop body.  One warp.  It
+// runs between the stream kernel of the next H-step and its fold kernel: every kernel after it sees the decision, the
+// stream kernel before it has at worst streamed A once for an iteration R would not have started (it writes partials
+// and the Gram of W only; if it found that Gram singular, the convergence found here takes precedence, as in R).
+__global__ void __launch_bounds__(32) als_shard_close_kernel(const HalfParams p) {
+    pdl_prologue();
+    AlsCtrl *c = p.ctrl;
+    const int e = *(volatile int *)&c->pending_epoch;
+    if (e == 0 || p.peers == nullptr) return;
+    const ShardPeers *sp = p.peers;
+    const int lane = threadIdx.x;
+    if (lane < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, e, lane, c);
+    __syncwarp();
+    // lane q fetches rank q's three sums (all remote loads in flight at once); lane 0 adds them in rank order
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+    if (lane < sp->world) {
+        const double *xq = shard_xscal(sp, lane, e & 1);
+        x0 = ldcg(xq + 0); x1 = ldcg(xq + 1); x2 = ldcg(xq + 2);
+    }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int q = 0; q < sp->world; ++q) {
+        a0 += __shfl_sync(0xffffffffu, x0, q);
+        a1 += __shfl_sync(0xffffffffu, x1, q);
+        a2 += __shfl_sync(0xffffffffu, x2, q);
+    }
+    if (lane == 0) {
+        if (c->reason != 5) finish_iteration(c, p.trace, a0, a1, a2);      // (5: a peer never arrived)
+        c->pending_epoch = 0;
+        __threadfence();
     }
 }
 
@@ -1941,6 +1964,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         cudaStream_t st = s->ctx->stream;
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1, xh));
+        if (peer) MFB_CUDA(launch_pdl(als_shard_close_kernel, 1, 32, 0, st, pdl, h));   // closes the previous iteration
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
         MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, 0, st, pdl, h, s->KP, xbuf));
         MFB_TRY(prof_mark(s));
@@ -2002,6 +2026,7 @@ int mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fi
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = fixed_iters ? 1 : 0; hc->eps = eps_conv;
         hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
         hc->count_draws = count ? 1 : 0;
+        hc->pending_epoch = 0;
         if (first_batch) { draws0 = hc->draws; first_batch = false; }
         if (batch > s->max_trace) { mfb_set_error("too many iterations in one batch"); return MFB_ERR_ARG; }
         MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
@@ -2009,6 +2034,12 @@ int mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fi
         for (int b = 0; b < batch; ++b) {
             MFB_TRY(enqueue_iteration(s, cur, s->restart_pending && b == 0));
             cur ^= 1;
+        }
+        if (als_peer_mode(s)) {          // the last iteration of the batch is still open
+            HalfParams hc2;
+            memset(&hc2, 0, sizeof(hc2));
+            hc2.ctrl = s->ctrl; hc2.trace = s->trace_dev; hc2.peers = s->peers_dev;
+            MFB_CUDA(launch_pdl(als_shard_close_kernel, 1, 32, 0, st, als_use_pdl(s), hc2));
         }
         MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
         MFB_CUDA(cudaStreamSynchronize(st));
