@@ -187,6 +187,31 @@ int  mfb_nnls(mfb_context *ctx, const double *C, const double *B, int64_t r, int
 int  mfb_nnls_draws(mfb_context *ctx, const double *C, const double *B, int64_t r, int k, int64_t pcols,
                     double *K, long long *maxcol_draws);
 
+/* ---- snmf (R/bicluster.R:341-441; the NMF::nmf(method = "snmf/r") call at :363) ---------------------------------
+ * Kim & Park's sparse NMF by alternating NNLS as shipped in NMF 0.21.0 (.nmf_snmf, version "R"):
+ *   H <- argmin_{H >= 0} ||[W; sqrt(beta) 1'] H - [A; 0]||     i.e. (W'W + beta 11') H = W'A
+ *   W <- argmin_{W >= 0} ||[H'; eta I] W' - [A'; 0]||          i.e. (HH' + eta^2 I) W' = H A'
+ * on the ALS kernels (same two passes over A per iteration; the regularisers are added where the Gram matrices are
+ * formed).  An snmf session is an mfb_als session: mfb_als_result / mfb_als_end apply (resid / trace are not R's).
+ *   W0    m x k start (NMF's seed; its columns are scaled to unit length here, as .nmf_snmf does)
+ *   eta < 0 means max(A) (NMF's default); mfBiclust passes beta = eta = mean(A) (R/bicluster.R:351-352)
+ */
+int  mfb_snmf_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, double beta, double eta, mfb_als **out);
+/*
+ * Up to `max_new_iters` further iterations including NMF's convergence test -- on the first iteration after a
+ * (re)start and on every fifth: arg-max memberships of the rows of W and columns of H (max.col, ties "first")
+ * changed in at most `wminchange` rows / no column for `iconv` consecutive tests (bi_conv = c(0, 10)) AND the mean
+ * absolute KKT residual <= eps_conv (1e-4) times its first value.  The residual needs W'A of the NEW W: the stream
+ * kernel of the next H-step runs ahead for it and is not repeated when the iteration goes on.
+ * Returns MFB_OK (*converged = 1, or budget used), MFB_ZERO_ROW (zero row in H: .nmf_snmf redraws W -- call
+ * mfb_snmf_restart with matrix(runif(m * k), m, k) and iterate again; it gives up at the 10th), MFB_SINGULAR (solve()
+ * inside .fcnnls failed: R/bicluster.R:399-410 halves eta and starts over).  The iteration counter is advanced for a
+ * failed iteration as in R.  *objective = .snmf.objective = 1/2 (||A - WH||^2 + eta sum(W^2) + beta sum(colSums(H)^2)).
+ */
+int  mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, double eps_conv,
+                      int *iters_total, int *converged, double *objective);
+int  mfb_snmf_restart(mfb_als *s, const double *Wnew);
+
 /* ---- otsuHelper / threshold (R/BiclusterStrategy.R:442-456, 508-528; EBImage::otsu call site :448) */
 /* One Otsu threshold per COLUMN of the rows x cols matrix M. */
 int  mfb_otsu(mfb_context *ctx, const double *M, int64_t rows, int64_t cols, double *th);

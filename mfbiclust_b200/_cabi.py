@@ -58,6 +58,9 @@ PROTOTYPES = {
                               _dp, _dp, _dp, _ip, _ip, _dp]),
     "mfb_als_run_host": (C.c_int, [_vp, _dp, _i64, _i64, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_int,
                                    _dp, _dp, _dp, _ip, _ip, _dp]),
+    "mfb_snmf_begin": (C.c_int, [_vp, _vp, C.c_int, _dp, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "mfb_snmf_iterate": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _ip, _dp]),
+    "mfb_snmf_restart": (C.c_int, [_vp, _dp]),
     "mfb_nnls": (C.c_int, [_vp, _dp, _dp, _i64, C.c_int, _i64, _dp]),
     "mfb_nnls_draws": (C.c_int, [_vp, _dp, _dp, _i64, C.c_int, _i64, _dp, C.POINTER(C.c_longlong)]),
     "mfb_otsu": (C.c_int, [_vp, _dp, _i64, _i64, _dp]),

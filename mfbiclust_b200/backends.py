@@ -231,6 +231,164 @@ def als_nmf(A, k, reps=4, maxIter=100, eps_conv=1e-4, verbose=False, rng=None, i
 
 
 # ---------------------------------------------------------------------------
+# snmf (R/bicluster.R:341-441) and the NMF::nmf(method = "snmf/r") run it delegates to
+# ---------------------------------------------------------------------------
+class SnmfSession(AlsSession):
+    """One ``NMF::nmf(method = "snmf/r")`` run on the device (``mfb_snmf_*``; an ALS session with regularised Gram
+    matrices and NMF's convergence test)."""
+
+    def __init__(self, A: _cabi.Matrix, k: int, W0, beta: float, eta: float):
+        self.A = A
+        self.k = int(k)
+        self.m, self.n = A.shape
+        W0 = as_f(W0)
+        if W0.shape != (self.m, self.k):
+            raise ValueError("W0 must be m x k")
+        self._h = C.c_void_p()
+        check(lib().mfb_snmf_begin(A.ctx.handle, A.handle, self.k, dptr(W0), float(beta), float(eta), C.byref(self._h)))
+        self.iters = 0
+
+    def iterate(self, max_new_iters, bi_conv=(0, 10), eps_conv=1e-4):
+        it, conv, obj = C.c_int(0), C.c_int(0), C.c_double(float("nan"))
+        st = check(lib().mfb_snmf_iterate(self._h, int(max_new_iters), int(bi_conv[0]), int(bi_conv[1]), float(eps_conv),
+                                          C.byref(it), C.byref(conv), C.byref(obj)))
+        self.iters = it.value
+        return st, it.value, bool(conv.value), obj.value
+
+    def restart(self, Wnew):
+        Wnew = as_f(Wnew)
+        check(lib().mfb_snmf_restart(self._h, dptr(Wnew)))
+
+    def result(self):
+        W = np.zeros((self.m, self.k), order="F")
+        H = np.zeros((self.k, self.n), order="F")
+        check(lib().mfb_als_result(self._h, dptr(W), dptr(H), None, None))
+        return W, H
+
+
+class SnmfTooManyRestarts(UserWarning):
+    """``NMF::snmf - Too many restarts due to too big 'beta' value`` (``snmf`` halves beta on it, R/bicluster.R:380-390)."""
+
+
+def nmf_snmf(A, k, W0=None, beta=0.01, eta=-1.0, maxIter=20000, bi_conv=(0, 10), eps_conv=1e-4, rng=None, ctx=None):
+    """What ``NMF::nmf(x = A, rank = k, method = "snmf/r", beta, eta)`` computes (the call at ``R/bicluster.R:363``):
+    NMF 0.21.0's ``.nmf_snmf`` from the start ``W0`` (default: NMF's ``"random"`` seed drawn from ``rng``), including
+    its restart protocol -- a zero row in H redraws ``W = matrix(runif(m * k), m, k)`` from ``rng``; the 10th such
+    failure stops with NMF's warning (:class:`SnmfTooManyRestarts`).  A singular system raises ``MfbError`` with
+    status ``MFB_SINGULAR`` (R: "system is computationally singular").  Returns ``dict(W, H, iters, converged,
+    objective, restarts, beta, eta)``."""
+    ctx = ctx or _cabi.default_context()
+    own = not isinstance(A, _cabi.Matrix)
+    Ad = _cabi.Matrix(ctx, host=A) if own else A
+    try:
+        m, n = Ad.shape
+        if W0 is None:
+            if rng is None:
+                rng = HostRng()
+            mx = Ad.stats()["max"]
+            W0 = (np.asarray(rng.runif(m * k), dtype=np.float64) * mx).reshape((m, k), order="F")   # rnmf: basis ...
+            rng.runif(k * n)                                                                        # ... then coef
+        sess = SnmfSession(Ad, k, W0, beta, eta)
+        try:
+            nrestart, total, converged, objective = 0, 0, False, float("nan")
+            stopped_by_restarts = False
+            while total < maxIter:
+                status, total, converged, objective = sess.iterate(maxIter - total, bi_conv, eps_conv)
+                if status == MFB_OK:
+                    break
+                if status != _cabi.MFB_ZERO_ROW:
+                    raise _cabi.MfbError(status, "snmf: system is computationally singular (solve() inside .fcnnls)")
+                nrestart += 1
+                if nrestart >= 10:
+                    warnings.warn("NMF::snmf - Too many restarts due to too big 'beta' value "
+                                  "[Computation stopped after the 9th restart]", SnmfTooManyRestarts)
+                    stopped_by_restarts = True
+                    break
+                if rng is None:
+                    raise _cabi.MfbError(status, "snmf: zero row in H and no rng was supplied for the restart")
+                sess.restart(np.asarray(rng.runif(m * k), dtype=np.float64).reshape((m, k), order="F"))
+            W, H = sess.result()
+        finally:
+            sess.close()
+    finally:
+        if own:
+            Ad.free()
+    return dict(W=W, H=H, iters=total, converged=converged, objective=objective, restarts=nrestart,
+                too_many_restarts=stopped_by_restarts, beta=beta, eta=eta)
+
+
+def snmf(A, k, verbose=True, rng=None, starts=None, ctx=None, beta=None, eta=None, **args):
+    """``snmf(A, k, verbose = TRUE, ...)`` (``R/bicluster.R:341-441``) -> :class:`genericFit`.
+
+    ``beta`` / ``eta`` default to ``mean(A)`` (:351-352); ``beta`` is halved when NMF gives up after too many
+    restarts (:380-390), ``eta`` when a system is singular (:399-410); every attempt starts from the same seed
+    (``rng = .Random.seed`` at :366: ``rng`` needs ``get_state`` / ``set_state`` for that, otherwise attempts continue
+    the stream).  ``starts(attempt)`` -> iterator of start matrices replaces the RNG ("identical initialisation").
+    An empty factorization is returned when the loop ends without a fit (:436-440)."""
+    ctx = ctx or _cabi.default_context()
+    A = as_f(A)
+    eps = np.finfo(np.float64).eps
+    pass_on = {key: args[key] for key in ("maxIter", "bi_conv", "eps_conv") if key in args}        # :345-346
+    if beta is None:
+        beta = float(A.mean())
+    if eta is None:
+        eta = float(A.mean())
+    if eta < 0 or beta < eps:
+        raise ValueError("eta must be >= 0 and beta must be > 0")
+    m, n = A.shape
+    Ad = _cabi.Matrix(ctx, host=A)
+    state = rng.get_state() if hasattr(rng, "get_state") else None
+    res = None
+    attempt = 0
+    try:
+        while eta >= 0 and beta >= eps and res is None:
+            attempt += 1
+            if starts is not None:
+                it = iter(starts(attempt))
+                W0 = next(it)
+
+                class _Replay:
+                    def runif(self, cnt):
+                        return np.asarray(next(it), dtype=np.float64).ravel(order="F")
+                use_rng = _Replay()
+            else:
+                if state is not None:
+                    rng.set_state(state)
+                W0, use_rng = None, (rng or HostRng())
+            try:
+                with warnings.catch_warnings(record=True) as caught:
+                    warnings.simplefilter("always")
+                    out = nmf_snmf(Ad, k, W0=W0, beta=beta, eta=eta, rng=use_rng, ctx=ctx, **pass_on)
+                for wmsg in caught:
+                    if not issubclass(wmsg.category, SnmfTooManyRestarts):
+                        warnings.warn(wmsg.message)
+                if out["too_many_restarts"]:
+                    beta = beta / 2
+                    if verbose:
+                        print(f"mfBiclust::snmf: Restarting with beta =  {beta}")
+                    continue
+                res = out
+            except _cabi.MfbError as e:
+                if e.status != _cabi.MFB_SINGULAR:
+                    raise
+                if eta == 0.0:
+                    raise RuntimeError("Aborting snmf because dataset is singular") from e
+                eta = eta / 2 if eta > eps else 0.0
+                if verbose:
+                    print(f"mfBiclust::snmf: Restarting with eta =  {eta}")
+    finally:
+        Ad.free()
+    if res is None:
+        fit = genericFit(genericFactorization(W=np.zeros((0, 0)), H=np.zeros((0, 0))), "snmf")
+        return fit
+    if verbose:
+        print("method: snmf/r \nparameters:\nbeta: %g \neta: %g " % (res["beta"], res["eta"]))
+    fit = genericFit(genericFactorization(W=res["W"], H=res["H"]), "snmf")
+    fit.iters, fit.objective, fit.parameters, fit.attempts = res["iters"], res["objective"], dict(beta=beta, eta=eta), attempt
+    return fit
+
+
+# ---------------------------------------------------------------------------
 # als_nmf on one very large matrix: rows of A and W sharded over the ranks (SURVEY.md section 8e)
 # ---------------------------------------------------------------------------
 def row_range(m, rank, world):
@@ -1024,7 +1182,7 @@ def thresholdHelper(W, H, k, featureThresh="otsu", sampleThresh="otsu", threshAl
             threshold(H, sampleThresh, 1, ctx=ctx))
 
 
-_METHODS = {"als-nmf": "als_nmf", "svd-pca": "svd_pca", "nipals-pca": "nipals_pca"}
+_METHODS = {"als-nmf": "als_nmf", "svd-pca": "svd_pca", "nipals-pca": "nipals_pca", "snmf": "snmf"}
 
 
 def BiclusterStrategy(obj, k, method="als-nmf", threshAlgo="otsu", featureThresh=None, sampleThresh=None, ctx=None,
@@ -1035,9 +1193,9 @@ def BiclusterStrategy(obj, k, method="als-nmf", threshAlgo="otsu", featureThresh
     sampleThresh = threshAlgo if sampleThresh is None else sampleThresh
     if not isinstance(obj, genericFit):
         if method not in _METHODS:
-            raise ValueError(f"method '{method}' is outside the GPU hot path (als-nmf | svd-pca | nipals-pca)")
+            raise ValueError(f"method '{method}' is outside the GPU hot path (als-nmf | svd-pca | nipals-pca | snmf)")
         obj = np.asarray(obj, dtype=np.float64)
-        if method == "als-nmf":
+        if method in ("als-nmf", "snmf"):
             obj = pseudovalues(obj)                                    # :79
         try:
             if method == "nipals-pca":
@@ -1054,7 +1212,7 @@ def BiclusterStrategy(obj, k, method="als-nmf", threshAlgo="otsu", featureThresh
     W, H = fit.fit.W, fit.fit.H
     k = min(int(k), W.shape[1])                                        # :138
     algo, fth, sth, rn, nc = thresholdHelper(W, H, W.shape[1], featureThresh, sampleThresh, threshAlgo, ctx=ctx)
-    pretty = {"als-nmf": "ALS-NMF", "svd-pca": "SVD-PCA", "nipals-pca": "NIPALS-PCA"}.get(method, method)
+    pretty = {"als-nmf": "ALS-NMF", "svd-pca": "SVD-PCA", "nipals-pca": "NIPALS-PCA", "snmf": "SNMF"}.get(method, method)
     name = " | ".join([pretty, algo.capitalize() if algo != "user" else "User", str(k)])
     return BiclusterStrategyResult(factors=fit, featureThresh=np.asarray(fth), sampleThresh=np.asarray(sth),
                                    threshAlgo=algo, k=k, biclust=BiclustResult(rn, nc, W.shape[1]), name=name)

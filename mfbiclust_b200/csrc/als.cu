@@ -81,6 +81,7 @@ struct HalfParams {
     const struct ShardPeers *peers;       // shard mode over peer memory (NULL: the host's all-reduce callback is used)
     int epoch;                            // shard mode: number of this iteration since the session began (1-based)
     int invert_later;                     // != 0: the stream kernel's side job stops at G; als_shard_invert_kernel inverts it
+    double reg_all, reg_diag;             // snmf (R/bicluster.R:341-441): G <- G + reg_all 11' + reg_diag I before it is published / inverted
 };
 
 // Row-sharded mode over peer memory (NVLink / NVSwitch, cudaIpc mappings): every rank owns one SHARED BLOCK
@@ -305,6 +306,14 @@ __device__ __forceinline__ void finish_iteration(AlsCtrl *c, double *trace, doub
     }
 }
 
+// number of partial slots the stream kernel fills for a tile (see its flush())
+__device__ __forceinline__ int expected_slots(const HalfParams &p, int tile) {
+    const long long tb = (long long)tile * p.SPT;
+    if (p.U >= p.Gstream)
+        return ALS_NG * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
+    return ALS_NG * p.SPT;
+}
+
 template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : ((KB >= 5 && KB <= 7) ? SOLVE_MINB_LARGE : 1)) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
@@ -327,15 +336,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     const int tile = (int)(unit0 / TILE_UNITS), uoff = (int)(unit0 - (long long)tile * TILE_UNITS);
     const int nvalid_local = (int)((p.nvalid - unit0 < SU) ? (p.nvalid - unit0) : SU);
     // number of partial slots the stream kernel filled for this tile (see its flush())
-    int expected;
-    {
-        const long long tb = (long long)tile * p.SPT;
-        if (p.U >= p.Gstream)
-            expected = ALS_NG * (cta_of_unit(tb + p.SPT - 1, p.U, p.Gstream) - cta_of_unit(tb, p.U, p.Gstream) + 1);
-        else
-            expected = ALS_NG * p.SPT;
-        if (p.shard && !WSTEP) expected = 1;                 // P = the all-reduced W'A, one slot per tile
-    }
+    int expected = expected_slots(p, tile);
+    if (p.shard && !WSTEP) expected = 1;                     // P = the all-reduced W'A, one slot per tile
     // (a) right-hand sides: sum the partials in slot order
     const bool peer_sum = !WSTEP && p.shard && p.peers != nullptr;
     for (int e = tid; e < SU * KP; e += SOLVE_THREADS) {
@@ -685,7 +687,10 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
     // --- level 2 (one CTA per launch): fold the groups, publish G, invert ---
     if (t == 0) { g_gram_stamps[0] = t_begin; g_gram_stamps[1] = t_part; g_gram_stamps[2] = t_l1; }
     GRAM_STAMP(3);
+    const double reg_all = p.reg_all, reg_diag = p.reg_diag;    // 0 for als_nmf (x + 0.0 is exact)
     gram_fold_upper<KB>(p.gram_part2, ngroups, t, [&](int row, int col, double v0, double v1) {
+        v0 += reg_all + (row == col ? reg_diag : 0.0);
+        v1 += reg_all + (row == col + 1 ? reg_diag : 0.0);
         if (!(row < k && col < k)) v0 = 0.0;
         if (!(row < k && col + 1 < k)) v1 = 0.0;
         sGm[row * KP + col] = v0;      p.G[row * KP + col] = v0;
@@ -1369,6 +1374,65 @@ static int launch_nnls_columns(const double *G, const double *Minv, const double
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// snmf: the convergence test of NMF::.nmf_snmf (every fifth iteration; R/bicluster.R:363 delegates to it)
+// ---------------------------------------------------------------------------
+// One launch per factor X (H after the stream kernel of the NEXT H-step has run ahead, W after its own W-step): for the
+// units [128 b, 128 b + 128) of block b
+//   res = pmin(x, G x - r)   G = the regularised Gram matrix the half-step's solve kernel uses (W'W + beta 11' or
+//                            HH' + eta^2 I), r = W'A / A H' = the stream-K partials summed in slot order
+// and part[b][0..4] = sum |res|, #{|res| > 0}, #{arg-max membership != previous test's}, sum x^2, sum (sum_c x_c)^2.
+// The memberships are max.col(ties.method = "first"), 1-based like R's (the previous ones start as 0).
+__global__ void __launch_bounds__(TILE_UNITS) snmf_check_kernel(const HalfParams p, int KP, int with_grad,
+                                                                 const int *__restrict__ idx_old, int *__restrict__ idx_new,
+                                                                 double *__restrict__ part) {
+    __shared__ double sG[64 * 64];
+    __shared__ double sred[TILE_UNITS / 32][5];
+    const int u = threadIdx.x, tile = blockIdx.x, k = p.k;
+    const long long unit = (long long)tile * TILE_UNITS + u;
+    const bool valid = unit < p.nvalid;
+    for (int e = u; e < KP * KP; e += TILE_UNITS) sG[e] = with_grad ? p.G[e] : 0.0;
+    double x[64];
+    double sx2 = 0.0, cs = 0.0;
+    int best = 0;
+    for (int c = 0; c < k; ++c) {
+        x[c] = valid ? p.Fout[(size_t)c * p.ldout + unit] : 0.0;
+        sx2 += x[c] * x[c];
+        cs += x[c];
+        if (x[c] > x[best]) best = c;
+    }
+    __syncthreads();
+    double sabs = 0.0, cnt = 0.0, changed = 0.0;
+    if (valid) {
+        idx_new[unit] = best + 1;
+        changed = (idx_old[unit] != best + 1) ? 1.0 : 0.0;
+        if (with_grad) {
+            const int expected = expected_slots(p, tile);
+            for (int c = 0; c < k; ++c) {
+                const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + u;
+                double r = 0.0;
+                for (int sl = 0; sl < expected; ++sl) r += ldcg(Pt + (size_t)sl * (KP * TILE_UNITS));
+                double g = 0.0;
+                for (int j = 0; j < k; ++j) g += sG[j * KP + c] * x[j];       // G symmetric: conflict-free
+                const double res = fabs(fmin(x[c], g - r));
+                sabs += res;
+                if (res > 0.0) cnt += 1.0;
+            }
+        }
+    }
+    double v[5] = {sabs, cnt, changed, sx2, valid ? cs * cs : 0.0};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v[q] = warp_sum(v[q]);
+    if ((u & 31) == 0)
+        for (int q = 0; q < 5; ++q) sred[u >> 5][q] = v[q];
+    __syncthreads();
+    if (u < 5) {
+        double a = 0.0;
+        for (int w = 0; w < TILE_UNITS / 32; ++w) a += sred[w][u];
+        part[(size_t)tile * 8 + u] = a;
+    }
+}
+
 struct mfb_als {
     mfb_context *ctx;
     mfb_matrix *A;
@@ -1416,6 +1480,16 @@ struct mfb_als {
     ShardPeers *peers_dev = nullptr;
     std::vector<void *> peer_maps;              // cudaIpcOpenMemHandle mappings to close
     int epoch = 0;
+    // snmf sessions (mfb_snmf_begin): NMF::nmf(method = "snmf/r") on the same kernels with regularised Gram matrices
+    bool snmf = false;
+    double beta = 0.0, eta = 0.0;
+    bool prestreamed = false;     // the stream kernel of the next H-step has already run (for the convergence test)
+    int inc = 0;                  // consecutive tests with stable arg-max memberships
+    double erravg1 = -1.0;        // first mean KKT residual since the last (re)start (< 0: not set)
+    int *idxW[2] = {nullptr, nullptr}, *idxH[2] = {nullptr, nullptr};   // arg-max memberships: [idx_cur] = previous test
+    int idx_cur = 0;
+    double *chk_part = nullptr;   // [blocks of both check launches][8]
+    double objective = NAN;
 };
 
 static int max_slots(long long T, long long SPT, int G) {
@@ -1931,10 +2005,13 @@ int mfb_als_restart(mfb_als *s, const double *Wnew) {
     return MFB_OK;
 }
 
-static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
-    HalfParams h;
+// h_which: 0 = the whole iteration; 1 = only the stream kernel of the H-step (snmf: run ahead for the convergence
+// test); 2 = the iteration without that stream kernel (it has run ahead)
+// parameter blocks of the two half-steps of the iteration that reads W / H from buffer `cur` and writes `cur ^ 1`
+static void half_params(const mfb_als *s, int cur, bool use_restart_w, HalfParams &h, HalfParams &w) {
     memset(&h, 0, sizeof(h));
     const int nxt = cur ^ 1;
+    if (s->snmf) h.reg_all = s->beta;     // H-step: (W'W + beta 11') H = W'A
     // H-step: fixed W (or the restart draw), solve H
     h.Fin = use_restart_w ? s->Wr : s->Wb[cur]; h.ldin = s->ldw; h.nfix = s->m;
     h.Fout = s->Hb[nxt]; h.Fold = s->Hb[cur]; h.ldout = s->ldh;
@@ -1946,10 +2023,26 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
     h.Gstream = s->ctx->sm_count;
     h.shard = s->shard ? 1 : 0; h.xscal = s->xscal;
     h.invert_later = (!s->shard && s->KB >= 7 && !getenv("MFB_INVERT_IN_STREAM")) ? 1 : 0;
+    h.peers = als_peer_mode(s) ? s->peers_dev : nullptr;
+    // W-step: fixed H (just solved), solve W
+    w = h;
+    w.Fin = s->Hb[nxt]; w.ldin = s->ldh; w.nfix = s->n;
+    w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
+    w.G = s->G_H; w.Minv = s->Minv_H;
+    w.P = s->P_w; w.maxslots = s->maxslots_w;
+    w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
+    if (s->snmf) { w.reg_all = 0.0; w.reg_diag = s->eta * s->eta; }     // W-step: (HH' + eta^2 I) W' = H A'
+}
+
+// h_which: 0 = the whole iteration; 1 = only the stream kernel of the H-step (snmf: run ahead for the convergence
+// test); 2 = the iteration without that stream kernel (it has run ahead)
+static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w, int h_which = 0) {
+    HalfParams h, w;
+    half_params(s, cur, use_restart_w, h, w);
+    const int nxt = cur ^ 1;
     const bool peer = als_peer_mode(s);
     const bool pdl = als_use_pdl(s);
-    if (s->shard) h.epoch = ++s->epoch;
-    h.peers = peer ? s->peers_dev : nullptr;
+    if (s->shard) h.epoch = w.epoch = ++s->epoch;
     const CUtensorMap &tmW = use_restart_w ? s->tm_W[2] : s->tm_W[cur];
     Tf32Extra xh, xw;
     if (s->tf32) {
@@ -1958,7 +2051,8 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         xw.bhi = &s->tmf_Hhi[nxt]; xw.blo = &s->tmf_Hlo[nxt]; xw.out_hi = s->Whi[nxt]; xw.out_lo = s->Wlo[nxt];
     }
     if (!s->shard) {
-        MFB_TRY(launch_half_dispatch(s, false, h, tmW, 0, xh));
+        MFB_TRY(launch_half_dispatch(s, false, h, tmW, h_which, xh));
+        if (h_which == 1) return MFB_OK;
     } else {
         // local W_r'A_r and W_r'W_r -> one buffer -> sum over the ranks -> invert -> NNLS (replicated, identical H)
         cudaStream_t st = s->ctx->stream;
@@ -1981,12 +2075,6 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w) {
         hs.P = s->xchg; hs.maxslots = 1;
         MFB_TRY(launch_half_dispatch(s, false, hs, tmW, 2, xh));
     }
-    HalfParams w = h;
-    w.Fin = s->Hb[nxt]; w.ldin = s->ldh; w.nfix = s->n;
-    w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
-    w.G = s->G_H; w.Minv = s->Minv_H;
-    w.P = s->P_w; w.maxslots = s->maxslots_w;
-    w.T = s->T_w; w.SPT = s->SPT_w; w.U = (long long)s->T_w * s->SPT_w; w.nvalid = s->m;
     MFB_TRY(launch_half_dispatch(s, true, w, s->tm_H[nxt], 0, xw));
     if (s->shard && !peer) {
         cudaStream_t st = s->ctx->stream;
@@ -2074,6 +2162,190 @@ int mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fi
     }
     if (iters_total) *iters_total = s->iters_total;
     if (count) *maxcol_draws = (long long)(draws1 - draws0);
+    return status;
+}
+
+// ---------------------------------------------------------------------------
+// snmf sessions: NMF::nmf(method = "snmf/r") (the call at R/bicluster.R:363) on the ALS kernels
+// ---------------------------------------------------------------------------
+// W = apply(W, 2, function(x) x / sqrt(sum(x^2)))
+static void unit_columns(const double *W, int64_t m, int k, std::vector<double> &out) {
+    out.resize((size_t)m * k);
+    for (int c = 0; c < k; ++c) {
+        long double ss = 0.0L;                      // R's sum() accumulates in long double
+        for (int64_t i = 0; i < m; ++i) ss += (long double)(W[(size_t)c * m + i] * W[(size_t)c * m + i]);
+        const double nrm = sqrt((double)ss);
+        for (int64_t i = 0; i < m; ++i) out[(size_t)c * m + i] = W[(size_t)c * m + i] / nrm;
+    }
+}
+
+static int snmf_reset_test_state(mfb_als *s) {
+    cudaStream_t st = s->ctx->stream;
+    for (int i = 0; i < 2; ++i) {
+        MFB_CUDA(cudaMemsetAsync(s->idxW[i], 0, (size_t)s->m * sizeof(int), st));   // idxWold = rep(0, m)
+        MFB_CUDA(cudaMemsetAsync(s->idxH[i], 0, (size_t)s->n * sizeof(int), st));   // idxHold = rep(0, n)
+    }
+    s->idx_cur = 0;
+    s->inc = 0;
+    s->erravg1 = -1.0;
+    s->prestreamed = false;
+    return MFB_OK;
+}
+
+int mfb_snmf_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, double beta, double eta, mfb_als **out) {
+    MFB_ARG(ctx && A && W0 && out, "NULL argument");
+    MFB_ARG(A->elem_bytes == 8, "snmf needs the FP64 resident matrix");
+    MFB_ARG(beta >= 0.0, "snmf: beta must be >= 0");
+    double stats[5];
+    MFB_TRY(mfb_matrix_stats(A, stats));
+    if (eta < 0.0) eta = stats[1];                  // .nmf_snmf: if (eta < 0) eta = max(A)
+    std::vector<double> Wn, Hz((size_t)(k > 0 ? k : 1) * A->n, 0.0);
+    MFB_ARG(k >= 1 && k <= 64, "k must be in 1..64");
+    unit_columns(W0, A->m, k, Wn);
+    mfb_als *s = nullptr;
+    MFB_TRY(als_begin_impl(ctx, A, A->m, k, Wn.data(), Hz.data(), stats[1], nullptr, nullptr, &s));
+    s->snmf = true;
+    s->beta = beta;
+    s->eta = eta;
+    int rc;
+#define ALLOC(ptr, cnt) if ((rc = dev_alloc(s, &(ptr), (cnt))) != MFB_OK) { mfb_als_end(s); return rc; }
+    ALLOC(s->idxW[0], (size_t)s->m) ALLOC(s->idxW[1], (size_t)s->m) ALLOC(s->idxH[0], (size_t)s->n) ALLOC(s->idxH[1], (size_t)s->n)
+    ALLOC(s->chk_part, (size_t)(s->T_h + s->T_w) * 8)
+#undef ALLOC
+    if ((rc = snmf_reset_test_state(s)) != MFB_OK) { mfb_als_end(s); return rc; }
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return MFB_OK;
+}
+
+int mfb_snmf_restart(mfb_als *s, const double *Wnew) {
+    MFB_ARG(s && Wnew && s->snmf, "not an snmf session");
+    std::vector<double> Wn;
+    unit_columns(Wnew, s->m, s->k, Wn);
+    MFB_TRY(mfb_als_restart(s, Wn.data()));
+    return snmf_reset_test_state(s);
+}
+
+// the two launches of the convergence test on the factors in buffer `cur`; with_grad = 0: only the sums of squares
+static int snmf_enqueue_check(mfb_als *s, int cur, int with_grad) {
+    // half-step blocks of the iteration that PRODUCED buffer `cur` (its W-step: G_H, P_w are still in place) ...
+    HalfParams hp, wp, hn, wn;
+    half_params(s, cur ^ 1, false, hp, wp);
+    // ... and of the iteration that will READ it (its H-step's stream kernel has run ahead: G_W, P_h)
+    half_params(s, cur, false, hn, wn);
+    hn.Fout = s->Hb[cur];              // the factor under test, not the one the next H-step will write
+    cudaStream_t st = s->ctx->stream;
+    const int oi = s->idx_cur, ni = oi ^ 1;
+    snmf_check_kernel<<<s->T_h, TILE_UNITS, 0, st>>>(hn, s->KP, with_grad, s->idxH[oi], s->idxH[ni], s->chk_part);
+    snmf_check_kernel<<<s->T_w, TILE_UNITS, 0, st>>>(wp, s->KP, with_grad, s->idxW[oi], s->idxW[ni], s->chk_part + (size_t)s->T_h * 8);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
+int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, double eps_conv, int *iters_total,
+                     int *converged, double *objective) {
+    MFB_ARG(s && s->snmf, "not an snmf session");
+    MFB_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    if (converged) *converged = 0;
+    int status = MFB_OK;
+    int remaining = max_new_iters;
+    bool stopped = false, sums_current = false;
+    AlsCtrl *hc = (AlsCtrl *)s->ctx->pinned;
+    std::vector<double> part((size_t)(s->T_h + s->T_w) * 8);
+    double tot[2][5];
+    auto read_check = [&]() -> int {
+        MFB_CUDA(cudaMemcpyAsync(part.data(), s->chk_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        for (int f = 0; f < 2; ++f)
+            for (int q = 0; q < 5; ++q) {
+                double a = 0.0;
+                const int b0 = f ? s->T_h : 0, b1 = f ? s->T_h + s->T_w : s->T_h;
+                for (int b = b0; b < b1; ++b) a += part[(size_t)b * 8 + q];       // block order
+                tot[f][q] = a;
+            }
+        return MFB_OK;
+    };
+    auto set_objective = [&]() {
+        // .snmf.objective = 1/2 (||A - WH||^2 + eta sum(W^2) + beta sum(colSums(H)^2)); the W-step solve kernel's scalars
+        // give  ||A||^2 - 2 sum w.(AH') + sum w'(HH' + eta^2 I) w  = resid^2 m n
+        const double mn = (double)s->m * (double)s->n;
+        const double fit = s->resid * s->resid * mn - s->eta * s->eta * tot[1][3];
+        s->objective = 0.5 * (fit + s->eta * tot[1][3] + s->beta * tot[0][4]);
+    };
+    while (remaining > 0 && !stopped) {
+        const bool first = s->erravg1 < 0.0;                       // length(erravg1) == 0
+        int run = first ? 1 : 5 - (s->iters_total % 5);
+        if (run > remaining) run = remaining;
+        const bool check = first || ((s->iters_total + run) % 5 == 0);
+        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = 1; hc->eps = 1.0;
+        hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
+        hc->count_draws = 0; hc->pending_epoch = 0;
+        MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
+        int cur = s->cur;
+        for (int b = 0; b < run; ++b) {
+            MFB_TRY(enqueue_iteration(s, cur, s->restart_pending && b == 0, (b == 0 && s->prestreamed) ? 2 : 0));
+            cur ^= 1;
+        }
+        s->prestreamed = false;
+        sums_current = false;
+        if (check) {
+            MFB_TRY(enqueue_iteration(s, cur, false, 1));           // W'A and W'W + beta 11' of the new W
+            MFB_TRY(snmf_enqueue_check(s, cur, 1));
+        }
+        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+        MFB_CUDA(cudaStreamSynchronize(st));
+        MFB_TRY(check_mbar_abort("mfb_snmf_iterate"));
+        const int done = hc->iters_done;
+        if (done > 0) {
+            s->resid = hc->resid;
+            s->restart_pending = false;
+        }
+        s->iters_total += done;
+        if (done & 1) s->cur ^= 1;
+        remaining -= done;
+        if (done < run) {
+            // the iteration that was running failed (`i <- i + 1` precedes the failure in R as well)
+            s->iters_total += 1;
+            status = (hc->reason == 2) ? MFB_ZERO_ROW : MFB_SINGULAR;
+            break;
+        }
+        if (check) {
+            MFB_TRY(read_check());
+            sums_current = true;
+            const double conv = tot[0][0] + tot[1][0], convnum = tot[0][1] + tot[1][1];
+            const double erravg = conv / convnum;
+            const long long changedW = (long long)tot[1][2], changedH = (long long)tot[0][2];
+            s->inc = (changedW <= wminchange && changedH == 0) ? s->inc + 1 : 0;
+            if (s->erravg1 < 0.0) s->erravg1 = (erravg == erravg) ? erravg : 0.0;
+            if (getenv("MFB_SNMF_DEBUG"))
+                fprintf(stderr, "snmf test i=%d inc=%d changedW=%lld changedH=%lld convH=%.17g convW=%.17g numH=%.0f numW=%.0f erravg=%.6e erravg1=%.6e\n",
+                        s->iters_total, s->inc, changedW, changedH, tot[0][0], tot[1][0], tot[0][1], tot[1][1], erravg, s->erravg1);
+            if (s->inc >= iconv && erravg <= eps_conv * s->erravg1) {
+                stopped = true;
+                if (converged) *converged = 1;
+            } else {
+                s->idx_cur ^= 1;                                    // idxWold = idxW; idxHold = idxH
+                if (hc->stop && hc->reason == 3) {
+                    // W'W + beta 11' of the new W is singular: the next iteration's .fcnnls fails in solve()
+                    if (remaining > 0) { s->iters_total += 1; status = MFB_SINGULAR; break; }
+                } else {
+                    s->prestreamed = true;
+                }
+            }
+        }
+    }
+    if (status == MFB_OK && objective) {
+        if (!sums_current) {
+            MFB_TRY(snmf_enqueue_check(s, s->cur, 0));
+            MFB_TRY(read_check());
+        }
+        set_objective();
+        *objective = s->objective;
+    }
+    if (iters_total) *iters_total = s->iters_total;
     return status;
 }
 

@@ -68,6 +68,20 @@ class RRng:
         y ^= y >> 18
         return y & 0xFFFFFFFF
 
+    @classmethod
+    def from_random_seed(cls, seed_vector) -> "RRng":
+        """Position the stream from an R ``.Random.seed`` integer vector (kind code, mti, 624 state words)."""
+        r = cls()
+        r.mti = int(seed_vector[1])
+        r.mt = [int(v) & 0xFFFFFFFF for v in seed_vector[2:2 + _N]]
+        return r
+
+    def get_state(self):
+        return list(self.mt), self.mti, self.draws
+
+    def set_state(self, state) -> None:
+        self.mt, self.mti, self.draws = list(state[0]), state[1], state[2]
+
     def unif_rand(self) -> float:
         self.draws += 1
         v = self._genrand() * 2.3283064365386963e-10

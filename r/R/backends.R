@@ -77,6 +77,87 @@ als_nmf <- function(A, k, reps = 4L, maxIter = 100L, eps_conv = 1e-4, verbose = 
     new("genericFit", fit = res, method = "als-nmf")
 }
 
+# What NMF::nmf(x = A, rank = k, method = "snmf/r", beta, eta, rng = .Random.seed) computes (NMF 0.21.0 .nmf_snmf,
+# version "R"), on the device.  Seeding is NMF's "random" method (rnmf: basis, then coef, runif(max = max(A))), drawn
+# here; the session's RNG is put back on exit as NMF::nmf does.  Signals NMF's own warning / error texts, which the
+# handlers of snmf() below match on.
+.nmf_snmf <- function(A, k, beta = 0.01, eta = -1, maxIter = 20000L, bi_conv = c(0, 10), eps_conv = 1e-4, ...) {
+    m <- nrow(A); n <- ncol(A)
+    seed <- .Random.seed
+    on.exit(assign(".Random.seed", seed, envir = .GlobalEnv))
+    Ad <- .Call(C_mfb_upload, .mfb_ctx(), A)
+    W <- matrix(runif(m * k, max = max(A)), m, k)
+    invisible(runif(k * n, max = max(A)))
+    s <- .Call(C_mfb_snmf_begin, .mfb_ctx(), Ad, as.integer(k), W, beta, eta)
+    nrestart <- 0L; i <- 0L
+    repeat {
+        r <- .Call(C_mfb_snmf_iterate, s, as.integer(maxIter - i), as.numeric(bi_conv), eps_conv)
+        i <- r[2]
+        if (r[1] == 1) stop("system is computationally singular")          # solve() inside .fcnnls
+        if (r[1] == 0 || i >= maxIter) break
+        nrestart <- nrestart + 1L                                           # zero row in H
+        if (nrestart >= 10L) {
+            warning("NMF::snmf - Too many restarts due to too big 'beta' value [Computation stopped after the 9th restart]")
+            break
+        }
+        .Call(C_mfb_snmf_restart, s, matrix(runif(m * k), m, k))
+    }
+    res <- .Call(C_mfb_als_result, s, m, n, as.integer(k), 0L)
+    fit <- new("genericFit", fit = new("genericFactorization", W = res[[1]], H = res[[2]]), method = "snmf/r")
+    attr(fit, "parameters") <- list(beta = beta, eta = eta)
+    attr(fit, "niter") <- i
+    attr(fit, "residuals") <- r[4]
+    fit
+}
+
+# R/bicluster.R:341-441 with the NMF::nmf call (:361-367) replaced by .nmf_snmf; the beta / eta search is the
+# reference's own
+snmf <- function(A, k, verbose = TRUE, ...) {
+    eta <- list(...)$eta
+    beta <- list(...)$beta
+    args <- list(...)
+    args <- c(maxIter = args$maxIter, bi_conv = list(args$bi_conv), eps_conv = args$eps_conv)
+    args <- args[!vapply(args, is.null, logical(1))]
+    res <- NULL
+    if (is.null(beta)) beta <- mean(A)                                                            # :351
+    if (is.null(eta)) eta <- mean(A)                                                              # :352
+    if (eta < 0 || beta < .Machine$double.eps) stop("eta must be >= 0 and beta must be > 0")      # :353-355
+    while (eta >= 0 && beta >= .Machine$double.eps && !inherits(res, "genericFit")) {             # :357
+        res <- tryCatch({
+            res <- do.call(.nmf_snmf, c(list(A = A, k = k, beta = beta, eta = eta), args))
+            if (verbose) {
+                cat(paste("method:", res@method, "\n"))
+                cat(paste("parameters:\nbeta:", beta, "\neta:", eta, "\n"))
+            }
+            res
+        },
+        warning = function(w) {                                                                   # :378-394
+            if (grepl("too big 'beta' value", w$message, fixed = TRUE)) {
+                beta <<- beta / 2
+                if (verbose) cat(paste("mfBiclust::snmf: Restarting with beta = ", beta, "\n"))
+            } else {
+                warning(w)
+            }
+            NULL
+        },
+        error = function(e) {                                                                     # :395-429
+            if (grepl("system is computationally singular", e[[1]], fixed = TRUE)) {
+                eta <<- if (eta > .Machine$double.eps) eta / 2 else 0
+                if (verbose) cat(paste("mfBiclust::snmf: Restarting with eta = ", eta, "\n"))
+            } else {
+                stop(e)
+            }
+            NULL
+        })
+    }
+    if (inherits(res, "genericFit")) {                                                            # :432-435
+        res@method <- "snmf"
+        return(res)
+    }
+    res <- new("genericFactorization", W = matrix(data = numeric()), H = matrix(numeric()))       # :436-440
+    new("genericFit", fit = res, method = "snmf")
+}
+
 svd_pca <- function(A, k, ...) {                                   # R/bicluster.R:528-539
     Ad <- .Call(C_mfb_upload, .mfb_ctx(), A)
     res <- .Call(C_mfb_svd_pca, .mfb_ctx(), Ad, as.integer(k), nrow(A), ncol(A))

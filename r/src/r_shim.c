@@ -202,6 +202,31 @@ SEXP C_mfb_bicluster_union(SEXP ctx, SEXP rowx, SEXP bicx, SEXP choose) {
     return out;
 }
 
+/* ---- snmf: the NMF::nmf(method = "snmf/r") run behind R/bicluster.R:363 ---- */
+SEXP C_mfb_snmf_begin(SEXP ctx, SEXP A, SEXP k, SEXP W0, SEXP beta, SEXP eta) {
+    mfb_als *s = NULL;
+    CHECK(mfb_snmf_begin(ctx_of(ctx), (mfb_matrix *) R_ExternalPtrAddr(A), Rf_asInteger(k), REAL(W0), Rf_asReal(beta),
+                         Rf_asReal(eta), &s));
+    SEXP p = PROTECT(R_MakeExternalPtr(s, R_NilValue, A));
+    R_RegisterCFinalizerEx(p, als_finalizer, TRUE);
+    UNPROTECT(1);
+    return p;
+}
+
+SEXP C_mfb_snmf_iterate(SEXP s, SEXP maxNew, SEXP biConv, SEXP epsConv) {   /* c(status, i, converged, objective) */
+    int it = 0, conv = 0;
+    double obj = NA_REAL;
+    int st = mfb_snmf_iterate((mfb_als *) R_ExternalPtrAddr(s), Rf_asInteger(maxNew), (int) REAL(biConv)[0],
+                              (int) REAL(biConv)[1], Rf_asReal(epsConv), &it, &conv, &obj);
+    if (st < 0) Rf_error("%s", mfb_last_error());
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, 4));
+    REAL(out)[0] = st; REAL(out)[1] = it; REAL(out)[2] = conv; REAL(out)[3] = obj;
+    UNPROTECT(1);
+    return out;
+}
+
+SEXP C_mfb_snmf_restart(SEXP s, SEXP Wnew) { CHECK(mfb_snmf_restart((mfb_als *) R_ExternalPtrAddr(s), REAL(Wnew))); return R_NilValue; }
+
 static const R_CallMethodDef calls[] = {
     {"C_mfb_context", (DL_FUNC) &C_mfb_context, 1}, {"C_mfb_upload", (DL_FUNC) &C_mfb_upload, 2},
     {"C_mfb_stats", (DL_FUNC) &C_mfb_stats, 1}, {"C_mfb_als_begin", (DL_FUNC) &C_mfb_als_begin, 6},
@@ -213,5 +238,7 @@ static const R_CallMethodDef calls[] = {
     {"C_mfb_bcv_cells_multi", (DL_FUNC) &C_mfb_bcv_cells_multi, 8}, {"C_mfb_trim", (DL_FUNC) &C_mfb_trim, 1},
     {"C_mfb_bcv_cells_na", (DL_FUNC) &C_mfb_bcv_cells_na, 8},
     {"C_mfb_bicluster_overlap", (DL_FUNC) &C_mfb_bicluster_overlap, 3}, {"C_mfb_bicluster_union", (DL_FUNC) &C_mfb_bicluster_union, 4},
+    {"C_mfb_snmf_begin", (DL_FUNC) &C_mfb_snmf_begin, 6}, {"C_mfb_snmf_iterate", (DL_FUNC) &C_mfb_snmf_iterate, 4},
+    {"C_mfb_snmf_restart", (DL_FUNC) &C_mfb_snmf_restart, 2},
     {NULL, NULL, 0}};
 void R_init_mfBiclust(DllInfo *dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

@@ -6,6 +6,8 @@
 #define LGLSXP 10
 #define VECSXP 19
 extern SEXP R_NilValue, R_DimSymbol;
+extern double R_NaReal;
+#define NA_REAL R_NaReal
 SEXP Rf_protect(SEXP);
 void Rf_unprotect(int);
 #define PROTECT(s) Rf_protect(s)

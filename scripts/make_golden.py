@@ -6,9 +6,10 @@ Reads ONLY data artefacts of the reference (no source is copied):
 * ``/root/reference/data/simdata.rda``            -> ``simdata.npz``
 * ``/root/reference/data/yeast_benchmark.rda``    -> ``yeast_benchmark.npz``
 * ``/root/reference/tests/testdata/ref_bces.rda`` -> ``ref_bces.json``
-  (W, H, thresholds, memberships of the als-nmf / svd-pca / nipals-pca
-  strategies the reference's own testthat file compares against, plus the
-  6x6 input matrix)
+  (W, H, thresholds, memberships of the als-nmf / svd-pca / nipals-pca / snmf
+  strategies the reference's own testthat file compares against -- for snmf
+  also the NMFfit's start seed, parameters, iteration count and objective --
+  plus the 6x6 input matrix)
 * ``/root/reference/vignettes/my-vignette.html``  -> ``vignette.json``
   (printed outputs of ``addStrat(k=3, 'als-nmf')`` and ``auto_bcv`` under
   ``set.seed(12345)`` on ``yeast_benchmark[[1]]``)
@@ -62,6 +63,29 @@ def main():
             NumberxCol=bc.slot("NumberxCol").array().astype(int).tolist(),
             k=int(strat.slot("k").value[0]),
         )
+    # bce.snmf: the stored NMFfit of NMF::nmf(method = "snmf/r") -- start seed, parameters, factors, iteration count
+    # and final objective (test_BiclusterExperiment.R:16, :43-54)
+    bce = ref["bce.snmf"]
+    strat = bce.slot("strategies").value[0]
+    nf = strat.slot("factors")
+    fit = nf.slot("fit")
+    bc = strat.slot("biclust")
+    par = nf.slot("parameters")
+    out["bce.snmf"] = dict(
+        name=bce.slot("strategies").names()[0],
+        W=fit.slot("W").array().tolist(),
+        H=fit.slot("H").array().tolist(),
+        beta=float(np.asarray(par.value[par.names().index("beta")].value)[0]),
+        eta=float(np.asarray(par.value[par.names().index("eta")].value)[0]),
+        iterations=int(np.asarray(nf.slot("extra").value[0].value)[0]),
+        residual=float(np.asarray(nf.slot("residuals").value)[-1]),
+        random_seed=[int(v) for v in np.asarray(nf.slot("rng").value)],
+        featureThresh=np.asarray(strat.slot("featureThresh").value).tolist(),
+        sampleThresh=np.asarray(strat.slot("sampleThresh").value).tolist(),
+        RowxNumber=bc.slot("RowxNumber").array().astype(int).tolist(),
+        NumberxCol=bc.slot("NumberxCol").array().astype(int).tolist(),
+        k=int(strat.slot("k").value[0]),
+    )
     abund = ref["bce.als_nmf"].slot("assayData")
     # assayData is a list (storageMode "list") or environment holding `abund`
     a = abund["abund"] if abund.kind == "list" else abund.value["abund"]

@@ -10,6 +10,7 @@ from oracle.fcnnls import fcnnls, nnls_reference
 from oracle.helpers import pseudovalues
 from oracle.pca import nipals_pca, svd_pca
 from oracle.r_rng import RRng
+from oracle.snmf import nmf_snmf, snmf
 
 
 def test_runif_reproduces_fixture_input(ref_bces):
@@ -120,3 +121,28 @@ def test_fcnnls_matches_per_column_nnls():
         x = nnls_reference(G, R[:, j])
         assert np.abs(x - K[:, j]).max() < 1e-12
     assert (K == 0).any() and (K >= 0).all()
+
+
+def test_fixture_snmf_from_the_stored_seed(ref_bces):
+    """bce.snmf (test_BiclusterExperiment.R:16,43-54): the NMFfit stores the .Random.seed the run started from, beta /
+    eta, the factors, the iteration count and the final objective -- NMF::nmf(method = "snmf/r") restated in
+    oracle/snmf.py reproduces all of them, which pins the algorithm (regularisers, restart / convergence protocol,
+    "random" seeding order) and mfBiclust's wrapper (beta = eta = mean(A), R/bicluster.R:351-352)."""
+    g = ref_bces["bce.snmf"]
+    A = np.array(ref_bces["input"])
+    assert g["beta"] == A.mean() and g["eta"] == A.mean()
+    res = snmf(A, 1, rng=RRng.from_random_seed(g["random_seed"]))
+    assert res["attempts"] == 1 and res["restarts"] == 0
+    assert res["iters"] == g["iterations"] == 50
+    assert np.abs(res["W"] - np.array(g["W"])).max() < 1e-14
+    assert np.abs(res["H"] - np.array(g["H"])).max() < 1e-14
+    assert abs(res["objective"] - g["residual"]) < 1e-12 * g["residual"]
+    ft, st, rn, nc = O.threshold_helper(res["W"], res["H"])
+    assert np.allclose(ft, g["featureThresh"], rtol=1e-14) and np.allclose(st, g["sampleThresh"], rtol=1e-14)
+    assert np.array_equal(rn.astype(int), np.array(g["RowxNumber"]))
+    assert np.array_equal(nc.astype(int), np.array(g["NumberxCol"]))
+    # the seeding order matters at the 1e-10 level even at k = 1: coef-first draws miss the stored factors
+    rng = RRng.from_random_seed(g["random_seed"])
+    rng.runif(6)
+    other = nmf_snmf(A, rng.runif(6).reshape(6, 1), eta=g["eta"], beta=g["beta"])
+    assert np.abs(other["W"] - np.array(g["W"])).max() > 1e-12
