@@ -226,6 +226,27 @@ def run_k64(mfb, ctx, Ad, m, n, k=64, iters=10):
             "kernel_ms": {"h_stream": kern[0], "h_solve": kern[1], "w_stream": kern[2], "w_solve": kern[3]}}
 
 
+def run_snmf(mfb, ctx, Ad, A, m, n, k=RANK, iters=40):
+    """snmf (R/bicluster.R:341-441; NMF's snmf/r) on the same resident matrix: the ALS kernels with regularised Gram
+    matrices plus NMF's convergence test on every fifth iteration (the next H-step's stream kernel runs ahead for it
+    and is not repeated): 2*m*n*8 algorithmic bytes per iteration as for als_nmf."""
+    W0 = np.asfortranarray(np.random.default_rng(43).random((m, k)))
+    mean = float(Ad.stats()["sum"]) / (float(m) * n)
+    sess = mfb.SnmfSession(Ad, k, W0, mean, mean)
+    st, _, _, _ = sess.iterate(5, bi_conv=(0, 10 ** 6))      # (no stop: iconv out of reach)
+    assert st == 0, st
+    ctx.sync()
+    t0 = time.perf_counter()
+    st, it, conv, obj = sess.iterate(iters, bi_conv=(0, 10 ** 6))
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    sess.close()
+    peak, _ = peaks()
+    gbs = 2.0 * m * n * 8 * iters / dt / 1e9
+    return {"workload": "snmf/r 20000x5000 k=16 FP64, beta = eta = mean(A), %d iterations incl. %d convergence tests" % (iters, iters // 5),
+            "iters_per_s": iters / dt, "step_achieved_GBps": gbs, "step_frac_of_hbm": gbs / peak, "objective": obj}
+
+
 def run_f32(mfb, ctx, A, W0, H0, m, n, k=RANK, iters=40):
     """FP32 leg of BASELINE configs[3]: the same workload with A resident in single precision (half the
     algorithmic bytes: 2*m*n*4 per iteration); roofline fraction against the same HBM peak."""
@@ -625,6 +646,7 @@ def main():
         sec = run_secondary(mfb, ctx, Ad, m, n)
         if RANK_ == RANK:
             sec["als_k64"] = run_k64(mfb, ctx, Ad, m, n)
+            sec["snmf"] = run_snmf(mfb, ctx, Ad, A, m, n)
             sec["als_fp32"] = run_f32(mfb, ctx, A, W0, H0, m, n)
         detail["secondary"] = sec
     Ad.free()
@@ -662,6 +684,8 @@ def main():
         legs.update({"f32_iters_s": _r(sec["als_fp32"]["iters_per_s"]), "f32_frac": _r(sec["als_fp32"]["step_frac_of_hbm"], 3)})
     if "als_k64" in sec:
         legs.update({"k64_iters_s": _r(sec["als_k64"]["iters_per_s"]), "k64_tflops": _r(sec["als_k64"]["fp64_tflops_stream_kernels"], 3)})
+    if "snmf" in sec:
+        legs["snmf_iters_s"] = _r(sec["snmf"]["iters_per_s"])
     if "nipals" in sec:
         legs.update({"nipals_frac": _r(sec["nipals"]["frac_of_hbm"], 3), "svd_pca_s": _r(sec["svd_pca"]["wall_s"], 3)})
 

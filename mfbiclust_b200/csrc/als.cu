@@ -86,14 +86,18 @@ struct HalfParams {
 
 // Row-sharded mode over peer memory (NVLink / NVSwitch, cudaIpc mappings): every rank owns one SHARED BLOCK
 //   int flagsA[16] | int flagsB[16] | int fold_counter | stamps @192 | double xscal[2][4] @256 | int flagsG[16] @320
-//   | double xchg[2][cnt] @512 | double gram[2][64*64]
+//   | double xchg[2][slots][cnt] @512 | double gram[2][64*64]
 // mapped into every peer.  Epoch e uses the buffers of parity e & 1.  flagsG[q] = e: rank q's W_q'W_q is in its
 // gram buffer; flagsA[q] = e: rank q's folded W_q'A_q is in its exchange buffer; flagsB[q] = e: rank q's W-step
 // scalars are complete (all written by rank q into EVERY rank's block with a system-scope release store).  The
 // consumers read all ranks' buffers straight over NVLink and add them in rank order, so every rank forms
 // bit-identical sums -- a one-shot all-reduce fused into the kernels that need the result, no collective launch:
 //   * W'W: the Gram side job of the H-step stream kernel publishes, waits, sums and inverts while A is streaming;
-//   * W'A: the fold kernel publishes and waits; the H-step solve kernel sums while it loads its right-hand sides;
+//   * W'A: the fold kernel publishes and waits; the H-step solve kernel sums while it loads its right-hand sides.
+//     With at most `slots` ranks the fold kernel PUSHES: it stores its folded W_q'A_q into slot q of every rank's block
+//     (posted remote stores, fire and forget), and the solve kernel sums `world` LOCAL buffers instead of pulling
+//     (world - 1) x 655 KB over NVLink on its critical path (H-step solve 30 -> 19 us at eight GPUs); with more ranks
+//     than slots, slot 0 holds the rank's own buffer and the solve kernel pulls;
 //   * scalars: the last warp of the W-step solve kernel publishes; als_shard_close_kernel, placed after the next H-step's
 //     stream kernel (and at the end of a batch), waits, sums and closes the iteration.
 #define SHARD_MAXP 16
@@ -106,14 +110,16 @@ struct HalfParams {
 #define SHARD_GRAM_DOUBLES 4096           // 64 x 64
 struct ShardPeers {
     int world, rank;
+    int slots, push;                      // exchange buffers per parity in every block; push != 0: slot q of every block is written by rank q
     long long cnt;                        // doubles per exchange buffer: T * KP * 128 + KP * KP
     unsigned char *base[SHARD_MAXP];      // base[q] = rank q's shared block as mapped here (base[rank] = local)
 };
-__device__ __forceinline__ double *shard_xchg(const ShardPeers *sp, int q, int parity) {
-    return (double *)(sp->base[q] + SHARD_OFF_XCHG) + (size_t)parity * sp->cnt;
+// exchange buffer `slot` of parity `parity` in rank q's block (pull layout: slot 0 = rank q's own folded buffer)
+__device__ __forceinline__ double *shard_xchg(const ShardPeers *sp, int q, int parity, int slot = 0) {
+    return (double *)(sp->base[q] + SHARD_OFF_XCHG) + ((size_t)parity * sp->slots + slot) * (size_t)sp->cnt;
 }
 __device__ __forceinline__ double *shard_gram(const ShardPeers *sp, int q, int parity) {
-    return (double *)(sp->base[q] + SHARD_OFF_XCHG) + 2 * (size_t)sp->cnt + (size_t)parity * SHARD_GRAM_DOUBLES;
+    return (double *)(sp->base[q] + SHARD_OFF_XCHG) + 2 * (size_t)sp->slots * (size_t)sp->cnt + (size_t)parity * SHARD_GRAM_DOUBLES;
 }
 __device__ __forceinline__ double *shard_xscal(const ShardPeers *sp, int q, int parity) {
     return (double *)(sp->base[q] + SHARD_OFF_XSCAL) + parity * 4;
@@ -350,8 +356,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
                 const size_t off = ((size_t)tile * KP + c) * (size_t)TILE_UNITS + uoff + u;
                 const int world = sp->world, par = p.epoch & 1;
                 double v[SHARD_MAXP];
+                if (sp->push) {      // every rank has stored its buffer into slot q of THIS rank's block
+                    const double *mine = shard_xchg(sp, sp->rank, par) + off;
+                    const size_t stride = (size_t)sp->cnt;
 #pragma unroll
-                for (int q = 0; q < SHARD_MAXP; ++q) v[q] = (q < world) ? ldcg(shard_xchg(sp, q, par) + off) : 0.0;
+                    for (int q = 0; q < SHARD_MAXP; ++q) v[q] = (q < world) ? ldcg(mine + (size_t)q * stride) : 0.0;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < SHARD_MAXP; ++q) v[q] = (q < world) ? ldcg(shard_xchg(sp, q, par) + off) : 0.0;
+                }
 #pragma unroll
                 for (int q = 0; q < SHARD_MAXP; ++q) r += v[q];
             }
@@ -1195,8 +1208,17 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
             for (int s = 0; s < expected; ++s) r += ldcg(Pt + (size_t)s * (KP * TILE_UNITS));
         }
     }
-    xchg[((size_t)tile * KP + c) * TILE_UNITS + u] = r;
     const ShardPeers *sp = p.peers;
+    const size_t xoff = ((size_t)tile * KP + c) * TILE_UNITS + u;
+    if (sp && sp->push) {
+        // slot `rank` of every rank's block (this rank's included): posted stores over NVLink, all in flight
+        const int par = p.epoch & 1, me = sp->rank;
+#pragma unroll
+        for (int q = 0; q < SHARD_MAXP; ++q)
+            if (q < sp->world) shard_xchg(sp, q, par, me)[xoff] = r;
+    } else {
+        xchg[xoff] = r;
+    }
     if (!sp) {                                               // callback exchange: W_r'W_r rides in the same buffer
         if (blockIdx.x == 0)
             for (int e = u; e < KP * KP; e += TILE_UNITS) xchg[(size_t)p.T * KP * TILE_UNITS + e] = ldcg(&p.G[e]);
@@ -1209,7 +1231,8 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
     __syncthreads();                                         // the block's stores happen-before thread 0's fence
     if (u == 0) {
         int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
-        __threadfence();
+        if (sp->push) __threadfence_system();               // the block's stores went to the peers' memories
+        else __threadfence();
         const int last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
         if (last) *counter = 0;
         is_last = last;
@@ -1476,6 +1499,7 @@ struct mfb_als {
     // ... over peer memory (mfb_als_shard_export / mfb_als_shard_connect)
     unsigned char *shared = nullptr;            // this rank's shared block (cudaMalloc, cudaIpc-exported)
     size_t xchg_cnt = 0;
+    int shard_slots = 1;                        // exchange buffers per parity in the shared block (push exchange up to this many ranks)
     ShardPeers peers_host;
     ShardPeers *peers_dev = nullptr;
     std::vector<void *> peer_maps;              // cudaIpcOpenMemHandle mappings to close
@@ -1850,7 +1874,12 @@ static int als_begin_impl(mfb_context *ctx, mfb_matrix *A, int64_t m_global, int
         ALLOC(s->peers_dev, 1)
         {
             // the shared block is a cudaMalloc of its own (not pooled): it is exported through cudaIpc
-            const size_t bytes = SHARD_OFF_XCHG + (2 * s->xchg_cnt + 2 * SHARD_GRAM_DOUBLES) * sizeof(double);
+            // one exchange buffer per rank and parity for up to 8 ranks (a node), so that the fold kernels can push;
+            // MFB_SHARD_SLOTS=1 keeps the pull layout (A/B runs; also used when the slots would not fit)
+            s->shard_slots = getenv("MFB_SHARD_SLOTS") ? atoi(getenv("MFB_SHARD_SLOTS")) : 8;
+            if (s->shard_slots < 1 || s->shard_slots > SHARD_MAXP) s->shard_slots = 1;
+            if (2.0 * s->shard_slots * (double)s->xchg_cnt * sizeof(double) > 2e9) s->shard_slots = 1;
+            const size_t bytes = SHARD_OFF_XCHG + (2 * (size_t)s->shard_slots * s->xchg_cnt + 2 * SHARD_GRAM_DOUBLES) * sizeof(double);
             if (cudaMalloc((void **)&s->shared, bytes) != cudaSuccess) { cudaGetLastError(); s->shared = nullptr; mfb_als_end(s); mfb_set_error("cudaMalloc of the shared exchange block failed"); return MFB_ERR_ALLOC; }
             MFB_CUDA(cudaMemsetAsync(s->shared, 0, bytes, ctx->stream));
         }
@@ -1946,6 +1975,8 @@ int mfb_als_shard_connect(mfb_als *s, int rank, int world, const void *handles) 
     ShardPeers &sp = s->peers_host;
     memset(&sp, 0, sizeof(sp));
     sp.world = world; sp.rank = rank; sp.cnt = (long long)s->xchg_cnt;
+    sp.slots = s->shard_slots;
+    sp.push = (s->shard_slots > 1 && world <= s->shard_slots) ? 1 : 0;
     for (int q = 0; q < world; ++q) {
         if (q == rank) { sp.base[q] = s->shared; continue; }
         cudaIpcMemHandle_t h;
@@ -2059,7 +2090,7 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w, int h_whic
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1, xh));
         if (peer) MFB_CUDA(launch_pdl(als_shard_close_kernel, 1, 32, 0, st, pdl, h));   // closes the previous iteration
-        double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->xchg_cnt : s->xchg;
+        double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->shard_slots * s->xchg_cnt : s->xchg;
         MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, 0, st, pdl, h, s->KP, xbuf));
         MFB_TRY(prof_mark(s));
         if (!peer) {
