@@ -82,6 +82,7 @@ struct HalfParams {
     int epoch;                            // shard mode: number of this iteration since the session began (1-based)
     int invert_later;                     // != 0: the stream kernel's side job stops at G; als_shard_invert_kernel inverts it
     double reg_all, reg_diag;             // snmf (R/bicluster.R:341-441): G <- G + reg_all 11' + reg_diag I before it is published / inverted
+    int peer_invert_later;                // peer-memory H-step: the side job only publishes W_r'W_r; als_shard_close_invert_kernel sums and inverts
 };
 
 // Row-sharded mode over peer memory (NVLink / NVSwitch, cudaIpc mappings): every rank owns one SHARED BLOCK
@@ -92,7 +93,12 @@ struct HalfParams {
 // scalars are complete (all written by rank q into EVERY rank's block with a system-scope release store).  The
 // consumers read all ranks' buffers straight over NVLink and add them in rank order, so every rank forms
 // bit-identical sums -- a one-shot all-reduce fused into the kernels that need the result, no collective launch:
-//   * W'W: the Gram side job of the H-step stream kernel publishes, waits, sums and inverts while A is streaming;
+//   * W'W: the Gram side job of the H-step stream kernel publishes its W_q'W_q early in the launch; the sum over the
+//     ranks and the inversion happen AFTER the stream kernel, when every flag has long arrived: in an extra block of
+//     the fold kernel (ranks up to 32; next to the folding blocks and their rendezvous, off the critical path) or in
+//     als_shard_close_invert_kernel (larger ranks).  (MFB_SHARD_INVERT_IN_STREAM=1: the side job itself waits, sums and
+//     inverts while A is streaming, as in round 1 -- on warps that share issue slots with the streaming warps this
+//     chain stretched the stream kernel by 10-30 us);
 //   * W'A: the fold kernel publishes and waits; the H-step solve kernel sums while it loads its right-hand sides.
 //     With at most `slots` ranks the fold kernel PUSHES: it stores its folded W_q'A_q into slot q of every rank's block
 //     (posted remote stores, fire and forget), and the solve kernel sums `world` LOCAL buffers instead of pulling
@@ -726,6 +732,7 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
         for (int e = t; e < KP * KP; e += GRAM_THREADS) mine[e] = sGm[e];
         gram_bar();
         shard_publish(sp, SHARD_OFF_FLAGSG, p.epoch, t);
+        if (p.peer_invert_later) return;     // summed and inverted after the stream kernel (als_shard_close_invert_kernel)
         if (t < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + t, p.epoch, t, p.ctrl);
         gram_bar();
         if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
@@ -1184,9 +1191,53 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const double *__rest
 // 8 (k n + k^2) bytes).  The buffer has the layout of a partial array with ONE slot per tile, so the H-step solve
 // kernel reads it unchanged.  The W-step is local to a rank (its rows of W); only its three iteration scalars are
 // summed over the ranks (second, 32-byte collective).
-__global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg) {
+// (W'W)^-1 of a peer-memory session for ranks up to 32, by ONE extra block of the fold kernel: the ranks' side jobs
+// published their W_q'W_q a hundred microseconds ago, so nothing waits here; the sum (rank order) and the
+// Gauss-Jordan elimination (gauss_jordan_inverse, as in the side job of a one-device session: bit-identical G^-1)
+// run on an idle SM next to the folding blocks and the rendezvous of their last block, off the critical path --
+// instead of on side-job warps that share their issue slots with the streaming warps, where the chain
+// publish -> wait -> remote loads -> sum -> invert stretched the stream kernel by 10-30 us.
+__device__ __noinline__ void shard_gram_sum_invert(const HalfParams &p, int KP) {
+    __shared__ double sGi[32 * 32 + 2];
+    const ShardPeers *sp = p.peers;
+    const int t = threadIdx.x, k = p.k, par = p.epoch & 1;
+    if (t < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + t, p.epoch, t, p.ctrl);
+    __syncthreads();
+    if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
+    for (int e = t; e < KP * KP; e += TILE_UNITS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        double v = 0.0;
+        if (c1 < k && c2 < k) {
+            double g[SHARD_MAXP];                        // all ranks' loads in flight, then added in rank order
+#pragma unroll
+            for (int q = 0; q < SHARD_MAXP; ++q) g[q] = (q < sp->world) ? ldcg(shard_gram(sp, q, par) + e) : 0.0;
+#pragma unroll
+            for (int q = 0; q < SHARD_MAXP; ++q) v += g[q];
+        }
+        sGi[e] = v;
+        p.G[e] = v;
+    }
+    __syncthreads();
+    const int sing = gauss_jordan_inverse(sGi, k, KP, t, TILE_UNITS, sGi + KP * KP, [] { __syncthreads(); });
+    for (int e = t; e < KP * KP; e += TILE_UNITS) {
+        const int c1 = e / KP, c2 = e - c1 * KP;
+        p.Minv[e] = (c1 < k && c2 < k) ? sGi[e] : 0.0;
+    }
+    if (t == 0 && sing) {
+        p.ctrl->reason = 3;
+        __threadfence();
+        p.ctrl->stop = 1;
+    }
+}
+
+__global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg, int invert_block) {
     pdl_prologue();
     if (*(volatile int *)&p.ctrl->stop) return;
+    if ((int)blockIdx.x == invert_block) {
+        shard_gram_sum_invert(p, KP);
+        return;
+    }
+    const int nfold = invert_block >= 0 ? (int)gridDim.x - 1 : (int)gridDim.x;
     const int tile = (int)blockIdx.x / KP, c = (int)blockIdx.x % KP, u = threadIdx.x;
     const long long tb = (long long)tile * p.SPT;
     int expected;
@@ -1233,7 +1284,7 @@ __global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfPa
         int *counter = (int *)(sp->base[sp->rank] + SHARD_OFF_COUNTER);
         if (sp->push) __threadfence_system();               // the block's stores went to the peers' memories
         else __threadfence();
-        const int last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+        const int last = atomicAdd(counter, 1) == nfold - 1;
         if (last) *counter = 0;
         is_last = last;
     }
@@ -1322,6 +1373,133 @@ __global__ void __launch_bounds__(1024) als_shard_invert_kernel(const HalfParams
             p.ctrl->reason = reason;
             __threadfence();
             p.ctrl->stop = 1;
+        }
+    }
+}
+
+// Peer-memory sessions, between the H-step's stream kernel and its fold kernel: closes the previous iteration
+// (als_shard_close_kernel's job, warp 0) and forms (W'W)^-1 from the ranks' W_q'W_q, which their side jobs published
+// a hundred microseconds ago: no rank waits here, the rendezvous is off the critical path, and the serial chain
+// wait -> remote loads -> sum -> Gauss-Jordan runs on an idle SM in ~5 us instead of on side-job warps that share
+// their issue slots with the streaming warps (where it stretched the stream kernel by 10-25 us).  The sum is in rank
+// order and the elimination is als_shard_invert_kernel's: every rank gets bit-identical G and G^-1.
+__global__ void __launch_bounds__(1024) als_shard_close_invert_kernel(const HalfParams p, int KP) {
+    __shared__ double rowb[2][64], colb[2][64];
+    __shared__ unsigned long long nrm[2];
+    pdl_prologue();
+    AlsCtrl *c = p.ctrl;
+    const ShardPeers *sp = p.peers;
+    const int k = p.k, t = threadIdx.x;
+    // a batch that stopped earlier (converged, zero row, ...): the stream kernel before this one returned at once and
+    // published nothing -- identically on every rank
+    if (*(volatile int *)&c->stop) return;
+    if (t < 32) {
+        // ---- close the iteration whose W-step scalars were published last ----
+        const int e = *(volatile int *)&c->pending_epoch;
+        if (e != 0) {
+            const int lane = t;
+            if (lane < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, e, lane, c);
+            __syncwarp();
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (lane < sp->world) {
+                const double *xq = shard_xscal(sp, lane, e & 1);
+                x0 = ldcg(xq + 0); x1 = ldcg(xq + 1); x2 = ldcg(xq + 2);
+            }
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int q = 0; q < sp->world; ++q) {
+                a0 += __shfl_sync(0xffffffffu, x0, q);
+                a1 += __shfl_sync(0xffffffffu, x1, q);
+                a2 += __shfl_sync(0xffffffffu, x2, q);
+            }
+            if (lane == 0) {
+                if (c->reason != 5) finish_iteration(c, p.trace, a0, a1, a2);      // (5: a peer never arrived)
+                c->pending_epoch = 0;
+                __threadfence();
+            }
+        }
+    } else if (t < 32 + sp->world) {
+        // ---- every rank's W_q'W_q of this epoch has been published ----
+        const int q = t - 32;
+        shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + q, p.epoch, q, c);
+    }
+    if (t < 2) nrm[t] = 0ull;
+    __syncthreads();
+    if (*(volatile int *)&c->stop) return;               // converged just now, failed earlier, or a peer never arrived
+    const int i = t >> 4, jq = t & 15, j0 = jq * 4;
+    double v[4];
+    double rs = 0.0;
+    {
+        const int par = p.epoch & 1, world = sp->world;
+        // the ranks' loads of two entries in flight at once (64 registers per thread at 1024 threads), added in rank order
+#pragma unroll
+        for (int u0 = 0; u0 < 4; u0 += 2) {
+            double a[2] = {0.0, 0.0};
+            for (int q0 = 0; q0 < world; q0 += 8) {
+                double g[2][8];
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        g[uu][q] = (q0 + q < world && i < k && j0 + u0 + uu < k) ? ldcg(shard_gram(sp, q0 + q, par) + i * KP + j0 + u0 + uu) : 0.0;
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[uu] += g[uu][q];
+            }
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+                v[u0 + uu] = a[uu];
+                if (i < KP && j0 + u0 + uu < KP) p.G[i * KP + j0 + u0 + uu] = a[uu];
+                rs += fabs(a[uu]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (jq == 0 && i < k) atomicMax(&nrm[0], (unsigned long long)__double_as_longlong(rs));
+    int sing = 0;
+    for (int pv = 0; pv < k; ++pv) {
+        const int b = pv & 1;
+        if (i == pv) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rowb[b][j0 + u] = v[u];
+        }
+        if (jq == (pv >> 2)) {
+            const int u = pv & 3;
+            colb[b][i] = (u == 0) ? v[0] : (u == 1) ? v[1] : (u == 2) ? v[2] : v[3];
+        }
+        __syncthreads();
+        double piv = rowb[b][pv];
+        if (!(piv > 0.0) || !isfinite(piv)) { sing = 1; piv = 1.0; }
+        const double ipiv = 1.0 / piv;
+        const double f = colb[b][i] * ipiv;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            const double rj = rowb[b][j];
+            if (i != pv) v[u] = (j != pv) ? v[u] - f * rj : -f;
+            else v[u] = (j != pv) ? rj * ipiv : ipiv;
+        }
+    }
+    rs = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        const bool in = i < k && j < k;
+        if (i < KP && j < KP) p.Minv[i * KP + j] = in ? v[u] : 0.0;
+        if (in) rs += fabs(v[u]);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (jq == 0 && i < k) atomicMax(&nrm[1], (unsigned long long)__double_as_longlong(rs));
+    __syncthreads();
+    if (t == 0) {
+        const double an = __longlong_as_double((long long)nrm[0]), in = __longlong_as_double((long long)nrm[1]);
+        if (!isfinite(in) || an * in * 2.220446049250313e-16 > 1.0) sing = 1;
+        if (sing) {
+            c->reason = 3;
+            __threadfence();
+            c->stop = 1;
         }
     }
 }
@@ -2055,8 +2233,10 @@ static void half_params(const mfb_als *s, int cur, bool use_restart_w, HalfParam
     h.shard = s->shard ? 1 : 0; h.xscal = s->xscal;
     h.invert_later = (!s->shard && s->KB >= 7 && !getenv("MFB_INVERT_IN_STREAM")) ? 1 : 0;
     h.peers = als_peer_mode(s) ? s->peers_dev : nullptr;
+    h.peer_invert_later = (h.peers && !getenv("MFB_SHARD_INVERT_IN_STREAM")) ? 1 : 0;
     // W-step: fixed H (just solved), solve W
     w = h;
+    w.peer_invert_later = 0;
     w.Fin = s->Hb[nxt]; w.ldin = s->ldh; w.nfix = s->n;
     w.Fout = s->Wb[nxt]; w.Fold = s->Wb[cur]; w.ldout = s->ldw;
     w.G = s->G_H; w.Minv = s->Minv_H;
@@ -2089,9 +2269,16 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w, int h_whic
         cudaStream_t st = s->ctx->stream;
         const size_t cnt = (size_t)s->T_h * s->KP * TILE_UNITS + (size_t)s->KP * s->KP;
         MFB_TRY(launch_half_dispatch(s, false, h, tmW, 1, xh));
-        if (peer) MFB_CUDA(launch_pdl(als_shard_close_kernel, 1, 32, 0, st, pdl, h));   // closes the previous iteration
+        // peer memory: (W'W)^-1 is formed from the published W_q'W_q after the stream kernel -- by an extra block of
+        // the fold kernel (ranks up to 32) or by the kernel that closes the previous iteration (1024 threads, above)
+        const bool inv_in_fold = peer && h.peer_invert_later && s->KP <= 32;
+        if (peer) {
+            if (h.peer_invert_later && !inv_in_fold) MFB_CUDA(launch_pdl(als_shard_close_invert_kernel, 1, 1024, 0, st, pdl, h, s->KP));
+            else MFB_CUDA(launch_pdl(als_shard_close_kernel, 1, 32, 0, st, pdl, h));
+        }
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->shard_slots * s->xchg_cnt : s->xchg;
-        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP, TILE_UNITS, 0, st, pdl, h, s->KP, xbuf));
+        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP + (inv_in_fold ? 1 : 0), TILE_UNITS, 0, st, pdl, h, s->KP, xbuf,
+                            inv_in_fold ? s->T_h * s->KP : -1));
         MFB_TRY(prof_mark(s));
         if (!peer) {
             if (s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
