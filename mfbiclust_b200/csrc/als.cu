@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
     unsigned long long nz = 0ull;
     double t1;
     if constexpr (KP <= 32)      // tableau in registers, one lane per row
-        t1 = nnls_lanes<KP, XS>(sG, sM, k, xs, warp * UPW, UPW, nvalid_local, lane, p.ctrl->count_draws ? &p.ctrl->draws : nullptr);
+        t1 = nnls_lanes<KP, XS>(sG, sM, k, xs, warp * UPW, UPW, nvalid_local, lane, scr + warp * NnlsCfg<KP>::SCR,
+                                p.ctrl->count_draws ? &p.ctrl->draws : nullptr);
     else                         // compressed active-set solves, two variables per lane
         t1 = nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * UPW, UPW, nvalid_local, lane);
     __syncwarp();
@@ -1552,7 +1553,7 @@ __global__ void __launch_bounds__(128) nnls_columns_kernel(const double *__restr
         xs[c * XS + u] = (c < k && u < nvalid) ? R[(j0 + u) * k + c] : 0.0;
     }
     __syncthreads();
-    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sG, sM, k, xs, warp * 2, 2, nvalid, lane, draws);
+    if constexpr (KP <= 32) nnls_lanes<KP, XS>(sG, sM, k, xs, warp * 2, 2, nvalid, lane, scr + warp * NnlsCfg<KP>::SCR, draws);
     else nnls_warp<KP, XS>(sG, sM, k, xs, scr + warp * NnlsCfg<KP>::SCR, warp * 2, 2, nvalid, lane);
     __syncthreads();
     for (int e = tid; e < SU * KP; e += 128) {

@@ -199,7 +199,8 @@ __device__ __forceinline__ int r_max_col_draws(double v, int k, unsigned gmask, 
 // one per variable entering the passive set (row = (!Pset) * W).
 template <int KP, int XS>
 __device__ double nnls_lanes(const double *__restrict__ sG, const double *__restrict__ sM, int k, double *xs, int first,
-                             int count, int nvalid, int lane, unsigned long long *draws = nullptr) {   // (each lane leaves x_i of its problem in xs)
+                             int count, int nvalid, int lane, double *rowbuf /* this warp's, >= (32 / LP) * (KP + 2) doubles, 16-byte aligned */,
+                             unsigned long long *draws = nullptr) {   // (each lane leaves x_i of its problem in xs)
     constexpr int LP = (KP <= 16) ? 16 : 32;
     constexpr int PPW = 32 / LP;
     const unsigned FULL = 0xffffffffu;
@@ -291,13 +292,25 @@ __device__ double nnls_lanes(const double *__restrict__ sG, const double *__rest
             if (!__any_sync(FULL, piv >= 0)) break;
             // exchange x_piv <-> w_piv: every row becomes a * row + b * (pivot row), then column piv is patched;
             // a problem that does not pivot in this pass runs with (a, b) = (1, 0)
+            // The pivot row goes through shared memory: its owner stores it (8 x 16 bytes), every lane reads it back
+            // with broadcast loads -- instead of 2 KP shuffles.  The pivot COLUMN entry of row i is taken from the same
+            // copy: a principal-pivot tableau of a symmetric matrix stays sign-symmetric, T[i][p] = +-T[p][i] with
+            // + when i and p are in the same class (both in S or both out), so the KP-way select of a dynamically
+            // indexed register (3 KP instructions) becomes one load.  (Equal up to rounding, not bit for bit.)
             const int pq = piv >= 0 ? piv : 0;
             const int src = base + pq;
-            double tiq = 0.0;
+            double *rb = rowbuf + sub * (KP + 2);
+            if (i == pq) {
 #pragma unroll
-            for (int j = 0; j < KP; ++j) tiq = (j == pq) ? T[j] : tiq;
+                for (int j = 0; j < KP; j += 2) *reinterpret_cast<double2 *>(rb + j) = make_double2(T[j], T[j + 1]);
+                rb[KP] = inS ? 1.0 : 0.0;
+            }
+            __syncwarp();
             const double qq = __shfl_sync(FULL, qv, src);
-            const double pp = __shfl_sync(FULL, tiq, src);
+            const double pp = rb[pq];
+            const bool sameclass = (rb[KP] != 0.0) == inS;
+            double tiq = (i < KP) ? rb[i] : 0.0;
+            tiq = sameclass ? tiq : -tiq;
             const double ip = 1.0 / pp;
             const bool act = piv >= 0, isrow = act && (i == piv);
             const double f = tiq * ip;
@@ -306,13 +319,15 @@ __device__ double nnls_lanes(const double *__restrict__ sG, const double *__rest
             const double fix = isrow ? ip : f;
             const int pfix = act ? pq : -1;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                const double rq = __shfl_sync(FULL, T[j], src);
-                const double t = fma(b, rq, a * T[j]);
-                T[j] = (j == pfix) ? fix : t;
+            for (int j = 0; j < KP; j += 2) {
+                const double2 rq = *reinterpret_cast<const double2 *>(rb + j);
+                const double t0 = fma(b, rq.x, a * T[j]), t1 = fma(b, rq.y, a * T[j + 1]);
+                T[j] = (j == pfix) ? fix : t0;
+                T[j + 1] = (j + 1 == pfix) ? fix : t1;
             }
             qv = fma(b, qq, a * qv);
             if (isrow) inS = !inS;
+            __syncwarp();                                    // the row buffer is rewritten by the next exchange
         }
         const double x = (inS && rowvalid && uvalid && qv > 0.0) ? qv : 0.0;
         t1 += x * ri;
