@@ -1585,53 +1585,59 @@ static int launch_nnls_columns(const double *G, const double *Minv, const double
 //                            HH' + eta^2 I), r = W'A / A H' = the stream-K partials summed in slot order
 // and part[b][0..4] = sum |res|, #{|res| > 0}, #{arg-max membership != previous test's}, sum x^2, sum (sum_c x_c)^2.
 // The memberships are max.col(ties.method = "first"), 1-based like R's (the previous ones start as 0).
-__global__ void __launch_bounds__(TILE_UNITS) snmf_check_kernel(const HalfParams p, int KP, int with_grad,
-                                                                 const int *__restrict__ idx_old, int *__restrict__ idx_new,
-                                                                 double *__restrict__ part) {
-    __shared__ double sG[64 * 64];
-    __shared__ double sred[TILE_UNITS / 32][5];
-    const int u = threadIdx.x, tile = blockIdx.x, k = p.k;
+#define SNMF_CHECK_Y 4            // rank slices per unit: blockDim = (128 units, 4)
+__global__ void __launch_bounds__(TILE_UNITS * SNMF_CHECK_Y) snmf_check_kernel(const HalfParams p, int KP, int with_grad,
+                                                                               const int *__restrict__ idx_old, int *__restrict__ idx_new,
+                                                                               double *__restrict__ part) {
+    // thread (u, y) evaluates the entries c = y, y + 4, ... of unit u; the unit's factor values are staged in shared
+    // memory (dynamic: KP x 128 doubles after the KP x KP Gram matrix) so that every slice sees all of x
+    extern __shared__ double chk_sh[];
+    double *sG = chk_sh, *sx = chk_sh + KP * KP;
+    __shared__ double sred[TILE_UNITS * SNMF_CHECK_Y / 32][5];
+    const int u = threadIdx.x, y = threadIdx.y, tid = y * TILE_UNITS + u, tile = blockIdx.x, k = p.k;
     const long long unit = (long long)tile * TILE_UNITS + u;
     const bool valid = unit < p.nvalid;
-    for (int e = u; e < KP * KP; e += TILE_UNITS) sG[e] = with_grad ? p.G[e] : 0.0;
-    double x[64];
-    double sx2 = 0.0, cs = 0.0;
-    int best = 0;
-    for (int c = 0; c < k; ++c) {
-        x[c] = valid ? p.Fout[(size_t)c * p.ldout + unit] : 0.0;
-        sx2 += x[c] * x[c];
-        cs += x[c];
-        if (x[c] > x[best]) best = c;
-    }
+    for (int e = tid; e < KP * KP; e += TILE_UNITS * SNMF_CHECK_Y) sG[e] = with_grad ? p.G[e] : 0.0;
+    for (int c = y; c < k; c += SNMF_CHECK_Y) sx[c * TILE_UNITS + u] = valid ? p.Fout[(size_t)c * p.ldout + unit] : 0.0;
     __syncthreads();
-    double sabs = 0.0, cnt = 0.0, changed = 0.0;
-    if (valid) {
+    double sabs = 0.0, cnt = 0.0, changed = 0.0, sx2 = 0.0, cs2 = 0.0;
+    if (valid && y == 0) {
+        // memberships (first maximum), sum x^2, (sum_c x_c)^2: one thread per unit, c in order
+        int best = 0;
+        double bx = sx[u], cs = 0.0;
+        for (int c = 0; c < k; ++c) {
+            const double x = sx[c * TILE_UNITS + u];
+            sx2 += x * x;
+            cs += x;
+            if (x > bx) { bx = x; best = c; }
+        }
+        cs2 = cs * cs;
         idx_new[unit] = best + 1;
         changed = (idx_old[unit] != best + 1) ? 1.0 : 0.0;
-        if (with_grad) {
-            const int expected = expected_slots(p, tile);
-            for (int c = 0; c < k; ++c) {
-                const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + u;
-                double r = 0.0;
-                for (int sl = 0; sl < expected; ++sl) r += ldcg(Pt + (size_t)sl * (KP * TILE_UNITS));
-                double g = 0.0;
-                for (int j = 0; j < k; ++j) g += sG[j * KP + c] * x[j];       // G symmetric: conflict-free
-                const double res = fabs(fmin(x[c], g - r));
-                sabs += res;
-                if (res > 0.0) cnt += 1.0;
-            }
+    }
+    if (valid && with_grad) {
+        const int expected = expected_slots(p, tile);
+        for (int c = y; c < k; c += SNMF_CHECK_Y) {
+            const double *Pt = p.P + ((size_t)tile * p.maxslots * KP + c) * (size_t)TILE_UNITS + u;
+            double r = 0.0;
+            for (int sl = 0; sl < expected; ++sl) r += ldcg(Pt + (size_t)sl * (KP * TILE_UNITS));
+            double g = 0.0;
+            for (int j = 0; j < k; ++j) g += sG[j * KP + c] * sx[j * TILE_UNITS + u];   // G symmetric: broadcast reads
+            const double res = fabs(fmin(sx[c * TILE_UNITS + u], g - r));
+            sabs += res;
+            if (res > 0.0) cnt += 1.0;
         }
     }
-    double v[5] = {sabs, cnt, changed, sx2, valid ? cs * cs : 0.0};
+    double v[5] = {sabs, cnt, changed, sx2, cs2};
 #pragma unroll
     for (int q = 0; q < 5; ++q) v[q] = warp_sum(v[q]);
-    if ((u & 31) == 0)
-        for (int q = 0; q < 5; ++q) sred[u >> 5][q] = v[q];
+    if ((tid & 31) == 0)
+        for (int q = 0; q < 5; ++q) sred[tid >> 5][q] = v[q];
     __syncthreads();
-    if (u < 5) {
+    if (tid < 5) {
         double a = 0.0;
-        for (int w = 0; w < TILE_UNITS / 32; ++w) a += sred[w][u];
-        part[(size_t)tile * 8 + u] = a;
+        for (int w = 0; w < TILE_UNITS * SNMF_CHECK_Y / 32; ++w) a += sred[w][tid];      // warp order: deterministic
+        part[(size_t)tile * 8 + tid] = a;
     }
 }
 
@@ -2455,8 +2461,11 @@ static int snmf_enqueue_check(mfb_als *s, int cur, int with_grad) {
     hn.Fout = s->Hb[cur];              // the factor under test, not the one the next H-step will write
     cudaStream_t st = s->ctx->stream;
     const int oi = s->idx_cur, ni = oi ^ 1;
-    snmf_check_kernel<<<s->T_h, TILE_UNITS, 0, st>>>(hn, s->KP, with_grad, s->idxH[oi], s->idxH[ni], s->chk_part);
-    snmf_check_kernel<<<s->T_w, TILE_UNITS, 0, st>>>(wp, s->KP, with_grad, s->idxW[oi], s->idxW[ni], s->chk_part + (size_t)s->T_h * 8);
+    const size_t smem = ((size_t)s->KP * s->KP + (size_t)s->KP * TILE_UNITS) * sizeof(double);
+    MFB_CUDA(cudaFuncSetAttribute(snmf_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 blk(TILE_UNITS, SNMF_CHECK_Y);
+    snmf_check_kernel<<<s->T_h, blk, smem, st>>>(hn, s->KP, with_grad, s->idxH[oi], s->idxH[ni], s->chk_part);
+    snmf_check_kernel<<<s->T_w, blk, smem, st>>>(wp, s->KP, with_grad, s->idxW[oi], s->idxW[ni], s->chk_part + (size_t)s->T_h * 8);
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
