@@ -2478,18 +2478,23 @@ int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, d
     if (converged) *converged = 0;
     int status = MFB_OK;
     int remaining = max_new_iters;
-    bool stopped = false, sums_current = false;
+    bool stopped = false, sums_current = false, have_ctrl = false;
     AlsCtrl *hc = (AlsCtrl *)s->ctx->pinned;
-    std::vector<double> part((size_t)(s->T_h + s->T_w) * 8);
+    const size_t npart = (size_t)(s->T_h + s->T_w) * 8;
+    std::vector<double> part_vec;
+    double *part_h = (double *)((char *)s->ctx->pinned + 4096);                       // pinned, after the control block
+    if (4096 + npart * sizeof(double) > s->ctx->pinned_bytes) { part_vec.resize(npart); part_h = part_vec.data(); }
     double tot[2][5];
-    auto read_check = [&]() -> int {
-        MFB_CUDA(cudaMemcpyAsync(part.data(), s->chk_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
+    auto read_check = [&](bool copied) -> int {
+        if (!copied) {
+            MFB_CUDA(cudaMemcpyAsync(part_h, s->chk_part, npart * sizeof(double), cudaMemcpyDeviceToHost, st));
+            MFB_CUDA(cudaStreamSynchronize(st));
+        }
         for (int f = 0; f < 2; ++f)
             for (int q = 0; q < 5; ++q) {
                 double a = 0.0;
                 const int b0 = f ? s->T_h : 0, b1 = f ? s->T_h + s->T_w : s->T_h;
-                for (int b = b0; b < b1; ++b) a += part[(size_t)b * 8 + q];       // block order
+                for (int b = b0; b < b1; ++b) a += part_h[(size_t)b * 8 + q];     // block order
                 tot[f][q] = a;
             }
         return MFB_OK;
@@ -2506,8 +2511,11 @@ int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, d
         int run = first ? 1 : 5 - (s->iters_total % 5);
         if (run > remaining) run = remaining;
         const bool check = first || ((s->iters_total + run) % 5 == 0);
-        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
+        if (!have_ctrl) {      // (later batches of this call re-arm the copy they read back at the end of the previous one)
+            MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+            MFB_CUDA(cudaStreamSynchronize(st));
+            have_ctrl = true;
+        }
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = 1; hc->eps = 1.0;
         hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
         hc->count_draws = 0; hc->pending_epoch = 0;
@@ -2522,6 +2530,7 @@ int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, d
         if (check) {
             MFB_TRY(enqueue_iteration(s, cur, false, 1));           // W'A and W'W + beta 11' of the new W
             MFB_TRY(snmf_enqueue_check(s, cur, 1));
+            MFB_CUDA(cudaMemcpyAsync(part_h, s->chk_part, npart * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
         MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
         MFB_CUDA(cudaStreamSynchronize(st));
@@ -2541,7 +2550,7 @@ int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, d
             break;
         }
         if (check) {
-            MFB_TRY(read_check());
+            MFB_TRY(read_check(true));
             sums_current = true;
             const double conv = tot[0][0] + tot[1][0], convnum = tot[0][1] + tot[1][1];
             const double erravg = conv / convnum;
@@ -2568,7 +2577,7 @@ int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, d
     if (status == MFB_OK && objective) {
         if (!sums_current) {
             MFB_TRY(snmf_enqueue_check(s, s->cur, 0));
-            MFB_TRY(read_check());
+            MFB_TRY(read_check(false));
         }
         set_objective();
         *objective = s->objective;
