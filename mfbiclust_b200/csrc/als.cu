@@ -2333,9 +2333,12 @@ int mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fi
     AlsCtrl *hc = (AlsCtrl *)s->ctx->pinned;
     while (remaining > 0) {
         const int batch = fixed_iters ? remaining : (remaining < 8 ? remaining : 8);
-        // arm the control block for this batch
-        MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
-        MFB_CUDA(cudaStreamSynchronize(st));
+        // arm the control block for this batch (later batches of the call re-arm the copy read back at the end of the
+        // previous one: nothing else writes the block in between)
+        if (first_batch) {
+            MFB_CUDA(cudaMemcpyAsync(hc, s->ctrl, sizeof(AlsCtrl), cudaMemcpyDeviceToHost, st));
+            MFB_CUDA(cudaStreamSynchronize(st));
+        }
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = fixed_iters ? 1 : 0; hc->eps = eps_conv;
         hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
         hc->count_draws = count ? 1 : 0;
