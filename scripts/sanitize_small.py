@@ -17,3 +17,6 @@ rf, cf = mfb.draw_folds(mfb.HostRng(1), 300, 40, 3)
 print("bcv", mfb.bcvGivenKs(A, np.arange(1, 9), 3, folds=(rf, cf))[:3])
 th = mfb.otsuHelper(A); print("otsu", th[:3], mfb.threshold(A, th, 2).sum())
 print("nnls", mfb.nnls(rs.random((50, 6)), rs.standard_normal((50, 9))).shape)
+A = np.asfortranarray(rs.random((150, 70)) + 0.05)
+r = mfb.nmf_snmf(A, 5, W0=rs.random((150, 5)), beta=float(A.mean()), eta=float(A.mean()), maxIter=12)
+print("snmf", r["iters"], r["objective"])
