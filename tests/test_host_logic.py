@@ -316,3 +316,65 @@ def test_filter_biclust_host_loop_replays_the_oracle(monkeypatch):
         ref = H.filter_biclust(rowx, bicx, max=mx, overlap_limit=lim)
         assert np.array_equal(got["chosen"], ref["chosen"]), trial
         assert np.array_equal(got["biclustered"], ref["biclustered"]), trial
+
+
+def test_snmf_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import mfbiclust_b200 as mfb
+    with pytest.raises(mfb.MfbError):
+        mfb.snmf(np.arange(1.0, 37.0).reshape(6, 6), 2, verbose=False)
+
+
+def test_snmf_wrapper_search_mirrors_the_reference(monkeypatch):
+    """R/bicluster.R:357-431 with the device run stubbed: beta is halved while NMF gives up after too many restarts
+    (:380-390), eta while a system is singular (:399-410), every attempt restarts from the same RNG state (:366), the
+    defaults are mean(A) (:351-352) and the validation message is the reference's (:353-355)."""
+    from mfbiclust_b200 import _cabi, backends as B
+
+    class FakeMatrix:
+        def __init__(self, ctx, host=None, **_):
+            self.shape = host.shape
+
+        def free(self):
+            pass
+    monkeypatch.setattr(_cabi, "Matrix", FakeMatrix)
+    monkeypatch.setattr(_cabi, "default_context", lambda *a, **k: object())
+    calls = []
+
+    class Rng:
+        def __init__(self):
+            self.state = 7
+
+        def get_state(self):
+            return self.state
+
+        def set_state(self, s):
+            self.state = s
+
+        def runif(self, n):
+            self.state += 1
+            return np.zeros(n)
+
+    def fake_run(Ad, k, W0=None, beta=0.01, eta=-1.0, rng=None, ctx=None, **kw):
+        calls.append((beta, eta, rng.state, kw))
+        rng.runif(3)                                   # the run consumes draws; the next attempt must not see that
+        if len(calls) <= 2:
+            return dict(W=None, H=None, iters=20, converged=False, objective=0.0, restarts=10, too_many_restarts=True,
+                        beta=beta, eta=eta)
+        if len(calls) == 3:
+            raise _cabi.MfbError(_cabi.MFB_SINGULAR, "system is computationally singular")
+        return dict(W=np.ones((4, 2)), H=np.ones((2, 3)), iters=55, converged=True, objective=1.5, restarts=0,
+                    too_many_restarts=False, beta=beta, eta=eta)
+    monkeypatch.setattr(B, "nmf_snmf", fake_run)
+    A = np.arange(1.0, 13.0).reshape(4, 3)
+    fit = B.snmf(A, 2, verbose=False, rng=Rng(), maxIter=77, unknown_option=1)
+    mean = A.mean()
+    assert [c[0] for c in calls] == [mean, mean / 2, mean / 4, mean / 4]
+    assert [c[1] for c in calls] == [mean, mean, mean, mean / 2]
+    assert all(c[2] == 7 for c in calls) and all(c[3] == {"maxIter": 77} for c in calls)
+    assert fit.method == "snmf" and fit.attempts == 4 and fit.iters == 55
+    assert fit.parameters == dict(beta=mean / 4, eta=mean / 2)
+    with pytest.raises(ValueError, match="eta must be >= 0 and beta must be > 0"):
+        B.snmf(A, 2, verbose=False, beta=0.0)
