@@ -193,3 +193,22 @@ def test_snmf_strategy_shifts_negative_input():
         warnings.simplefilter("error")
         bcs = B.BiclusterStrategy(A, 2, method="snmf", verbose=False, rng=B.HostRng(3))
     assert bcs.name == "SNMF | Otsu | 2" and bcs.biclust.RowxNumber.shape == (80, 2)
+
+
+def test_snmf_full_size_matches_oracle():
+    """The bench workload (20000 x 5000, k = 16; eta = mean(A), beta = mean(A) / 256 -- the first beta of mfBiclust's
+    halving sequence that keeps every row of H alive on it): two literal oracle iterations, with the convergence test
+    of iteration 1 on the way, against the device -- factors to 1e-8, identical zero patterns, same objective."""
+    from mfbiclust_b200 import backends as B
+    from oracle.snmf import nmf_snmf
+    from bench import make_workload
+    A, _, _ = make_workload()
+    m, n = A.shape
+    W0 = np.random.default_rng(43).random((m, 16))
+    mean = float(A.mean())
+    ref = nmf_snmf(A, W0, eta=mean, beta=mean / 256, max_iter=2)
+    out = B.nmf_snmf(A, 16, W0=W0, beta=mean / 256, eta=mean, maxIter=2)
+    assert out["iters"] == ref["iters"] == 2 and out["restarts"] == ref["restarts"] == 0
+    assert relfro(out["W"], ref["W"]) < 1e-8 and relfro(out["H"], ref["H"]) < 1e-8
+    assert np.array_equal(out["W"] == 0, ref["W"] == 0) and np.array_equal(out["H"] == 0, ref["H"] == 0)
+    assert abs(out["objective"] - ref["objective"]) < 1e-9 * ref["objective"]
