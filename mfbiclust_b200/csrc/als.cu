@@ -58,7 +58,8 @@ struct AlsCtrl {
     double dH2;
     double resid, dW, dH;
     unsigned long long draws;  // running total of those draws (ranks up to 32)
-    int pending_epoch;         // peer-memory sessions: epoch whose W-step scalars are published but not yet summed (0: none)
+    int pending_epoch;         // peer-memory sessions: epoch whose W-step scalars are written but not yet summed (0: none)
+    int unpublished_epoch;     // ... and whose flag has not been raised in the peers' blocks yet (0: none)
 };
 
 struct HalfParams {
@@ -225,9 +226,23 @@ __device__ __forceinline__ int pin_reg(int v) {
 // started (its CTAs only become resident as ours retire), then wait until the previous grid has completed and its
 // writes are visible before touching anything it produced.  Hides the launch latency between the four kernels of
 // an iteration; a no-op when the launch does not carry the attribute.
-__device__ __forceinline__ void pdl_prologue() {
+// development aid (mfb_als_timeline): globaltimer of block 0 / thread 0 of the kernels of the last iteration, when the
+// CTA was scheduled [2 slot] and when the kernel before it had completed [2 slot + 1]; slots: 0 H stream, 1 close,
+// 2 fold, 3 H solve, 4 W stream, 5 W solve; [24], [25] = the H stream of the iteration before
+__device__ unsigned long long g_tl[32];
+__device__ int g_tl_on = 0;
+__device__ __forceinline__ void pdl_prologue(int slot = -1) {
+    const bool rec = slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && *(volatile int *)&g_tl_on;
+    if (rec) {
+        if (slot == 0) g_tl[24] = g_tl[0];
+        g_tl[2 * slot] = globaltimer_ns();
+    }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (rec) {
+        if (slot == 0) g_tl[25] = g_tl[1];
+        g_tl[2 * slot + 1] = globaltimer_ns();
+    }
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, " ALS_STR(ALS_CONSUMERS) ";" ::: "memory"); }
 
@@ -330,7 +345,7 @@ template <int KB, bool WSTEP>
 __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREADS) : ((KB >= 5 && KB <= 7) ? SOLVE_MINB_LARGE : 1)) als_solve_kernel(const HalfParams p) {
     using Cfg = SolveCfg<KB>;
     constexpr int KP = Cfg::KP, SU = Cfg::SU, XS = Cfg::XS, UPW = Cfg::UPW, LP = Cfg::LP, R = Cfg::R;
-    pdl_prologue();
+    pdl_prologue(WSTEP ? 5 : 3);
     const int stopped = *(volatile int *)&p.ctrl->stop;     // consumed after the loads below are in flight
     extern __shared__ __align__(16) unsigned char solve_smem[];
     double *sG = (double *)solve_smem;
@@ -513,28 +528,34 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (KB <= 2) ? (768 / SOLVE_THREAD
         // host places after the NEXT H-step's stream kernel (or at the end of the batch): by then every rank's flag has
         // long arrived, so the skew between the ranks' last warps is absorbed by 140 us of streaming instead of sitting
         // on the critical path (+23 us per iteration at eight GPUs).
-        const ShardPeers *sp = p.peers;
-        __syncwarp();
-        shard_publish(sp, SHARD_OFF_FLAGSB, p.epoch, lane);
+        // (the flag itself -- a system-scope fence and `world` remote stores -- is raised by the next kernel that has
+        // time for it: the side job of the next H-step's stream kernel, or the kernel that closes the batch)
         if (lane == 0) {
             p.ctrl->pending_epoch = p.epoch;
+            p.ctrl->unpublished_epoch = p.epoch;
             __threadfence();
         }
     }
 }
 
-// Closes the iteration whose W-step scalars were published last (peer-memory sessions): waits for every rank's flag,
-// adds the ranks' sums in rank order (bit-identical on every rank) and runs the end of R's loop body.  One warp.  It
-// runs between the stream kernel of the next H-step and its fold kernel: every kernel after it sees the decision, the
-// stream kernel before it has at worst streamed A once for an iteration R would not have started (it writes partials
-// and the Gram of W only; if it found that Gram singular, the convergence found here takes precedence, as in R).
-__global__ void __launch_bounds__(32) als_shard_close_kernel(const HalfParams p) {
-    pdl_prologue();
+// Raises the flag of the W-step scalars this rank wrote last (flagsB) in every rank's block, if nobody has yet.  Called by
+// thread t of a group of at least `world` threads of ONE block per launch; the W-step solve kernel that wrote the
+// scalars is an earlier launch of the same stream.
+__device__ __forceinline__ void shard_publish_scalars(const HalfParams &p, int t) {
+    const int e = *(volatile int *)&p.ctrl->unpublished_epoch;
+    if (e == 0 || p.peers == nullptr) return;
+    shard_publish(p.peers, SHARD_OFF_FLAGSB, e, t);
+}
+
+// the end of R's loop body for the iteration whose W-step scalars were written last (one warp, peer-memory sessions):
+// waits for every rank's flag, adds the ranks' sums in rank order (bit-identical on every rank)
+__device__ __forceinline__ void shard_close_iteration(const HalfParams &p, int lane) {
     AlsCtrl *c = p.ctrl;
     const int e = *(volatile int *)&c->pending_epoch;
     if (e == 0 || p.peers == nullptr) return;
     const ShardPeers *sp = p.peers;
-    const int lane = threadIdx.x;
+    shard_publish_scalars(p, lane);                       // (end of a batch: no stream kernel has done it)
+    __syncwarp();
     if (lane < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, e, lane, c);
     __syncwarp();
     // lane q fetches rank q's three sums (all remote loads in flight at once); lane 0 adds them in rank order
@@ -552,8 +573,19 @@ __global__ void __launch_bounds__(32) als_shard_close_kernel(const HalfParams p)
     if (lane == 0) {
         if (c->reason != 5) finish_iteration(c, p.trace, a0, a1, a2);      // (5: a peer never arrived)
         c->pending_epoch = 0;
+        c->unpublished_epoch = 0;
         __threadfence();
     }
+}
+
+// Closes the iteration whose W-step scalars were published last (peer-memory sessions): waits for every rank's flag,
+// adds the ranks' sums in rank order (bit-identical on every rank) and runs the end of R's loop body.  One warp.  It
+// runs between the stream kernel of the next H-step and its fold kernel: every kernel after it sees the decision, the
+// stream kernel before it has at worst streamed A once for an iteration R would not have started (it writes partials
+// and the Gram of W only; if it found that Gram singular, the convergence found here takes precedence, as in R).
+__global__ void __launch_bounds__(32) als_shard_close_kernel(const HalfParams p) {
+    pdl_prologue(1);
+    shard_close_iteration(p, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -659,6 +691,16 @@ __device__ __noinline__ void gram_side_job(const HalfParams &p, const int t, dou
     constexpr int KP = KB * 8;
     const int k = p.k, G = (int)gridDim.x, b = (int)blockIdx.x;
     const int w = t >> 5, lane = t & 31;
+    // peer-memory sessions: the flag of the previous W-step's scalars (written by its solve kernel's last warp) is
+    // raised here, where nobody waits for the fence
+    if (!WSTEP && p.shard && p.peers && b == 0) {
+        const int e = *(volatile int *)&p.ctrl->unpublished_epoch;      // (uniform: cleared only after the barrier)
+        if (e != 0) {
+            shard_publish(p.peers, SHARD_OFF_FLAGSB, e, t);
+            gram_bar();
+            if (t == 0) p.ctrl->unpublished_epoch = 0;
+        }
+    }
     // --- partial Gram of this CTA's slice of units ---
     const unsigned long long t_begin = globaltimer_ns();
     const long long lo = (long long)b * p.nfix / G, hi = (long long)(b + 1) * p.nfix / G;
@@ -787,7 +829,7 @@ als_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int F_BOX = KP * 128;                      // one 16-unit box of the fixed factor: [KP][16] doubles
     constexpr int NFB = (WSTEP || F32) ? 2 : 1;          // factor boxes per stage (32 columns / 32 or 16 rows of reduction)
     constexpr int STAGE_BYTES = A_BYTES + NFB * F_BOX;
-    pdl_prologue();
+    pdl_prologue(WSTEP ? 4 : 0);
     if (*(volatile int *)&p.ctrl->stop) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1199,46 +1241,116 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const double *__rest
 // instead of on side-job warps that share their issue slots with the streaming warps, where the chain
 // publish -> wait -> remote loads -> sum -> invert stretched the stream kernel by 10-30 us.
 __device__ __noinline__ void shard_gram_sum_invert(const HalfParams &p, int KP) {
-    __shared__ double sGi[32 * 32 + 2];
+    // 128 threads, the matrix (up to 32 x 32) in registers: thread t owns the entries (i = t / 4, j = 8 (t % 4) .. + 7).
+    // Per pivot the owners put row p and column p into a double-buffered shared strip, ONE barrier, and every thread
+    // updates its entries -- the arithmetic and the acceptance rule of gauss_jordan_inverse / als_shard_invert_kernel:
+    //   a_ij - ((a_ip * ipiv) * a_pj) off the pivot cross, -a_ip * ipiv down column p, a_pj * ipiv along row p, ipiv at (p, p)
+    // (~0.15 us per pivot; with the matrix in shared memory and two barriers per pivot this block was the tail of the
+    // launch on one rank: 16 us at k = 16)
+    __shared__ double rowb[2][32], colb[2][32];
+    __shared__ unsigned long long nrm[2];
     const ShardPeers *sp = p.peers;
-    const int t = threadIdx.x, k = p.k, par = p.epoch & 1;
-    if (t < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + t, p.epoch, t, p.ctrl);
+    const int t = threadIdx.x, k = p.k, par = p.epoch & 1, world = sp->world;
+    if (t < world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSG) + t, p.epoch, t, p.ctrl);
+    if (t < 2) nrm[t] = 0ull;
     __syncthreads();
-    if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived
-    for (int e = t; e < KP * KP; e += TILE_UNITS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        double v = 0.0;
-        if (c1 < k && c2 < k) {
-            double g[SHARD_MAXP];                        // all ranks' loads in flight, then added in rank order
+    if (*(volatile int *)&p.ctrl->stop) return;          // a peer never arrived (or the previous iteration has just converged)
+    const int i = t >> 2, jq = t & 3, j0 = jq * 8;
+    double v[8];
+    double rs = 0.0;
 #pragma unroll
-            for (int q = 0; q < SHARD_MAXP; ++q) g[q] = (q < sp->world) ? ldcg(shard_gram(sp, q, par) + e) : 0.0;
+    for (int u0 = 0; u0 < 8; u0 += 2) {
+        double a[2] = {0.0, 0.0};
+        for (int q0 = 0; q0 < world; q0 += 8) {          // the ranks' loads of two entries in flight, added in rank order
+            double g[2][8];
 #pragma unroll
-            for (int q = 0; q < SHARD_MAXP; ++q) v += g[q];
+            for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    g[uu][q] = (q0 + q < world && i < k && j0 + u0 + uu < k) ? ldcg(shard_gram(sp, q0 + q, par) + i * KP + j0 + u0 + uu) : 0.0;
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a[uu] += g[uu][q];
         }
-        sGi[e] = v;
-        p.G[e] = v;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+            v[u0 + uu] = a[uu];
+            if (i < KP && j0 + u0 + uu < KP) p.G[i * KP + j0 + u0 + uu] = a[uu];
+            rs += fabs(a[uu]);
+        }
     }
+    // 1-norm of the symmetric matrix = largest absolute row sum (the 4 owners of a row are neighbouring lanes)
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    if (jq == 0 && i < k) atomicMax(&nrm[0], (unsigned long long)__double_as_longlong(rs));
+    int sing = 0;
+    for (int pv = 0; pv < k; ++pv) {
+        const int b = pv & 1;
+        if (i == pv) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rowb[b][j0 + u] = v[u];
+        }
+        if (jq == (pv >> 3)) {
+            double cv = v[0];
+#pragma unroll
+            for (int u = 1; u < 8; ++u) cv = ((pv & 7) == u) ? v[u] : cv;
+            colb[b][i] = cv;
+        }
+        __syncthreads();
+        double piv = rowb[b][pv];
+        if (!(piv > 0.0) || !isfinite(piv)) { sing = 1; piv = 1.0; }
+        const double ipiv = 1.0 / piv;
+        const double f = colb[b][i] * ipiv;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            const double rj = rowb[b][j];
+            if (i != pv) v[u] = (j != pv) ? v[u] - f * rj : -f;
+            else v[u] = (j != pv) ? rj * ipiv : ipiv;
+        }
+    }
+    rs = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        const bool in = i < k && j < k;
+        if (i < KP && j < KP) p.Minv[i * KP + j] = in ? v[u] : 0.0;
+        if (in) rs += fabs(v[u]);
+    }
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    if (jq == 0 && i < k) atomicMax(&nrm[1], (unsigned long long)__double_as_longlong(rs));
     __syncthreads();
-    const int sing = gauss_jordan_inverse(sGi, k, KP, t, TILE_UNITS, sGi + KP * KP, [] { __syncthreads(); });
-    for (int e = t; e < KP * KP; e += TILE_UNITS) {
-        const int c1 = e / KP, c2 = e - c1 * KP;
-        p.Minv[e] = (c1 < k && c2 < k) ? sGi[e] : 0.0;
-    }
-    if (t == 0 && sing) {
-        p.ctrl->reason = 3;
-        __threadfence();
-        p.ctrl->stop = 1;
+    if (t == 0) {
+        const double an = __longlong_as_double((long long)nrm[0]), in = __longlong_as_double((long long)nrm[1]);
+        if (!isfinite(in) || an * in * 2.220446049250313e-16 > 1.0) sing = 1;
+        if (sing) {
+            // (the close block of the same launch may find that the previous iteration converged: that takes precedence, as
+            // in R, whichever block comes first -- it overwrites the reason, this one only sets it if there is none)
+            atomicCAS(&p.ctrl->reason, 0, 3);
+            __threadfence();
+            p.ctrl->stop = 1;
+        }
     }
 }
 
-__global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg, int invert_block) {
-    pdl_prologue();
+__global__ void __launch_bounds__(TILE_UNITS) als_shard_fold_kernel(const HalfParams p, int KP, double *__restrict__ xchg, int invert_block,
+                                                                    int close_block) {
+    pdl_prologue(2);
     if (*(volatile int *)&p.ctrl->stop) return;
     if ((int)blockIdx.x == invert_block) {
         shard_gram_sum_invert(p, KP);
         return;
     }
-    const int nfold = invert_block >= 0 ? (int)gridDim.x - 1 : (int)gridDim.x;
+    if ((int)blockIdx.x == close_block) {
+        // The previous iteration is closed HERE, by one more block of this launch instead of a launch of its own (every
+        // flag has long arrived).  If it converged, this launch has folded and exchanged W'A of an iteration R would not
+        // have started -- on every rank alike, and the kernels after it see the decision and return.
+        if (threadIdx.x < 32) shard_close_iteration(p, threadIdx.x);
+        return;
+    }
+    const int nfold = (int)gridDim.x - (invert_block >= 0 ? 1 : 0) - (close_block >= 0 ? 1 : 0);
     const int tile = (int)blockIdx.x / KP, c = (int)blockIdx.x % KP, u = threadIdx.x;
     const long long tb = (long long)tile * p.SPT;
     int expected;
@@ -1395,29 +1507,7 @@ __global__ void __launch_bounds__(1024) als_shard_close_invert_kernel(const Half
     // published nothing -- identically on every rank
     if (*(volatile int *)&c->stop) return;
     if (t < 32) {
-        // ---- close the iteration whose W-step scalars were published last ----
-        const int e = *(volatile int *)&c->pending_epoch;
-        if (e != 0) {
-            const int lane = t;
-            if (lane < sp->world) shard_wait_flag((const int *)(sp->base[sp->rank] + SHARD_OFF_FLAGSB) + lane, e, lane, c);
-            __syncwarp();
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-            if (lane < sp->world) {
-                const double *xq = shard_xscal(sp, lane, e & 1);
-                x0 = ldcg(xq + 0); x1 = ldcg(xq + 1); x2 = ldcg(xq + 2);
-            }
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            for (int q = 0; q < sp->world; ++q) {
-                a0 += __shfl_sync(0xffffffffu, x0, q);
-                a1 += __shfl_sync(0xffffffffu, x1, q);
-                a2 += __shfl_sync(0xffffffffu, x2, q);
-            }
-            if (lane == 0) {
-                if (c->reason != 5) finish_iteration(c, p.trace, a0, a1, a2);      // (5: a peer never arrived)
-                c->pending_epoch = 0;
-                __threadfence();
-            }
-        }
+        shard_close_iteration(p, t);                     // the iteration whose W-step scalars were written last
     } else if (t < 32 + sp->world) {
         // ---- every rank's W_q'W_q of this epoch has been published ----
         const int q = t - 32;
@@ -2196,6 +2286,13 @@ int mfb_als_shard_stamps(mfb_als *s, unsigned long long out[8], int reset) {
     return MFB_OK;
 }
 
+// development aid: the kernel-start stamps of the last iteration (see g_tl); enable != 0 switches recording on
+int mfb_als_timeline(unsigned long long out[32], int enable) {
+    if (out) MFB_CUDA(cudaMemcpyFromSymbol(out, g_tl, 32 * sizeof(unsigned long long)));
+    MFB_CUDA(cudaMemcpyToSymbol(g_tl_on, &enable, sizeof(int)));
+    return MFB_OK;
+}
+
 int mfb_als_shard_disconnect(mfb_als *s) {
     MFB_ARG(s && s->shard, "not a row-sharded session");
     MFB_ARG(s->epoch == 0, "disconnect before the first iteration");
@@ -2279,13 +2376,14 @@ static int enqueue_iteration(mfb_als *s, int cur, bool use_restart_w, int h_whic
         // peer memory: (W'W)^-1 is formed from the published W_q'W_q after the stream kernel -- by an extra block of
         // the fold kernel (ranks up to 32) or by the kernel that closes the previous iteration (1024 threads, above)
         const bool inv_in_fold = peer && h.peer_invert_later && s->KP <= 32;
-        if (peer) {
-            if (h.peer_invert_later && !inv_in_fold) MFB_CUDA(launch_pdl(als_shard_close_invert_kernel, 1, 1024, 0, st, pdl, h, s->KP));
+        if (peer && !inv_in_fold) {
+            if (h.peer_invert_later) MFB_CUDA(launch_pdl(als_shard_close_invert_kernel, 1, 1024, 0, st, pdl, h, s->KP));
             else MFB_CUDA(launch_pdl(als_shard_close_kernel, 1, 32, 0, st, pdl, h));
         }
         double *xbuf = peer ? (double *)(s->shared + SHARD_OFF_XCHG) + (size_t)(h.epoch & 1) * s->shard_slots * s->xchg_cnt : s->xchg;
-        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP + (inv_in_fold ? 1 : 0), TILE_UNITS, 0, st, pdl, h, s->KP, xbuf,
-                            inv_in_fold ? s->T_h * s->KP : -1));
+        // (ranks up to 32: the fold launch carries two more blocks, one for (W'W)^-1 and one that closes the previous iteration)
+        MFB_CUDA(launch_pdl(als_shard_fold_kernel, s->T_h * s->KP + (inv_in_fold ? 2 : 0), TILE_UNITS, 0, st, pdl, h, s->KP, xbuf,
+                            inv_in_fold ? s->T_h * s->KP : -1, inv_in_fold ? s->T_h * s->KP + 1 : -1));
         MFB_TRY(prof_mark(s));
         if (!peer) {
             if (s->allreduce(s->allreduce_user, s->xchg, (int64_t)cnt, (void *)st) != 0) {
@@ -2342,7 +2440,7 @@ int mfb_als_iterate_draws(mfb_als *s, int max_new_iters, double eps_conv, int fi
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = fixed_iters ? 1 : 0; hc->eps = eps_conv;
         hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
         hc->count_draws = count ? 1 : 0;
-        hc->pending_epoch = 0;
+        hc->pending_epoch = 0; hc->unpublished_epoch = 0;
         if (first_batch) { draws0 = hc->draws; first_batch = false; }
         if (batch > s->max_trace) { mfb_set_error("too many iterations in one batch"); return MFB_ERR_ARG; }
         MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
@@ -2521,7 +2619,7 @@ int mfb_snmf_iterate(mfb_als *s, int max_new_iters, int wminchange, int iconv, d
         }
         hc->stop = 0; hc->reason = 0; hc->iters_done = 0; hc->fixed = 1; hc->eps = 1.0;
         hc->groups_done[0] = hc->groups_done[1] = 0; hc->nzmask = 0ull;
-        hc->count_draws = 0; hc->pending_epoch = 0;
+        hc->count_draws = 0; hc->pending_epoch = 0; hc->unpublished_epoch = 0;
         MFB_CUDA(cudaMemcpyAsync(s->ctrl, hc, sizeof(AlsCtrl), cudaMemcpyHostToDevice, st));
         int cur = s->cur;
         for (int b = 0; b < run; ++b) {
