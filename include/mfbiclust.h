@@ -141,11 +141,12 @@ int  mfb_als_begin_sharded(mfb_context *ctx, mfb_matrix *A_rows, int64_t m_globa
 /*
  * Optional, when all ranks are on ONE node: exchange over peer memory instead of the callback.  Every rank exports
  * the cudaIpc handle (64 bytes) of its exchange block, the host gathers the handles of all ranks (rank order) and
- * every rank connects BEFORE the first iteration.  From then on the two per-iteration exchanges are a one-shot
- * all-reduce fused into the kernels that consume the sums: each rank publishes its folded [W_r'A_r | W_r'W_r] and
- * its scalars with a system-scope release flag in every peer's block, and the invert / H-step solve / finish kernels
- * read all ranks' buffers over NVLink and add them in rank order (bit-identical on every rank; no collective launch,
- * no host involvement).  At most 16 ranks.  mfb_als_shard_connect returns MFB_ERR_UNSUPPORTED when a peer block
+ * every rank connects BEFORE the first iteration.  From then on the per-iteration exchanges are one-shot all-reduces
+ * fused into the kernels that consume the sums: each rank raises a system-scope release flag in every peer's block
+ * once its W_r'W_r, its folded W_r'A_r (stored straight into every peer's block for up to 8 ranks, read remotely
+ * beyond) and its scalars are in place, and the consumers add the ranks' buffers in rank order (bit-identical on
+ * every rank; no collective launch, no host involvement).  Only the W'A exchange is a rendezvous on the critical
+ * path; W'W and the scalars are consumed a kernel later, when every flag has long arrived.  At most 16 ranks.  mfb_als_shard_connect returns MFB_ERR_UNSUPPORTED when a peer block
  * cannot be mapped (the session then keeps using the callback; the ranks must agree on the outcome).  No rank may
  * call mfb_als_end before every rank has its result (the blocks are read remotely until then).  A peer that never
  * arrives makes the waiting kernels time out (20 s) and the call fail with MFB_ERR_CUDA.
