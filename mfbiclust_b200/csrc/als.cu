@@ -2525,8 +2525,8 @@ int mfb_snmf_begin(mfb_context *ctx, mfb_matrix *A, int k, const double *W0, dou
     double stats[5];
     MFB_TRY(mfb_matrix_stats(A, stats));
     if (eta < 0.0) eta = stats[1];                  // .nmf_snmf: if (eta < 0) eta = max(A)
-    std::vector<double> Wn, Hz((size_t)(k > 0 ? k : 1) * A->n, 0.0);
     MFB_ARG(k >= 1 && k <= 64, "k must be in 1..64");
+    std::vector<double> Wn, Hz((size_t)k * A->n, 0.0);
     unit_columns(W0, A->m, k, Wn);
     mfb_als *s = nullptr;
     MFB_TRY(als_begin_impl(ctx, A, A->m, k, Wn.data(), Hz.data(), stats[1], nullptr, nullptr, &s));
