@@ -462,7 +462,7 @@ def run_sharded_e2e(mfb, ctx, A, W0, H0, rank, world, local_rank, K, k=RANK):
     dt = float(t.item())
     h2d = (A.nbytes + W0.nbytes + H0.nbytes) / K
     d2h = (r["W"].nbytes + r["H"].nbytes) / K
-    return {"value": _r(world * K / dt), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    return {"value": _r(world * K / dt), "unit": UNIT, "h2d_bytes_per_step": int(round(h2d)), "d2h_bytes_per_step": int(round(d2h)),
             "call": "als_replicate_sharded (%s)" % r["exchange"]}
 
 
@@ -598,7 +598,7 @@ def main():
         ref = als_replicate(A, W0, H0, max_iter=nit, fixed_iters=True, literal=True)
         dt = time.perf_counter() - t0
         cpu = {"value": _r(nit / dt), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{nit} literal oracle iterations of the same workload"}
+               "sample": f"{nit} oracle iterations of this workload"}
         got = mfb.als_replicate(Ad, RANK_, W0, H0, maxIter=nit, fixed_iters=True, ctx=ctx)
         parity = {"iters": nit,
                   "rel_fro_W": _r(float(np.linalg.norm(got["W"] - ref["W"]) / np.linalg.norm(ref["W"])), 3),
@@ -644,7 +644,7 @@ def main():
             # per step (= per iteration) byte counts, from the buffers actually copied by the call
             h2d = (A.nbytes + W0.nbytes + H0.nbytes) / K
             d2h = (Wout.nbytes + Hout.nbytes + tr.nbytes) / K
-            e2e = {"value": _r(world * K / dt), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            e2e = {"value": _r(world * K / dt), "unit": UNIT, "h2d_bytes_per_step": int(round(h2d)), "d2h_bytes_per_step": int(round(d2h)),
                    "call": "mfb_als_run_host"}
             # the host-buffer call must return what the resident session computes from the same start
             chk = mfb.als_replicate(Ad, RANK_, W0, H0, maxIter=K, fixed_iters=True, ctx=ctx)
