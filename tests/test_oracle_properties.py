@@ -78,3 +78,28 @@ def test_otsu_maximises_the_between_class_variance_of_the_histogram():
                 arg.append(i)
         got = O.otsu_from_counts(counts)
         assert abs(got - (mids[arg[0]] + mids[arg[-1]]) / 2.0) < 1e-12, (got, arg)
+
+
+def test_snmf_oracle_is_block_coordinate_descent_on_its_objective():
+    """oracle/snmf.py beyond its k = 1 fixture (ref_bces.rda): each half-step of NMF's snmf/r is the exact minimiser of
+    1/2 (||A - WH||^2 + eta ||W||^2 + beta sum_j (sum_c H_cj)^2) over one factor, so the objective never increases from
+    one iteration to the next, and at the iteration where the run stops both KKT blocks are small against their
+    first values; memberships are max.col(ties = "first")."""
+    from oracle.snmf import kkt_residual, max_col_first, nmf_snmf, snmf_objective
+    rs = np.random.default_rng(12)
+    m, n, k = 70, 50, 4
+    Wt = np.where(rs.random((m, k)) < 0.3, rs.random((m, k)) + 0.5, 0.0)
+    Ht = np.where(rs.random((k, n)) < 0.3, rs.random((k, n)) + 0.5, 0.0)
+    A = Wt @ Ht + 0.05 * rs.random((m, n))
+    W0 = rs.random((m, k))
+    beta = eta = float(A.mean())
+    objs = [nmf_snmf(A, W0, eta=eta, beta=beta, max_iter=t)["objective"] for t in range(1, 13)]
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(objs, objs[1:])), objs
+    first = nmf_snmf(A, W0, eta=eta, beta=beta, max_iter=1)
+    done = nmf_snmf(A, W0, eta=eta, beta=beta)
+    assert done["iters"] % 5 == 0 and done["iters"] >= 50 and done["restarts"] == 0      # 10 stable tests, every fifth iteration
+    c1, n1 = kkt_residual(A, first["W"], first["H"], eta, beta)
+    c2, n2 = kkt_residual(A, done["W"], done["H"], eta, beta)
+    assert c2 / n2 <= 1e-4 * c1 / n1
+    assert abs(done["objective"] - snmf_objective(A, done["W"], done["H"], eta, beta)) < 1e-12 * done["objective"]
+    assert list(max_col_first(np.array([[1.0, 3.0, 3.0], [2.0, 2.0, 1.0], [0.0, 0.0, 0.0]]))) == [2, 1, 1]
