@@ -378,3 +378,37 @@ def test_snmf_wrapper_search_mirrors_the_reference(monkeypatch):
     assert fit.parameters == dict(beta=mean / 4, eta=mean / 2)
     with pytest.raises(ValueError, match="eta must be >= 0 and beta must be > 0"):
         B.snmf(A, 2, verbose=False, beta=0.0)
+
+
+def test_built_library_uses_the_blackwell_paths():
+    """The hot kernels are compiled for sm_100a with the hardware paths DESIGN.md claims (cuobjdump on the in-tree
+    objects, no GPU needed): tcgen05.mma + tensor memory + TMA in the FP32 stream kernels, FP64 tensor cores + TMA +
+    mbarriers in the FP64 ones, TMA bulk loads in the NIPALS stream kernel, and no legacy mma.sync tiles."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    obj = os.path.join(ROOT, "mfbiclust_b200", "lib", "als.o")
+    if not os.path.exists(obj):
+        pytest.skip("objects not built in-tree")
+    head = subprocess.run(["cuobjdump", "-lelf", obj], capture_output=True, text=True).stdout
+    assert "sm_100a" in head, head
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    per = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = set()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        if m and cur:
+            per[cur].add(m.group(1))
+    tf32 = [ops for k, ops in per.items() if "als_stream_tf32_kernel" in k]
+    f64 = [ops for k, ops in per.items() if "als_stream_kernel" in k]
+    assert tf32 and all({"UTCHMMA", "LDTM", "STTM", "UTMALDG", "SYNCS"} <= ops for ops in tf32)
+    assert f64 and all({"DMMA", "UTMALDG", "SYNCS"} <= ops for ops in f64)
+    assert not any({"HMMA", "IMMA"} & ops for ops in per.values())
+    nip = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "mfbiclust_b200", "lib", "nipals.o")],
+                         capture_output=True, text=True).stdout
+    assert "UTMALDG" in nip
